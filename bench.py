@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""Benchmark of the batched SE(3) reverse-diffusion sampling path (BASELINE.json metric:
+residue-steps/s = B * L * num_steps / time of the denoiser call).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One bench "step" = ONE complete `dpm_solver` call (config/denoiser/dpm.yaml: 50 diffusion steps,
+0.99 -> 0.001, i.e. 100 score-model evaluations + prior sampling) over one batch of synthetic input:
+PSD95-PDZ3 length (L = 84), batch 256 per GPU, bioemu-v1.0 architecture with seeded random-init
+weights, synthetic N(0,1) embeddings (BASELINE.json configs[1]).  See DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="PSD95-PDZ3 dpm_solver", L=84, B=256, num_steps=50, max_t=0.99, min_t=0.001)
+FULL_SDE = dict(eps_t=0.001, num_sigma=1000, num_omega=2000, omega_exponent=3, l_max=2000, sigma_min=0.02, sigma_max=2.33,
+                tol=1e-7)
+METRIC, UNIT = "SE(3) reverse-diffusion residue-steps/sec", "residue-steps/s"
+
+
+def synthetic_inputs(L: int):
+    g = torch.Generator().manual_seed(0)
+    return torch.randn(L, 384, generator=g), torch.randn(L * L, 128, generator=g)
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference sampler on the host cores (bounded sample)
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_run(L: int, sample_B: int, sample_steps: int, state_dict, tables: dict | None, repeats: int = 1):
+    """Times oracle.samplers.dpm_solver (the CPU restatement of bioemu.denoiser.dpm_solver driving the DiG
+    score model exactly as the reference does, per-sample pair tensors recomputed every call)."""
+    from oracle import samplers as osamp
+    from oracle import so3 as oso3
+    from oracle.score_model import ScoreModelOracle
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    single, pair = synthetic_inputs(L)
+    if tables is None:  # reduced table resolution: table construction is not part of the timed path
+        tab = oso3.SO3Tables(eps_t=0.001, num_sigma=200, num_omega=500, l_max=500, sigma_min=0.02, sigma_max=2.33)
+    else:
+        tab = oso3.SO3Tables(**FULL_SDE, tables=tables)
+    r3 = osamp.CosineVP(0.008)
+    model = ScoreModelOracle(state_dict, num_heads=32)
+    model.set_context(single.repeat(sample_B, 1), [pair.view(L, L, 128)] * sample_B, [L] * sample_B)
+    times = []
+    with torch.no_grad():
+        for rep in range(repeats):
+            torch.manual_seed(rep)
+            t0 = time.perf_counter()
+            osamp.dpm_solver(model, [L] * sample_B, r3, tab, sample_steps, WORKLOAD["max_t"], WORKLOAD["min_t"])
+            times.append(time.perf_counter() - t0)
+    return times, cores
+
+
+def reference_arm(args):
+    """`--impl reference`: rank 0 only, CPU, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.score_model import init_state_dict
+
+    L = WORKLOAD["L"]
+    sB, sS = 2, 2
+    sd = init_state_dict(seed=0)
+    total = args.steps + args.warmup
+    times, cores = cpu_reference_run(L, sB, sS, sd, None, repeats=total)
+    timed = times[args.warmup:]
+    per = sum(timed) / len(timed)
+    value = sB * L * sS / per
+    sample = f"dpm_solver on B={sB} of {WORKLOAD['B']} samples, {sS} of {WORKLOAD['num_steps']} diffusion steps, L={L}, fp32, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD['name']} L={L} B={WORKLOAD['B']} steps={WORKLOAD['num_steps']} (bounded CPU sample)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=WORKLOAD["B"], help="samples per GPU")
+    ap.add_argument("--length", type=int, default=WORKLOAD["L"])
+    ap.add_argument("--diffusion-steps", type=int, default=WORKLOAD["num_steps"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch.distributed as dist
+
+    from se3diff_b200 import ops, shortcuts
+    from se3diff_b200.chemgraph import Batch, ChemGraph, complete_graph_edge_index
+    from se3diff_b200.distributed import gather_ensemble, init_from_env
+
+    rank, world, local_rank = init_from_env(args.gpus)
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    L, B, S = args.length, args.batch, args.diffusion_steps
+
+    # model, SDEs (table construction excluded from timing, as BASELINE.md section 2 prescribes)
+    torch.manual_seed(0)
+    model = shortcuts.DiGConditionalScoreModel(precision=args.precision).eval().to(dev)
+    so3 = shortcuts.DiGSO3SDE(**FULL_SDE).to(dev)
+    sdes = {"node_orientations": so3, "pos": shortcuts.CosineVPSDE(0.008)}
+    single, pair = synthetic_inputs(L)
+    nan = float("nan")
+    graph = ChemGraph(pos=torch.full((L, 3), nan), node_orientations=torch.full((L, 3, 3), nan),
+                      edge_index=complete_graph_edge_index(L), single_embeds=single, pair_embeds=pair)
+    host_batch = Batch.from_data_list([graph] * B)                      # sample.py:223
+    for k, v in host_batch.items():
+        if torch.is_tensor(v):
+            host_batch[k] = v.pin_memory()
+    dev_batch = host_batch.to(dev)
+    kw = dict(sdes=sdes, score_model=model, num_steps=S, max_t=WORKLOAD["max_t"], min_t=WORKLOAD["min_t"], device=dev)
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def one_step(seed, batch, gather):
+        torch.manual_seed(seed)                                             # seed = global sample offset (sample.py:288-306)
+        out = shortcuts.dpm_solver(batch=batch, **kw)
+        frames = torch.cat([out["pos"].view(B, L, 3), out["node_orientations"].view(B, L, 9)], dim=-1)
+        return gather_ensemble(frames) if gather else frames
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing (value) -----------------------------------------------------------------
+    for w in range(args.warmup):
+        one_step(rank * B + w, dev_batch, True)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    ops.launch_count_reset()
+    evs = []
+    for k in range(args.steps):
+        flush.zero_()                                                        # L2 flush between timed iterations (untimed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        one_step(1000 + rank * B + k, dev_batch, True)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    launches = ops.launch_count()
+    clk = clocks.stop() if rank == 0 else None
+    t_dev = sum(a.elapsed_time(b) for a, b in evs) / 1e3
+    # ---- end-to-end timing through the public API with host buffers ----------------------------------------
+    h2d = sum(v.numel() * v.element_size() for _, v in host_batch.items() if torch.is_tensor(v))
+    d2h = B * L * 12 * 4
+    barrier()
+    evs = []
+    for k in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        frames = one_step(2000 + rank * B + k, host_batch, False)             # batch.to(device) inside dpm_solver
+        host_frames = frames.to("cpu")                                       # sample.py:235-236
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    t_e2e = sum(a.elapsed_time(b) for a, b in evs) / 1e3
+    assert host_frames.shape == (B, L, 12) and bool(torch.isfinite(host_frames).all())
+    times = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = times.tolist()
+
+    # ---- per-kernel roofline pass (same workload, instrumented, after the timed region) -------------------
+    roof, roof_extra = None, []
+    if rank == 0:
+        try:
+            from se3diff_b200.profiling import kernel_rooflines
+
+            roof, roof_extra = kernel_rooflines(lambda: one_step(3000, dev_batch, False), L=L, B=B)
+        except Exception as e:  # noqa: BLE001
+            roof = {"error": repr(e)}
+
+    if rank == 0:
+        value = world * B * L * S * args.steps / t_dev
+        e2e = world * B * L * S * args.steps / t_e2e
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+                tables = dict(omega_grid=so3.igso3.omega_grid.cpu(), cdf_igso3=so3.igso3.cdf_igso3.cpu(),
+                              cdf_uso3=so3.uso3.cdf_igso3.cpu(), score_scaling=so3.score_function.score_scaling.cpu())
+                sB, sS = 2, 2
+                (t_cpu,), cores = cpu_reference_run(L, sB, sS, sd, tables)
+                cpu = {"value": sB * L * sS / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+                       "sample": f"oracle dpm_solver, B={sB} of {B} samples, {sS} of {S} diffusion steps, L={L}, fp32, "
+                                 f"{cores} threads, {t_cpu:.1f} s"}
+            except Exception as e:  # noqa: BLE001
+                cpu = {"error": repr(e)}
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
+            "config": {"workload": f"{WORKLOAD['name']} L={L} B={B}/GPU {S} diffusion steps (2 score evals each), "
+                                   f"bioemu-v1.0 architecture random-init, synthetic embeddings",
+                       "step": "one dpm_solver call incl. prior sampling" + (" + NCCL ensemble all_gather" if world > 1 else ""),
+                       "l2": "512 MiB buffer written between timed iterations", "parallelism": f"dp{world} (independent samples)"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": t_e2e / args.steps * 1e3},
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_other_kernels": roof_extra, "cpu_baseline": cpu,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,246 @@
+/*
+ * se3diff_b200 -- C ABI of the B200 (sm_100a) kernels behind the SE(3) reverse-diffusion
+ * sampling path of ddrichman/SE3Diff (vendored BioEmu 0.1.12).
+ *
+ * Boundary rules:
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer unless the
+ *     parameter is named `h_*`;
+ *   - the caller owns and allocates every buffer; kernels never allocate and never synchronise
+ *     the host (CUDA-graph capturable); work is enqueued on `stream` (a cudaStream_t cast to void*);
+ *   - return 0 on success, a negative SE3_E* code otherwise, text via se3_last_error();
+ *   - no global mutable state other than the thread-local last-error string.
+ *
+ * Each entry point cites the reference interface it replaces as file:line relative to
+ * /root/reference/bioemu/src/bioemu/ .  Arrays use the reference's own memory layout: rotations
+ * are row-major [n,3,3] fp32 (ChemGraph.node_orientations), vectors [n,3] fp32 (ChemGraph.pos and
+ * the axis-angle scores).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ */
+#ifndef SE3DIFF_B200_H
+#define SE3DIFF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SE3_OK 0
+#define SE3_EINVAL (-1)   /* bad argument (null pointer, negative size, unsupported shape) */
+#define SE3_ECUDA (-2)    /* CUDA runtime error; see se3_last_error() */
+#define SE3_EUNSUPPORTED (-3)
+
+typedef void* se3_stream_t; /* cudaStream_t */
+
+const char* se3_last_error(void);
+int se3_abi_version(void);
+/* number of kernels launched by this library in the calling thread since the last reset
+ * (bench.py's `gpu_launches`). */
+int64_t se3_launch_count(void);
+void se3_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K2 -- SO(3) exp / log / composition                         so3_sde.py:478-554, 557-676, 782-911
+ * ------------------------------------------------------------------------------------------ */
+/* rotvec_to_rotmat (so3_sde.py:533-554): Rodrigues, Taylor coefficients when |theta| < tol. */
+int se3_so3_exp(const float* rotvec, float* rotmat, int64_t n, float tol, se3_stream_t stream);
+int se3_so3_exp_f64(const double* rotvec, double* rotmat, int64_t n, double tol, se3_stream_t stream);
+/* rotmat_to_rotvec (so3_sde.py:557-648): atan2 angle, three regimes with the reference's isclose
+ * thresholds (|theta| <= 1e-8 ; |theta-pi| <= 1e-2 + 1e-5*pi ; else). */
+int se3_so3_log(const float* rotmat, float* rotvec, int64_t n, se3_stream_t stream);
+int se3_so3_log_f64(const double* rotmat, double* rotvec, int64_t n, se3_stream_t stream);
+/* angle_from_rotmat (so3_sde.py:651-676): any of angle/sin/cos may be NULL. */
+int se3_so3_angle(const float* rotmat, float* angle, float* sin_out, float* cos_out, int64_t n,
+                  se3_stream_t stream);
+/* apply_rotvec_to_rotmat (so3_sde.py:782-802): out = R . Exp(v).  `out` may alias `rotmat`. */
+int se3_so3_compose_rotvec(const float* rotmat, const float* rotvec, float* out, int64_t n, float tol,
+                           se3_stream_t stream);
+/* rot_mult with optional transpose of the left factor (so3_sde.py:870-877): out = op(A) . B */
+int se3_so3_matmul(const float* a, const float* b, float* out, int64_t n, int transpose_a,
+                   se3_stream_t stream);
+/* rot_vf (so3_sde.py:880-891): out = Log(base^T . target) */
+int se3_so3_rel_log(const float* base, const float* target, float* rotvec, int64_t n, se3_stream_t stream);
+/* scale_rotmat / geodesic_t (so3_sde.py:406-425, 894-911): out = base . Exp(t * Log(base^T . target)) */
+int se3_so3_geodesic(const float* base, const float* target, float t, float* out, int64_t n, float tol,
+                     se3_stream_t stream);
+/* rotquat_to_rotvec / rotquat_to_rotmat (so3_sde.py:725-779); quaternion [r,i,j,k]; either output
+ * may be NULL. */
+int se3_so3_from_quat(const float* quat, float* rotvec, float* rotmat, int64_t n, float tol,
+                      se3_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3 + frame update -- the per-step SDE algebra fused with the score conversion of
+ * _get_score (denoiser.py:169-203).  `m_rot`/`m_pos` are the RAW score-model outputs
+ * (out["node_orientations"], out["pos"]); the conversion rot_score = m_rot*rot_scale and
+ * pos_score = m_pos/pos_std happens in-kernel.  All per-graph schedule quantities are identical
+ * for every graph of a batch on this path (one t per step), so they travel as by-value scalars
+ * computed on the host in fp32 (0 bytes of HBM traffic, graph-capturable).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct se3_em_scalars {
+    float dt;            /* dts[i]                                   denoiser.py:232,258       */
+    float sqrt_abs_dt;   /* sqrt(|dt|)                               denoiser.py:81            */
+    float noise_weight;  /* EulerMaruyamaPredictor.noise_weight      denoiser.py:51            */
+    float score_weight;  /* 0.5*mcf*(1+nw^2)                         denoiser.py:64            */
+    float rot_g;         /* DiGSO3SDE.beta(t) = g(t)                 so3_sde.py:346-363        */
+    float rot_scale;     /* get_score_scaling(t)                     so3_sde.py:142-161        */
+    float pos_beta;      /* CosineVPSDE.beta(t)                      sde_lib.py:160-162        */
+    float pos_sqrt_beta; /* sqrt(beta(t))  (the R3 diffusion)        sde_lib.py:148            */
+    float pos_std;       /* sqrt(1-alpha(t)^2)                       sde_lib.py:128            */
+    float tol;           /* SO3SDE.tol                               so3_sde.py:78             */
+} se3_em_scalars;
+
+/* One Euler-Maruyama reverse step on both fields (EulerMaruyamaPredictor.update_given_score,
+ * denoiser.py:54-116; loop body denoiser.py:254-262 and 324-338).
+ *   u_rot/u_pos   : optional control from the fine-tune model (finetune_score), NULL for plain EM
+ *   z_rot/z_pos   : standard normals [n,3] (the randn_like of denoiser.py:80), drawn by the caller
+ *   dw_rot/dw_pos : optional outputs dW = nw*sqrt|dt|*z (denoiser.py:81,335), NULL to skip
+ * rot_out/pos_out may alias rot/pos. */
+int se3_frame_update_em(const float* rot, const float* pos, const float* m_rot, const float* m_pos,
+                        const float* u_rot, const float* u_pos, const float* z_rot, const float* z_pos,
+                        float* rot_out, float* pos_out, float* dw_rot, float* dw_pos, int64_t n,
+                        const se3_em_scalars* h_scalars, se3_stream_t stream);
+
+typedef struct se3_dpm_scalars {
+    float pos_std_t;      /* sigma_t = sqrt(1-alpha_t^2)              denoiser.py:677          */
+    float pos_c_x_mid;    /* alpha_lambda/alpha_t                     denoiser.py:700          */
+    float pos_c_s_mid;    /* sigma_lambda*sigma_t*(exp(h/2)-1)        denoiser.py:701          */
+    float pos_std_lam;    /* sigma_lambda                             denoiser.py:693          */
+    float pos_c_x_fin;    /* alpha_next/alpha_t                       denoiser.py:734          */
+    float pos_c_s_fin;    /* sigma_next*sigma_lambda*(exp(h)-1)       denoiser.py:735          */
+    float rot_scale_t;    /* get_score_scaling(t)                                              */
+    float rot_scale_lam;  /* get_score_scaling(t_lambda)                                       */
+    float rot_g_t;        /* g(t)                                                              */
+    float rot_g_lam;      /* g(t_lambda)                                                       */
+    float dt_mid;         /* (t_lambda - t)[0]                        denoiser.py:721,745      */
+    float dt;             /* dts[i]                                   denoiser.py:746,756      */
+    float tol;
+} se3_dpm_scalars;
+
+/* DPM-Solver-2 first half (denoiser.py:699-727): pos_u = c_x*pos + c_s*(m_pos/std_t),
+ * rot_u = rot . Exp(-0.5*g_t^2*(m_rot*scale_t) * dt_mid). */
+int se3_frame_update_dpm_mid(const float* rot, const float* pos, const float* m_rot, const float* m_pos,
+                             float* rot_u, float* pos_u, int64_t n, const se3_dpm_scalars* h_scalars,
+                             se3_stream_t stream);
+/* DPM-Solver-2 second half (denoiser.py:733-762): needs the first call's raw rotation output
+ * (m_rot_t) and the second call's outputs at (pos_u, rot_u, t_lambda); updates from the ORIGINAL
+ * rot/pos.  rot_out/pos_out may alias rot/pos. */
+int se3_frame_update_dpm_final(const float* rot, const float* pos, const float* m_rot_t,
+                               const float* m_rot_lam, const float* m_pos_lam, float* rot_out,
+                               float* pos_out, int64_t n, const se3_dpm_scalars* h_scalars,
+                               se3_stream_t stream);
+
+typedef struct se3_heun_scalars {
+    /* churn t -> t_hat (forward SDE step, denoiser.py:413-418, 118-131) */
+    float churn_dt;         /* (t_hat - t)[0] */
+    float churn_sqrt_abs_dt;
+    float churn_rot_g;      /* g(t) */
+    float churn_pos_beta;   /* beta(t) */
+    float churn_pos_sqrt_beta;
+    /* deterministic Euler step t_hat -> t_next (denoiser.py:423-437), noise_weight 0 => w = 0.5 */
+    float step_dt;          /* (t_next - t_hat)[0] */
+    float hat_rot_g, hat_rot_scale, hat_pos_beta, hat_pos_sqrt_beta, hat_pos_std;
+    /* second-order correction at t_next (denoiser.py:440-459) */
+    float next_rot_g, next_rot_scale, next_pos_beta, next_pos_sqrt_beta, next_pos_std;
+    float tol;
+} se3_heun_scalars;
+
+int se3_frame_heun_churn(const float* rot, const float* pos, const float* z_rot, const float* z_pos,
+                         float* rot_hat, float* pos_hat, int64_t n, const se3_heun_scalars* h_scalars,
+                         se3_stream_t stream);
+int se3_frame_heun_predict(const float* rot_hat, const float* pos_hat, const float* m_rot_hat,
+                           const float* m_pos_hat, float* rot_out, float* pos_out, int64_t n,
+                           const se3_heun_scalars* h_scalars, se3_stream_t stream);
+/* pos_pred is the predictor output (needed by the R3 drift at t_next); m_*_next the raw model output
+ * evaluated at (rot_pred, pos_pred, t_next). */
+int se3_frame_heun_correct(const float* rot_hat, const float* pos_hat, const float* m_rot_hat,
+                           const float* m_pos_hat, const float* pos_pred, const float* m_rot_next,
+                           const float* m_pos_next, float* rot_out, float* pos_out, int64_t n,
+                           const se3_heun_scalars* h_scalars, se3_stream_t stream);
+
+/* traceback_brownian_motion (denoiser.py:133-166): dW_rot = Log(mean^T x_next)/g with
+ * mean = rot . Exp(drift*dt); dW_pos = (x_next - mean)/sqrt(beta).  u_* optional (NULL). */
+int se3_frame_traceback(const float* rot, const float* pos, const float* rot_next, const float* pos_next,
+                        const float* m_rot, const float* m_pos, const float* u_rot, const float* u_pos,
+                        float* dw_rot, float* dw_pos, int64_t n, const se3_em_scalars* h_scalars,
+                        se3_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1 -- IGSO(3): truncated series, lookup tables, inverse-CDF sampling       so3_sde.py:993-2042
+ * ------------------------------------------------------------------------------------------ */
+/* igso3_expansion / digso3_expansion / dlog_igso3_expansion (so3_sde.py:1731-1940) for n
+ * (omega, sigma) pairs, l = 0..l_max inclusive.  One warp per element, lanes stride l, terms whose
+ * exponential underflows to exactly 0 are skipped (bit-identical sum), warp-shuffle reduction.
+ * Any of f/df/dlog may be NULL. */
+int se3_igso3_series_f32(const float* omega, const float* sigma, float* f, float* df, float* dlog,
+                         int64_t n, int l_max, float tol, se3_stream_t stream);
+int se3_igso3_series_f64(const double* omega, const double* sigma, double* f, double* df, double* dlog,
+                         int64_t n, int l_max, double tol, se3_stream_t stream);
+/* ScoreSO3.forward (so3_sde.py:1698-1715): score = q/(|q|+tol) * dlog f(|q|, sigma). */
+int se3_igso3_score(const float* rotvec, const float* sigma, float* score, int64_t n, int l_max, float tol,
+                    se3_stream_t stream);
+/* igso3_marginal_pdf (so3_sde.py:1795-1854), l = 0..l_count-1 (se3diff/train.py:90 passes
+ * arange(l_max), i.e. l_count = l_max). */
+int se3_igso3_marginal_pdf(const float* omega, const float* omega0, const float* sigma, float* pdf, int64_t n,
+                           int l_count, float tol, se3_stream_t stream);
+/* BaseSampleSO3._generate_lookup (so3_sde.py:1131-1187): fp64 series + cumulative trapezoid,
+ * normalised.  sigma_grid [num_sigma] fp32; omega_pts [n_pts] fp64 is the full angle grid
+ * pi*linspace(0,1,num_omega+1)^k, built by the caller exactly as so3_sde.py:1165-1170 does (the
+ * fp32 linspace is part of the reference's numerics); cdf [num_sigma, n_pts-1] fp32 out.
+ * uniform != 0 builds the one-row USO3 table (so3_sde.py:1455-1472; cdf is [1, n_pts-1]). */
+int se3_igso3_build_cdf(const float* sigma_grid, int num_sigma, const double* omega_pts, int n_pts, int l_max,
+                        double tol, int uniform, float* cdf, se3_stream_t stream);
+/* ScoreSO3._compute_score_scaling (so3_sde.py:1637-1696) on the caller's grid
+ * pi*linspace(0,1,num_omega)^k; score_scaling [num_sigma] fp32 out. */
+int se3_igso3_build_score_scaling(const float* sigma_grid, int num_sigma, const double* omega_pts, int n_pts,
+                                  int l_max, double tol, float* score_scaling, se3_stream_t stream);
+/* BaseSampleSO3.sample for one sample per element (so3_sde.py:1189-1286, 1374-1391) fused with the
+ * optional left-multiplication of sample_marginal (so3_sde.py:283): out = x . Exp(axis*omega).
+ *   sigma   : [n] per-element std dev; NULL => uniform SO(3) (row 0, no small-sigma zeroing)
+ *   normals : [n,3] axis normals, u : [n] uniforms in [0,1) -- drawn by the caller (parity mode);
+ *             both NULL => in-kernel Philox4x32-10 keyed by (seed, element index)
+ *   x       : optional [n,3,3]; NULL => out = Exp(axis*omega)
+ *   angle_out optional [n]. */
+int se3_igso3_sample(const float* sigma, const float* sigma_grid, int num_sigma, const float* cdf,
+                     const float* omega_grid, int num_omega, const float* normals, const float* u,
+                     uint64_t seed, const float* x, float* out, float* angle_out, int64_t n, float tol,
+                     se3_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4 -- structure-module (invariant point) attention         structure_module.py:109-220
+ * ------------------------------------------------------------------------------------------ */
+typedef struct se3_ipa_shape {
+    int32_t batch;       /* B samples */
+    int32_t len;         /* L residues (dense, padded) */
+    int32_t heads;       /* H */
+    int32_t dk;          /* scalar channels per head (16) */
+    int32_t pq;          /* query/key points per head (4) */
+    int32_t pv;          /* value points per head (8) */
+    int32_t proj_stride; /* row stride (elements) of the fused projection matrix */
+    int32_t off_q, off_k, off_v, off_qp, off_kp, off_vp; /* column offsets inside a projection row */
+    int32_t pair_batch;  /* 1: pair tensors shared by all samples (B copies of one sequence,
+                            sample.py:223); B: one per sample */
+} se3_ipa_shape;
+
+/* SAAttention.forward between the input projections and fc_out (structure_module.py:131-216).
+ *   proj      [B*L, proj_stride] fp32: columns q|k|v (h*dk+c), qp|kp ((h*pq+p)*3+xyz), vp ((h*pv+p)*3+xyz)
+ *             in the LOCAL frame (straight out of the fused Linear)
+ *   rot [B*L,9], trans [B*L,3]: frames (rotation, not inverse)           structure_module.py:125-166
+ *   pair_bias [pair_batch,H,L,L] fp32 = pair_weight * Linear(x2d)        structure_module.py:179
+ *   pair_value[pair_batch,L,L,H*dk] fp32 = pair_value(x2d)               structure_module.py:209
+ *   key_bias  [B,L] fp32 additive mask (0 / -inf) or NULL                models.py:285-293
+ *   head_weight [H] fp32 = -0.5*point_weight*softplus(gamma_h)           structure_module.py:171-176
+ *   scalar_weight = 1/sqrt(3*dk)
+ *   out [B*L, H*(2*dk + 4*pv)] fp32 = [scalar | point_local | pair | point_norm] (structure_module.py:216)
+ *   flags : SE3_IPA_EXACT (fp32 SIMT, IEEE sqrt/exp -- the parity path) or SE3_IPA_FAST_MATH
+ *           (same kernel with sqrt.approx / ex2.approx).
+ */
+#define SE3_IPA_EXACT 0
+#define SE3_IPA_FAST_MATH 1
+int se3_ipa_attention_fwd(const float* proj, const float* rot, const float* trans, const float* pair_bias,
+                          const float* pair_value, const float* key_bias, const float* head_weight,
+                          float scalar_weight, float* out, const se3_ipa_shape* h_shape, int flags,
+                          se3_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SE3DIFF_B200_H */

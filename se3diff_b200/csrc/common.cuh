@@ -1,0 +1,191 @@
+// Shared device helpers for the se3diff_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/se3diff_b200.h"
+
+namespace se3 {
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+void count_launch(int n = 1);
+
+#define SE3_REQUIRE(cond, msg)                       \
+    do {                                             \
+        if (!(cond)) {                               \
+            se3::set_error("%s: %s", __func__, msg); \
+            return SE3_EINVAL;                       \
+        }                                            \
+    } while (0)
+
+constexpr int kTile = 256;  // elements (rotations / residues) per CTA == threads per CTA
+
+// ---------------------------------------------------------------------------------------------
+// Coalesced tile movement.  A CTA owns `kTile` consecutive elements of W scalars each (W = 3, 9,
+// 4...).  Global<->shared traffic is issued as 128-bit accesses over the contiguous byte range of
+// the tile (every lane of a warp touches consecutive 16 B => full 128 B sectors), then each thread
+// reads its own element from shared memory at stride W (W odd => bank-conflict free).
+// Falls back to scalar accesses on the ragged last tile or for unaligned base pointers.
+// ---------------------------------------------------------------------------------------------
+template <int W, typename T>
+__device__ __forceinline__ void tile_load(const T* __restrict__ g, T* __restrict__ s, int64_t first, int count) {
+    const T* src = g + first * W;
+    constexpr int kPerVec = 16 / sizeof(T);
+    if (count == kTile && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (kTile * W) % kPerVec == 0) {
+        const float4* v = reinterpret_cast<const float4*>(src);
+        float4* d = reinterpret_cast<float4*>(s);
+        constexpr int nvec = kTile * W / kPerVec;
+#pragma unroll
+        for (int i = threadIdx.x; i < nvec; i += kTile) d[i] = __ldg(v + i);
+    } else {
+        for (int i = threadIdx.x; i < count * W; i += kTile) s[i] = src[i];
+    }
+}
+
+template <int W, typename T>
+__device__ __forceinline__ void tile_store(T* __restrict__ g, const T* __restrict__ s, int64_t first, int count) {
+    T* dst = g + first * W;
+    constexpr int kPerVec = 16 / sizeof(T);
+    if (count == kTile && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (kTile * W) % kPerVec == 0) {
+        float4* v = reinterpret_cast<float4*>(dst);
+        const float4* d = reinterpret_cast<const float4*>(s);
+        constexpr int nvec = kTile * W / kPerVec;
+#pragma unroll
+        for (int i = threadIdx.x; i < nvec; i += kTile) v[i] = d[i];
+    } else {
+        for (int i = threadIdx.x; i < count * W; i += kTile) dst[i] = s[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SO(3) maps on register-resident 3-vectors / row-major 3x3 matrices.
+// Operation order follows the reference expression by expression (so3_sde.py) so that, with FMA
+// contraction disabled for these translation units, the arithmetic differs from the CPU reference
+// only in the libm calls (sin, cos, atan2).
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Math;
+template <> struct Math<float> {
+    static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ void sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+    static __device__ __forceinline__ float atan2(float y, float x) { return atan2f(y, x); }
+    static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
+    static __device__ __forceinline__ float pi() { return 3.14159274101257324f; }
+    // torch.isclose(theta, pi, atol=1e-2): |theta - pi| <= atol + rtol*|pi| evaluated in fp32
+    static __device__ __forceinline__ float pi_band() { return 1e-2f + 1e-5f * 3.14159274101257324f; }
+};
+template <> struct Math<double> {
+    static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+    static __device__ __forceinline__ void sincos(double x, double* s, double* c) { ::sincos(x, s, c); }
+    static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
+    static __device__ __forceinline__ double abs(double x) { return fabs(x); }
+    static __device__ __forceinline__ double pi() { return 3.141592653589793; }
+    static __device__ __forceinline__ double pi_band() { return 1e-2 + 1e-5 * 3.141592653589793; }
+};
+
+// rotvec_to_rotmat / skew_matrix_exponential_map (so3_sde.py:478-554)
+template <typename T>
+__device__ __forceinline__ void so3_exp(const T v[3], T tol, T r[9]) {
+    const T x = v[0], y = v[1], z = v[2];
+    const T th = Math<T>::sqrt(x * x + y * y + z * z);
+    const T th2 = th * th;
+    T a, b;
+    if (Math<T>::abs(th) < tol) {
+        a = T(1) - th2 / T(6);
+        b = T(0.5) - th2 / T(24);
+    } else {
+        T s, c;
+        Math<T>::sincos(th, &s, &c);
+        a = s / th;
+        b = (T(1) - c) / th2;
+    }
+    // K = [[0,-z,y],[z,0,-x],[-y,x,0]];  K2 = K.K summed in k order as the einsum does
+    const T k2_00 = (-z) * z + y * (-y), k2_01 = y * x, k2_02 = (-z) * (-x);
+    const T k2_10 = (-x) * (-y), k2_11 = z * (-z) + (-x) * x, k2_12 = z * y;
+    const T k2_20 = x * z, k2_21 = (-y) * (-z), k2_22 = (-y) * y + x * (-x);
+    r[0] = (T(1) + a * T(0)) + b * k2_00;
+    r[1] = (T(0) + a * (-z)) + b * k2_01;
+    r[2] = (T(0) + a * y) + b * k2_02;
+    r[3] = (T(0) + a * z) + b * k2_10;
+    r[4] = (T(1) + a * T(0)) + b * k2_11;
+    r[5] = (T(0) + a * (-x)) + b * k2_12;
+    r[6] = (T(0) + a * (-y)) + b * k2_20;
+    r[7] = (T(0) + a * x) + b * k2_21;
+    r[8] = (T(1) + a * T(0)) + b * k2_22;
+}
+
+// rot_mult (so3_sde.py:875-877): c = a.b (TA: a^T.b)
+template <typename T, bool TA = false>
+__device__ __forceinline__ void so3_mul(const T a[9], const T b[9], T c[9]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const T a0 = TA ? a[0 * 3 + i] : a[i * 3 + 0];
+            const T a1 = TA ? a[1 * 3 + i] : a[i * 3 + 1];
+            const T a2 = TA ? a[2 * 3 + i] : a[i * 3 + 2];
+            c[i * 3 + j] = (a0 * b[0 * 3 + j] + a1 * b[1 * 3 + j]) + a2 * b[2 * 3 + j];
+        }
+}
+
+// angle_from_rotmat (so3_sde.py:651-676)
+template <typename T>
+__device__ __forceinline__ T so3_angle(const T r[9], T w[3], T* sin_out, T* cos_out) {
+    w[0] = r[7] - r[5];
+    w[1] = r[2] - r[6];
+    w[2] = r[3] - r[1];
+    const T s = Math<T>::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]) / T(2);
+    const T c = (((r[0] + r[4]) + r[8]) - T(1)) / T(2);
+    *sin_out = s;
+    *cos_out = c;
+    return Math<T>::atan2(s, c);
+}
+
+// rotmat_to_rotvec (so3_sde.py:557-648).  The reference blends the three regimes with 0/1 masks;
+// here they are branches with the same thresholds (isclose(theta,0): |theta| <= 1e-8;
+// isclose(theta,pi,atol=1e-2): |theta-pi| <= 1e-2+1e-5*pi), which is equivalent whenever the
+// disabled branches are finite and avoids NaN poisoning when they are not.
+template <typename T>
+__device__ __forceinline__ void so3_log(const T r[9], T v[3]) {
+    T w[3], s, c;
+    const T th = so3_angle(r, w, &s, &c);
+    const bool is_zero = Math<T>::abs(th) <= T(1e-8);
+    const bool is_pi = Math<T>::abs(th - Math<T>::pi()) <= Math<T>::pi_band();
+    if (is_pi) {
+        // outer = (I + R)/2 with the diagonal clamped at 0; axis = sqrt(max(diag, 1e-8));
+        // signs from the row of largest norm (first maximum wins, as torch.argmax)
+        T o[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) o[i] = ((i % 4 == 0 ? T(1) : T(0)) + r[i]) / T(2);
+        o[0] = o[0] > T(0) ? o[0] : T(0);
+        o[4] = o[4] > T(0) ? o[4] : T(0);
+        o[8] = o[8] > T(0) ? o[8] : T(0);
+        T n0 = Math<T>::sqrt(o[0] * o[0] + o[1] * o[1] + o[2] * o[2]);
+        T n1 = Math<T>::sqrt(o[3] * o[3] + o[4] * o[4] + o[5] * o[5]);
+        T n2 = Math<T>::sqrt(o[6] * o[6] + o[7] * o[7] + o[8] * o[8]);
+        int row = 0;
+        T best = n0;
+        if (n1 > best) { best = n1; row = 1; }
+        if (n2 > best) { row = 2; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const T d = o[k * 4];
+            const T ax = Math<T>::sqrt(d > T(1e-8) ? d : T(1e-8));
+            const T l = o[row * 3 + k];
+            const T sg = l > T(0) ? T(1) : (l < T(0) ? T(-1) : T(0));
+            // reference: vector*prefactor (prefactor = 0/1 = 0 in the pi regime) + vector_pi
+            v[k] = w[k] * T(0) + (ax * th) * sg;
+        }
+    } else if (is_zero) {
+        const T pre = T(0.5) / (T(1) - th * th / T(6));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[k] = w[k] * pre;
+    } else {
+        const T pre = th / (T(2) * s);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[k] = w[k] * pre;
+    }
+}
+
+}  // namespace se3

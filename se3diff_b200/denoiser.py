@@ -1,0 +1,256 @@
+"""Samplers at the drop-in boundary -- same keyword-only signatures and return types as
+bioemu/src/bioemu/denoiser.py:206-215 (euler_maruyama_predictor), :267-277 (..._finetune),
+:351-361 (heun_denoiser), :464-475 (heun_denoiser_finetune), :634-643 (dpm_solver).
+
+What differs from the reference is only *how* a step is executed:
+  * the schedule (alpha, sigma, lambda, h, t_lambda, beta, g, score scaling) is evaluated once per call
+    on the host (schedule.py) -- no `.item()` syncs inside the loop (denoiser.py:669, 692);
+  * the score conversion of `_get_score` (denoiser.py:169-203) and the whole per-field update
+    (`EulerMaruyamaPredictor`, denoiser.py:30-166) run as ONE fused CUDA kernel per half-step
+    (se3_frame_update_*), reading the raw score-model output;
+  * noise that the reference draws but multiplies by zero (denoiser.py:80 under diffusion=0.0) is not
+    generated, unless `sdes.host_noise()` parity mode is active, where every draw of the reference is
+    reproduced in order on the CPU generator.
+`score_model` may be any callable `(batch, t) -> mapping with "pos" and "node_orientations"` as in the
+reference (denoiser.py:219-221).
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+from typing import NamedTuple
+
+import torch
+from torch import nn
+
+from . import ops, schedule
+from . import sdes as S
+from .chemgraph import batch_lengths
+
+
+class DenoisedSDEPath(NamedTuple):
+    """denoiser.py:23-27."""
+
+    batches: list
+    timesteps: torch.Tensor
+    us_batch: dict
+    dWs_batch: dict
+
+
+def _prepare(batch, sdes, score_model, device, extra_models=()):
+    if device is None:
+        device = batch["pos"].device
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"se3diff_b200 samplers run on CUDA devices only (got device={device}); there is no CPU fallback")
+    batch = batch.to(device)
+    moved = []
+    for m in (score_model, *extra_models):
+        moved.append(m.to(device) if isinstance(m, nn.Module) else m)
+    so3 = sdes["node_orientations"]
+    if isinstance(so3, nn.Module):
+        so3 = so3.to(device)
+    return batch, device, so3, moved
+
+
+def _prior(batch, sdes, so3, device):
+    """denoiser.py:224-229: positions first, then orientations (kwarg evaluation order)."""
+    pos_shape, rot_shape = tuple(batch["pos"].shape), tuple(batch["node_orientations"].shape)
+    if isinstance(sdes["pos"], S.CosineVPSDE):
+        pos = S.noise_randn(pos_shape, device)
+    else:
+        pos = sdes["pos"].prior_sampling(pos_shape, device=device)
+    rot = so3.prior_sampling(rot_shape, device=device)
+    return batch.replace(pos=pos.float().contiguous(), node_orientations=rot.float().contiguous())
+
+
+def _dense(x, batch, lengths):
+    """to_dense_batch(x, batch_idx)[0] for the stored controls (denoiser.py:334-335)."""
+    lmax = max(lengths)
+    if all(n == lmax for n in lengths):
+        return x.reshape(len(lengths), lmax, *x.shape[1:])
+    out = x.new_zeros((len(lengths), lmax) + tuple(x.shape[1:]))
+    o = 0
+    for g, n in enumerate(lengths):
+        out[g, :n] = x[o:o + n]
+        o += n
+    return out
+
+
+def _t(value: float, num_graphs: int, device):
+    return torch.full((num_graphs,), value, device=device)
+
+
+def _fields(sdes):
+    return list(sdes.keys())
+
+
+# ------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def dpm_solver(*, batch, sdes, score_model, num_steps: int, max_t: float, min_t: float, device=None):
+    """DPM-Solver-2 on positions + midpoint / extrapolated-score exp-map step on orientations
+    (denoiser.py:634-764)."""
+    assert max_t < 1.0
+    batch, device, so3, (score_model,) = _prepare(batch, sdes, score_model, device)
+    steps = schedule.dpm_schedule(sdes["pos"], so3, num_steps, max_t, min_t)
+    batch = _prior(batch, sdes, so3, device)
+    B = batch.num_graphs
+    pos, rot = batch["pos"], batch["node_orientations"]
+    for st in steps:
+        out = score_model(batch, _t(st.t, B, device))
+        m_rot_t = out["node_orientations"]
+        if S._HOST_NOISE:  # the two randn_like of denoiser.py:80 that are multiplied by zero
+            torch.randn(pos.shape[0], 3)
+        rot_u, pos_u = ops.frame_update_dpm_mid(rot, pos, m_rot_t, out["pos"], st.scalars)
+        out_u = score_model(batch.replace(pos=pos_u, node_orientations=rot_u), _t(st.t_lambda, B, device))
+        if S._HOST_NOISE:
+            torch.randn(pos.shape[0], 3)
+        rot, pos = ops.frame_update_dpm_final(rot, pos, m_rot_t, out_u["node_orientations"], out_u["pos"], st.scalars)
+        batch = batch.replace(pos=pos, node_orientations=rot)
+    return batch
+
+
+def _em_loop(batch, sdes, score_model, finetune_model, num_steps, max_t, min_t, device):
+    batch, device, so3, (score_model, finetune_model) = _prepare(batch, sdes, score_model, device, (finetune_model,))
+    steps = schedule.em_schedule(sdes["pos"], so3, num_steps, max_t, min_t)
+    batch = _prior(batch, sdes, so3, device)
+    B = batch.num_graphs
+    fields = _fields(sdes)
+    record = finetune_model is not None
+    lengths = batch_lengths(batch) if record else None
+    batches, us, dWs = [batch], defaultdict(list), defaultdict(list)
+    for st in steps:
+        t = _t(st.t, B, device)
+        pos, rot = batch["pos"], batch["node_orientations"]
+        out = score_model(batch, t)
+        u = finetune_model(batch, t) if record else None
+        z = {f: S.noise_randn((pos.shape[0], 3), device) for f in fields}  # per-field draw order = sdes key order
+        rot, pos, dw_rot, dw_pos = ops.frame_update_em(
+            rot, pos, out["node_orientations"], out["pos"], z["node_orientations"], z["pos"], st.scalars,
+            u_rot=None if u is None else u["node_orientations"], u_pos=None if u is None else u["pos"], want_dw=record)
+        batch = batch.replace(pos=pos, node_orientations=rot)
+        if record:
+            dw = {"pos": dw_pos, "node_orientations": dw_rot}
+            for f in fields:
+                us[f].append(_dense(u[f], batch, lengths))
+                dWs[f].append(_dense(dw[f], batch, lengths))
+            batches.append(batch)
+    if not record:
+        return batch
+    ts, _ = schedule.timesteps(max_t, min_t, num_steps)
+    return DenoisedSDEPath(batches=batches, timesteps=ts.to(device), us_batch={f: torch.stack(us[f], dim=0) for f in fields},
+                           dWs_batch={f: torch.stack(dWs[f], dim=0) for f in fields})
+
+
+@torch.no_grad()
+def euler_maruyama_predictor(*, batch, sdes, score_model, num_steps: int, max_t: float, min_t: float, device=None):
+    """denoiser.py:206-264."""
+    return _em_loop(batch, sdes, score_model, None, num_steps, max_t, min_t, device)
+
+
+@torch.no_grad()
+def euler_maruyama_predictor_finetune(*, batch, sdes, score_model, finetune_model, num_steps: int, max_t: float,
+                                      min_t: float, device=None) -> DenoisedSDEPath:
+    """denoiser.py:267-348: EM with the fine-tune control u in the drift; records every batch, u_t and
+    dW_t = sqrt|dt| z as dense [T, B, L, 3]."""
+    return _em_loop(batch, sdes, score_model, finetune_model, num_steps, max_t, min_t, device)
+
+
+def _heun_loop(batch, sdes, score_model, finetune_model, num_steps, max_t, min_t, noise, device):
+    batch, device, so3, (score_model, finetune_model) = _prepare(batch, sdes, score_model, device, (finetune_model,))
+    steps = schedule.heun_schedule(sdes["pos"], so3, num_steps, max_t, min_t, noise)
+    batch = _prior(batch, sdes, so3, device)
+    B = batch.num_graphs
+    fields = _fields(sdes)
+    record = finetune_model is not None
+    if record:
+        raise NotImplementedError(
+            "heun_denoiser_finetune: the reference implementation stores aliases of one in-place-mutated batch "
+            "(denoiser.py:518,564,588,596) and is not used by finetune.sh; use euler_maruyama_predictor_finetune")
+    n = batch["pos"].shape[0]
+
+    def draws():
+        if S._HOST_NOISE:  # deterministic updates still consume randn_like in the reference
+            for _ in fields:
+                torch.randn(n, 3)
+
+    for st in steps:
+        pos, rot = batch["pos"], batch["node_orientations"]
+        z = {f: S.noise_randn((n, 3), device) for f in fields}
+        rot_h, pos_h = ops.frame_heun_churn(rot, pos, z["node_orientations"], z["pos"], st.scalars)
+        batch_hat = batch.replace(pos=pos_h, node_orientations=rot_h)
+        out_h = score_model(batch_hat, _t(st.t_hat, B, device))
+        draws()
+        rot1, pos1 = ops.frame_heun_predict(rot_h, pos_h, out_h["node_orientations"], out_h["pos"], st.scalars)
+        batch = batch.replace(pos=pos1, node_orientations=rot1)
+        if st.correct:
+            out_n = score_model(batch, _t(st.t_next, B, device))
+            draws()
+            rot2, pos2 = ops.frame_heun_correct(rot_h, pos_h, out_h["node_orientations"], out_h["pos"], pos1,
+                                                out_n["node_orientations"], out_n["pos"], st.scalars)
+            batch = batch.replace(pos=pos2, node_orientations=rot2)
+    return batch
+
+
+@torch.no_grad()
+def heun_denoiser(*, batch, sdes, score_model, num_steps: int, max_t: float, min_t: float, noise: float, device=None):
+    """Karras-style churn + Heun second-order correction on both fields (denoiser.py:351-461)."""
+    return _heun_loop(batch, sdes, score_model, None, num_steps, max_t, min_t, noise, device)
+
+
+@torch.no_grad()
+def heun_denoiser_finetune(*, batch, sdes, score_model, finetune_model, num_steps: int, max_t: float, min_t: float,
+                           noise: float, device=None):
+    """denoiser.py:464-620 -- see `_heun_loop` for why this raises."""
+    return _heun_loop(batch, sdes, score_model, finetune_model, num_steps, max_t, min_t, noise, device)
+
+
+def sde_dpm_solver_finetune(*, batch, sdes, score_model, finetune_model, num_steps, max_t, min_t, device=None):
+    """Unimplemented stub in the reference as well (denoiser.py:767-777 has body `...`)."""
+    raise NotImplementedError("sde_dpm_solver_finetune is an empty stub in the reference (denoiser.py:767-777)")
+
+
+class EulerMaruyamaPredictor:
+    """Per-field predictor object used directly by se3diff/train.py:54-70 and se3diff/finetune.py:33-56
+    (denoiser.py:30-166).  Works on `[n,3,3]` rotations (SO3SDE corruption) or `[n,d]` positions
+    (CosineVPSDE corruption) with per-element t."""
+
+    def __init__(self, *, corruption, noise_weight: float = 1.0, marginal_concentration_factor: float = 1.0):
+        self.corruption, self.noise_weight, self.marginal_concentration_factor = corruption, noise_weight, marginal_concentration_factor
+
+    def reverse_drift_and_diffusion(self, *, x, t, score, finetune_score=None, batch_idx=None):
+        w = 0.5 * self.marginal_concentration_factor * (1 + self.noise_weight**2)
+        drift, diffusion = self.corruption.sde(x=x, t=t, batch_idx=batch_idx)
+        drift = drift - diffusion**2 * score * w
+        if finetune_score is not None:
+            drift = drift + diffusion * finetune_score * w
+        return drift, diffusion
+
+    def update_given_drift_and_diffusion(self, *, x, dt, drift, diffusion):
+        z = S.noise_randn(tuple(drift.shape), drift.device)
+        dW = self.noise_weight * torch.sqrt(dt.abs()) * z
+        if isinstance(self.corruption, S.SO3SDE):
+            mean = ops.so3_compose_rotvec(x, drift * dt, self.corruption.tol)
+            sample = ops.so3_compose_rotvec(mean, diffusion * dW, self.corruption.tol)
+        elif isinstance(self.corruption, S.CosineVPSDE):
+            mean = x + drift * dt
+            sample = mean + diffusion * dW
+        else:
+            raise NotImplementedError(f"Update for {type(self.corruption)} not implemented.")
+        return sample, mean, dW
+
+    def update_given_score(self, *, x, t, dt, score, finetune_score=None, batch_idx=None):
+        drift, diffusion = self.reverse_drift_and_diffusion(x=x, t=t, score=score, finetune_score=finetune_score, batch_idx=batch_idx)
+        return self.update_given_drift_and_diffusion(x=x, dt=dt, drift=drift, diffusion=diffusion)
+
+    def forward_sde_step(self, *, x, t, dt, batch_idx=None):
+        drift, diffusion = self.corruption.sde(x=x, t=t, batch_idx=batch_idx)
+        return self.update_given_drift_and_diffusion(x=x, dt=dt, drift=drift, diffusion=diffusion)
+
+    def traceback_brownian_motion(self, *, x_next, x, t, dt, score, finetune_score=None, batch_idx=None):
+        drift, diffusion = self.reverse_drift_and_diffusion(x=x, t=t, score=score, finetune_score=finetune_score, batch_idx=batch_idx)
+        if isinstance(self.corruption, S.SO3SDE):
+            mean = ops.so3_compose_rotvec(x, drift * dt, self.corruption.tol)
+            return ops.so3_rel_log(mean, x_next) / diffusion
+        if isinstance(self.corruption, S.CosineVPSDE):
+            return (x_next - (x + drift * dt)) / diffusion
+        raise NotImplementedError(f"Update for {type(self.corruption)} not implemented.")

@@ -1,0 +1,372 @@
+"""DiG score model at the drop-in boundary: `DiGConditionalScoreModel(x: ChemGraph batch, t) -> batch`.
+
+Reference surface mirrored: bioemu/src/bioemu/models.py:326-384 (wrapper), :148-323
+(DistributionalGraphormer), :19-145 (time / relative-position embeddings) and
+bioemu/src/bioemu/structure_module.py:12-287 -- same constructor arguments, same parameter names
+(`model_nn.x1d_proj.0.weight`, `model_nn.st_module.encoder.layers.N.attn.scalar_query.weight`, ...) and
+the same registration order, so reference checkpoints load with `load_state_dict` and a seeded random
+init is identical to the reference's.
+
+The forward pass is re-designed for the GPU (DESIGN.md section "score model"):
+  * everything derived from the pair embedding (x2d, pair_bias_l, pair_value_l) depends only on the
+    sequence -- it is computed once per context and cached, shared by all samples when the batch is
+    B copies of one sequence (sample.py:223), kept per-sample otherwise;
+  * the six input projections of a layer are one fused GEMM; everything between that GEMM and fc_out
+    (frames applied to points, logits, softmax, three value aggregations, inverse frame, norms,
+    concat) is ONE hand-written kernel (se3_ipa_attention_fwd);
+  * GEMMs / LayerNorms go through torch (cuBLAS), in fp32 ("fp32" precision, the parity mode) or
+    with bf16 operands and fp32 accumulation ("bf16", the throughput mode).
+Dropout is never applied here: the path is inference (reference parity is defined in eval mode,
+SURVEY.md section 0); a model in training mode with dropout > 0 raises instead of silently differing.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib as L
+from . import ops
+from .chemgraph import batch_lengths
+
+EVOFORMER_NODE_DIM: int = 384
+EVOFORMER_EDGE_DIM: int = 128
+
+
+class SinusoidalPositionEmbedder(nn.Module):
+    """models.py:19-69."""
+
+    def __init__(self, dim: int, max_period: int = 10000, min_input: float = 0.0, max_input: float = 1000.0):
+        super().__init__()
+        self.dim, self.half_dim = dim, dim // 2
+        self.min_input, self.max_input = min_input, max_input
+        self.embedding_factor = -math.log(max_period) / (self.half_dim - 1)
+        self.dummy = nn.Parameter(torch.empty(0, dtype=torch.float), requires_grad=False)
+
+    def forward(self, time: torch.Tensor) -> torch.Tensor:
+        time = (time - self.min_input) * 1000.0 / (self.max_input - self.min_input)
+        freq = torch.exp(torch.arange(self.half_dim, device=time.device) * self.embedding_factor)
+        ang = time[:, None] * freq[None, :]
+        return torch.cat((ang.sin(), ang.cos()), dim=-1).to(self.dummy.dtype)
+
+
+class RelativePositionBias(nn.Module):
+    """models.py:72-145 (T5-style signed log buckets -> nn.Embedding)."""
+
+    def __init__(self, num_buckets: int = 64, max_distance: int = 256, out_dim: int = 2):
+        super().__init__()
+        self.num_buckets, self.max_distance = num_buckets, max_distance
+        self.relative_attention_bias = nn.Embedding(num_buckets, out_dim)
+
+    @staticmethod
+    def _relative_position_bucket(relative_position: torch.Tensor, num_buckets: int, max_distance: int):
+        half = num_buckets // 2
+        sign_offset = (relative_position < 0).to(relative_position) * half
+        dist = torch.abs(relative_position)
+        exact = half // 2
+        log_bucket = exact + (torch.log(dist / exact) / math.log(max_distance / exact) * (half - exact)).long()
+        log_bucket = torch.min(log_bucket, torch.full_like(log_bucket, half - 1))
+        return sign_offset + torch.where(dist < exact, dist, log_bucket)
+
+    def bucket_table(self, length: int) -> torch.Tensor:
+        """[L, L] int64 bucket of (i - j), evaluated on the host with the reference's fp32 expression
+        so the integer result is bit-exact (models.py:276-283)."""
+        seq = torch.arange(length)
+        return self._relative_position_bucket(seq.unsqueeze(1) - seq.unsqueeze(0), self.num_buckets, self.max_distance)
+
+    def forward(self, relative_position: torch.Tensor) -> torch.Tensor:
+        b = self._relative_position_bucket(relative_position, self.num_buckets, self.max_distance)
+        return self.relative_attention_bias(b)
+
+
+class FeedForward(nn.Module):
+    """structure_module.py:12-26 (indices 0 and 3 of `ff` carry the weights)."""
+
+    def __init__(self, d_model: int, dim_feedforward: int, dropout: float):
+        super().__init__()
+        self.ff = nn.Sequential(nn.Linear(d_model, dim_feedforward), nn.GELU(), nn.Dropout(dropout),
+                                nn.Linear(dim_feedforward, d_model), nn.Dropout(dropout))
+
+
+class DiffHead(nn.Module):
+    """structure_module.py:29-53."""
+
+    def __init__(self, ninp: int):
+        super().__init__()
+        self.fc_t = nn.Sequential(nn.LayerNorm(ninp), nn.Linear(ninp, ninp), nn.ReLU(), nn.Linear(ninp, 3))
+        self.fc_eps = nn.Sequential(nn.LayerNorm(ninp), nn.Linear(ninp, ninp), nn.ReLU(), nn.Linear(ninp, 3))
+
+
+class SAAttention(nn.Module):
+    """Parameter container of the DiG invariant point attention (structure_module.py:56-107)."""
+
+    N_QK_POINTS, N_V_POINTS = 4, 8
+
+    def __init__(self, d_model: int, d_pair: int, n_head: int, dropout: float = 0.1):
+        super().__init__()
+        if d_model % n_head != 0:
+            raise ValueError("The hidden size is not a multiple of the number of attention heads.")
+        self.n_head, self.d_k = n_head, d_model // n_head
+        self.scalar_query = nn.Linear(d_model, d_model, bias=False)
+        self.scalar_key = nn.Linear(d_model, d_model, bias=False)
+        self.scalar_value = nn.Linear(d_model, d_model, bias=False)
+        self.pair_bias = nn.Linear(d_pair, n_head, bias=False)
+        self.point_query = nn.Linear(d_model, n_head * 3 * 4, bias=False)
+        self.point_key = nn.Linear(d_model, n_head * 3 * 4, bias=False)
+        self.point_value = nn.Linear(d_model, n_head * 3 * 8, bias=False)
+        self.scalar_weight = 1.0 / math.sqrt(3 * self.d_k)
+        self.point_weight = 1.0 / math.sqrt(3 * 4 * 9 / 2)
+        self.trained_point_weight = nn.Parameter(torch.rand(n_head))
+        self.pair_weight = 1.0 / math.sqrt(3)
+        self.pair_value = nn.Linear(d_pair, d_model, bias=False)
+        self.fc_out = nn.Linear(d_model * 2 + n_head * 8 * 4, d_model, bias=True)
+        self.dropout = nn.Dropout(dropout)
+
+    def fused_projection_weight(self) -> torch.Tensor:
+        """[3*d_model + 48*H, d_model]: q | k | v | q_pt | k_pt | v_pt rows."""
+        return torch.cat([self.scalar_query.weight, self.scalar_key.weight, self.scalar_value.weight,
+                          self.point_query.weight, self.point_key.weight, self.point_value.weight], dim=0)
+
+
+class SAEncoderLayer(nn.Module):
+    def __init__(self, d_model: int, d_pair: int, n_head: int, dim_feedforward: int, dropout: float):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(d_model)
+        self.attn = SAAttention(d_model=d_model, d_pair=d_pair, n_head=n_head, dropout=dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.ffn = FeedForward(d_model=d_model, dim_feedforward=dim_feedforward, dropout=dropout)
+
+
+class SAEncoder(nn.Module):
+    def __init__(self, n_layer: int, **kwargs):
+        super().__init__()
+        self.layers = nn.ModuleList([SAEncoderLayer(**kwargs) for _ in range(n_layer)])
+
+
+class StructureModule(nn.Module):
+    def __init__(self, d_model: int, **kwargs):
+        super().__init__()
+        self.encoder = SAEncoder(d_model=d_model, **kwargs)
+        self.diff_head = DiffHead(ninp=d_model)
+
+
+class _Context:
+    """Per-sequence tensors that do not depend on the sample, on t or on the frames."""
+
+    __slots__ = ("key", "lengths", "lmax", "batch", "shared", "mask", "dense_index", "x1d_base", "pair_bias",
+                 "pair_value", "key_bias", "uniform")
+
+
+class DistributionalGraphormer(nn.Module):
+    """Parameters of models.py:148-215; GPU forward described in the module docstring."""
+
+    def __init__(self, dim_model=512, dim_pair=256, num_layers=8, num_heads=32, dim_single_rep=64, dim_hidden=1024,
+                 num_buckets=64, max_distance_relative=128, dropout=0.1):
+        super().__init__()
+        self.d_model = dim_model
+        self.dim_pair_rep = EVOFORMER_EDGE_DIM
+        self.step_emb = SinusoidalPositionEmbedder(dim=self.d_model)
+        self.x1d_proj = nn.Sequential(nn.LayerNorm(EVOFORMER_NODE_DIM), nn.Linear(EVOFORMER_NODE_DIM, self.d_model, bias=False))
+        self.x2d_proj = nn.Sequential(nn.LayerNorm(self.dim_pair_rep), nn.Linear(self.dim_pair_rep, dim_pair, bias=False))
+        self.rp_proj = RelativePositionBias(num_buckets=num_buckets, max_distance=max_distance_relative, out_dim=dim_pair)
+        self.st_module = StructureModule(d_pair=dim_pair, n_layer=num_layers, d_model=self.d_model, n_head=num_heads,
+                                         dim_feedforward=dim_hidden, dropout=dropout)
+        self.dropout_p = dropout
+        self.precision = "fp32"
+        self._ctx: _Context | None = None
+        self._wcache: dict = {}
+
+    # -- caches ---------------------------------------------------------------------------------------
+    def _weights_version(self) -> int:
+        return sum(p._version for p in self.parameters())
+
+    def _layer_weights(self, dtype: torch.dtype):
+        """Fused / cast weights, rebuilt when a parameter was updated in place or moved."""
+        dev = self.x1d_proj[1].weight.device
+        key = (dtype, dev, self._weights_version())
+        if self._wcache.get("key") != key:
+            layers = []
+            for lyr in self.st_module.encoder.layers:
+                a = lyr.attn
+                layers.append(dict(
+                    w_proj=a.fused_projection_weight().detach().to(dtype).contiguous(),
+                    w_out=a.fc_out.weight.detach().to(dtype).contiguous(),
+                    w_ff0=lyr.ffn.ff[0].weight.detach().to(dtype).contiguous(),
+                    w_ff3=lyr.ffn.ff[3].weight.detach().to(dtype).contiguous(),
+                    head_w=(-0.5 * a.point_weight * F.softplus(a.trained_point_weight.detach().float())).contiguous(),
+                ))
+            heads = {}
+            for name in ("fc_t", "fc_eps"):
+                seq = getattr(self.st_module.diff_head, name)
+                heads[name] = (seq[1].weight.detach().to(dtype).contiguous(), seq[3].weight.detach().float().contiguous())
+            self._wcache = dict(key=key, layers=layers, heads=heads)
+        return self._wcache
+
+    @torch.no_grad()
+    def _context(self, ctx_graph) -> _Context:
+        """Sequence-only precompute (models.py:243-293 + the x2d-dependent halves of
+        structure_module.py:179,209), cached on the identity of the embedding tensors."""
+        single, pair, bidx = ctx_graph["single_embeds"], ctx_graph["pair_embeds"], ctx_graph["batch"]
+        known = ctx_graph["pos_is_known"] if "pos_is_known" in ctx_graph else None
+        key = (single.data_ptr(), pair.data_ptr(), bidx.data_ptr(), single._version, pair._version, tuple(single.shape),
+               tuple(pair.shape), None if known is None else (known.data_ptr(), known._version), self._weights_version(),
+               self.precision)
+        if self._ctx is not None and self._ctx.key == key:
+            return self._ctx
+        dev = single.device
+        lengths = batch_lengths(ctx_graph)
+        B, lmax = len(lengths), max(lengths)
+        uniform = all(n == lmax for n in lengths)
+        c = _Context()
+        c.key, c.lengths, c.lmax, c.batch, c.uniform = key, lengths, lmax, B, uniform
+        n_tot = sum(lengths)
+        if uniform:
+            c.dense_index, mask = None, torch.ones(B, lmax, dtype=torch.bool, device=dev)
+        else:
+            ptr = torch.tensor([0] + lengths[:-1], device=dev).cumsum(0)
+            within = torch.arange(n_tot, device=dev) - ptr[bidx]
+            c.dense_index = bidx * lmax + within                      # to_dense_batch scatter index
+            mask = torch.zeros(B * lmax, dtype=torch.bool, device=dev)
+            mask[c.dense_index] = True
+            mask = mask.view(B, lmax)
+        c.mask = mask
+        # attention key mask (models.py:261-293)
+        attn_mask = ~mask
+        if known is not None:
+            attn_mask = ~(mask & self._to_dense(known, c).bool())
+        if bool(attn_mask.any()):
+            none_left = (~attn_mask).long().sum(-1, keepdim=True) == 0
+            attn_mask = attn_mask.masked_fill(none_left, False)
+            c.key_bias = torch.zeros(B, lmax, device=dev).masked_fill(attn_mask, float("-inf")).contiguous()
+        else:
+            c.key_bias = None
+        # shared context? (B copies of one sequence, sample.py:223) -- decided by value, once per context
+        single_d = self._to_dense(single.float(), c)                                # [B, L, 384]
+        pair_d = self._dense_pairs(ctx_graph, pair.float(), c, dev)                 # [B, L, L, 128]
+        c.shared = bool(uniform and B > 1 and torch.equal(single_d[1:], single_d[:1].expand(B - 1, -1, -1))
+                        and torch.equal(pair_d[1:], pair_d[:1].expand(B - 1, -1, -1, -1))) or (uniform and B == 1)
+        if c.shared:
+            single_d, pair_d = single_d[:1], pair_d[:1]
+        c.x1d_base = self.x1d_proj(single_d)                                        # [Bp, L, d_model]
+        bucket = self.rp_proj.bucket_table(lmax).to(dev)
+        x2d = self.x2d_proj(pair_d) + self.rp_proj.relative_attention_bias(bucket)[None]   # [Bp, L, L, d_pair]
+        c.pair_bias, c.pair_value = [], []
+        for lyr in self.st_module.encoder.layers:
+            a = lyr.attn
+            c.pair_bias.append((a.pair_weight * a.pair_bias(x2d)).permute(0, 3, 1, 2).contiguous())   # [Bp, H, L, L]
+            c.pair_value.append(a.pair_value(x2d).contiguous())                                        # [Bp, L, L, H*dk]
+        self._ctx = c
+        return c
+
+    @staticmethod
+    def _dense_pairs(ctx_graph, pair, c: _Context, dev):
+        """to_dense_adj(edge_index, batch, pair_embeds) (models.py:251-253): dense slot b*L^2 + i*L + j,
+        scatter-ADD semantics.  The row-major complete graph of sample.py:165-171 with equal lengths is a
+        pure view; anything else takes the general integer-exact scatter."""
+        B, lmax, lengths = c.batch, c.lmax, c.lengths
+        ei = ctx_graph["edge_index"] if "edge_index" in ctx_graph else None
+        if ei is None:
+            if not c.uniform or pair.shape[0] != B * lmax * lmax:
+                raise ValueError("pair_embeds without edge_index must be the dense complete graph of equal-length graphs")
+            return pair.view(B, lmax, lmax, -1)
+        ptr = torch.tensor([0] + lengths, device=dev).cumsum(0)
+        if c.uniform and ei.shape[1] == B * lmax * lmax:
+            seq = torch.arange(lmax, device=dev)
+            base = torch.stack([seq.repeat_interleave(lmax), seq.repeat(lmax)])             # [2, L^2]
+            expect = (base[:, None, :] + ptr[:-1][None, :, None]).reshape(2, -1)
+            if torch.equal(ei, expect):
+                return pair.view(B, lmax, lmax, -1)
+        g = ctx_graph["batch"][ei[0]]
+        flat = g * (lmax * lmax) + (ei[0] - ptr[g]) * lmax + (ei[1] - ptr[g])
+        out = pair.new_zeros(B * lmax * lmax, pair.shape[-1])
+        out.index_add_(0, flat, pair)
+        return out.view(B, lmax, lmax, -1)
+
+    @staticmethod
+    def _to_dense(x, c: _Context):
+        if c.dense_index is None:
+            return x.reshape(c.batch, c.lmax, *x.shape[1:])
+        out = x.new_zeros((c.batch * c.lmax,) + tuple(x.shape[1:]))
+        out[c.dense_index] = x
+        return out.view(c.batch, c.lmax, *x.shape[1:])
+
+    # -- forward ------------------------------------------------------------------------------------------
+    def _linear(self, x, w, bias=None, out_fp32=True):
+        if w.dtype == torch.float32:
+            return F.linear(x, w, bias)
+        y = torch.mm(x.to(w.dtype), w.t(), out_dtype=torch.float32) if out_fp32 else F.linear(x.to(w.dtype), w)
+        return y if bias is None else y + bias
+
+    @torch.no_grad()
+    def forward(self, x, node_orientations, batch_index, t, context):
+        """x [N,3] positions, node_orientations [N,3,3] ROTATIONS (not inverse: the reference transposes
+        twice, models.py:369 and structure_module.py:125-127), t [num_graphs] already scaled by 1000."""
+        if self.training and self.dropout_p > 0:
+            raise RuntimeError("se3diff_b200 score model is inference-only: call .eval() (reference parity is defined "
+                               "with dropout off)")
+        c = self._context(context)
+        w = self._layer_weights(torch.float32 if self.precision == "fp32" else torch.bfloat16)
+        B, Lm, D = c.batch, c.lmax, self.d_model
+        T = self._to_dense(x.float(), c).reshape(B * Lm, 3).contiguous()
+        R = self._to_dense(node_orientations.float(), c).reshape(B * Lm, 9).contiguous()
+        x1d = (c.x1d_base + self.step_emb(t.float()[:B])[:, None]).reshape(B * Lm, D)
+        attn0 = self.st_module.encoder.layers[0].attn
+        H, dk = attn0.n_head, attn0.d_k
+        shape = L.IpaShape(B, Lm, H, dk, 4, 8, 3 * D + 48 * H, 0, D, 2 * D, 3 * D, 3 * D + 12 * H, 3 * D + 24 * H,
+                           1 if c.shared else B)
+        flags = ops.IPA_EXACT if self.precision == "fp32" else ops.IPA_FAST_MATH
+        for n, lyr in enumerate(self.st_module.encoder.layers):
+            lw = w["layers"][n]
+            y = F.layer_norm(x1d, (D,), lyr.norm1.weight, lyr.norm1.bias, lyr.norm1.eps)
+            proj = self._linear(y, lw["w_proj"])
+            feat = ops.ipa_attention_fwd(proj, R, T, c.pair_bias[n], c.pair_value[n], c.key_bias, lw["head_w"],
+                                         lyr.attn.scalar_weight, shape, flags)
+            x1d = x1d + self._linear(feat, lw["w_out"], lyr.attn.fc_out.bias)
+            y = F.layer_norm(x1d, (D,), lyr.norm2.weight, lyr.norm2.bias, lyr.norm2.eps)
+            y = F.gelu(self._linear(y, lw["w_ff0"], lyr.ffn.ff[0].bias))
+            x1d = x1d + self._linear(y, lw["w_ff3"], lyr.ffn.ff[3].bias)
+        outs = []
+        for name in ("fc_t", "fc_eps"):
+            seq = getattr(self.st_module.diff_head, name)
+            w1, w3 = w["heads"][name]
+            y = F.layer_norm(x1d, (D,), seq[0].weight, seq[0].bias, seq[0].eps)
+            y = F.relu(self._linear(y, w1, seq[1].bias))
+            outs.append(F.linear(y, w3, seq[3].bias))
+        T_eps, IR_eps = outs
+        T_out = torch.bmm(R.view(-1, 3, 3), T_eps.unsqueeze(-1)).squeeze(-1)      # models.py:305
+        if c.dense_index is None:
+            return T_out, IR_eps
+        return T_out[c.dense_index], IR_eps[c.dense_index]
+
+
+class DiGConditionalScoreModel(nn.Module):
+    """models.py:326-384.  `precision`: "fp32" (default, parity mode) or "bf16" (bf16 GEMM operands with
+    fp32 accumulation + fast-math attention; the benchmark mode)."""
+
+    def __init__(self, dim_model=512, dim_pair=256, num_layers=8, num_heads=32, dim_single_rep=64, dim_hidden=1024,
+                 num_buckets=64, max_distance_relative=128, dropout=0.1, precision: str = "fp32"):
+        super().__init__()
+        self.model_nn = DistributionalGraphormer(
+            dim_model=dim_model, dim_pair=dim_pair, num_layers=num_layers, num_heads=num_heads,
+            dim_single_rep=dim_single_rep, dim_hidden=dim_hidden, num_buckets=num_buckets,
+            max_distance_relative=max_distance_relative, dropout=dropout)
+        self.set_precision(precision)
+
+    def set_precision(self, precision: str):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.model_nn.precision = precision
+        return self
+
+    def forward(self, x, t: torch.Tensor):
+        assert "batch" in x, "batch of ChemGraphs must have a 'batch' attribute."
+        if not x["pos"].is_cuda:
+            raise L.Se3LibraryError("se3diff_b200.DiGConditionalScoreModel runs on CUDA only (no CPU fallback); "
+                                    "move the batch and the model to a CUDA device")
+        context = x.replace(pos=None, node_orientations=None)
+        # models.py:365: t[x.batch]*1000, of which only the first residue of each graph is read (:268-269)
+        pos, rot = self.model_nn(x=x["pos"], node_orientations=x["node_orientations"], batch_index=x["batch"],
+                                 t=t * 1000, context=context)
+        return x.replace(pos=pos, node_orientations=rot)

@@ -1,0 +1,349 @@
+"""torch-tensor front end of the C ABI (include/se3diff_b200.h).
+
+torch is used here only for device memory and the current CUDA stream; every function hands raw
+device pointers to libse3diff_b200.so.  CPU tensors are rejected: there is no CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+__all__ = [
+    "so3_exp", "so3_log", "so3_angle", "so3_compose_rotvec", "so3_matmul", "so3_rel_log", "so3_geodesic",
+    "so3_from_quat", "frame_update_em", "frame_update_dpm_mid", "frame_update_dpm_final", "frame_heun_churn",
+    "frame_heun_predict", "frame_heun_correct", "frame_traceback", "igso3_series", "igso3_score",
+    "igso3_marginal_pdf", "igso3_build_cdf", "igso3_build_score_scaling", "igso3_sample", "ipa_attention_fwd",
+    "launch_count", "launch_count_reset",
+]
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _dev(t: torch.Tensor, dtype=torch.float32, name="tensor") -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise L.Se3LibraryError(f"{name}: se3diff_b200 ops run on CUDA tensors only (got {t.device}); "
+                                "there is no CPU fallback")
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _guard(t):
+    return torch.cuda.device(t.device)
+
+
+def launch_count() -> int:
+    return int(L.lib().se3_launch_count())
+
+
+def launch_count_reset() -> None:
+    L.lib().se3_launch_count_reset()
+
+
+# ------------------------------------------------------------------------------------------------
+# K2
+# ------------------------------------------------------------------------------------------------
+def so3_exp(rotvec: torch.Tensor, tol: float = 1e-7) -> torch.Tensor:
+    """rotvec_to_rotmat (so3_sde.py:533-554).  [...,3] -> [...,3,3]; fp32 or fp64."""
+    dt = torch.float64 if rotvec.dtype == torch.float64 else torch.float32
+    v = _dev(rotvec, dt, "rotvec")
+    out = torch.empty(v.shape + (3,), dtype=dt, device=v.device)
+    n = v.numel() // 3
+    with _guard(v):
+        fn = L.lib().se3_so3_exp_f64 if dt == torch.float64 else L.lib().se3_so3_exp
+        L.check(fn(_p(v), _p(out), n, tol, _stream(v)), "se3_so3_exp")
+    return out
+
+
+def so3_log(rotmat: torch.Tensor) -> torch.Tensor:
+    """rotmat_to_rotvec (so3_sde.py:557-648).  [...,3,3] -> [...,3]."""
+    dt = torch.float64 if rotmat.dtype == torch.float64 else torch.float32
+    r = _dev(rotmat, dt, "rotmat")
+    out = torch.empty(r.shape[:-1], dtype=dt, device=r.device)
+    with _guard(r):
+        fn = L.lib().se3_so3_log_f64 if dt == torch.float64 else L.lib().se3_so3_log
+        L.check(fn(_p(r), _p(out), r.numel() // 9, _stream(r)), "se3_so3_log")
+    return out
+
+
+def so3_angle(rotmat: torch.Tensor):
+    """angle_from_rotmat (so3_sde.py:651-676) -> (angle, sin, cos)."""
+    r = _dev(rotmat, name="rotmat")
+    a, s, c = (torch.empty(r.shape[:-2], dtype=torch.float32, device=r.device) for _ in range(3))
+    with _guard(r):
+        L.check(L.lib().se3_so3_angle(_p(r), _p(a), _p(s), _p(c), r.numel() // 9, _stream(r)), "se3_so3_angle")
+    return a, s, c
+
+
+def so3_compose_rotvec(rotmat: torch.Tensor, rotvec: torch.Tensor, tol: float = 1e-7, out=None) -> torch.Tensor:
+    """apply_rotvec_to_rotmat (so3_sde.py:782-802): R . Exp(v)."""
+    r, v = _dev(rotmat, name="rotmat"), _dev(rotvec, name="rotvec")
+    if r.shape[:-2] != v.shape[:-1]:
+        raise ValueError(f"shape mismatch {tuple(r.shape)} vs {tuple(v.shape)}")
+    out = torch.empty_like(r) if out is None else out
+    with _guard(r):
+        L.check(L.lib().se3_so3_compose_rotvec(_p(r), _p(v), _p(out), r.numel() // 9, tol, _stream(r)),
+                "se3_so3_compose_rotvec")
+    return out
+
+
+def so3_matmul(a: torch.Tensor, b: torch.Tensor, transpose_a: bool = False) -> torch.Tensor:
+    """rot_mult / rot_transpose (so3_sde.py:870-877)."""
+    a, b = _dev(a, name="a"), _dev(b, name="b")
+    if a.shape != b.shape:
+        raise ValueError("shape mismatch")
+    out = torch.empty_like(a)
+    with _guard(a):
+        L.check(L.lib().se3_so3_matmul(_p(a), _p(b), _p(out), a.numel() // 9, int(transpose_a), _stream(a)),
+                "se3_so3_matmul")
+    return out
+
+
+def so3_rel_log(base: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """rot_vf (so3_sde.py:880-891): Log(base^T target)."""
+    a, b = _dev(base, name="base"), _dev(target, name="target")
+    if a.shape != b.shape:
+        raise ValueError("shape mismatch")
+    out = torch.empty(a.shape[:-1], dtype=torch.float32, device=a.device)
+    with _guard(a):
+        L.check(L.lib().se3_so3_rel_log(_p(a), _p(b), _p(out), a.numel() // 9, _stream(a)), "se3_so3_rel_log")
+    return out
+
+
+def so3_geodesic(base: torch.Tensor, target: torch.Tensor, t: float, tol: float = 1e-7) -> torch.Tensor:
+    """geodesic_t (so3_sde.py:894-911): base . Exp(t Log(base^T target))."""
+    a, b = _dev(base, name="base"), _dev(target, name="target")
+    if a.shape != b.shape:
+        raise ValueError(f"Incompatible shapes: base_mat={tuple(a.shape)}, mat_t={tuple(b.shape)}")
+    out = torch.empty_like(a)
+    with _guard(a):
+        L.check(L.lib().se3_so3_geodesic(_p(a), _p(b), float(t), _p(out), a.numel() // 9, tol, _stream(a)),
+                "se3_so3_geodesic")
+    return out
+
+
+def so3_from_quat(quat: torch.Tensor, want_rotvec=True, want_rotmat=True, tol: float = 1e-7):
+    """rotquat_to_rotvec / rotquat_to_rotmat (so3_sde.py:725-779); quaternion [r,i,j,k]."""
+    q = _dev(quat, name="quat")
+    rv = torch.empty(q.shape[:-1] + (3,), dtype=torch.float32, device=q.device) if want_rotvec else None
+    rm = torch.empty(q.shape[:-1] + (3, 3), dtype=torch.float32, device=q.device) if want_rotmat else None
+    with _guard(q):
+        L.check(L.lib().se3_so3_from_quat(_p(q), _p(rv), _p(rm), q.numel() // 4, tol, _stream(q)), "se3_so3_from_quat")
+    return rv, rm
+
+
+# ------------------------------------------------------------------------------------------------
+# K3 + frame update
+# ------------------------------------------------------------------------------------------------
+def _chk_frames(rot, pos):
+    rot, pos = _dev(rot, name="rot"), _dev(pos, name="pos")
+    n = pos.numel() // 3
+    if rot.numel() != 9 * n:
+        raise ValueError(f"rot {tuple(rot.shape)} and pos {tuple(pos.shape)} disagree on the residue count")
+    return rot, pos, n
+
+
+def _vec(t, n, name):
+    if t is None:
+        return None
+    t = _dev(t, name=name)
+    if t.numel() != 3 * n:
+        raise ValueError(f"{name}: expected {n}x3 values, got {tuple(t.shape)}")
+    return t
+
+
+def frame_update_em(rot, pos, m_rot, m_pos, z_rot, z_pos, scalars: L.EmScalars, u_rot=None, u_pos=None,
+                    want_dw=False, rot_out=None, pos_out=None):
+    """One Euler-Maruyama reverse step on both fields (denoiser.py:54-116)."""
+    rot, pos, n = _chk_frames(rot, pos)
+    m_rot, m_pos, z_rot, z_pos = (_vec(t, n, k) for t, k in ((m_rot, "m_rot"), (m_pos, "m_pos"), (z_rot, "z_rot"), (z_pos, "z_pos")))
+    u_rot, u_pos = _vec(u_rot, n, "u_rot"), _vec(u_pos, n, "u_pos")
+    rot_out = torch.empty_like(rot) if rot_out is None else rot_out
+    pos_out = torch.empty_like(pos) if pos_out is None else pos_out
+    dw_rot = torch.empty_like(pos) if want_dw else None
+    dw_pos = torch.empty_like(pos) if want_dw else None
+    with _guard(rot):
+        L.check(L.lib().se3_frame_update_em(_p(rot), _p(pos), _p(m_rot), _p(m_pos), _p(u_rot), _p(u_pos), _p(z_rot),
+                                            _p(z_pos), _p(rot_out), _p(pos_out), _p(dw_rot), _p(dw_pos), n,
+                                            C.byref(scalars), _stream(rot)), "se3_frame_update_em")
+    return rot_out, pos_out, dw_rot, dw_pos
+
+
+def frame_update_dpm_mid(rot, pos, m_rot, m_pos, scalars: L.DpmScalars, rot_out=None, pos_out=None):
+    rot, pos, n = _chk_frames(rot, pos)
+    m_rot, m_pos = _vec(m_rot, n, "m_rot"), _vec(m_pos, n, "m_pos")
+    rot_out = torch.empty_like(rot) if rot_out is None else rot_out
+    pos_out = torch.empty_like(pos) if pos_out is None else pos_out
+    with _guard(rot):
+        L.check(L.lib().se3_frame_update_dpm_mid(_p(rot), _p(pos), _p(m_rot), _p(m_pos), _p(rot_out), _p(pos_out), n,
+                                                 C.byref(scalars), _stream(rot)), "se3_frame_update_dpm_mid")
+    return rot_out, pos_out
+
+
+def frame_update_dpm_final(rot, pos, m_rot_t, m_rot_lam, m_pos_lam, scalars: L.DpmScalars, rot_out=None, pos_out=None):
+    rot, pos, n = _chk_frames(rot, pos)
+    m_rot_t, m_rot_lam, m_pos_lam = _vec(m_rot_t, n, "m_rot_t"), _vec(m_rot_lam, n, "m_rot_lam"), _vec(m_pos_lam, n, "m_pos_lam")
+    rot_out = torch.empty_like(rot) if rot_out is None else rot_out
+    pos_out = torch.empty_like(pos) if pos_out is None else pos_out
+    with _guard(rot):
+        L.check(L.lib().se3_frame_update_dpm_final(_p(rot), _p(pos), _p(m_rot_t), _p(m_rot_lam), _p(m_pos_lam),
+                                                   _p(rot_out), _p(pos_out), n, C.byref(scalars), _stream(rot)),
+                "se3_frame_update_dpm_final")
+    return rot_out, pos_out
+
+
+def frame_heun_churn(rot, pos, z_rot, z_pos, scalars: L.HeunScalars):
+    rot, pos, n = _chk_frames(rot, pos)
+    z_rot, z_pos = _vec(z_rot, n, "z_rot"), _vec(z_pos, n, "z_pos")
+    rot_out, pos_out = torch.empty_like(rot), torch.empty_like(pos)
+    with _guard(rot):
+        L.check(L.lib().se3_frame_heun_churn(_p(rot), _p(pos), _p(z_rot), _p(z_pos), _p(rot_out), _p(pos_out), n,
+                                             C.byref(scalars), _stream(rot)), "se3_frame_heun_churn")
+    return rot_out, pos_out
+
+
+def frame_heun_predict(rot_hat, pos_hat, m_rot_hat, m_pos_hat, scalars: L.HeunScalars):
+    rot_hat, pos_hat, n = _chk_frames(rot_hat, pos_hat)
+    m_rot_hat, m_pos_hat = _vec(m_rot_hat, n, "m_rot_hat"), _vec(m_pos_hat, n, "m_pos_hat")
+    rot_out, pos_out = torch.empty_like(rot_hat), torch.empty_like(pos_hat)
+    with _guard(rot_hat):
+        L.check(L.lib().se3_frame_heun_predict(_p(rot_hat), _p(pos_hat), _p(m_rot_hat), _p(m_pos_hat), _p(rot_out),
+                                               _p(pos_out), n, C.byref(scalars), _stream(rot_hat)), "se3_frame_heun_predict")
+    return rot_out, pos_out
+
+
+def frame_heun_correct(rot_hat, pos_hat, m_rot_hat, m_pos_hat, pos_pred, m_rot_next, m_pos_next, scalars: L.HeunScalars):
+    rot_hat, pos_hat, n = _chk_frames(rot_hat, pos_hat)
+    m_rot_hat, m_pos_hat, pos_pred, m_rot_next, m_pos_next = (
+        _vec(t, n, k) for t, k in ((m_rot_hat, "m_rot_hat"), (m_pos_hat, "m_pos_hat"), (pos_pred, "pos_pred"),
+                                   (m_rot_next, "m_rot_next"), (m_pos_next, "m_pos_next")))
+    rot_out, pos_out = torch.empty_like(rot_hat), torch.empty_like(pos_hat)
+    with _guard(rot_hat):
+        L.check(L.lib().se3_frame_heun_correct(_p(rot_hat), _p(pos_hat), _p(m_rot_hat), _p(m_pos_hat), _p(pos_pred),
+                                               _p(m_rot_next), _p(m_pos_next), _p(rot_out), _p(pos_out), n,
+                                               C.byref(scalars), _stream(rot_hat)), "se3_frame_heun_correct")
+    return rot_out, pos_out
+
+
+def frame_traceback(rot, pos, rot_next, pos_next, m_rot, m_pos, scalars: L.EmScalars, u_rot=None, u_pos=None):
+    """traceback_brownian_motion (denoiser.py:133-166) for both fields -> (dW_rot, dW_pos)."""
+    rot, pos, n = _chk_frames(rot, pos)
+    rot_next, pos_next, _ = _chk_frames(rot_next, pos_next)
+    m_rot, m_pos = _vec(m_rot, n, "m_rot"), _vec(m_pos, n, "m_pos")
+    u_rot, u_pos = _vec(u_rot, n, "u_rot"), _vec(u_pos, n, "u_pos")
+    dw_rot, dw_pos = torch.empty_like(pos), torch.empty_like(pos)
+    with _guard(rot):
+        L.check(L.lib().se3_frame_traceback(_p(rot), _p(pos), _p(rot_next), _p(pos_next), _p(m_rot), _p(m_pos),
+                                            _p(u_rot), _p(u_pos), _p(dw_rot), _p(dw_pos), n, C.byref(scalars),
+                                            _stream(rot)), "se3_frame_traceback")
+    return dw_rot, dw_pos
+
+
+# ------------------------------------------------------------------------------------------------
+# K1
+# ------------------------------------------------------------------------------------------------
+def igso3_series(omega: torch.Tensor, sigma: torch.Tensor, l_max: int, tol: float = 1e-7, want=("f", "df", "dlog")):
+    """igso3_expansion / digso3_expansion / dlog_igso3_expansion (so3_sde.py:1731-1940), l = 0..l_max."""
+    dt = torch.float64 if omega.dtype == torch.float64 else torch.float32
+    omega, sigma = torch.broadcast_tensors(omega, sigma)
+    o, s = _dev(omega, dt, "omega"), _dev(sigma, dt, "sigma")
+    outs = {k: (torch.empty_like(o) if k in want else None) for k in ("f", "df", "dlog")}
+    with _guard(o):
+        fn = L.lib().se3_igso3_series_f64 if dt == torch.float64 else L.lib().se3_igso3_series_f32
+        L.check(fn(_p(o), _p(s), _p(outs["f"]), _p(outs["df"]), _p(outs["dlog"]), o.numel(), int(l_max), tol, _stream(o)),
+                "se3_igso3_series")
+    return outs
+
+
+def igso3_score(rotvec: torch.Tensor, sigma: torch.Tensor, l_max: int, tol: float = 1e-7) -> torch.Tensor:
+    """ScoreSO3.forward (so3_sde.py:1698-1715)."""
+    q = _dev(rotvec, name="rotvec")
+    s = _dev(sigma.expand(q.shape[:-1]) if sigma.shape != q.shape[:-1] else sigma, name="sigma")
+    out = torch.empty_like(q)
+    with _guard(q):
+        L.check(L.lib().se3_igso3_score(_p(q), _p(s), _p(out), q.numel() // 3, int(l_max), tol, _stream(q)), "se3_igso3_score")
+    return out
+
+
+def igso3_marginal_pdf(omega, omega_0, sigma, l_count: int, tol: float = 1e-7) -> torch.Tensor:
+    """igso3_marginal_pdf (so3_sde.py:1795-1854) with l = 0..l_count-1; inputs broadcast together."""
+    omega, omega_0, sigma = torch.broadcast_tensors(omega, omega_0, sigma)
+    o, o0, s = _dev(omega, name="omega"), _dev(omega_0, name="omega_0"), _dev(sigma, name="sigma")
+    out = torch.empty_like(o)
+    with _guard(o):
+        L.check(L.lib().se3_igso3_marginal_pdf(_p(o), _p(o0), _p(s), _p(out), o.numel(), int(l_count), tol, _stream(o)),
+                "se3_igso3_marginal_pdf")
+    return out
+
+
+def igso3_build_cdf(sigma_grid: torch.Tensor, omega_pts: torch.Tensor, l_max: int, tol: float = 1e-7, uniform=False):
+    sg = _dev(sigma_grid, name="sigma_grid")
+    om = _dev(omega_pts, torch.float64, "omega_pts")
+    rows = 1 if uniform else sg.numel()
+    cdf = torch.empty(rows, om.numel() - 1, dtype=torch.float32, device=sg.device)
+    with _guard(sg):
+        L.check(L.lib().se3_igso3_build_cdf(_p(sg), sg.numel(), _p(om), om.numel(), int(l_max), tol, int(uniform), _p(cdf),
+                                            _stream(sg)), "se3_igso3_build_cdf")
+    return cdf
+
+
+def igso3_build_score_scaling(sigma_grid: torch.Tensor, omega_pts: torch.Tensor, l_max: int, tol: float = 1e-7):
+    sg = _dev(sigma_grid, name="sigma_grid")
+    om = _dev(omega_pts, torch.float64, "omega_pts")
+    out = torch.empty(sg.numel(), dtype=torch.float32, device=sg.device)
+    with _guard(sg):
+        L.check(L.lib().se3_igso3_build_score_scaling(_p(sg), sg.numel(), _p(om), om.numel(), int(l_max), tol, _p(out),
+                                                      _stream(sg)), "se3_igso3_build_score_scaling")
+    return out
+
+
+def igso3_sample(cdf, omega_grid, n: int, sigma=None, sigma_grid=None, normals=None, u=None, seed: int = 0, x=None,
+                 tol: float = 1e-7, want_angle=False):
+    """BaseSampleSO3.sample with one sample per element (so3_sde.py:1189-1286) [+ x . r]."""
+    cdf, og = _dev(cdf, name="cdf"), _dev(omega_grid, name="omega_grid")
+    sigma = None if sigma is None else _dev(sigma, name="sigma")
+    sigma_grid = None if sigma_grid is None else _dev(sigma_grid, name="sigma_grid")
+    normals = None if normals is None else _dev(normals, name="normals")
+    u = None if u is None else _dev(u, name="u")
+    x = None if x is None else _dev(x, name="x")
+    out = torch.empty(n, 3, 3, dtype=torch.float32, device=cdf.device)
+    ang = torch.empty(n, dtype=torch.float32, device=cdf.device) if want_angle else None
+    with _guard(cdf):
+        L.check(L.lib().se3_igso3_sample(_p(sigma), _p(sigma_grid), 0 if sigma_grid is None else sigma_grid.numel(), _p(cdf),
+                                         _p(og), og.numel(), _p(normals), _p(u), int(seed) & (2**64 - 1), _p(x), _p(out),
+                                         _p(ang), n, tol, _stream(cdf)), "se3_igso3_sample")
+    return (out, ang) if want_angle else out
+
+
+# ------------------------------------------------------------------------------------------------
+# K4
+# ------------------------------------------------------------------------------------------------
+IPA_EXACT, IPA_FAST_MATH = 0, 1
+
+
+def ipa_attention_fwd(proj, rot, trans, pair_bias, pair_value, key_bias, head_weight, scalar_weight: float,
+                      shape: L.IpaShape, flags: int = IPA_EXACT, out=None):
+    """SAAttention.forward between the projections and fc_out (structure_module.py:131-216)."""
+    proj, rot, trans = _dev(proj, name="proj"), _dev(rot, name="rot"), _dev(trans, name="trans")
+    pair_bias, pair_value = _dev(pair_bias, name="pair_bias"), _dev(pair_value, name="pair_value")
+    key_bias = None if key_bias is None else _dev(key_bias, name="key_bias")
+    head_weight = _dev(head_weight, name="head_weight")
+    width = shape.heads * (2 * shape.dk + 4 * shape.pv)
+    if out is None:
+        out = torch.empty(shape.batch * shape.len, width, dtype=torch.float32, device=proj.device)
+    with _guard(proj):
+        L.check(L.lib().se3_ipa_attention_fwd(_p(proj), _p(rot), _p(trans), _p(pair_bias), _p(pair_value), _p(key_bias),
+                                              _p(head_weight), float(scalar_weight), _p(out), C.byref(shape), int(flags),
+                                              _stream(proj)), "se3_ipa_attention_fwd")
+    return out

@@ -1,0 +1,111 @@
+"""Live per-kernel timing for bench.py's `roofline` objects: CUDA events recorded on the launching
+stream around individual launches of this library's kernels (never under a profiler)."""
+from __future__ import annotations
+
+import json
+import os
+
+import torch
+
+from . import ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def measured_peaks():
+    """MEASURED_PEAKS.json (driver-written) or the fallback stated in B200_PROFILING.md."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tensor_burst=float(d["bf16_tflops"]),
+                    tensor_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback")
+
+
+class _Hook:
+    def __init__(self, name):
+        self.name, self.orig, self.events = name, getattr(ops, name), []
+
+    def __enter__(self):
+        def wrapped(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = self.orig(*a, **k)
+            e1.record()
+            self.events.append((e0, e1))
+            return r
+
+        setattr(ops, self.name, wrapped)
+        return self
+
+    def __exit__(self, *exc):
+        setattr(ops, self.name, self.orig)
+        return False
+
+    def mean_ms(self):
+        torch.cuda.synchronize()
+        ts = [a.elapsed_time(b) for a, b in self.events]
+        return sum(ts) / max(1, len(ts)), len(ts)
+
+
+def _time_alone(fn, iters=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def elementwise_rooflines(n: int = 10_000_000, device="cuda"):
+    """BASELINE config 3: SO(3) exp/log/compose, IGSO3 noising and the fused frame updates at n = 1e7
+    (inputs 120-1200 MB, i.e. larger than L2).  Algorithmic bytes per unit from SURVEY.md 8(d)."""
+    from . import _lib as L
+
+    pk = measured_peaks()
+    g = torch.Generator(device=device).manual_seed(0)
+    v = torch.randn(n, 3, generator=g, device=device)
+    r = ops.so3_exp(v)
+    w = torch.randn(n, 3, generator=g, device=device) * 0.1
+    z1, z2 = torch.randn(n, 3, generator=g, device=device), torch.randn(n, 3, generator=g, device=device)
+    pos = torch.randn(n, 3, generator=g, device=device)
+    out_r, out_p = torch.empty_like(r), torch.empty_like(pos)
+    em = L.EmScalars(-0.02, 0.1414, 1.0, 1.0, 0.67, 4.0, 3.1, 1.76, 0.7, 1e-7)
+    dp = L.DpmScalars(0.7, 1.01, 0.02, 0.69, 1.02, 0.04, 4.0, 4.1, 0.67, 0.65, -0.01, -0.02, 1e-7)
+    cases = [
+        ("se3_so3_exp", 48, lambda: ops.so3_exp(v)),
+        ("se3_so3_log", 48, lambda: ops.so3_log(r)),
+        ("se3_so3_compose_rotvec", 84, lambda: ops.so3_compose_rotvec(r, w, out=out_r)),
+        ("se3_frame_update_em", 144, lambda: ops.frame_update_em(r, pos, w, v, z1, z2, em, rot_out=out_r, pos_out=out_p)),
+        ("se3_frame_update_dpm_mid", 120, lambda: ops.frame_update_dpm_mid(r, pos, w, v, dp, rot_out=out_r, pos_out=out_p)),
+        ("se3_frame_update_dpm_final", 132, lambda: ops.frame_update_dpm_final(r, pos, w, z1, v, dp, rot_out=out_r, pos_out=out_p)),
+    ]
+    res = []
+    for name, bytes_per, fn in cases:
+        ms = _time_alone(fn)
+        gbs = bytes_per * n / ms / 1e6
+        res.append({"kernel": name, "bound": "hbm", "n": n, "bytes_per_unit": bytes_per, "ms": ms, "achieved": gbs,
+                    "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "peak_source": pk["source"], "traffic": None})
+    return res
+
+
+def kernel_rooflines(step_fn, L: int, B: int):
+    """(dominant-kernel roofline, other kernels).  The dominant kernel of this library inside the
+    sampling step is the IPA attention kernel; its tensor-eligible algorithmic work is
+    4608 * L^2 flop per sample per launch (QK^T + P.V scalar/point/pair)."""
+    pk = measured_peaks()
+    with _Hook("ipa_attention_fwd") as h:
+        step_fn()
+        ms, n = h.mean_ms()
+    flops = 4608.0 * L * L * B
+    tf = flops / ms / 1e9
+    roof = {"kernel": "se3_ipa_attention_fwd", "bound": "tensor", "achieved": tf, "peak": pk["tensor_sustained"],
+            "unit": "TFLOP/s", "frac": tf / pk["tensor_sustained"], "traffic": None, "launches_timed": n, "ms_per_launch": ms,
+            "algorithmic_flops_per_launch": flops, "peak_source": pk["source"] + " (sustained bf16, kernel timed inside a long step)",
+            "note": "fp32 SIMT edition: logits, point distances (128 sqrt per pair) and all three value aggregations run on the "
+                    "FP32/MUFU pipes; tensor-eligible flops are reported against the bf16 tensor peak as north_star asks"}
+    return roof, elementwise_rooflines()

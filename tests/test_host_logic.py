@@ -1,0 +1,163 @@
+"""CPU tests of the host side of se3diff_b200: library export table, schedule scalars against the
+reference-generated goldens, container semantics, state_dict surface.  No compute calls."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from se3diff_b200 import _lib
+    from se3diff_b200.build import build
+
+    path = build()
+    assert os.path.exists(path)
+    header = open(os.path.join(ROOT, "include", "se3diff_b200.h")).read()
+    declared = set(re.findall(r"\b(se3_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    h = ctypes.CDLL(path)
+    for name in declared:
+        assert hasattr(h, name), f"{name} declared in include/se3diff_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    lib = _lib.lib()
+    assert lib.se3_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from se3diff_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "se3diff_b200.h")).read()
+    for cname, cls in (("se3_em_scalars", _lib.EmScalars), ("se3_dpm_scalars", _lib.DpmScalars),
+                       ("se3_heun_scalars", _lib.HeunScalars), ("se3_ipa_shape", _lib.IpaShape)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), header, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            decl = re.sub(r"^(float|int32_t)\s+", "", decl)
+            names += [n.strip() for n in decl.split(",")]
+        assert names == [f[0] for f in cls._fields_], cname
+
+
+def test_ops_reject_cpu_tensors():
+    from se3diff_b200 import _lib, ops
+
+    with pytest.raises(_lib.Se3LibraryError):
+        ops.so3_exp(torch.zeros(4, 3))
+
+
+def test_schedule_scalars_match_reference_goldens():
+    """schedule.py against tests/golden/schedules.npz (minted by the reference SDE objects)."""
+    from se3diff_b200 import schedule
+    from se3diff_b200.sdes import CosineVPSDE
+
+    g = load_golden("schedules.npz")
+    tab = load_golden("so3_tables.npz")
+    cols = list(g["columns"])
+
+    class So3Stub:  # schedule only needs _marginal_std, beta, tol and the two CPU tables
+        tol = 1e-7
+        sigma_min, sigma_max = 0.02, 2.33
+
+        class score_function:
+            sigma_grid = torch.from_numpy(tab["small_sigma_grid"])
+            score_scaling = torch.from_numpy(tab["small_score_scaling"])
+
+        def _marginal_std(self, t):
+            return self.sigma_min * (self.sigma_max / self.sigma_min) ** t
+
+        def beta(self, t):
+            return self._marginal_std(t) * np.sqrt(2.0 * np.log(self.sigma_max / self.sigma_min))
+
+    r3, so3 = CosineVPSDE(0.008), So3Stub()
+    d = g["dpm"]
+    c = {n: i for i, n in enumerate(cols)}
+    steps = schedule.dpm_schedule(r3, so3, 50, 0.99, 0.001)
+    f32 = lambda x: float(np.float32(x))
+    for i, st in enumerate(steps):
+        s = st.scalars
+        assert st.t == d[i, c["t"]] and st.t_lambda == d[i, c["t_lambda"]]
+        assert s.pos_std_t == d[i, c["std_t"]] and s.pos_std_lam == d[i, c["std_lambda"]]
+        assert s.rot_g_t == d[i, c["so3_g_t"]] and s.rot_g_lam == d[i, c["so3_g_lambda"]]
+        assert s.rot_scale_t == d[i, c["score_scaling_t"]] and s.rot_scale_lam == d[i, c["score_scaling_lambda"]]
+        assert s.dt == d[i, c["dt"]]
+        assert s.pos_c_x_mid == f32(np.float32(d[i, c["alpha_lambda"]]) / np.float32(d[i, c["alpha_t"]]))
+        assert s.pos_c_x_fin == f32(np.float32(d[i, c["alpha_next"]]) / np.float32(d[i, c["alpha_t"]]))
+        assert s.dt_mid == f32(np.float32(d[i, c["t_lambda"]]) - np.float32(d[i, c["t"]]))
+    e = g["em"]
+    for i, st in enumerate(schedule.em_schedule(r3, so3, 200, 0.99, 0.001)):
+        s = st.scalars
+        assert st.t == e[i, c["t"]] and s.dt == e[i, c["dt"]] and s.pos_beta == e[i, c["beta_t"]]
+        assert s.pos_std == e[i, c["std_t"]] and s.rot_g == e[i, c["so3_g_t"]] and s.rot_scale == e[i, c["score_scaling_t"]]
+        assert s.score_weight == 1.0 and s.noise_weight == 1.0
+    hs = schedule.heun_schedule(r3, so3, 100, 0.99, 0.001, 0.5)
+    hgold = g["heun"]
+    assert hs[0].t_hat == hs[0].t and hs[0].scalars.churn_dt == 0.0
+    for i, st in enumerate(hs):
+        assert st.t == hgold[i, c["t"]] and st.t_next == hgold[i, c["t_next"]]
+        assert st.scalars.next_pos_std == hgold[i, c["std_next"]]
+        if i > 0:
+            assert st.t_hat > st.t and st.scalars.churn_dt > 0
+        assert st.correct
+
+
+def test_chemgraph_container_semantics():
+    from se3diff_b200.chemgraph import Batch, ChemGraph, batch_lengths, complete_graph_edge_index
+
+    gs = []
+    for n in (3, 5):
+        gs.append(ChemGraph(pos=torch.randn(n, 3), node_orientations=torch.eye(3).repeat(n, 1, 1),
+                            edge_index=complete_graph_edge_index(n), single_embeds=torch.randn(n, 384),
+                            pair_embeds=torch.randn(n * n, 128), system_id=f"g{n}"))
+    b = Batch.from_data_list(gs)
+    assert b.num_graphs == 2 and batch_lengths(b) == [3, 5]
+    assert b.batch.tolist() == [0] * 3 + [1] * 5 and b.ptr.tolist() == [0, 3, 8]
+    assert torch.equal(b.edge_index[:, 9:], complete_graph_edge_index(5) + 3)
+    b2 = b.replace(pos=None)
+    assert b2.pos is None and b.pos is not None and "pos" in b2 and b2.single_embeds is b.single_embeds
+    b["pos"] = torch.zeros(8, 3)
+    assert b.pos.abs().sum() == 0
+    back = b.to_data_list()
+    assert [x.num_nodes for x in back] == [3, 5] and torch.equal(back[1].edge_index, complete_graph_edge_index(5))
+    assert torch.equal(back[1].pair_embeds, gs[1].pair_embeds) and back[0].system_id == "g3"
+    # edge_index layout is the reference's (sample.py:165-171)
+    assert complete_graph_edge_index(3).tolist() == [[0, 0, 0, 1, 1, 1, 2, 2, 2], [0, 1, 2, 0, 1, 2, 0, 1, 2]]
+
+
+def test_state_dict_surface_matches_reference_golden():
+    """Same keys and shapes as the reference checkpoint layout (tests/state_dict.ptkeep re-exported into
+    score_model_tiny.npz) and bit-exact relative-position buckets."""
+    import yaml
+
+    from se3diff_b200.models import DiGConditionalScoreModel, RelativePositionBias
+
+    g = load_golden("score_model_tiny.npz")
+    cfg = yaml.safe_load(str(g["cfg_json"]))
+    m = DiGConditionalScoreModel(**cfg)
+    sd = {k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd::")}
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    m.load_state_dict(sd)
+    full = DiGConditionalScoreModel()
+    assert sum(p.numel() for p in full.parameters()) == 31_284_486
+    assert sum(p.numel() for p in full.model_nn.st_module.encoder.layers[0].parameters()) == 3_813_408
+    ft = DiGConditionalScoreModel(dim_model=64, dim_pair=32, num_layers=2, num_heads=4, dim_hidden=256)
+    assert sum(p.numel() for p in ft.parameters()) == 193_806
+    b = RelativePositionBias._relative_position_bucket(torch.arange(40), 64, 128).tolist()
+    assert b == list(range(16)) + [16, 16, 16, 17, 17, 18, 18, 18, 19, 19, 19, 20, 20, 20, 20, 21, 21, 21, 21, 22, 22, 22, 22, 22]
+
+
+def test_samplers_refuse_cpu():
+    from se3diff_b200 import shortcuts
+    from se3diff_b200.chemgraph import Batch, ChemGraph
+
+    b = Batch.from_data_list([ChemGraph(pos=torch.zeros(2, 3), node_orientations=torch.zeros(2, 3, 3))])
+    with pytest.raises(RuntimeError):
+        shortcuts.dpm_solver(batch=b, sdes={"pos": shortcuts.CosineVPSDE(), "node_orientations": None},
+                             score_model=lambda x, t: x, num_steps=2, max_t=0.99, min_t=0.001, device="cpu")
