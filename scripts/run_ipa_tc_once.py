@@ -1,0 +1,13 @@
+"""One warm + a few launches of the tensor-core IPA at the bench shape (ncu target)."""
+import sys, os, math
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import torch
+from debug_ipa_tc_common import make, ops, dev, H
+B, Lm = int(os.environ.get("IPA_B", 256)), int(os.environ.get("IPA_L", 84))
+proj, rot, trans, pb, pv, hw, shape = make(B, Lm)
+ws = ops.ipa_tc_workspace(shape, dev); pvp = ops.ipa_tc_pack_pair_value(pv, H)
+out = torch.empty(B * Lm, 2048, dtype=torch.bfloat16, device=dev)
+for _ in range(3):
+    ops.ipa_attention_tc_fwd(proj, rot, trans, pb, pvp, None, hw, 1 / math.sqrt(48), shape, ws, out=out)
+torch.cuda.synchronize()
+print("ok", float(out.float().abs().mean()))

@@ -21,6 +21,8 @@ SOURCES = {
     "frame_kernels.cu": ["-fmad=false"],
     "igso3_kernels.cu": ["-fmad=false"],
     "ipa_simt.cu": [],
+    "tc_selftest.cu": [],
+    "ipa_tc.cu": [],
 }
 
 

@@ -156,7 +156,7 @@ class _Context:
     """Per-sequence tensors that do not depend on the sample, on t or on the frames."""
 
     __slots__ = ("key", "lengths", "lmax", "batch", "shared", "mask", "dense_index", "x1d_base", "pair_bias",
-                 "pair_value", "key_bias", "uniform")
+                 "pair_value", "key_bias", "uniform", "tc", "pair_value_packed", "workspace")
 
 
 class DistributionalGraphormer(nn.Module):
@@ -252,11 +252,19 @@ class DistributionalGraphormer(nn.Module):
         c.x1d_base = self.x1d_proj(single_d)                                        # [Bp, L, d_model]
         bucket = self.rp_proj.bucket_table(lmax).to(dev)
         x2d = self.x2d_proj(pair_d) + self.rp_proj.relative_attention_bias(bucket)[None]   # [Bp, L, L, d_pair]
-        c.pair_bias, c.pair_value = [], []
+        attn0 = self.st_module.encoder.layers[0].attn
+        probe = L.IpaShape(B, lmax, attn0.n_head, attn0.d_k, 4, 8, 0, 0, 0, 0, 0, 0, 0, 1 if c.shared else B)
+        c.tc = self.precision == "bf16" and ops.ipa_tc_supported(probe)      # tcgen05 attention path
+        c.pair_bias, c.pair_value, c.pair_value_packed = [], [], []
         for lyr in self.st_module.encoder.layers:
             a = lyr.attn
             c.pair_bias.append((a.pair_weight * a.pair_bias(x2d)).permute(0, 3, 1, 2).contiguous())   # [Bp, H, L, L]
-            c.pair_value.append(a.pair_value(x2d).contiguous())                                        # [Bp, L, L, H*dk]
+            pv = a.pair_value(x2d)                                                                     # [Bp, L, L, H*dk]
+            if c.tc:
+                c.pair_value_packed.append(ops.ipa_tc_pack_pair_value(pv, a.n_head))
+            else:
+                c.pair_value.append(pv.contiguous())
+        c.workspace = ops.ipa_tc_workspace(probe, dev) if c.tc else None
         self._ctx = c
         return c
 
@@ -321,8 +329,12 @@ class DistributionalGraphormer(nn.Module):
             lw = w["layers"][n]
             y = F.layer_norm(x1d, (D,), lyr.norm1.weight, lyr.norm1.bias, lyr.norm1.eps)
             proj = self._linear(y, lw["w_proj"])
-            feat = ops.ipa_attention_fwd(proj, R, T, c.pair_bias[n], c.pair_value[n], c.key_bias, lw["head_w"],
-                                         lyr.attn.scalar_weight, shape, flags)
+            if c.tc:
+                feat = ops.ipa_attention_tc_fwd(proj, R, T, c.pair_bias[n], c.pair_value_packed[n], c.key_bias, lw["head_w"],
+                                                lyr.attn.scalar_weight, shape, c.workspace)
+            else:
+                feat = ops.ipa_attention_fwd(proj, R, T, c.pair_bias[n], c.pair_value[n], c.key_bias, lw["head_w"],
+                                             lyr.attn.scalar_weight, shape, flags)
             x1d = x1d + self._linear(feat, lw["w_out"], lyr.attn.fc_out.bias)
             y = F.layer_norm(x1d, (D,), lyr.norm2.weight, lyr.norm2.bias, lyr.norm2.eps)
             y = F.gelu(self._linear(y, lw["w_ff0"], lyr.ffn.ff[0].bias))

@@ -347,3 +347,52 @@ def ipa_attention_fwd(proj, rot, trans, pair_bias, pair_value, key_bias, head_we
                                               _p(head_weight), float(scalar_weight), _p(out), C.byref(shape), int(flags),
                                               _stream(proj)), "se3_ipa_attention_fwd")
     return out
+
+
+def debug_umma_gemm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """tcgen05 self-test: a [128,K] bf16, b [N,K] bf16 -> a @ b.T in fp32 via UMMA/TMEM."""
+    a, b = _dev(a, torch.bfloat16, "a"), _dev(b, torch.bfloat16, "b")
+    out = torch.empty(128, b.shape[0], dtype=torch.float32, device=a.device)
+    with _guard(a):
+        L.check(L.lib().se3_debug_umma_gemm(_p(a), _p(b), _p(out), b.shape[0], a.shape[1], _stream(a)), "se3_debug_umma_gemm")
+    return out
+
+
+def ipa_tc_supported(shape: L.IpaShape) -> bool:
+    return shape.dk == 16 and shape.pq == 4 and shape.pv == 8 and shape.pair_batch == 1 and shape.len <= 256 and shape.heads % 8 == 0
+
+
+def ipa_tc_pack_pair_value(pair_value: torch.Tensor, heads: int) -> torch.Tensor:
+    """[1, L, L, H*16] (pair_value(x2d), structure_module.py:209) -> bf16 [L][H][Lp/8][16][8], the UMMA K-major
+    operand layout read by pass 2 of the tensor-core attention."""
+    Lq = pair_value.shape[1]
+    Lp = (Lq + 15) // 16 * 16
+    pv = pair_value.reshape(Lq, Lq, heads, 16)
+    if Lp != Lq:
+        pv = torch.nn.functional.pad(pv, (0, 0, 0, 0, 0, Lp - Lq))
+    return pv.view(Lq, Lp // 8, 8, heads, 16).permute(0, 3, 1, 4, 2).contiguous().to(torch.bfloat16)
+
+
+def ipa_tc_workspace(shape: L.IpaShape, device) -> tuple[torch.Tensor, torch.Tensor]:
+    pb, ib = C.c_int64(0), C.c_int64(0)
+    L.lib().se3_ipa_tc_workspace_bytes(C.byref(shape), C.byref(pb), C.byref(ib))
+    return (torch.empty(pb.value // 2, dtype=torch.bfloat16, device=device), torch.empty(ib.value // 4, dtype=torch.float32, device=device))
+
+
+def ipa_attention_tc_fwd(proj, rot, trans, pair_bias, pair_value_packed, key_bias, head_weight, scalar_weight: float,
+                         shape: L.IpaShape, workspace, out_dtype=torch.bfloat16, out=None):
+    """Tensor-core edition (tcgen05/TMEM) of SAAttention.forward between the projections and fc_out."""
+    proj, rot, trans = _dev(proj, name="proj"), _dev(rot, name="rot"), _dev(trans, name="trans")
+    pair_bias = _dev(pair_bias, name="pair_bias")
+    pvp = _dev(pair_value_packed, torch.bfloat16, "pair_value_packed")
+    key_bias = None if key_bias is None else _dev(key_bias, name="key_bias")
+    head_weight = _dev(head_weight, name="head_weight")
+    width = shape.heads * (2 * shape.dk + 4 * shape.pv)
+    if out is None:
+        out = torch.empty(shape.batch * shape.len, width, dtype=out_dtype, device=proj.device)
+    pws, iws = workspace
+    with _guard(proj):
+        L.check(L.lib().se3_ipa_attention_tc_fwd(_p(proj), _p(rot), _p(trans), _p(pair_bias), _p(pvp), _p(key_bias), _p(head_weight),
+                                                 float(scalar_weight), _p(out), int(out.dtype == torch.bfloat16), _p(pws), _p(iws),
+                                                 C.byref(shape), _stream(proj)), "se3_ipa_attention_tc_fwd")
+    return out
