@@ -242,15 +242,18 @@ int se3_ipa_attention_fwd(const float* proj, const float* rot, const float* tran
 
 /* Tensor-core edition of the same operator (tcgen05.mma + TMEM, bf16 operands, fp32 accumulation): two
  * passes, see se3diff_b200/csrc/ipa_tc.cu.  Requirements: dk = 16, shared pair tensors (pair_batch = 1),
- * L <= 256, heads % 8 == 0.  Differences from se3_ipa_attention_fwd:
+ * L <= 256.  Differences from se3_ipa_attention_fwd:
+ *   pair_bias_packed  : TRANSPOSED bf16 [H][L (key j)][round_up(L,8) (query i)] = pair_weight*pair_bias(x2d), zero padded;
+ *                       the (head, query-tile) slab is fetched by TMA into shared memory
  *   pair_value_packed : bf16 [L][H][Lp/8][16][8] with Lp = round_up(L,16): pair_value[i, j, h*16+c] stored at
  *                       [i][h][j/8][c][j%8], zero for j >= L (the UMMA K-major operand layout, built once per
  *                       sequence by the caller)
  *   out               : fp32 or bf16 (out_is_bf16) concat layout
- *   p_workspace / inv_workspace : scratch of the sizes reported by se3_ipa_tc_workspace_bytes (probabilities
- *                       bf16 [H][L][round_up(B,128)][Lp] and 1/rowsum fp32 [H][L][round_up(B,128)]) */
+ *   p_workspace / inv_workspace : scratch of the sizes reported by se3_ipa_tc_workspace_bytes (un-normalised probabilities,
+ *                       bf16 in UMMA tile layout [H][L][round_up(B,128)/128][Lp/8][128][8], and 1/rowsum fp32
+ *                       [H][L][round_up(B,128)]) */
 int64_t se3_ipa_tc_workspace_bytes(const se3_ipa_shape* h_shape, int64_t* p_bytes, int64_t* inv_bytes);
-int se3_ipa_attention_tc_fwd(const float* proj, const float* rot, const float* trans, const float* pair_bias,
+int se3_ipa_attention_tc_fwd(const float* proj, const float* rot, const float* trans, const void* pair_bias_packed,
                              const void* pair_value_packed, const float* key_bias, const float* head_weight,
                              float scalar_weight, void* out, int out_is_bf16, void* p_workspace, float* inv_workspace,
                              const se3_ipa_shape* h_shape, se3_stream_t stream);

@@ -48,9 +48,9 @@ for B, Lm, scale in ((3, 84, 1.5), (2, 56, 1.5), (130, 20, 1.5), (2, 200, 1.5), 
     proj, rot, trans, pb, pv, hw, shape = make(B, Lm, seed=Lm, pos_scale=scale)
     r64 = ref(proj, rot, trans, pb, pv, hw, B, Lm)
     ws = ops.ipa_tc_workspace(shape, dev)
-    pvp = ops.ipa_tc_pack_pair_value(pv, H)
+    pvp = ops.ipa_tc_pack_pair_value(pv, H); pbt = ops.ipa_tc_pack_pair_bias(pb.permute(0, 2, 3, 1))
     for odt in (torch.float32, torch.bfloat16):
-        o = ops.ipa_attention_tc_fwd(proj, rot, trans, pb, pvp, None, hw, 1 / math.sqrt(48), shape, ws, out_dtype=odt)
+        o = ops.ipa_attention_tc_fwd(proj, rot, trans, pbt, pvp, None, hw, 1 / math.sqrt(48), shape, ws, out_dtype=odt)
         torch.cuda.synchronize()
         e = (o.double() - r64).abs()
         print(f"B={B} L={Lm} scale={scale} out={odt}:", {n: f"{e[:, a:b].max().item():.2e}/{r64[:, a:b].abs().max().item():.1f}" for n, a, b in names},
@@ -59,7 +59,7 @@ for B, Lm, scale in ((3, 84, 1.5), (2, 56, 1.5), (130, 20, 1.5), (2, 200, 1.5), 
 # timing at the bench shape
 B, Lm = 256, 84
 proj, rot, trans, pb, pv, hw, shape = make(B, Lm)
-ws = ops.ipa_tc_workspace(shape, dev); pvp = ops.ipa_tc_pack_pair_value(pv, H)
+ws = ops.ipa_tc_workspace(shape, dev); pvp = ops.ipa_tc_pack_pair_value(pv, H); pbt = ops.ipa_tc_pack_pair_bias(pb.permute(0, 2, 3, 1))
 out = torch.empty(B * Lm, 2048, dtype=torch.bfloat16, device=dev)
 def t(fn, n=10):
     for _ in range(3): fn()
@@ -67,5 +67,5 @@ def t(fn, n=10):
     e0.record()
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1) / n
-print("tc   ms:", t(lambda: ops.ipa_attention_tc_fwd(proj, rot, trans, pb, pvp, None, hw, 1 / math.sqrt(48), shape, ws, out=out)))
+print("tc   ms:", t(lambda: ops.ipa_attention_tc_fwd(proj, rot, trans, pbt, pvp, None, hw, 1 / math.sqrt(48), shape, ws, out=out)))
 print("simt ms:", t(lambda: ops.ipa_attention_fwd(proj, rot, trans, pb, pv, None, hw, 1 / math.sqrt(48), shape, 1)))

@@ -13,12 +13,13 @@
 //   MMA 2  O[128 x 64] = P.V                       accumulator reuses the TMEM columns of S
 //   SIMT   normalise, undo the re-centring, inverse frame R_i^T(. - T_i), norms; writes the scalar | point |
 //          norm columns of the concat layout (structure_module.py:216)
-// Pass 2, one CTA per (128-sample tile, query i, 8-head group):
+// Pass 2, one CTA per (128-sample tile, query i, head h):
 //   out_pair[b, i, h, :] = sum_j P[h,i,b,j] * pair_value[i,j,h,:]   (structure_module.py:209-213)
-//   as a tensor-core GEMM with the SAMPLE index as M: A = P[h][i][b0:b0+128][Lp] (cp.async into the UMMA
-//   layout, double buffered), B = pair_value pre-packed per (i,h) in UMMA layout, D[128 x 16] per head in TMEM.
-//   pair_value is therefore read once per 128 samples instead of once per sample (3.7 GB -> 30 MB per layer
-//   at B=256, L=84).
+//   as a tensor-core GEMM with the SAMPLE index as M.  Pass 1 writes P directly in the UMMA operand layout
+//   ([h][i][b/128][j/8][b%128][j%8]), so the A tile (128 x Lp bf16) and the pre-packed pair_value tile
+//   (16 x Lp bf16) are two contiguous blocks fetched with TMA bulk copies (cp.async.bulk -> UBLKCP) that
+//   signal an mbarrier; D[128 x 16] accumulates in TMEM.  pair_value is therefore read once per 128 samples
+//   instead of once per sample (3.7 GB -> 30 MB per layer at B=256, L=84).
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -39,6 +40,18 @@ template <typename T> __device__ __forceinline__ T to_out(float v);
 template <> __device__ __forceinline__ float to_out<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// N contiguous outputs (N % 8 == 0, destination 16-byte aligned) as 128-bit stores
+template <int N> __device__ __forceinline__ void store_vec(float* dst, const float (&v)[N]) {
+#pragma unroll
+    for (int c = 0; c < N / 4; ++c) reinterpret_cast<float4*>(dst)[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+template <int N> __device__ __forceinline__ void store_vec(__nv_bfloat16* dst, const float (&v)[N]) {
+#pragma unroll
+    for (int c = 0; c < N / 8; ++c)
+        reinterpret_cast<uint4*>(dst)[c] = make_uint4(tc::pack_bf16(v[8 * c], v[8 * c + 1]), tc::pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+                                                      tc::pack_bf16(v[8 * c + 4], v[8 * c + 5]), tc::pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+}
+
 struct Pass1Smem {
     uint8_t *q, *k, *vt, *p;
     float *kp, *kb;
@@ -58,11 +71,11 @@ inline size_t pass1_smem_bytes(int Lp) { return 2 * 128 * 16 + (size_t)Lp * (32 
 template <typename OutT>
 __global__ void __launch_bounds__(128)
 k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, const float* __restrict__ trans,
-               const float* __restrict__ pair_bias, const float* __restrict__ key_bias, const float* __restrict__ head_weight,
+               const __nv_bfloat16* __restrict__ pair_bias_t, const float* __restrict__ key_bias, const float* __restrict__ head_weight,
                float scalar_weight, OutT* __restrict__ out, __nv_bfloat16* __restrict__ pbuf, float* __restrict__ inv_sum,
                const se3_ipa_shape sh, int Lp, int Bpad, int tmem_cols) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, bar_bias;
     __shared__ uint32_t tmem_slot;
     const Pass1Smem s = carve1(smem_raw, Lp);
     const int L = sh.len, H = sh.heads;
@@ -72,8 +85,24 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
     const bool row_ok = i < L;
     const bool warp_ok = q0 + warp * 32 < L;
 
+    // pair-bias tile of this (head, query tile): bf16 [L keys][ncol queries], fetched by TMA into the region that
+    // later holds P (P is only written after every warp has finished the logit pass)
+    const int Lpi = (L + 7) & ~7;                         // row pitch of the transposed bias matrix
+    const int ncol = min(128, Lpi - q0);                  // multiple of 8 -> 16-byte rows
+    const __nv_bfloat16* s_bias = reinterpret_cast<const __nv_bfloat16*>(s.p);
     if (warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)tmem_cols);
-    if (tid == 0) { tc::mbar_init(&bar, 1); tc::mbar_fence_init(); }
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::mbar_init(&bar_bias, 1);
+        tc::mbar_fence_init();
+        const __nv_bfloat16* src = pair_bias_t + (int64_t)h * L * Lpi + q0;
+        tc::mbar_expect_tx(&bar_bias, (uint32_t)(L * ncol * 2));
+        if (ncol == Lpi) {
+            tc::tma_bulk_g2s(s.p, src, (uint32_t)(L * ncol * 2), &bar_bias);
+        } else {
+            for (int j = 0; j < L; ++j) tc::tma_bulk_g2s(s.p + (size_t)j * ncol * 2, src + (int64_t)j * Lpi, (uint32_t)(ncol * 2), &bar_bias);
+        }
+    }
 
     const float cx = trans[(int64_t)b * L * 3], cy = trans[(int64_t)b * L * 3 + 1], cz = trans[(int64_t)b * L * 3 + 2];
 
@@ -83,7 +112,9 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
         float kpg[12];
 #pragma unroll
         for (int c = 0; c < 12; ++c) kpg[c] = 0.f;
-        __nv_bfloat16* vt_col = reinterpret_cast<__nv_bfloat16*>(s.vt + (size_t)(j >> 3) * NV * 16) + (j & 7);  // + row*8
+        uint32_t vv[NV / 2];  // 64 bf16 value channels of key j: v | v_pt hi | v_pt lo
+#pragma unroll
+        for (int c = 0; c < NV / 2; ++c) vv[c] = 0u;
         if (j < L) {
             const int64_t rj = (int64_t)b * L + j;
             const float* pr = proj + rj * sh.proj_stride;
@@ -95,10 +126,8 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
                 const float4 v = __ldg(vq + c4);
-                vt_col[(c4 * 4 + 0) * 8] = __float2bfloat16_rn(v.x);
-                vt_col[(c4 * 4 + 1) * 8] = __float2bfloat16_rn(v.y);
-                vt_col[(c4 * 4 + 2) * 8] = __float2bfloat16_rn(v.z);
-                vt_col[(c4 * 4 + 3) * 8] = __float2bfloat16_rn(v.w);
+                vv[c4 * 2] = tc::pack_bf16(v.x, v.y);
+                vv[c4 * 2 + 1] = tc::pack_bf16(v.z, v.w);
             }
             float R[9], T[3];
 #pragma unroll
@@ -114,20 +143,26 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
             }
             const float* vpl = pr + sh.off_vp + h * PV * 3;
             const float cc[3] = {cx, cy, cz};
+            float gv[3 * PV];
 #pragma unroll
             for (int p = 0; p < PV; ++p) {
                 const float x = __ldg(vpl + p * 3), y = __ldg(vpl + p * 3 + 1), z = __ldg(vpl + p * 3 + 2);
 #pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    const float g = R[r * 3] * x + R[r * 3 + 1] * y + R[r * 3 + 2] * z + (T[r] - cc[r]);
-                    const __nv_bfloat16 hi = __float2bfloat16_rn(g);
-                    vt_col[(DK + p * 3 + r) * 8] = hi;
-                    vt_col[(DK + 3 * PV + p * 3 + r) * 8] = __float2bfloat16_rn(g - __bfloat162float(hi));
-                }
+                for (int r = 0; r < 3; ++r) gv[p * 3 + r] = R[r * 3] * x + R[r * 3 + 1] * y + R[r * 3 + 2] * z + (T[r] - cc[r]);
             }
-        } else {
-#pragma unroll 8
-            for (int c = 0; c < NV; ++c) vt_col[c * 8] = __float2bfloat16_rn(0.f);
+#pragma unroll
+            for (int c = 0; c < 3 * PV / 2; ++c) {
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(gv[2 * c]), h1 = __float2bfloat16_rn(gv[2 * c + 1]);
+                const __nv_bfloat162 hi = __halves2bfloat162(h0, h1);
+                vv[DK / 2 + c] = *reinterpret_cast<const uint32_t*>(&hi);
+                vv[DK / 2 + 3 * PV / 2 + c] = tc::pack_bf16(gv[2 * c] - __bfloat162float(h0), gv[2 * c + 1] - __bfloat162float(h1));
+            }
+        }
+        {   // MN-major value operand: [j/8][c/8][j%8][c%8] -> eight 16-byte pieces per key
+            uint8_t* dst = s.vt + (size_t)(j >> 3) * (NV * 16) + (size_t)(j & 7) * 16;
+#pragma unroll
+            for (int cg = 0; cg < NV / 8; ++cg)
+                *reinterpret_cast<uint4*>(dst + cg * 128) = make_uint4(vv[cg * 4], vv[cg * 4 + 1], vv[cg * 4 + 2], vv[cg * 4 + 3]);
         }
         *reinterpret_cast<uint4*>(s.k + (size_t)j * 16) = k0;
         *reinterpret_cast<uint4*>(s.k + (size_t)(Lp + j) * 16) = k1;
@@ -181,12 +216,12 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
 
     const int nchunk = Lp / 16;
     const uint32_t lane_base = (uint32_t)warp * 32;
-    float inv = 0.f;
+    float inv = 0.f, m = -CUDART_INF_F;
+    tc::mbar_wait(&bar_bias, 0);
     if (warp_ok) {
         // ---- pass A: logits (log2 domain) -> TMEM, row max -------------------------------------------------
         const float hw = head_weight[h] * kLog2e;
-        const float* bias_row = pair_bias + ((int64_t)h * L + (row_ok ? i : 0)) * L;
-        float m = -CUDART_INF_F;
+        const __nv_bfloat16* bias_col = s_bias + min(tid, ncol - 1);   // [j][query]: conflict-free 2-byte LDS
         for (int c = 0; c < nchunk; ++c) {
             uint32_t r[16];
             tc::tmem_ld16(tc::tmem_addr(tmem, lane_base, c * 16), r);
@@ -205,7 +240,7 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
                 ds += fast_sqrt(dx * dx + dy * dy + dz * dz);
                 dx = qp[9] - k2.y; dy = qp[10] - k2.z; dz = qp[11] - k2.w;
                 ds += fast_sqrt(dx * dx + dy * dy + dz * dz);
-                const float pb = (j < L) ? __ldg(bias_row + j) : 0.f;
+                const float pb = (j < L) ? __bfloat162float(bias_col[j * ncol]) : 0.f;
                 const float l2 = fmaf(pb, kLog2e, fmaf(hw, ds, __uint_as_float(r[u]))) + s.kb[j];
                 m = fmaxf(m, l2);
                 r[u] = __float_as_uint(l2);
@@ -214,9 +249,13 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
         }
         tc::tmem_wait_st();
         if (m == -CUDART_INF_F) m = 0.f;
+    }
+    __syncthreads();  // every warp is done with the bias tile: its shared memory becomes the P operand
+    if (warp_ok) {
         // ---- pass B: P = exp2(l - m) -> bf16 -> smem (A operand) + global (pass 2) ------------------------------
         float sum = 0.f;
-        __nv_bfloat16* prow = pbuf + (((int64_t)h * L + (row_ok ? i : 0)) * Bpad + b) * Lp;
+        // P tile of (h, i, b/128) in UMMA layout: [j/8][b%128][j%8]
+        uint8_t* ptile = reinterpret_cast<uint8_t*>(pbuf) + ((((int64_t)h * L + (row_ok ? i : 0)) * (Bpad / 128) + (b >> 7)) * Lp) * 256 + (size_t)(b & 127) * 16;
         for (int c = 0; c < nchunk; ++c) {
             uint32_t r[16], pk[8];
             tc::tmem_ld16(tc::tmem_addr(tmem, lane_base, c * 16), r);
@@ -232,8 +271,8 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
             *reinterpret_cast<uint4*>(s.p + ((size_t)(2 * c) * 128 + tid) * 16) = lo;
             *reinterpret_cast<uint4*>(s.p + ((size_t)(2 * c + 1) * 128 + tid) * 16) = hi;
             if (row_ok) {
-                reinterpret_cast<uint4*>(prow + c * 16)[0] = lo;
-                reinterpret_cast<uint4*>(prow + c * 16)[1] = hi;
+                *reinterpret_cast<uint4*>(ptile + (size_t)(2 * c) * 2048) = lo;
+                *reinterpret_cast<uint4*>(ptile + (size_t)(2 * c + 1) * 2048) = hi;
             }
         }
         inv = 1.0f / sum;
@@ -246,9 +285,10 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
 
     // ---- MMA 2: O = P.V (accumulator overwrites the consumed S columns) -------------------------------------------
     if (tid == 0) {
-        const uint32_t idesc = tc::make_idesc_bf16(128, NV);
+        const uint32_t idesc = tc::make_idesc_bf16(128, NV, /*b_mn_major=*/true);
         for (int ks = 0; ks < nchunk; ++ks)
-            tc::mma_bf16(tmem, tc::make_desc_kstep(tc::smem_u32(s.p), 128, ks), tc::make_desc_kstep(tc::smem_u32(s.vt), NV, ks), idesc, ks > 0);
+            tc::mma_bf16(tmem, tc::make_desc_kstep(tc::smem_u32(s.p), 128, ks),
+                         tc::make_desc_raw(tc::smem_u32(s.vt) + (uint32_t)ks * 2u * NV * 16u, /*K-group*/ NV * 16u, /*MN-group*/ 128u), idesc, ks > 0);
         tc::mma_commit(&bar);
     }
     tc::mbar_wait(&bar, 1);
@@ -267,21 +307,22 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
         if (row_ok) {
             const int HD = H * DK;
             OutT* orow = out + ((int64_t)b * L + i) * (int64_t)(2 * HD + 4 * H * PV);
+            float sc[DK], pl[3 * PV], nr[PV];
 #pragma unroll
-            for (int c = 0; c < DK; ++c) orow[h * DK + c] = to_out<OutT>(o[c] * inv);
+            for (int c = 0; c < DK; ++c) sc[c] = o[c] * inv;
 #pragma unroll
             for (int p = 0; p < PV; ++p) {
                 const float gx = (o[DK + p * 3] + o[DK + 3 * PV + p * 3]) * inv + (cx - Ti[0]);
                 const float gy = (o[DK + p * 3 + 1] + o[DK + 3 * PV + p * 3 + 1]) * inv + (cy - Ti[1]);
                 const float gz = (o[DK + p * 3 + 2] + o[DK + 3 * PV + p * 3 + 2]) * inv + (cz - Ti[2]);
-                const float lx = Ri[0] * gx + Ri[3] * gy + Ri[6] * gz;
-                const float ly = Ri[1] * gx + Ri[4] * gy + Ri[7] * gz;
-                const float lz = Ri[2] * gx + Ri[5] * gy + Ri[8] * gz;
-                orow[HD + (h * PV + p) * 3] = to_out<OutT>(lx);
-                orow[HD + (h * PV + p) * 3 + 1] = to_out<OutT>(ly);
-                orow[HD + (h * PV + p) * 3 + 2] = to_out<OutT>(lz);
-                orow[2 * HD + 3 * H * PV + h * PV + p] = to_out<OutT>(sqrtf(lx * lx + ly * ly + lz * lz));
+                pl[p * 3] = Ri[0] * gx + Ri[3] * gy + Ri[6] * gz;
+                pl[p * 3 + 1] = Ri[1] * gx + Ri[4] * gy + Ri[7] * gz;
+                pl[p * 3 + 2] = Ri[2] * gx + Ri[5] * gy + Ri[8] * gz;
+                nr[p] = sqrtf(pl[p * 3] * pl[p * 3] + pl[p * 3 + 1] * pl[p * 3 + 1] + pl[p * 3 + 2] * pl[p * 3 + 2]);
             }
+            store_vec<DK>(orow + h * DK, sc);
+            store_vec<3 * PV>(orow + HD + h * PV * 3, pl);
+            store_vec<PV>(orow + 2 * HD + 3 * H * PV + h * PV, nr);
         }
     }
     tc::fence_before();
@@ -290,90 +331,62 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int HG = 8;  // heads per pass-2 CTA -> 128 TMEM columns
-
 template <typename OutT>
 __global__ void __launch_bounds__(128)
 k_ipa_tc_pass2(const __nv_bfloat16* __restrict__ pbuf, const float* __restrict__ inv_sum, const __nv_bfloat16* __restrict__ pvc,
                OutT* __restrict__ out, const se3_ipa_shape sh, int Lp, int Bpad) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ uint64_t bar[3];
+    __shared__ uint64_t bar_tma, bar_mma;
     __shared__ uint32_t tmem_slot;
     const int L = sh.len, H = sh.heads, B = sh.batch;
-    const int b0 = blockIdx.x * 128, i = blockIdx.y, h0 = blockIdx.z * HG;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const size_t a_bytes = (size_t)Lp * 256, b_bytes = (size_t)Lp * 32, stage_bytes = a_bytes + b_bytes;
-    if (warp == 0) tc::tmem_alloc(&tmem_slot, 128);
-    if (tid == 0) { tc::mbar_init(&bar[0], 1); tc::mbar_init(&bar[1], 1); tc::mbar_init(&bar[2], 1); tc::mbar_fence_init(); }
-
-    auto load_head = [&](int hl, int stage) {
-        uint8_t* sA = smem_raw + stage * stage_bytes;
-        uint8_t* sB = sA + a_bytes;
-        const int h = h0 + hl;
-        const __nv_bfloat16* src = pbuf + (((int64_t)h * L + i) * Bpad + b0) * Lp;
-        // a warp instruction covers 16 rows x 2 K-chunks: 32-byte global sectors, <= 2-way smem conflicts
-        const int r16 = lane & 15, kcs = lane >> 4;
-        for (int kcp = 0; kcp < Lp / 16; ++kcp)
-#pragma unroll
-            for (int rb = 0; rb < 2; ++rb) {
-                const int row = (rb * 4 + warp) * 16 + r16, kc = kcp * 2 + kcs;
-                tc::cp_async16(sA + ((size_t)kc * 128 + row) * 16, src + (size_t)row * Lp + kc * 8);
-            }
-        const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(pvc + ((int64_t)i * H + h) * Lp * 16);
-        for (int p = tid; p < (int)(b_bytes / 16); p += 128) tc::cp_async16(sB + (size_t)p * 16, bsrc + (size_t)p * 16);
-        tc::cp_async_commit();
-    };
-
-    load_head(0, 0);
+    const int bt = blockIdx.x, i = blockIdx.y, h = blockIdx.z;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t a_bytes = (uint32_t)Lp * 256u, b_bytes = (uint32_t)Lp * 32u;
+    uint8_t* sA = smem_raw;
+    uint8_t* sB = smem_raw + a_bytes;
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, 32);
+    if (tid == 0) {
+        tc::mbar_init(&bar_tma, 1);
+        tc::mbar_init(&bar_mma, 1);
+        tc::mbar_fence_init();
+        // TMA: both operand tiles are contiguous in global memory and already in the UMMA layout
+        tc::mbar_expect_tx(&bar_tma, a_bytes + b_bytes);
+        tc::tma_bulk_g2s(sA, reinterpret_cast<const uint8_t*>(pbuf) + (((int64_t)h * L + i) * (Bpad / 128) + bt) * (int64_t)a_bytes, a_bytes, &bar_tma);
+        tc::tma_bulk_g2s(sB, reinterpret_cast<const uint8_t*>(pvc) + ((int64_t)i * H + h) * (int64_t)b_bytes, b_bytes, &bar_tma);
+    }
+    const int b = bt * 128 + tid;
+    const float inv = (b < B) ? inv_sum[((int64_t)h * L + i) * Bpad + b] : 0.f;
     tc::fence_before();
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem = tmem_slot;
-    const uint32_t idesc = tc::make_idesc_bf16(128, DK);
-    for (int hl = 0; hl < HG; ++hl) {
-        const int stage = hl & 1;
-        if (hl + 1 < HG) {
-            if (hl >= 1) tc::mbar_wait(&bar[stage ^ 1], ((hl - 1) >> 1) & 1);  // MMAs of head hl-1 have drained that stage
-            load_head(hl + 1, stage ^ 1);
-            tc::cp_async_wait<1>();
-        } else {
-            tc::cp_async_wait<0>();
-        }
-        tc::fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            tc::fence_after();
-            const uint32_t a_addr = tc::smem_u32(smem_raw + stage * stage_bytes), b_addr = a_addr + (uint32_t)a_bytes;
-            for (int ks = 0; ks < Lp / 16; ++ks)
-                tc::mma_bf16(tmem + hl * DK, tc::make_desc_kstep(a_addr, 128, ks), tc::make_desc_kstep(b_addr, DK, ks), idesc, ks > 0);
-            tc::mma_commit(&bar[stage]);
-            if (hl == HG - 1) tc::mma_commit(&bar[2]);
-        }
+    tc::mbar_wait(&bar_tma, 0);
+    if (tid == 0) {
+        const uint32_t idesc = tc::make_idesc_bf16(128, DK);
+        const uint32_t a_addr = tc::smem_u32(sA), b_addr = tc::smem_u32(sB);
+        for (int ks = 0; ks < Lp / 16; ++ks)
+            tc::mma_bf16(tmem, tc::make_desc_kstep(a_addr, 128, ks), tc::make_desc_kstep(b_addr, DK, ks), idesc, ks > 0);
+        tc::mma_commit(&bar_mma);
     }
-    tc::mbar_wait(&bar[2], 0);
+    tc::mbar_wait(&bar_mma, 0);
     tc::fence_after();
-    const int b = b0 + tid;
-    const int HD = H * DK;
-#pragma unroll 1
-    for (int hl = 0; hl < HG; ++hl) {
-        uint32_t r[16];
-        tc::tmem_ld16(tc::tmem_addr(tmem, (uint32_t)warp * 32, hl * DK), r);
-        tc::tmem_wait_ld();
-        if (b < B) {
-            const int h = h0 + hl;
-            const float inv = inv_sum[((int64_t)h * L + i) * Bpad + b];
-            OutT* o = out + ((int64_t)b * L + i) * (int64_t)(2 * HD + 4 * H * PV) + HD + 3 * H * PV + h * DK;
+    uint32_t r[16];
+    tc::tmem_ld16(tc::tmem_addr(tmem, (uint32_t)warp * 32, 0), r);
+    tc::tmem_wait_ld();
+    if (b < B) {
+        const int HD = H * DK;
+        float v[DK];
 #pragma unroll
-            for (int c = 0; c < DK; ++c) o[c] = to_out<OutT>(__uint_as_float(r[c]) * inv);
-        }
+        for (int c = 0; c < DK; ++c) v[c] = __uint_as_float(r[c]) * inv;
+        store_vec<DK>(out + ((int64_t)b * L + i) * (int64_t)(2 * HD + 4 * H * PV) + HD + 3 * H * PV + h * DK, v);
     }
     tc::fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 128);
+    if (warp == 0) tc::tmem_dealloc(tmem, 32);
 }
 
 template <typename OutT>
-int launch_tc(const float* proj, const float* rot, const float* trans, const float* pair_bias, const __nv_bfloat16* pvc,
+int launch_tc(const float* proj, const float* rot, const float* trans, const __nv_bfloat16* pair_bias, const __nv_bfloat16* pvc,
               const float* key_bias, const float* head_weight, float scalar_weight, OutT* out, __nv_bfloat16* pbuf, float* inv_sum,
               const se3_ipa_shape& sh, int Lp, int Bpad, cudaStream_t st) {
     const int L = sh.len;
@@ -388,11 +401,11 @@ int launch_tc(const float* proj, const float* rot, const float* trans, const flo
     count_launch();
     int rc = check_launch("se3_ipa_attention_tc_fwd(pass 1)");
     if (rc) return rc;
-    const size_t smem2 = 2 * ((size_t)Lp * 256 + (size_t)Lp * 32);
+    const size_t smem2 = (size_t)Lp * 256 + (size_t)Lp * 32;
     auto k2 = k_ipa_tc_pass2<OutT>;
     e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     if (e != cudaSuccess) { set_error("ipa_tc pass2 smem attribute (%zu B): %s", smem2, cudaGetErrorString(e)); return SE3_ECUDA; }
-    dim3 g2(Bpad / 128, L, sh.heads / HG);
+    dim3 g2(Bpad / 128, L, sh.heads);
     k2<<<g2, 128, smem2, st>>>(pbuf, inv_sum, pvc, out, sh, Lp, Bpad);
     count_launch();
     return check_launch("se3_ipa_attention_tc_fwd(pass 2)");
@@ -411,16 +424,16 @@ int64_t se3_ipa_tc_workspace_bytes(const se3_ipa_shape* h_shape, int64_t* p_byte
     return pb + ib;
 }
 
-int se3_ipa_attention_tc_fwd(const float* proj, const float* rot, const float* trans, const float* pair_bias,
+int se3_ipa_attention_tc_fwd(const float* proj, const float* rot, const float* trans, const void* pair_bias_packed,
                              const void* pair_value_packed, const float* key_bias, const float* head_weight, float scalar_weight,
                              void* out, int out_is_bf16, void* p_workspace, float* inv_workspace, const se3_ipa_shape* h_shape,
                              se3_stream_t stream) {
     SE3_REQUIRE(h_shape, "null shape");
     const se3_ipa_shape& sh = *h_shape;
     if (sh.batch == 0 || sh.len == 0) return SE3_OK;
-    SE3_REQUIRE(proj && rot && trans && pair_bias && pair_value_packed && head_weight && out && p_workspace && inv_workspace, "null pointer");
-    if (sh.dk != DK || sh.pq != PQ || sh.pv != PV || sh.pair_batch != 1 || sh.len > 256 || sh.heads % HG != 0 || sh.batch > 65535) {
-        set_error("se3_ipa_attention_tc_fwd: needs dk=16, 4/8 points, shared pair tensors, L <= 256, heads %% 8 == 0 "
+    SE3_REQUIRE(proj && rot && trans && pair_bias_packed && pair_value_packed && head_weight && out && p_workspace && inv_workspace, "null pointer");
+    if (sh.dk != DK || sh.pq != PQ || sh.pv != PV || sh.pair_batch != 1 || sh.len > 256 || sh.heads > 65535 || sh.batch > 65535) {
+        set_error("se3_ipa_attention_tc_fwd: needs dk=16, 4/8 points, shared pair tensors, L <= 256 "
                   "(got dk=%d L=%d H=%d pair_batch=%d); use se3_ipa_attention_fwd", sh.dk, sh.len, sh.heads, sh.pair_batch);
         return SE3_EUNSUPPORTED;
     }
@@ -429,9 +442,9 @@ int se3_ipa_attention_tc_fwd(const float* proj, const float* rot, const float* t
     const int Lp = (sh.len + 15) / 16 * 16, Bpad = (sh.batch + 127) / 128 * 128;
     cudaStream_t st = (cudaStream_t)stream;
     if (out_is_bf16)
-        return launch_tc<__nv_bfloat16>(proj, rot, trans, pair_bias, (const __nv_bfloat16*)pair_value_packed, key_bias, head_weight,
+        return launch_tc<__nv_bfloat16>(proj, rot, trans, (const __nv_bfloat16*)pair_bias_packed, (const __nv_bfloat16*)pair_value_packed, key_bias, head_weight,
                                         scalar_weight, (__nv_bfloat16*)out, (__nv_bfloat16*)p_workspace, inv_workspace, sh, Lp, Bpad, st);
-    return launch_tc<float>(proj, rot, trans, pair_bias, (const __nv_bfloat16*)pair_value_packed, key_bias, head_weight, scalar_weight,
+    return launch_tc<float>(proj, rot, trans, (const __nv_bfloat16*)pair_bias_packed, (const __nv_bfloat16*)pair_value_packed, key_bias, head_weight, scalar_weight,
                             (float*)out, (__nv_bfloat16*)p_workspace, inv_workspace, sh, Lp, Bpad, st);
 }
 

@@ -23,14 +23,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t rows)
     const uint64_t lbo = (uint64_t)((rows * 16u) >> 4), sbo = (uint64_t)(128u >> 4);
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (lbo << 16) | (sbo << 32) | (1ull << 46);
 }
+// general form: byte strides given explicitly (see the MN-major use for the value operand in ipa_tc.cu)
+__device__ __forceinline__ uint64_t make_desc_raw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
 // the K=16 slice number `ks` of a tile with `rows` rows starts 2 K-chunks further
 __device__ __forceinline__ uint64_t make_desc_kstep(uint32_t smem_base, uint32_t rows, int ks) {
     return make_desc(smem_base + (uint32_t)ks * 2u * rows * 16u, rows);
 }
 // 32-bit instruction descriptor, kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, both K-major,
 // N>>3 [17,23), M>>4 [24,29)
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool b_mn_major = false) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] . B[smem]^T, issued by ONE thread

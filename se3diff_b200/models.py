@@ -258,7 +258,9 @@ class DistributionalGraphormer(nn.Module):
         c.pair_bias, c.pair_value, c.pair_value_packed = [], [], []
         for lyr in self.st_module.encoder.layers:
             a = lyr.attn
-            c.pair_bias.append((a.pair_weight * a.pair_bias(x2d)).permute(0, 3, 1, 2).contiguous())   # [Bp, H, L, L]
+            pb = a.pair_weight * a.pair_bias(x2d)                                                      # [Bp, L(i), L(j), H]
+            # SIMT kernel: fp32 [Bp, H, i, j]; tensor-core kernel: transposed bf16 slabs [H, j, i] fetched by TMA
+            c.pair_bias.append(ops.ipa_tc_pack_pair_bias(pb) if c.tc else pb.permute(0, 3, 1, 2).contiguous())
             pv = a.pair_value(x2d)                                                                     # [Bp, L, L, H*dk]
             if c.tc:
                 c.pair_value_packed.append(ops.ipa_tc_pack_pair_value(pv, a.n_head))

@@ -359,7 +359,7 @@ def debug_umma_gemm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 def ipa_tc_supported(shape: L.IpaShape) -> bool:
-    return shape.dk == 16 and shape.pq == 4 and shape.pv == 8 and shape.pair_batch == 1 and shape.len <= 256 and shape.heads % 8 == 0
+    return shape.dk == 16 and shape.pq == 4 and shape.pv == 8 and shape.pair_batch == 1 and shape.len <= 256
 
 
 def ipa_tc_pack_pair_value(pair_value: torch.Tensor, heads: int) -> torch.Tensor:
@@ -373,17 +373,28 @@ def ipa_tc_pack_pair_value(pair_value: torch.Tensor, heads: int) -> torch.Tensor
     return pv.view(Lq, Lp // 8, 8, heads, 16).permute(0, 3, 1, 4, 2).contiguous().to(torch.bfloat16)
 
 
+def ipa_tc_pack_pair_bias(pair_bias: torch.Tensor) -> torch.Tensor:
+    """[1, L(i), L(j), H] (= pair_weight * pair_bias(x2d), structure_module.py:179) -> bf16 [H][L(j)][round_up(L,8)(i)],
+    the transposed slab layout the tensor-core attention fetches with TMA."""
+    Lq = pair_bias.shape[1]
+    t = pair_bias[0].permute(2, 1, 0)                                  # [H, j, i]
+    pad = (-Lq) % 8
+    if pad:
+        t = torch.nn.functional.pad(t, (0, pad))
+    return t.contiguous().to(torch.bfloat16)
+
+
 def ipa_tc_workspace(shape: L.IpaShape, device) -> tuple[torch.Tensor, torch.Tensor]:
     pb, ib = C.c_int64(0), C.c_int64(0)
     L.lib().se3_ipa_tc_workspace_bytes(C.byref(shape), C.byref(pb), C.byref(ib))
     return (torch.empty(pb.value // 2, dtype=torch.bfloat16, device=device), torch.empty(ib.value // 4, dtype=torch.float32, device=device))
 
 
-def ipa_attention_tc_fwd(proj, rot, trans, pair_bias, pair_value_packed, key_bias, head_weight, scalar_weight: float,
+def ipa_attention_tc_fwd(proj, rot, trans, pair_bias_packed, pair_value_packed, key_bias, head_weight, scalar_weight: float,
                          shape: L.IpaShape, workspace, out_dtype=torch.bfloat16, out=None):
     """Tensor-core edition (tcgen05/TMEM) of SAAttention.forward between the projections and fc_out."""
     proj, rot, trans = _dev(proj, name="proj"), _dev(rot, name="rot"), _dev(trans, name="trans")
-    pair_bias = _dev(pair_bias, name="pair_bias")
+    pair_bias = _dev(pair_bias_packed, torch.bfloat16, "pair_bias_packed")
     pvp = _dev(pair_value_packed, torch.bfloat16, "pair_value_packed")
     key_bias = None if key_bias is None else _dev(key_bias, name="key_bias")
     head_weight = _dev(head_weight, name="head_weight")
