@@ -258,6 +258,13 @@ int se3_ipa_attention_tc_fwd(const float* proj, const float* rot, const float* t
                              float scalar_weight, void* out, int out_is_bf16, void* p_workspace, float* inv_workspace,
                              const se3_ipa_shape* h_shape, se3_stream_t stream);
 
+/* Fused residual update + pre-LayerNorm of the next block (bf16 throughput mode of the score network):
+ *   x[rows,dim] += y[rows,dim] + bias[dim]      (y, bias optional: NULL skips the update; structure_module.py:247-248)
+ *   out[rows,dim] = LayerNorm(x; gamma, beta, eps)   written as fp32 or bf16
+ * dim in {128, 256, 512, 1024}; all pointers 16-byte aligned. */
+int se3_residual_layernorm(float* x, const float* y, const float* bias, const float* gamma, const float* beta, float eps,
+                           void* out, int out_is_bf16, int64_t rows, int dim, se3_stream_t stream);
+
 /* tcgen05 self-test: d[128,n] fp32 = a[128,k] . b[n,k]^T with bf16 operands, through the operand staging,
  * UMMA descriptors, TMEM allocation and mbarrier completion the attention kernels use. */
 int se3_debug_umma_gemm(const void* a_bf16, const void* b_bf16, float* d, int n, int k, se3_stream_t stream);

@@ -23,6 +23,7 @@ SOURCES = {
     "ipa_simt.cu": [],
     "tc_selftest.cu": [],
     "ipa_tc.cu": [],
+    "fused_rows.cu": [],
 }
 
 

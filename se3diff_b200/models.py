@@ -195,6 +195,7 @@ class DistributionalGraphormer(nn.Module):
                     w_out=a.fc_out.weight.detach().to(dtype).contiguous(),
                     w_ff0=lyr.ffn.ff[0].weight.detach().to(dtype).contiguous(),
                     w_ff3=lyr.ffn.ff[3].weight.detach().to(dtype).contiguous(),
+                    b_ff0=lyr.ffn.ff[0].bias.detach().to(dtype).contiguous(),
                     head_w=(-0.5 * a.point_weight * F.softplus(a.trained_point_weight.detach().float())).contiguous(),
                 ))
             heads = {}
@@ -309,6 +310,59 @@ class DistributionalGraphormer(nn.Module):
         y = torch.mm(x.to(w.dtype), w.t(), out_dtype=torch.float32) if out_fp32 else F.linear(x.to(w.dtype), w)
         return y if bias is None else y + bias
 
+    def _attention(self, proj, R, T, c, lw, lyr, n, shape, flags):
+        if c.tc:
+            return ops.ipa_attention_tc_fwd(proj, R, T, c.pair_bias[n], c.pair_value_packed[n], c.key_bias, lw["head_w"],
+                                            lyr.attn.scalar_weight, shape, c.workspace)
+        return ops.ipa_attention_fwd(proj, R, T, c.pair_bias[n], c.pair_value[n], c.key_bias, lw["head_w"],
+                                     lyr.attn.scalar_weight, shape, flags)
+
+    def _forward_plain(self, x1d, R, T, c, w, shape, flags):
+        """torch LayerNorm / Linear around the attention kernel (fp32 parity mode; bf16 for odd widths)."""
+        D = self.d_model
+        for n, lyr in enumerate(self.st_module.encoder.layers):
+            lw = w["layers"][n]
+            y = F.layer_norm(x1d, (D,), lyr.norm1.weight, lyr.norm1.bias, lyr.norm1.eps)
+            feat = self._attention(self._linear(y, lw["w_proj"]), R, T, c, lw, lyr, n, shape, flags)
+            x1d = x1d + self._linear(feat, lw["w_out"], lyr.attn.fc_out.bias)
+            y = F.layer_norm(x1d, (D,), lyr.norm2.weight, lyr.norm2.bias, lyr.norm2.eps)
+            y = F.gelu(self._linear(y, lw["w_ff0"], lyr.ffn.ff[0].bias))
+            x1d = x1d + self._linear(y, lw["w_ff3"], lyr.ffn.ff[3].bias)
+        outs = []
+        for name in ("fc_t", "fc_eps"):
+            seq = getattr(self.st_module.diff_head, name)
+            w1, w3 = w["heads"][name]
+            y = F.layer_norm(x1d, (D,), seq[0].weight, seq[0].bias, seq[0].eps)
+            y = F.relu(self._linear(y, w1, seq[1].bias))
+            outs.append(F.linear(y, w3, seq[3].bias))
+        return outs
+
+    def _forward_fused(self, x, R, T, c, w, shape, flags):
+        """bf16 throughput path: every GEMM takes bf16 operands and accumulates in fp32; the residual stream `x`
+        stays fp32; bias + residual + the next block's LayerNorm + bf16 cast are one kernel
+        (se3_residual_layernorm), so activations make one round trip per block."""
+        mm = lambda a, wt: torch.mm(a, wt.t(), out_dtype=torch.float32)
+        y = bias = None
+        for n, lyr in enumerate(self.st_module.encoder.layers):
+            lw = w["layers"][n]
+            h1 = ops.residual_layernorm(x, y, bias, lyr.norm1.weight, lyr.norm1.bias, lyr.norm1.eps)
+            feat = self._attention(mm(h1, lw["w_proj"]), R, T, c, lw, lyr, n, shape, flags)
+            if feat.dtype != torch.bfloat16:
+                feat = feat.to(torch.bfloat16)
+            y, bias = mm(feat, lw["w_out"]), lyr.attn.fc_out.bias
+            h2 = ops.residual_layernorm(x, y, bias, lyr.norm2.weight, lyr.norm2.bias, lyr.norm2.eps)
+            hid = F.gelu(F.linear(h2, lw["w_ff0"], lw["b_ff0"]))
+            y, bias = mm(hid, lw["w_ff3"]), lyr.ffn.ff[3].bias
+        outs = []
+        for name in ("fc_t", "fc_eps"):
+            seq = getattr(self.st_module.diff_head, name)
+            w1, w3 = w["heads"][name]
+            hh = ops.residual_layernorm(x, y, bias, seq[0].weight, seq[0].bias, seq[0].eps)
+            y = bias = None   # the residual update is applied once
+            hh = F.relu(mm(hh, w1) + seq[1].bias)
+            outs.append(F.linear(hh, w3, seq[3].bias))
+        return outs
+
     @torch.no_grad()
     def forward(self, x, node_orientations, batch_index, t, context):
         """x [N,3] positions, node_orientations [N,3,3] ROTATIONS (not inverse: the reference transposes
@@ -327,28 +381,11 @@ class DistributionalGraphormer(nn.Module):
         shape = L.IpaShape(B, Lm, H, dk, 4, 8, 3 * D + 48 * H, 0, D, 2 * D, 3 * D, 3 * D + 12 * H, 3 * D + 24 * H,
                            1 if c.shared else B)
         flags = ops.IPA_EXACT if self.precision == "fp32" else ops.IPA_FAST_MATH
-        for n, lyr in enumerate(self.st_module.encoder.layers):
-            lw = w["layers"][n]
-            y = F.layer_norm(x1d, (D,), lyr.norm1.weight, lyr.norm1.bias, lyr.norm1.eps)
-            proj = self._linear(y, lw["w_proj"])
-            if c.tc:
-                feat = ops.ipa_attention_tc_fwd(proj, R, T, c.pair_bias[n], c.pair_value_packed[n], c.key_bias, lw["head_w"],
-                                                lyr.attn.scalar_weight, shape, c.workspace)
-            else:
-                feat = ops.ipa_attention_fwd(proj, R, T, c.pair_bias[n], c.pair_value[n], c.key_bias, lw["head_w"],
-                                             lyr.attn.scalar_weight, shape, flags)
-            x1d = x1d + self._linear(feat, lw["w_out"], lyr.attn.fc_out.bias)
-            y = F.layer_norm(x1d, (D,), lyr.norm2.weight, lyr.norm2.bias, lyr.norm2.eps)
-            y = F.gelu(self._linear(y, lw["w_ff0"], lyr.ffn.ff[0].bias))
-            x1d = x1d + self._linear(y, lw["w_ff3"], lyr.ffn.ff[3].bias)
-        outs = []
-        for name in ("fc_t", "fc_eps"):
-            seq = getattr(self.st_module.diff_head, name)
-            w1, w3 = w["heads"][name]
-            y = F.layer_norm(x1d, (D,), seq[0].weight, seq[0].bias, seq[0].eps)
-            y = F.relu(self._linear(y, w1, seq[1].bias))
-            outs.append(F.linear(y, w3, seq[3].bias))
-        T_eps, IR_eps = outs
+        fused = self.precision == "bf16" and D % 128 == 0 and D <= 1024
+        if fused:
+            T_eps, IR_eps = self._forward_fused(x1d.contiguous(), R, T, c, w, shape, flags)
+        else:
+            T_eps, IR_eps = self._forward_plain(x1d, R, T, c, w, shape, flags)
         T_out = torch.bmm(R.view(-1, 3, 3), T_eps.unsqueeze(-1)).squeeze(-1)      # models.py:305
         if c.dense_index is None:
             return T_out, IR_eps
