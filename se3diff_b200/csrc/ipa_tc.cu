@@ -21,6 +21,7 @@
 //   signal an mbarrier; D[128 x 16] accumulates in TMEM.  pair_value is therefore read once per 128 samples
 //   instead of once per sample (3.7 GB -> 30 MB per layer at B=256, L=84).
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -56,20 +57,31 @@ struct Pass1Smem {
     uint8_t *q, *k, *vt, *p;
     float *kp, *kb;
 };
-__device__ __forceinline__ Pass1Smem carve1(uint8_t* base, int Lp) {
+// Shared-memory plan of pass 1.  The P operand (written in the second half of the kernel) can overlay everything
+// that is dead by then -- the bias slab, the key points, the key bias and the K operand -- when those fit into
+// its 256*Lp bytes (`alias`): 40.5 KB per CTA at Lp = 96, i.e. 5 resident CTAs per SM instead of 4.
+__host__ __device__ inline uint32_t bias_slab_bytes(int L) {
+    const int lpi = (L + 7) & ~7;
+    return (uint32_t)((L * (lpi < 128 ? lpi : 128) * 2 + 15) & ~15);
+}
+__host__ __device__ inline bool pass1_can_alias(int L, int Lp) { return bias_slab_bytes(L) + (uint32_t)Lp * (48 + 4 + 32) <= (uint32_t)Lp * 256; }
+__host__ __device__ inline size_t pass1_smem_bytes(int L, int Lp) {
+    return pass1_can_alias(L, Lp) ? (size_t)Lp * (128 + 256) + 4096 : (size_t)Lp * (128 + 256 + 48 + 4 + 32) + 4096;
+}
+__device__ __forceinline__ Pass1Smem carve1(uint8_t* base, int L, int Lp) {
     Pass1Smem s;
-    s.q = base;                                  // [2][128][16 B]
-    s.k = s.q + 2 * 128 * 16;                    // [2][Lp][16 B]
-    s.vt = s.k + 2 * Lp * 16;                    // [Lp/8][64][16 B]
-    s.p = s.vt + (Lp / 8) * NV * 16;             // [Lp/8][128][16 B]
-    s.kp = reinterpret_cast<float*>(s.p + (Lp / 8) * 128 * 16);  // [Lp][12]
+    s.vt = base;                                 // [Lp/8][8][8][8] bf16, MN-major value operand
+    s.q = s.vt + (size_t)Lp * 128;               // [2][128][16 B]
+    s.p = s.q + 4096;                            // [Lp/8][128][16 B]; the bias slab lives at its start until pass B
+    uint8_t* rest = pass1_can_alias(L, Lp) ? s.p + bias_slab_bytes(L) : s.p + (size_t)Lp * 256;
+    s.kp = reinterpret_cast<float*>(rest);       // [Lp][12] fp32
     s.kb = s.kp + Lp * 12;                       // [Lp]
+    s.k = reinterpret_cast<uint8_t*>(s.kb + Lp); // [2][Lp][16 B]
     return s;
 }
-inline size_t pass1_smem_bytes(int Lp) { return 2 * 128 * 16 + (size_t)Lp * (32 + 128 + 256 + 48 + 4); }
 
 template <typename OutT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, const float* __restrict__ trans,
                const __nv_bfloat16* __restrict__ pair_bias_t, const float* __restrict__ key_bias, const float* __restrict__ head_weight,
                float scalar_weight, OutT* __restrict__ out, __nv_bfloat16* __restrict__ pbuf, float* __restrict__ inv_sum,
@@ -77,8 +89,8 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t bar, bar_bias;
     __shared__ uint32_t tmem_slot;
-    const Pass1Smem s = carve1(smem_raw, Lp);
     const int L = sh.len, H = sh.heads;
+    const Pass1Smem s = carve1(smem_raw, L, Lp);
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int i = q0 + tid;
@@ -90,7 +102,9 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
     const int Lpi = (L + 7) & ~7;                         // row pitch of the transposed bias matrix
     const int ncol = min(128, Lpi - q0);                  // multiple of 8 -> 16-byte rows
     const __nv_bfloat16* s_bias = reinterpret_cast<const __nv_bfloat16*>(s.p);
-    if (warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)tmem_cols);
+    const bool late_alloc = (tmem_cols & 1) != 0;   // experiment switch folded into the column count
+    tmem_cols &= ~1;
+    if (!late_alloc && warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)tmem_cols);
     if (tid == 0) {
         tc::mbar_init(&bar, 1);
         tc::mbar_init(&bar_bias, 1);
@@ -166,8 +180,11 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
         }
         *reinterpret_cast<uint4*>(s.k + (size_t)j * 16) = k0;
         *reinterpret_cast<uint4*>(s.k + (size_t)(Lp + j) * 16) = k1;
+        {   // negated key points, interleaved by key pair: [j/2][component][j%2]
+            float* dstp = s.kp + (size_t)(j >> 1) * 24 + (j & 1);
 #pragma unroll
-        for (int c4 = 0; c4 < 3; ++c4) reinterpret_cast<float4*>(s.kp + j * 12)[c4] = make_float4(kpg[c4 * 4], kpg[c4 * 4 + 1], kpg[c4 * 4 + 2], kpg[c4 * 4 + 3]);
+            for (int c = 0; c < 12; ++c) dstp[c * 2] = -kpg[c];
+        }
         s.kb[j] = (j < L) ? (key_bias ? key_bias[(int64_t)b * L + j] * kLog2e : 0.f) : -CUDART_INF_F;
     }
     // ---- this thread's query row -----------------------------------------------------------------------
@@ -199,6 +216,8 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
         *reinterpret_cast<uint4*>(s.q + (size_t)tid * 16) = q0v;
         *reinterpret_cast<uint4*>(s.q + (size_t)(128 + tid) * 16) = q1v;
     }
+    // TMEM is claimed only now: staging of this CTA overlapped with the tensor-memory phase of its neighbours
+    if (late_alloc && warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)tmem_cols);
     tc::fence_async_smem();
     tc::fence_before();
     __syncthreads();
@@ -222,28 +241,45 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
         // ---- pass A: logits (log2 domain) -> TMEM, row max -------------------------------------------------
         const float hw = head_weight[h] * kLog2e;
         const __nv_bfloat16* bias_col = s_bias + min(tid, ncol - 1);   // [j][query]: conflict-free 2-byte LDS
+        // Packed fp32x2 arithmetic (FADD2/FMUL2/FFMA2, sm_100): two keys per instruction.  The key points are staged
+        // NEGATED and interleaved by key pair ([pair][component][2]) so that q + (-k) is a single packed add.
+        float2 q2[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) q2[k] = make_float2(qp[k], qp[k]);
+        const float2 hw2 = make_float2(hw, hw), l2e2 = make_float2(kLog2e, kLog2e);
         for (int c = 0; c < nchunk; ++c) {
             uint32_t r[16];
             tc::tmem_ld16(tc::tmem_addr(tmem, lane_base, c * 16), r);
             tc::tmem_wait_ld();
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const int j = c * 16 + u;
-                const float4* kp4 = reinterpret_cast<const float4*>(s.kp + j * 12);
-                const float4 k0 = kp4[0], k1 = kp4[1], k2 = kp4[2];
-                float dx, dy, dz, ds;
-                dx = qp[0] - k0.x; dy = qp[1] - k0.y; dz = qp[2] - k0.z;
-                ds = fast_sqrt(dx * dx + dy * dy + dz * dz);
-                dx = qp[3] - k0.w; dy = qp[4] - k1.x; dz = qp[5] - k1.y;
-                ds += fast_sqrt(dx * dx + dy * dy + dz * dz);
-                dx = qp[6] - k1.z; dy = qp[7] - k1.w; dz = qp[8] - k2.x;
-                ds += fast_sqrt(dx * dx + dy * dy + dz * dz);
-                dx = qp[9] - k2.y; dy = qp[10] - k2.z; dz = qp[11] - k2.w;
-                ds += fast_sqrt(dx * dx + dy * dy + dz * dz);
-                const float pb = (j < L) ? __bfloat162float(bias_col[j * ncol]) : 0.f;
-                const float l2 = fmaf(pb, kLog2e, fmaf(hw, ds, __uint_as_float(r[u]))) + s.kb[j];
-                m = fmaxf(m, l2);
-                r[u] = __float_as_uint(l2);
+            for (int u = 0; u < 8; ++u) {
+                const int j = c * 16 + 2 * u;
+                const float4* kp4 = reinterpret_cast<const float4*>(s.kp + j * 12);   // pair block: 24 floats
+                float2 ds = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    // components 3p, 3p+1, 3p+2 of the pair: float4 #(3p/2) ... laid out {c_j, c_j1, c'_j, c'_j1}
+                    float2 nk[3];
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        const int comp = 3 * p + t;
+                        const float4 v = kp4[comp >> 1];
+                        nk[t] = (comp & 1) ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+                    }
+                    const float2 dx = __fadd2_rn(q2[3 * p], nk[0]), dy = __fadd2_rn(q2[3 * p + 1], nk[1]), dz = __fadd2_rn(q2[3 * p + 2], nk[2]);
+                    float2 d2 = __fmul2_rn(dx, dx);
+                    d2 = __ffma2_rn(dy, dy, d2);
+                    d2 = __ffma2_rn(dz, dz, d2);
+                    ds = __fadd2_rn(ds, make_float2(fast_sqrt(d2.x), fast_sqrt(d2.y)));
+                }
+                const float pb0 = (j < L) ? __bfloat162float(bias_col[j * ncol]) : 0.f;
+                const float pb1 = (j + 1 < L) ? __bfloat162float(bias_col[(j + 1) * ncol]) : 0.f;
+                const float2 kb2 = *reinterpret_cast<const float2*>(s.kb + j);
+                float2 l2 = __ffma2_rn(hw2, ds, make_float2(__uint_as_float(r[2 * u]), __uint_as_float(r[2 * u + 1])));
+                l2 = __fadd2_rn(__ffma2_rn(make_float2(pb0, pb1), l2e2, l2), kb2);
+                m = fmaxf(m, fmaxf(l2.x, l2.y));
+                r[2 * u] = __float_as_uint(l2.x);
+                r[2 * u + 1] = __float_as_uint(l2.y);
             }
             tc::tmem_st16(tc::tmem_addr(tmem, lane_base, c * 16), r);
         }
@@ -392,12 +428,20 @@ int launch_tc(const float* proj, const float* rot, const float* trans, const __n
     const int L = sh.len;
     int cols = 64;
     while (cols < Lp) cols *= 2;
-    const size_t smem1 = pass1_smem_bytes(Lp);
+    size_t smem1 = pass1_smem_bytes(L, Lp);
+    {   // tensor memory (512 columns per SM) allows 512/cols resident CTAs; a CTA that is resident but blocked in
+        // tcgen05.alloc only steals issue slots, so shared memory is padded to admit exactly that many
+        static const int pad = getenv("SE3_IPA_NO_PAD") ? 0 : 1;
+        const size_t per_cta = (size_t)(227 * 1024) / (size_t)(512 / cols) - 1024;
+        const size_t floor_bytes = (size_t)(227 * 1024) / (size_t)(512 / cols + 1) + 1;
+        if (pad && smem1 < floor_bytes && floor_bytes <= per_cta) smem1 = floor_bytes;
+    }
     auto k1 = k_ipa_tc_pass1<OutT>;
     cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
     if (e != cudaSuccess) { set_error("ipa_tc pass1 smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
     dim3 g1((L + 127) / 128, sh.heads, sh.batch);
-    k1<<<g1, 128, smem1, st>>>(proj, rot, trans, pair_bias, key_bias, head_weight, scalar_weight, out, pbuf, inv_sum, sh, Lp, Bpad, cols);
+    static const int late = getenv("SE3_IPA_LATE_ALLOC") ? atoi(getenv("SE3_IPA_LATE_ALLOC")) : 0;
+    k1<<<g1, 128, smem1, st>>>(proj, rot, trans, pair_bias, key_bias, head_weight, scalar_weight, out, pbuf, inv_sum, sh, Lp, Bpad, cols | late);
     count_launch();
     int rc = check_launch("se3_ipa_attention_tc_fwd(pass 1)");
     if (rc) return rc;
