@@ -50,15 +50,15 @@ def gather_ensemble(frames: torch.Tensor, counts: list[int] | None = None) -> to
         return frames
     world = dist.get_world_size()
     if counts is None:
-        out = torch.empty((world,) + tuple(frames.shape), dtype=frames.dtype, device=frames.device)
-        dist.all_gather_into_tensor(out, frames.contiguous())
-        return out.view(-1, *frames.shape[1:])
+        out = torch.empty((world * frames.shape[0],) + tuple(frames.shape[1:]), dtype=frames.dtype, device=frames.device)
+        dist.all_gather_into_tensor(out, frames.contiguous())      # concatenated form: accepted by NCCL and gloo
+        return out
     bmax = max(counts)
     pad = frames.new_zeros((bmax,) + tuple(frames.shape[1:]))
     pad[: frames.shape[0]] = frames
-    out = torch.empty((world, bmax) + tuple(frames.shape[1:]), dtype=frames.dtype, device=frames.device)
+    out = torch.empty((world * bmax,) + tuple(frames.shape[1:]), dtype=frames.dtype, device=frames.device)
     dist.all_gather_into_tensor(out, pad)
-    return torch.cat([out[r, : counts[r]] for r in range(world)], dim=0)
+    return torch.cat([out[r * bmax: r * bmax + counts[r]] for r in range(world)], dim=0)
 
 
 def allreduce_gradients(params, average: bool = True) -> None:
