@@ -151,6 +151,8 @@ def main():
     from se3diff_b200.chemgraph import Batch, ChemGraph, complete_graph_edge_index
     from se3diff_b200.distributed import gather_ensemble, init_from_env
 
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line (NCCL prints its version banner there)
     rank, world, local_rank = init_from_env(args.gpus)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
