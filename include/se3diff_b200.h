@@ -215,14 +215,19 @@ typedef struct se3_ipa_shape {
     int32_t pq;          /* query/key points per head (4) */
     int32_t pv;          /* value points per head (8) */
     int32_t proj_stride; /* row stride (elements) of the fused projection matrix */
-    int32_t off_q, off_k, off_v, off_qp, off_kp, off_vp; /* column offsets inside a projection row */
+    int32_t off_q, off_k, off_v, off_qp, off_kp, off_vp; /* column offsets of head 0's blocks inside a projection row */
+    int32_t hs_scalar, hs_point, hs_vpoint; /* column stride between consecutive heads of the q/k/v blocks, of the
+                            q/k point blocks and of the v point block.  Block-major rows (reference weight order):
+                            dk, 3*pq, 3*pv.  Head-major rows [h][q|k|v|qp|kp|vp] (what the tensor-core kernel wants,
+                            one contiguous 4*(3dk+6pq+3pv)-byte record per head): 3*dk+6*pq+3*pv for all three. */
     int32_t pair_batch;  /* 1: pair tensors shared by all samples (B copies of one sequence,
                             sample.py:223); B: one per sample */
 } se3_ipa_shape;
 
 /* SAAttention.forward between the input projections and fc_out (structure_module.py:131-216).
- *   proj      [B*L, proj_stride] fp32: columns q|k|v (h*dk+c), qp|kp ((h*pq+p)*3+xyz), vp ((h*pv+p)*3+xyz)
- *             in the LOCAL frame (straight out of the fused Linear)
+ *   proj      [B*L, proj_stride] fp32, LOCAL frame (straight out of the fused Linear): element c of head h's q block at
+ *             off_q + h*hs_scalar + c (k, v alike); point p of head h at off_qp + h*hs_point + 3p + xyz (kp alike),
+ *             value points at off_vp + h*hs_vpoint + 3p + xyz
  *   rot [B*L,9], trans [B*L,3]: frames (rotation, not inverse)           structure_module.py:125-166
  *   pair_bias [pair_batch,H,L,L] fp32 = pair_weight * Linear(x2d)        structure_module.py:179
  *   pair_value[pair_batch,L,L,H*dk] fp32 = pair_value(x2d)               structure_module.py:209
@@ -242,7 +247,8 @@ int se3_ipa_attention_fwd(const float* proj, const float* rot, const float* tran
 
 /* Tensor-core edition of the same operator (tcgen05.mma + TMEM, bf16 operands, fp32 accumulation): two
  * passes, see se3diff_b200/csrc/ipa_tc.cu.  Requirements: dk = 16, shared pair tensors (pair_batch = 1),
- * L <= 256.  Differences from se3_ipa_attention_fwd:
+ * L <= 256, head-major projection rows (off_q..off_vp = 0,16,32,48,60,72 and all head strides 96).  Differences
+ * from se3_ipa_attention_fwd:
  *   pair_bias_packed  : TRANSPOSED bf16 [H][L (key j)][round_up(L,8) (query i)] = pair_weight*pair_bias(x2d), zero padded;
  *                       the (head, query-tile) slab is fetched by TMA into shared memory
  *   pair_value_packed : bf16 [L][H][Lp/8][16][8] with Lp = round_up(L,16): pair_value[i, j, h*16+c] stored at

@@ -17,7 +17,7 @@ pair_bias = torch.randn(1, H, Lm, Lm, generator=g, device=dev)
 pair_value = torch.randn(1, Lm, Lm, H * dk, generator=g, device=dev)
 hw = -0.5 * (1 / math.sqrt(54)) * F.softplus(torch.rand(H, generator=g, device=dev))
 sw = 1 / math.sqrt(3 * dk)
-shape = L.IpaShape(B, Lm, H, dk, 4, 8, 3 * D + 48 * H, 0, D, 2 * D, 3 * D, 3 * D + 12 * H, 3 * D + 24 * H, 1)
+shape = ops.ipa_shape(B, Lm, H, dk, 1, head_major=False)
 
 
 def ref(proj, rot, trans, pair_bias, pair_value, hw, dt):

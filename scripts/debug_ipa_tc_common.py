@@ -17,8 +17,12 @@ def make(B, Lm, seed=0, pos_scale=1.5):
     pair_bias = torch.randn(1, H, Lm, Lm, generator=g, device=dev)
     pair_value = torch.randn(1, Lm, Lm, H * dk, generator=g, device=dev)
     hw = -0.5 * (1 / math.sqrt(54)) * F.softplus(torch.rand(H, generator=g, device=dev))
-    shape = L.IpaShape(B, Lm, H, dk, 4, 8, 3 * D + 48 * H, 0, D, 2 * D, 3 * D, 3 * D + 12 * H, 3 * D + 24 * H, 1)
+    shape = ops.ipa_shape(B, Lm, H, dk, 1, head_major=False)
     return proj, rot, trans, pair_bias, pair_value, hw, shape
+
+
+def head_major(proj, shape):
+    return proj[:, ops.ipa_head_major_perm(H, dk, proj.device)].contiguous(), ops.ipa_shape(shape.batch, shape.len, H, dk, 1, head_major=True)
 
 
 def ref(proj, rot, trans, pair_bias, pair_value, hw, B, Lm, dt=torch.float64):

@@ -1,0 +1,24 @@
+"""Per-phase clock64 timeline of the pass-1 CTAs (developer diagnostics)."""
+import sys, os, math, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import torch
+from debug_ipa_tc_common import make, head_major, ops, dev, H
+from se3diff_b200 import _lib
+B, Lm = 256, 84
+proj, rot, trans, pb, pv, hw, shape = make(B, Lm)
+ws = ops.ipa_tc_workspace(shape, dev); pvp = ops.ipa_tc_pack_pair_value(pv, H); pbt = ops.ipa_tc_pack_pair_bias(pb.permute(0, 2, 3, 1)); proj_hm, shape_hm = head_major(proj, shape)
+out = torch.empty(B * Lm, 2048, dtype=torch.bfloat16, device=dev)
+run = lambda: ops.ipa_attention_tc_fwd(proj_hm, rot, trans, pbt, pvp, None, hw, 1 / math.sqrt(48), shape_hm, ws, out=out)
+for _ in range(3): run()
+buf = torch.zeros(B * H * 16, dtype=torch.int64, device=dev)
+lib = _lib.lib(); lib.se3_debug_set_phase_buffer.argtypes = [C.c_void_p]; lib.se3_debug_set_phase_buffer.restype = None
+lib.se3_debug_set_phase_buffer(C.c_void_p(buf.data_ptr())); run(); torch.cuda.synchronize(); lib.se3_debug_set_phase_buffer(None)
+t = buf.view(-1, 16).double().cpu()
+st = t[:, [0, 8, 9, 10, 11, 12, 1]]
+ds = st[:, 1:] - st[:, :-1]
+print('staging detail:', {n: round(v) for n, v in zip(['alloc', 'frames+kb issue', 'kv batch loads+stores', 'barrier', 'point transforms', 'q tile'], ds.mean(0).tolist())})
+t = t[:, :8]
+d = t[:, 1:] - t[:, :-1]
+names = ["staging(+alloc)", "sync+MMA1+wait", "passA(+bias wait)", "passB", "sync+MMA2+wait", "epilogue", "dealloc"]
+print("mean cycles per phase:", {n: round(v) for n, v in zip(names, d.mean(0).tolist())}, "total", round((t[:, 7] - t[:, 0]).mean().item()))
+print("p90:", {n: round(v) for n, v in zip(names, d.quantile(0.9, dim=0).tolist())})

@@ -2,12 +2,12 @@
 import sys, os, math
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
-from debug_ipa_tc_common import make, ops, dev, H
+from debug_ipa_tc_common import make, head_major, ops, dev, H
 B, Lm = int(os.environ.get("IPA_B", 256)), int(os.environ.get("IPA_L", 84))
 proj, rot, trans, pb, pv, hw, shape = make(B, Lm)
-ws = ops.ipa_tc_workspace(shape, dev); pvp = ops.ipa_tc_pack_pair_value(pv, H); pbt = ops.ipa_tc_pack_pair_bias(pb.permute(0, 2, 3, 1))
+ws = ops.ipa_tc_workspace(shape, dev); pvp = ops.ipa_tc_pack_pair_value(pv, H); pbt = ops.ipa_tc_pack_pair_bias(pb.permute(0, 2, 3, 1)); proj_hm, shape_hm = head_major(proj, shape)
 out = torch.empty(B * Lm, 2048, dtype=torch.bfloat16, device=dev)
 for _ in range(3):
-    ops.ipa_attention_tc_fwd(proj, rot, trans, pbt, pvp, None, hw, 1 / math.sqrt(48), shape, ws, out=out)
+    ops.ipa_attention_tc_fwd(proj_hm, rot, trans, pbt, pvp, None, hw, 1 / math.sqrt(48), shape_hm, ws, out=out)
 torch.cuda.synchronize()
 print("ok", float(out.float().abs().mean()))

@@ -36,7 +36,7 @@ class HeunScalars(C.Structure):
 class IpaShape(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "batch", "len", "heads", "dk", "pq", "pv", "proj_stride", "off_q", "off_k", "off_v", "off_qp", "off_kp",
-        "off_vp", "pair_batch")]
+        "off_vp", "hs_scalar", "hs_point", "hs_vpoint", "pair_batch")]
 
 
 # name -> argtypes (all return int unless listed in _RESTYPES).  Must list every symbol of the header.

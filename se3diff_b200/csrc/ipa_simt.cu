@@ -48,14 +48,14 @@ k_ipa_rows(const float* __restrict__ proj, const float* __restrict__ rot, const 
     {
         const float* pr = proj + row_i * sh.proj_stride;
 #pragma unroll
-        for (int c = 0; c < DK; ++c) q[c] = pr[sh.off_q + h * DK + c] * scalar_weight;
+        for (int c = 0; c < DK; ++c) q[c] = pr[sh.off_q + h * sh.hs_scalar + c] * scalar_weight;
 #pragma unroll
         for (int k = 0; k < 9; ++k) Ri[k] = rot[row_i * 9 + k];
 #pragma unroll
         for (int k = 0; k < 3; ++k) Ti[k] = trans[row_i * 3 + k];
 #pragma unroll
         for (int p = 0; p < PQ; ++p) {
-            const float x = pr[sh.off_qp + (h * PQ + p) * 3], y = pr[sh.off_qp + (h * PQ + p) * 3 + 1], z = pr[sh.off_qp + (h * PQ + p) * 3 + 2];
+            const float x = pr[sh.off_qp + h * sh.hs_point + p * 3], y = pr[sh.off_qp + h * sh.hs_point + p * 3 + 1], z = pr[sh.off_qp + h * sh.hs_point + p * 3 + 2];
 #pragma unroll
             for (int r = 0; r < 3; ++r) qp[p * 3 + r] = ((Ri[r * 3] * x + Ri[r * 3 + 1] * y) + Ri[r * 3 + 2] * z) + Ti[r];
         }
@@ -78,13 +78,13 @@ k_ipa_rows(const float* __restrict__ proj, const float* __restrict__ rot, const 
         for (int idx = threadIdx.x; idx < nk * DK; idx += blockDim.x) {
             const int j = idx / DK, c = idx - j * DK;
             const float* pr = proj + ((int64_t)b * L + j0 + j) * sh.proj_stride;
-            keys[j * KW + O_KS + c] = pr[sh.off_k + h * DK + c];
-            keys[j * KW + O_VS + c] = pr[sh.off_v + h * DK + c];
+            keys[j * KW + O_KS + c] = pr[sh.off_k + h * sh.hs_scalar + c];
+            keys[j * KW + O_VS + c] = pr[sh.off_v + h * sh.hs_scalar + c];
         }
         for (int idx = threadIdx.x; idx < nk * (PQ + PV); idx += blockDim.x) {
             const int j = idx / (PQ + PV), p = idx - j * (PQ + PV);
             const int64_t rj = (int64_t)b * L + j0 + j;
-            const float* pr = proj + rj * sh.proj_stride + (p < PQ ? sh.off_kp + (h * PQ + p) * 3 : sh.off_vp + (h * PV + (p - PQ)) * 3);
+            const float* pr = proj + rj * sh.proj_stride + (p < PQ ? sh.off_kp + h * sh.hs_point + p * 3 : sh.off_vp + h * sh.hs_vpoint + (p - PQ) * 3);
             const float x = pr[0], y = pr[1], z = pr[2];
             const float* R = rot + rj * 9;
             const float* T = trans + rj * 3;

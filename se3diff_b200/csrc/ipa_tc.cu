@@ -55,7 +55,7 @@ template <int N> __device__ __forceinline__ void store_vec(__nv_bfloat16* dst, c
 
 struct Pass1Smem {
     uint8_t *q, *k, *vt, *p;
-    float *kp, *kb;
+    float *kp, *kb, *frm, *qp;
 };
 // Shared-memory plan of pass 1.  The P operand (written in the second half of the kernel) can overlay everything
 // that is dead by then -- the bias slab, the key points, the key bias and the K operand -- when those fit into
@@ -64,30 +64,41 @@ __host__ __device__ inline uint32_t bias_slab_bytes(int L) {
     const int lpi = (L + 7) & ~7;
     return (uint32_t)((L * (lpi < 128 ? lpi : 128) * 2 + 15) & ~15);
 }
-__host__ __device__ inline bool pass1_can_alias(int L, int Lp) { return bias_slab_bytes(L) + (uint32_t)Lp * (48 + 4 + 32) <= (uint32_t)Lp * 256; }
+__host__ __device__ inline uint32_t pass1_front_bytes(int L) {   // bias slab and (earlier) the raw local points share it
+    const uint32_t raw = (uint32_t)L * 48 * 4;
+    return bias_slab_bytes(L) > raw ? bias_slab_bytes(L) : raw;
+}
+__host__ __device__ inline bool pass1_can_alias(int L, int Lp) { return pass1_front_bytes(L) + (uint32_t)Lp * (48 + 4 + 32) <= (uint32_t)Lp * 256; }
+__host__ __device__ inline size_t pass1_frames_bytes(int L) { return (size_t)L * 16 * 4 + 128 * 12 * 4; }  // frames [L][16] | qp [128][12]
 __host__ __device__ inline size_t pass1_smem_bytes(int L, int Lp) {
-    return pass1_can_alias(L, Lp) ? (size_t)Lp * (128 + 256) + 4096 : (size_t)Lp * (128 + 256 + 48 + 4 + 32) + 4096;
+    return (pass1_can_alias(L, Lp) ? (size_t)Lp * (128 + 256) + 4096 : (size_t)Lp * (128 + 256 + 48 + 4 + 32) + 4096) + pass1_frames_bytes(L);
 }
 __device__ __forceinline__ Pass1Smem carve1(uint8_t* base, int L, int Lp) {
     Pass1Smem s;
     s.vt = base;                                 // [Lp/8][8][8][8] bf16, MN-major value operand
     s.q = s.vt + (size_t)Lp * 128;               // [2][128][16 B]
     s.p = s.q + 4096;                            // [Lp/8][128][16 B]; the bias slab lives at its start until pass B
-    uint8_t* rest = pass1_can_alias(L, Lp) ? s.p + bias_slab_bytes(L) : s.p + (size_t)Lp * 256;
+    uint8_t* rest = pass1_can_alias(L, Lp) ? s.p + pass1_front_bytes(L) : s.p + (size_t)Lp * 256;
     s.kp = reinterpret_cast<float*>(rest);       // [Lp][12] fp32
     s.kb = s.kp + Lp * 12;                       // [Lp]
     s.k = reinterpret_cast<uint8_t*>(s.kb + Lp); // [2][Lp][16 B]
+    uint8_t* tail = pass1_can_alias(L, Lp) ? s.p + (size_t)Lp * 256 : s.k + (size_t)Lp * 32;
+    s.qp = reinterpret_cast<float*>(tail);       // [128][12] global-frame query points of the tile
+    s.frm = s.qp + 128 * 12;                     // [L][16]: R rows padded to 4 floats | T
     return s;
 }
 
 template <typename OutT>
-__global__ void __launch_bounds__(128, 5)
+__global__ void __launch_bounds__(128, 4)
 k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, const float* __restrict__ trans,
                const __nv_bfloat16* __restrict__ pair_bias_t, const float* __restrict__ key_bias, const float* __restrict__ head_weight,
                float scalar_weight, OutT* __restrict__ out, __nv_bfloat16* __restrict__ pbuf, float* __restrict__ inv_sum,
-               const se3_ipa_shape sh, int Lp, int Bpad, int tmem_cols) {
+               const se3_ipa_shape sh, int Lp, int Bpad, int tmem_cols, long long* __restrict__ dbg) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t bar, bar_bias;
+    // optional phase timestamps: 16 clock64 slots per CTA, written by thread 0 (scripts/ipa_phase_times.py)
+#define SE3_STAMP(k) do { if (dbg && threadIdx.x == 0) dbg[(((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (k)] = clock64(); } while (0)
+    SE3_STAMP(0);
     __shared__ uint32_t tmem_slot;
     const int L = sh.len, H = sh.heads;
     const Pass1Smem s = carve1(smem_raw, L, Lp);
@@ -105,117 +116,137 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
     const bool late_alloc = (tmem_cols & 1) != 0;   // experiment switch folded into the column count
     tmem_cols &= ~1;
     if (!late_alloc && warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)tmem_cols);
+    SE3_STAMP(8);
     if (tid == 0) {
         tc::mbar_init(&bar, 1);
         tc::mbar_init(&bar_bias, 1);
         tc::mbar_fence_init();
-        const __nv_bfloat16* src = pair_bias_t + (int64_t)h * L * Lpi + q0;
-        tc::mbar_expect_tx(&bar_bias, (uint32_t)(L * ncol * 2));
-        if (ncol == Lpi) {
-            tc::tma_bulk_g2s(s.p, src, (uint32_t)(L * ncol * 2), &bar_bias);
-        } else {
-            for (int j = 0; j < L; ++j) tc::tma_bulk_g2s(s.p + (size_t)j * ncol * 2, src + (int64_t)j * Lpi, (uint32_t)(ncol * 2), &bar_bias);
-        }
     }
 
-    const float cx = trans[(int64_t)b * L * 3], cy = trans[(int64_t)b * L * 3 + 1], cz = trans[(int64_t)b * L * 3 + 2];
-
-    // ---- stage keys / values of (b, h) --------------------------------------------------------------
-    for (int j = tid; j < Lp; j += 128) {
-        uint4 k0 = make_uint4(0, 0, 0, 0), k1 = k0;
-        float kpg[12];
-#pragma unroll
-        for (int c = 0; c < 12; ++c) kpg[c] = 0.f;
-        uint32_t vv[NV / 2];  // 64 bf16 value channels of key j: v | v_pt hi | v_pt lo
-#pragma unroll
-        for (int c = 0; c < NV / 2; ++c) vv[c] = 0u;
-        if (j < L) {
-            const int64_t rj = (int64_t)b * L + j;
-            const float* pr = proj + rj * sh.proj_stride;
-            const float4* kq = reinterpret_cast<const float4*>(pr + sh.off_k + h * DK);
-            const float4 a0 = __ldg(kq), a1 = __ldg(kq + 1), a2 = __ldg(kq + 2), a3 = __ldg(kq + 3);
-            k0 = make_uint4(tc::pack_bf16(a0.x, a0.y), tc::pack_bf16(a0.z, a0.w), tc::pack_bf16(a1.x, a1.y), tc::pack_bf16(a1.z, a1.w));
-            k1 = make_uint4(tc::pack_bf16(a2.x, a2.y), tc::pack_bf16(a2.z, a2.w), tc::pack_bf16(a3.x, a3.y), tc::pack_bf16(a3.z, a3.w));
-            const float4* vq = reinterpret_cast<const float4*>(pr + sh.off_v + h * DK);
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                const float4 v = __ldg(vq + c4);
-                vv[c4 * 2] = tc::pack_bf16(v.x, v.y);
-                vv[c4 * 2 + 1] = tc::pack_bf16(v.z, v.w);
-            }
-            float R[9], T[3];
-#pragma unroll
-            for (int c = 0; c < 9; ++c) R[c] = __ldg(rot + rj * 9 + c);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) T[c] = __ldg(trans + rj * 3 + c);
-            const float* kpl = pr + sh.off_kp + h * PQ * 3;
-#pragma unroll
-            for (int p = 0; p < PQ; ++p) {
-                const float x = __ldg(kpl + p * 3), y = __ldg(kpl + p * 3 + 1), z = __ldg(kpl + p * 3 + 2);
-#pragma unroll
-                for (int r = 0; r < 3; ++r) kpg[p * 3 + r] = R[r * 3] * x + R[r * 3 + 1] * y + R[r * 3 + 2] * z + T[r];
-            }
-            const float* vpl = pr + sh.off_vp + h * PV * 3;
-            const float cc[3] = {cx, cy, cz};
-            float gv[3 * PV];
-#pragma unroll
-            for (int p = 0; p < PV; ++p) {
-                const float x = __ldg(vpl + p * 3), y = __ldg(vpl + p * 3 + 1), z = __ldg(vpl + p * 3 + 2);
-#pragma unroll
-                for (int r = 0; r < 3; ++r) gv[p * 3 + r] = R[r * 3] * x + R[r * 3 + 1] * y + R[r * 3 + 2] * z + (T[r] - cc[r]);
-            }
-#pragma unroll
-            for (int c = 0; c < 3 * PV / 2; ++c) {
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(gv[2 * c]), h1 = __float2bfloat16_rn(gv[2 * c + 1]);
-                const __nv_bfloat162 hi = __halves2bfloat162(h0, h1);
-                vv[DK / 2 + c] = *reinterpret_cast<const uint32_t*>(&hi);
-                vv[DK / 2 + 3 * PV / 2 + c] = tc::pack_bf16(gv[2 * c] - __bfloat162float(h0), gv[2 * c + 1] - __bfloat162float(h1));
-            }
-        }
-        {   // MN-major value operand: [j/8][c/8][j%8][c%8] -> eight 16-byte pieces per key
-            uint8_t* dst = s.vt + (size_t)(j >> 3) * (NV * 16) + (size_t)(j & 7) * 16;
-#pragma unroll
-            for (int cg = 0; cg < NV / 8; ++cg)
-                *reinterpret_cast<uint4*>(dst + cg * 128) = make_uint4(vv[cg * 4], vv[cg * 4 + 1], vv[cg * 4 + 2], vv[cg * 4 + 3]);
-        }
-        *reinterpret_cast<uint4*>(s.k + (size_t)j * 16) = k0;
-        *reinterpret_cast<uint4*>(s.k + (size_t)(Lp + j) * 16) = k1;
-        {   // negated key points, interleaved by key pair: [j/2][component][j%2]
-            float* dstp = s.kp + (size_t)(j >> 1) * 24 + (j & 1);
-#pragma unroll
-            for (int c = 0; c < 12; ++c) dstp[c * 2] = -kpg[c];
-        }
-        s.kb[j] = (j < L) ? (key_bias ? key_bias[(int64_t)b * L + j] * kLog2e : 0.f) : -CUDART_INF_F;
-    }
-    // ---- this thread's query row -----------------------------------------------------------------------
-    float qp[12], Ri[9], Ti[3];
+    // ---- cooperative staging ---------------------------------------------------------------------------------
+    // The projection rows are HEAD-MAJOR: head h of residue j owns one contiguous 384-byte record
+    // [q 16 | k 16 | v 16 | qp 12 | kp 12 | vp 24] fp32.  The whole (b, h) slab is fetched as 24 float4 per residue with
+    // consecutive lanes on consecutive 16-byte pieces (3 full lines per residue: ~4x fewer L1 wavefronts than
+    // per-block strided loads, which bounded this phase), 8 independent loads in flight per thread.  Scalar pieces are
+    // converted and written straight into the UMMA operands; point pieces are parked raw in the (still unused) P
+    // region and transformed to the global frame after the barrier that also publishes the frames.
+    const float sc = scalar_weight * kLog2e;
+    float* s_raw = reinterpret_cast<float*>(s.p);          // [L][48] raw local points (qp 12 | kp 12 | vp 24)
     {
-        uint4 q0v = make_uint4(0, 0, 0, 0), q1v = q0v;
-        const int64_t ri = (int64_t)b * L + (row_ok ? i : 0);
-        const float* pr = proj + ri * sh.proj_stride;
+        const float* slab = proj + (int64_t)b * L * sh.proj_stride + h * 96;
+        const int nunits = L * 12;                         // 12 float4 of scalars + 12 float4 of points per residue
+        for (int base = 0; base < nunits; base += 128 * 4) {
+            float4 sv[4], pv4[4];
+            int rows[4], cs[4];
 #pragma unroll
-        for (int c = 0; c < 9; ++c) Ri[c] = __ldg(rot + ri * 9 + c);
+            for (int u = 0; u < 4; ++u) {                  // 8 independent 16-byte loads in flight per thread
+                const int idx = base + u * 128 + tid;
+                rows[u] = idx / 12;
+                cs[u] = idx - rows[u] * 12;
+                sv[u] = pv4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (idx < nunits) {
+                    const float4* rec = reinterpret_cast<const float4*>(slab + (int64_t)rows[u] * sh.proj_stride);
+                    sv[u] = __ldg(rec + cs[u]);
+                    pv4[u] = __ldg(rec + 12 + cs[u]);
+                }
+            }
+            if (base == 0) {                               // frames: contiguous [L,9] / [L,3] blocks, coalesced
+                for (int idx = tid; idx < L * 9; idx += 128) {       // frames as [L][R row0 | row1 | row2 | T], 4 floats each
+                    const int j = idx / 9, e = idx - j * 9;
+                    s.frm[j * 16 + (e / 3) * 4 + (e % 3)] = __ldg(rot + (int64_t)b * L * 9 + idx);
+                }
+                for (int idx = tid; idx < L * 3; idx += 128) s.frm[(idx / 3) * 16 + 12 + (idx % 3)] = __ldg(trans + (int64_t)b * L * 3 + idx);
+                for (int j = tid; j < Lp; j += 128) s.kb[j] = (j < L) ? (key_bias ? key_bias[(int64_t)b * L + j] * kLog2e : 0.f) : -CUDART_INF_F;
+            }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) Ti[c] = __ldg(trans + ri * 3 + c);
-        const float* qpl = pr + sh.off_qp + h * PQ * 3;
-#pragma unroll
-        for (int p = 0; p < PQ; ++p) {
-            const float x = __ldg(qpl + p * 3), y = __ldg(qpl + p * 3 + 1), z = __ldg(qpl + p * 3 + 2);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) qp[p * 3 + r] = Ri[r * 3] * x + Ri[r * 3 + 1] * y + Ri[r * 3 + 2] * z + Ti[r];
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * 128 + tid, row = rows[u], c4 = cs[u];
+                if (idx < nunits) {
+                    *reinterpret_cast<float4*>(s_raw + row * 48 + c4 * 4) = pv4[u];
+                    // branch-free routing of the scalar piece: block 0 = q (scaled, tile rows only), 1 = k, 2 = v
+                    const int blk = c4 >> 2, qt = c4 & 3, r = row - q0;
+                    const float f = blk == 0 ? sc : 1.0f;
+                    uint8_t* dq = s.q + ((size_t)(qt >> 1) * 128 + (r & 127)) * 16;
+                    uint8_t* dk = s.k + ((size_t)(qt >> 1) * Lp + row) * 16;
+                    uint8_t* dv = s.vt + (size_t)(row >> 3) * (NV * 16) + (size_t)(qt >> 1) * 128 + (size_t)(row & 7) * 16;
+                    uint8_t* dst = (blk == 0 ? dq : (blk == 1 ? dk : dv)) + (qt & 1) * 8;
+                    if (blk != 0 || (r >= 0 && r < 128))
+                        *reinterpret_cast<uint2*>(dst) = make_uint2(tc::pack_bf16(sv[u].x * f, sv[u].y * f), tc::pack_bf16(sv[u].z * f, sv[u].w * f));
+                }
+            }
         }
-        if (row_ok) {
-            const float sc = scalar_weight * kLog2e;
-            const float4* qq = reinterpret_cast<const float4*>(pr + sh.off_q + h * DK);
-            const float4 a0 = __ldg(qq), a1 = __ldg(qq + 1), a2 = __ldg(qq + 2), a3 = __ldg(qq + 3);
-            q0v = make_uint4(tc::pack_bf16(a0.x * sc, a0.y * sc), tc::pack_bf16(a0.z * sc, a0.w * sc), tc::pack_bf16(a1.x * sc, a1.y * sc),
-                             tc::pack_bf16(a1.z * sc, a1.w * sc));
-            q1v = make_uint4(tc::pack_bf16(a2.x * sc, a2.y * sc), tc::pack_bf16(a2.z * sc, a2.w * sc), tc::pack_bf16(a3.x * sc, a3.y * sc),
-                             tc::pack_bf16(a3.z * sc, a3.w * sc));
+        // zero padding: key rows L..Lp of K and V^T, query rows beyond the sequence end
+        for (int idx = tid; idx < (Lp - L) * 10; idx += 128) {
+            const int row = L + idx / 10, piece = idx % 10;
+            if (piece < 2) *reinterpret_cast<uint4*>(s.k + ((size_t)piece * Lp + row) * 16) = make_uint4(0, 0, 0, 0);
+            else *reinterpret_cast<uint4*>(s.vt + (size_t)(row >> 3) * (NV * 16) + (size_t)(piece - 2) * 128 + (size_t)(row & 7) * 16) = make_uint4(0, 0, 0, 0);
         }
-        *reinterpret_cast<uint4*>(s.q + (size_t)tid * 16) = q0v;
-        *reinterpret_cast<uint4*>(s.q + (size_t)(128 + tid) * 16) = q1v;
+        const int nq = min(128, L - q0);
+        for (int idx = tid; idx < (128 - nq) * 2; idx += 128)
+            *reinterpret_cast<uint4*>(s.q + ((size_t)(idx & 1) * 128 + nq + (idx >> 1)) * 16) = make_uint4(0, 0, 0, 0);
     }
+    SE3_STAMP(9);
+    SE3_STAMP(10);
+    __syncthreads();   // frames and raw points are in shared memory
+    SE3_STAMP(11);
+    const float cx = s.frm[12], cy = s.frm[13], cz = s.frm[14];
+    {
+        const int p4 = tid & 3, p8 = tid & 7;
+#pragma unroll 4
+        for (int row = tid >> 2; row < Lp; row += 32) {          // key points -> global frame, negated, pair-interleaved
+            float g[3] = {0.f, 0.f, 0.f};
+            if (row < L) {
+                const float* pl = s_raw + row * 48 + 12 + p4 * 3;
+                const float4* F4 = reinterpret_cast<const float4*>(s.frm + row * 16);
+                const float4 r0 = F4[0], r1 = F4[1], r2 = F4[2], tt = F4[3];
+                const float x = pl[0], y = pl[1], z = pl[2];
+                g[0] = r0.x * x + r0.y * y + r0.z * z + tt.x; g[1] = r1.x * x + r1.y * y + r1.z * z + tt.y; g[2] = r2.x * x + r2.y * y + r2.z * z + tt.z;
+            }
+            float* dstp = s.kp + (size_t)(row >> 1) * 24 + (row & 1) + p4 * 6;
+            dstp[0] = -g[0]; dstp[2] = -g[1]; dstp[4] = -g[2];
+        }
+#pragma unroll
+        for (int row = tid >> 2; row < 128; row += 32) {         // query points of the tile -> s.qp[row][12]
+            float g[3] = {0.f, 0.f, 0.f};
+            const int qi = q0 + row;
+            if (qi < L) {
+                const float* pl = s_raw + qi * 48 + p4 * 3;
+                const float4* F4 = reinterpret_cast<const float4*>(s.frm + qi * 16);
+                const float4 r0 = F4[0], r1 = F4[1], r2 = F4[2], tt = F4[3];
+                const float x = pl[0], y = pl[1], z = pl[2];
+                g[0] = r0.x * x + r0.y * y + r0.z * z + tt.x; g[1] = r1.x * x + r1.y * y + r1.z * z + tt.y; g[2] = r2.x * x + r2.y * y + r2.z * z + tt.z;
+            }
+            s.qp[row * 12 + p4 * 3] = g[0]; s.qp[row * 12 + p4 * 3 + 1] = g[1]; s.qp[row * 12 + p4 * 3 + 2] = g[2];
+        }
+#pragma unroll 4
+        for (int row = tid >> 3; row < Lp; row += 16) {          // value points: re-centred, split hi + lo bf16
+            __nv_bfloat16 hi[3], lo[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) hi[r] = lo[r] = __float2bfloat16_rn(0.f);
+            if (row < L) {
+                const float* pl = s_raw + row * 48 + 24 + p8 * 3;
+                const float4* F4 = reinterpret_cast<const float4*>(s.frm + row * 16);
+                const float4 r0 = F4[0], r1 = F4[1], r2 = F4[2], tt = F4[3];
+                const float x = pl[0], y = pl[1], z = pl[2];
+                const float gv[3] = {r0.x * x + r0.y * y + r0.z * z + (tt.x - cx), r1.x * x + r1.y * y + r1.z * z + (tt.y - cy),
+                                     r2.x * x + r2.y * y + r2.z * z + (tt.z - cz)};
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    hi[r] = __float2bfloat16_rn(gv[r]);
+                    lo[r] = __float2bfloat16_rn(gv[r] - __bfloat162float(hi[r]));
+                }
+            }
+            __nv_bfloat16* col = reinterpret_cast<__nv_bfloat16*>(s.vt + (size_t)(row >> 3) * (NV * 16) + (size_t)(row & 7) * 16);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int ch = DK + p8 * 3 + r, cl = DK + 3 * PV + p8 * 3 + r;   // channel c: group c/8 (128 B apart), c%8 in the piece
+                col[(ch >> 3) * 64 + (ch & 7)] = hi[r];
+                col[(cl >> 3) * 64 + (cl & 7)] = lo[r];
+            }
+        }
+    }
+    SE3_STAMP(12);
+    SE3_STAMP(1);
     // TMEM is claimed only now: staging of this CTA overlapped with the tensor-memory phase of its neighbours
     if (late_alloc && warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)tmem_cols);
     tc::fence_async_smem();
@@ -223,15 +254,37 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem = tmem_slot;
+    float qp[12], Ri[9], Ti[3];
+    {
+        const int qi = row_ok ? i : 0;
+#pragma unroll
+        for (int c4 = 0; c4 < 3; ++c4) {
+            const float4 v = reinterpret_cast<const float4*>(s.qp + tid * 12)[c4];
+            qp[c4 * 4] = v.x; qp[c4 * 4 + 1] = v.y; qp[c4 * 4 + 2] = v.z; qp[c4 * 4 + 3] = v.w;
+        }
+        const float4* F4 = reinterpret_cast<const float4*>(s.frm + qi * 16);
+        const float4 r0 = F4[0], r1 = F4[1], r2 = F4[2], tt = F4[3];
+        Ri[0] = r0.x; Ri[1] = r0.y; Ri[2] = r0.z; Ri[3] = r1.x; Ri[4] = r1.y; Ri[5] = r1.z; Ri[6] = r2.x; Ri[7] = r2.y; Ri[8] = r2.z;
+        Ti[0] = tt.x; Ti[1] = tt.y; Ti[2] = tt.z;
+    }
 
     // ---- MMA 1: S = Q.K^T -----------------------------------------------------------------------------------
     if (tid == 0) {
+        // the raw-point area is dead: fetch the pair-bias slab into it (TMA), it lands while the MMA runs
+        const __nv_bfloat16* src = pair_bias_t + (int64_t)h * L * Lpi + q0;
+        tc::mbar_expect_tx(&bar_bias, (uint32_t)(L * ncol * 2));
+        if (ncol == Lpi) {
+            tc::tma_bulk_g2s(s.p, src, (uint32_t)(L * ncol * 2), &bar_bias);
+        } else {
+            for (int j = 0; j < L; ++j) tc::tma_bulk_g2s(s.p + (size_t)j * ncol * 2, src + (int64_t)j * Lpi, (uint32_t)(ncol * 2), &bar_bias);
+        }
         tc::mma_bf16(tmem, tc::make_desc(tc::smem_u32(s.q), 128), tc::make_desc(tc::smem_u32(s.k), (uint32_t)Lp),
                      tc::make_idesc_bf16(128, Lp), false);
         tc::mma_commit(&bar);
     }
     tc::mbar_wait(&bar, 0);
     tc::fence_after();
+    SE3_STAMP(2);
 
     const int nchunk = Lp / 16;
     const uint32_t lane_base = (uint32_t)warp * 32;
@@ -287,6 +340,7 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
         if (m == -CUDART_INF_F) m = 0.f;
     }
     __syncthreads();  // every warp is done with the bias tile: its shared memory becomes the P operand
+    SE3_STAMP(3);
     if (warp_ok) {
         // ---- pass B: P = exp2(l - m) -> bf16 -> smem (A operand) + global (pass 2) ------------------------------
         float sum = 0.f;
@@ -319,6 +373,7 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
     __syncthreads();
     tc::fence_after();
 
+    SE3_STAMP(4);
     // ---- MMA 2: O = P.V (accumulator overwrites the consumed S columns) -------------------------------------------
     if (tid == 0) {
         const uint32_t idesc = tc::make_idesc_bf16(128, NV, /*b_mn_major=*/true);
@@ -329,6 +384,7 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
     }
     tc::mbar_wait(&bar, 1);
     tc::fence_after();
+    SE3_STAMP(5);
 
     if (warp_ok) {
         float o[NV];
@@ -363,7 +419,10 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
     }
     tc::fence_before();
     __syncthreads();
+    SE3_STAMP(6);
     if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)tmem_cols);
+    SE3_STAMP(7);
+#undef SE3_STAMP
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -421,6 +480,8 @@ k_ipa_tc_pass2(const __nv_bfloat16* __restrict__ pbuf, const float* __restrict__
     if (warp == 0) tc::tmem_dealloc(tmem, 32);
 }
 
+long long* g_phase_dbg = nullptr;  // set by se3_debug_set_phase_buffer
+
 template <typename OutT>
 int launch_tc(const float* proj, const float* rot, const float* trans, const __nv_bfloat16* pair_bias, const __nv_bfloat16* pvc,
               const float* key_bias, const float* head_weight, float scalar_weight, OutT* out, __nv_bfloat16* pbuf, float* inv_sum,
@@ -441,7 +502,8 @@ int launch_tc(const float* proj, const float* rot, const float* trans, const __n
     if (e != cudaSuccess) { set_error("ipa_tc pass1 smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
     dim3 g1((L + 127) / 128, sh.heads, sh.batch);
     static const int late = getenv("SE3_IPA_LATE_ALLOC") ? atoi(getenv("SE3_IPA_LATE_ALLOC")) : 0;
-    k1<<<g1, 128, smem1, st>>>(proj, rot, trans, pair_bias, key_bias, head_weight, scalar_weight, out, pbuf, inv_sum, sh, Lp, Bpad, cols | late);
+    k1<<<g1, 128, smem1, st>>>(proj, rot, trans, pair_bias, key_bias, head_weight, scalar_weight, out, pbuf, inv_sum, sh, Lp, Bpad, cols | late,
+                               g_phase_dbg);
     count_launch();
     int rc = check_launch("se3_ipa_attention_tc_fwd(pass 1)");
     if (rc) return rc;
@@ -458,6 +520,9 @@ int launch_tc(const float* proj, const float* rot, const float* trans, const __n
 }  // namespace
 
 extern "C" {
+
+/* developer hook (not in the public header): 8 clock64 stamps per pass-1 CTA are written to `buf` when non-null */
+void se3_debug_set_phase_buffer(long long* buf) { g_phase_dbg = buf; }
 
 int64_t se3_ipa_tc_workspace_bytes(const se3_ipa_shape* h_shape, int64_t* p_bytes, int64_t* inv_bytes) {
     if (!h_shape) return SE3_EINVAL;
@@ -481,8 +546,10 @@ int se3_ipa_attention_tc_fwd(const float* proj, const float* rot, const float* t
                   "(got dk=%d L=%d H=%d pair_batch=%d); use se3_ipa_attention_fwd", sh.dk, sh.len, sh.heads, sh.pair_batch);
         return SE3_EUNSUPPORTED;
     }
-    SE3_REQUIRE(sh.proj_stride % 4 == 0 && sh.off_q % 4 == 0 && sh.off_k % 4 == 0 && sh.off_v % 4 == 0 &&
-                (reinterpret_cast<uintptr_t>(proj) & 15) == 0, "projection matrix must be 16-byte aligned with offsets % 4 == 0");
+    SE3_REQUIRE(sh.off_q == 0 && sh.off_k == 16 && sh.off_v == 32 && sh.off_qp == 48 && sh.off_kp == 60 && sh.off_vp == 72 &&
+                sh.hs_scalar == 96 && sh.hs_point == 96 && sh.hs_vpoint == 96,
+                "the tensor-core kernel needs head-major projection rows: [h][q16|k16|v16|qp12|kp12|vp24]");
+    SE3_REQUIRE(sh.proj_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(proj) & 15) == 0, "projection matrix must be 16-byte aligned");
     const int Lp = (sh.len + 15) / 16 * 16, Bpad = (sh.batch + 127) / 128 * 128;
     cudaStream_t st = (cudaStream_t)stream;
     if (out_is_bf16)

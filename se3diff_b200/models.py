@@ -190,8 +190,11 @@ class DistributionalGraphormer(nn.Module):
             layers = []
             for lyr in self.st_module.encoder.layers:
                 a = lyr.attn
+                w_proj = a.fused_projection_weight().detach()
+                if dtype != torch.float32 and a.d_k == 16:       # bf16 mode: head-major records for the tensor-core attention
+                    w_proj = w_proj[ops.ipa_head_major_perm(a.n_head, a.d_k, w_proj.device)]
                 layers.append(dict(
-                    w_proj=a.fused_projection_weight().detach().to(dtype).contiguous(),
+                    w_proj=w_proj.to(dtype).contiguous(),
                     w_out=a.fc_out.weight.detach().to(dtype).contiguous(),
                     w_ff0=lyr.ffn.ff[0].weight.detach().to(dtype).contiguous(),
                     w_ff3=lyr.ffn.ff[3].weight.detach().to(dtype).contiguous(),
@@ -254,7 +257,7 @@ class DistributionalGraphormer(nn.Module):
         bucket = self.rp_proj.bucket_table(lmax).to(dev)
         x2d = self.x2d_proj(pair_d) + self.rp_proj.relative_attention_bias(bucket)[None]   # [Bp, L, L, d_pair]
         attn0 = self.st_module.encoder.layers[0].attn
-        probe = L.IpaShape(B, lmax, attn0.n_head, attn0.d_k, 4, 8, 0, 0, 0, 0, 0, 0, 0, 1 if c.shared else B)
+        probe = ops.ipa_shape(B, lmax, attn0.n_head, attn0.d_k, 1 if c.shared else B, head_major=False)
         c.tc = self.precision == "bf16" and ops.ipa_tc_supported(probe)      # tcgen05 attention path
         c.pair_bias, c.pair_value, c.pair_value_packed = [], [], []
         for lyr in self.st_module.encoder.layers:
@@ -378,8 +381,7 @@ class DistributionalGraphormer(nn.Module):
         x1d = (c.x1d_base + self.step_emb(t.float()[:B])[:, None]).reshape(B * Lm, D)
         attn0 = self.st_module.encoder.layers[0].attn
         H, dk = attn0.n_head, attn0.d_k
-        shape = L.IpaShape(B, Lm, H, dk, 4, 8, 3 * D + 48 * H, 0, D, 2 * D, 3 * D, 3 * D + 12 * H, 3 * D + 24 * H,
-                           1 if c.shared else B)
+        shape = ops.ipa_shape(B, Lm, H, dk, 1 if c.shared else B, head_major=self.precision != "fp32" and dk == 16)
         flags = ops.IPA_EXACT if self.precision == "fp32" else ops.IPA_FAST_MATH
         fused = self.precision == "bf16" and D % 128 == 0 and D <= 1024
         if fused:

@@ -358,6 +358,28 @@ def debug_umma_gemm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def ipa_head_major_perm(heads: int, dk: int, device=None) -> torch.Tensor:
+    """Row permutation of the fused projection weight [q | k | v | q_pt | k_pt | v_pt] (block-major, the reference's
+    parameter order) into head-major order: head h owns the contiguous record [q dk | k dk | v dk | qp 12 | kp 12 | vp 24]."""
+    hd = heads * dk
+    ar = lambda n: torch.arange(n, device=device)
+    idx = []
+    for h in range(heads):
+        idx += [h * dk + ar(dk), hd + h * dk + ar(dk), 2 * hd + h * dk + ar(dk), 3 * hd + h * 12 + ar(12),
+                3 * hd + 12 * heads + h * 12 + ar(12), 3 * hd + 24 * heads + h * 24 + ar(24)]
+    return torch.cat(idx)
+
+
+def ipa_shape(batch: int, length: int, heads: int, dk: int, pair_batch: int, head_major: bool) -> L.IpaShape:
+    """Column map of the fused projection output for the two supported row layouts."""
+    hd, rec = heads * dk, 3 * dk + 48
+    if head_major:
+        return L.IpaShape(batch, length, heads, dk, 4, 8, heads * rec, 0, dk, 2 * dk, 3 * dk, 3 * dk + 12, 3 * dk + 24, rec, rec, rec,
+                          pair_batch)
+    return L.IpaShape(batch, length, heads, dk, 4, 8, heads * rec, 0, hd, 2 * hd, 3 * hd, 3 * hd + 12 * heads, 3 * hd + 24 * heads,
+                      dk, 12, 24, pair_batch)
+
+
 def ipa_tc_supported(shape: L.IpaShape) -> bool:
     return shape.dk == 16 and shape.pq == 4 and shape.pv == 8 and shape.pair_batch == 1 and shape.len <= 256
 
