@@ -198,11 +198,16 @@ int se3_igso3_build_score_scaling(const float* sigma_grid, int num_sigma, const 
  *   normals : [n,3] axis normals, u : [n] uniforms in [0,1) -- drawn by the caller (parity mode);
  *             both NULL => in-kernel Philox4x32-10 keyed by (seed, element index)
  *   x       : optional [n,3,3]; NULL => out = Exp(axis*omega)
- *   angle_out optional [n]. */
+ *   angle_out optional [n]
+ *   cdf_index: optional search index built by se3_igso3_build_cdf_index (same row order as cdf); NULL => binary
+ *             search.  Either way the angle index equals the reference's `sum(cdf < u)` exactly. */
 int se3_igso3_sample(const float* sigma, const float* sigma_grid, int num_sigma, const float* cdf,
                      const float* omega_grid, int num_omega, const float* normals, const float* u,
                      uint64_t seed, const float* x, float* out, float* angle_out, int64_t n, float tol,
-                     se3_stream_t stream);
+                     const float* cdf_index, se3_stream_t stream);
+/* Blocked search index over the CDF rows (fan-out 8: one 32-byte sector per level, 4 sector reads per lookup
+ * instead of 11 scattered probes); index is [num_rows, 584] fp32, num_omega <= 2048. */
+int se3_igso3_build_cdf_index(const float* cdf, int num_rows, int num_omega, float* index, se3_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K4 -- structure-module (invariant point) attention         structure_module.py:109-220

@@ -64,7 +64,8 @@ SIGNATURES = {
     "se3_igso3_marginal_pdf": [f32p, f32p, f32p, f32p, i64, i32, f32, vp],
     "se3_igso3_build_cdf": [f32p, i32, f64p, i32, i32, f64, i32, f32p, vp],
     "se3_igso3_build_score_scaling": [f32p, i32, f64p, i32, i32, f64, f32p, vp],
-    "se3_igso3_sample": [f32p, f32p, i32, f32p, f32p, i32, f32p, f32p, u64, f32p, f32p, f32p, i64, f32, vp],
+    "se3_igso3_sample": [f32p, f32p, i32, f32p, f32p, i32, f32p, f32p, u64, f32p, f32p, f32p, i64, f32, f32p, vp],
+    "se3_igso3_build_cdf_index": [f32p, i32, i32, f32p, vp],
     "se3_ipa_attention_fwd": [f32p] * 7 + [f32, f32p, C.POINTER(IpaShape), i32, vp],
     "se3_ipa_tc_workspace_bytes": [C.POINTER(IpaShape), C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
     "se3_ipa_attention_tc_fwd": [f32p] * 3 + [vp, vp, f32p, f32p, f32, vp, i32, vp, f32p, C.POINTER(IpaShape), vp],

@@ -308,8 +308,21 @@ def igso3_build_score_scaling(sigma_grid: torch.Tensor, omega_pts: torch.Tensor,
     return out
 
 
+CDF_INDEX_PITCH = 584
+
+
+def igso3_build_cdf_index(cdf: torch.Tensor) -> torch.Tensor:
+    """Blocked fan-out-8 search index over the CDF rows (one 32-byte sector per level); [rows, 584] fp32."""
+    cdf = _dev(cdf, name="cdf")
+    rows, n = cdf.shape
+    out = torch.empty(rows, CDF_INDEX_PITCH, dtype=torch.float32, device=cdf.device)
+    with _guard(cdf):
+        L.check(L.lib().se3_igso3_build_cdf_index(_p(cdf), rows, n, _p(out), _stream(cdf)), "se3_igso3_build_cdf_index")
+    return out
+
+
 def igso3_sample(cdf, omega_grid, n: int, sigma=None, sigma_grid=None, normals=None, u=None, seed: int = 0, x=None,
-                 tol: float = 1e-7, want_angle=False):
+                 tol: float = 1e-7, want_angle=False, cdf_index=None):
     """BaseSampleSO3.sample with one sample per element (so3_sde.py:1189-1286) [+ x . r]."""
     cdf, og = _dev(cdf, name="cdf"), _dev(omega_grid, name="omega_grid")
     sigma = None if sigma is None else _dev(sigma, name="sigma")
@@ -317,12 +330,13 @@ def igso3_sample(cdf, omega_grid, n: int, sigma=None, sigma_grid=None, normals=N
     normals = None if normals is None else _dev(normals, name="normals")
     u = None if u is None else _dev(u, name="u")
     x = None if x is None else _dev(x, name="x")
+    cdf_index = None if cdf_index is None else _dev(cdf_index, name="cdf_index")
     out = torch.empty(n, 3, 3, dtype=torch.float32, device=cdf.device)
     ang = torch.empty(n, dtype=torch.float32, device=cdf.device) if want_angle else None
     with _guard(cdf):
         L.check(L.lib().se3_igso3_sample(_p(sigma), _p(sigma_grid), 0 if sigma_grid is None else sigma_grid.numel(), _p(cdf),
                                          _p(og), og.numel(), _p(normals), _p(u), int(seed) & (2**64 - 1), _p(x), _p(out),
-                                         _p(ang), n, tol, _stream(cdf)), "se3_igso3_sample")
+                                         _p(ang), n, tol, _p(cdf_index), _stream(cdf)), "se3_igso3_sample")
     return (out, ang) if want_angle else out
 
 

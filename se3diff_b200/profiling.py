@@ -84,6 +84,19 @@ def elementwise_rooflines(n: int = 10_000_000, device="cuda"):
         ("se3_frame_update_dpm_mid", 120, lambda: ops.frame_update_dpm_mid(r, pos, w, v, dp, rot_out=out_r, pos_out=out_p)),
         ("se3_frame_update_dpm_final", 132, lambda: ops.frame_update_dpm_final(r, pos, w, z1, v, dp, rot_out=out_r, pos_out=out_p)),
     ]
+    # IGSO3 noising (sample_marginal, so3_sde.py:249-288) with the full-size table (8 MB, L2-resident): 36 B in + 36 B out
+    # + 16 B of passed-in noise = 88 B/rotation; 72 B with in-kernel Philox
+    sig_grid = 0.02 * (2.33 / 0.02) ** torch.linspace(0.001, 1.0, 1000, device=device)
+    om = (torch.linspace(0.0, 1, 2001, device=device, dtype=torch.float64) ** 3 * 3.141592653589793)
+    cdf = ops.igso3_build_cdf(sig_grid, om, 2000)
+    omg = om[1:].float()
+    cidx = ops.igso3_build_cdf_index(cdf)
+    sig = 0.02 * (2.33 / 0.02) ** torch.rand(n, generator=g, device=device)
+    uu = torch.rand(n, generator=g, device=device)
+    cases += [
+        ("se3_igso3_sample(noise passed in)", 88, lambda: ops.igso3_sample(cdf, omg, n, sigma=sig, sigma_grid=sig_grid, normals=z1, u=uu, x=r, cdf_index=cidx)),
+        ("se3_igso3_sample(philox)", 72, lambda: ops.igso3_sample(cdf, omg, n, sigma=sig, sigma_grid=sig_grid, seed=1, x=r, cdf_index=cidx)),
+    ]
     res = []
     for name, bytes_per, fn in cases:
         ms = _time_alone(fn)
