@@ -140,6 +140,7 @@ def main():
     ap.add_argument("--diffusion-steps", type=int, default=WORKLOAD["num_steps"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the instrumented per-kernel pass (used for ncu launch lists)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -229,7 +230,7 @@ def main():
 
     # ---- per-kernel roofline pass (same workload, instrumented, after the timed region) -------------------
     roof, roof_extra = None, []
-    if rank == 0:
+    if rank == 0 and not args.no_roofline:
         try:
             from se3diff_b200.profiling import kernel_rooflines
 
