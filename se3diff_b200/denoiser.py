@@ -85,6 +85,87 @@ def _fields(sdes):
 
 
 # ------------------------------------------------------------------------------------------------
+# CUDA-graph replay of the deterministic dpm loop.  All per-step quantities are kernel arguments fixed at capture
+# time and the loop has no host synchronisation, so the whole 2*num_steps network evaluations + frame updates of one
+# call are a single graph launch.  Used when the same device-resident batch (same embedding tensors), model and SDEs
+# come back: first call eager, second call captures, later calls replay.  SE3DIFF_B200_CUDA_GRAPH=0 disables it.
+_GRAPHS: "collections.OrderedDict" = None  # type: ignore[assignment]
+_GRAPH_SEEN: set = set()
+_MAX_GRAPHS = 4
+
+
+def _graph_key(batch, sdes, so3, score_model, num_steps, max_t, min_t, device):
+    import os
+
+    from .models import DiGConditionalScoreModel
+
+    if os.environ.get("SE3DIFF_B200_CUDA_GRAPH", "1") == "0" or S._HOST_NOISE or torch.cuda.is_current_stream_capturing():
+        return None
+    if not isinstance(score_model, DiGConditionalScoreModel) or not isinstance(so3, S.DiGSO3SDE):
+        return None
+    if "single_embeds" not in batch or "pair_embeds" not in batch:
+        return None
+    sc = so3.score_function.score_scaling
+    nn_ = score_model.model_nn
+    ctx = nn_._context(batch)       # by identity, else by exact value: a fresh Batch of the same sequence maps to the same context
+    key = (id(score_model), id(ctx), nn_.precision, nn_._weights_version(), nn_.x1d_proj[1].weight.data_ptr(), tuple(batch["pos"].shape),
+           id(so3), sc.data_ptr(), sc._version, so3.sigma_min, so3.sigma_max, getattr(sdes["pos"], "s", None), num_steps, max_t, min_t,
+           str(device))
+    return key, (score_model, ctx, nn_._layer_weights(torch.bfloat16 if nn_.precision == "bf16" else torch.float32), so3, sc)
+
+
+def _dpm_loop(batch, score_model, steps, device):
+    B = batch.num_graphs
+    pos, rot = batch["pos"], batch["node_orientations"]
+    for st in steps:
+        out = score_model(batch, _t(st.t, B, device))
+        m_rot_t = out["node_orientations"]
+        rot_u, pos_u = ops.frame_update_dpm_mid(rot, pos, m_rot_t, out["pos"], st.scalars)
+        out_u = score_model(batch.replace(pos=pos_u, node_orientations=rot_u), _t(st.t_lambda, B, device))
+        rot, pos = ops.frame_update_dpm_final(rot, pos, m_rot_t, out_u["node_orientations"], out_u["pos"], st.scalars)
+        batch = batch.replace(pos=pos, node_orientations=rot)
+    return batch
+
+
+def _dpm_graphed(key, keep_alive, batch, score_model, steps, device):
+    """Returns the denoised batch through capture/replay, or None when this key has only been seen once.
+    `keep_alive` are the objects whose device pointers the graph bakes in (context, cached weights, SDE tables); the
+    entry owns them so that a replay can never read recycled memory."""
+    import collections
+
+    global _GRAPHS
+    if _GRAPHS is None:
+        _GRAPHS = collections.OrderedDict()
+    entry = _GRAPHS.get(key)
+    if entry is None:
+        if key not in _GRAPH_SEEN:      # first sighting: stay eager (one-shot callers never pay for a capture)
+            if len(_GRAPH_SEEN) > 256:
+                _GRAPH_SEEN.clear()
+            _GRAPH_SEEN.add(key)
+            return None
+        entry = dict(pos_in=torch.empty_like(batch["pos"]), rot_in=torch.empty_like(batch["node_orientations"]), keep_alive=keep_alive)
+        static = batch.replace(pos=entry["pos_in"], node_orientations=entry["rot_in"])
+        entry["pos_in"].copy_(batch["pos"])
+        entry["rot_in"].copy_(batch["node_orientations"])
+        graph = torch.cuda.CUDAGraph()
+        before = ops.launch_count()
+        torch.cuda.synchronize(device)
+        with torch.cuda.graph(graph):
+            out = _dpm_loop(static, score_model, steps, device)
+        entry.update(graph=graph, pos_out=out["pos"], rot_out=out["node_orientations"], launches=ops.launch_count() - before)
+        ops.count_replayed_launches(-entry["launches"])     # recorded, not executed: the replay below is what runs
+        _GRAPHS[key] = entry
+        while len(_GRAPHS) > _MAX_GRAPHS:
+            _GRAPHS.popitem(last=False)
+    else:
+        _GRAPHS.move_to_end(key)
+    entry["pos_in"].copy_(batch["pos"])
+    entry["rot_in"].copy_(batch["node_orientations"])
+    entry["graph"].replay()
+    ops.count_replayed_launches(entry["launches"])
+    return batch.replace(pos=entry["pos_out"].clone(), node_orientations=entry["rot_out"].clone())
+
+
 @torch.no_grad()
 def dpm_solver(*, batch, sdes, score_model, num_steps: int, max_t: float, min_t: float, device=None):
     """DPM-Solver-2 on positions + midpoint / extrapolated-score exp-map step on orientations
@@ -93,6 +174,13 @@ def dpm_solver(*, batch, sdes, score_model, num_steps: int, max_t: float, min_t:
     batch, device, so3, (score_model,) = _prepare(batch, sdes, score_model, device)
     steps = schedule.dpm_schedule(sdes["pos"], so3, num_steps, max_t, min_t)
     batch = _prior(batch, sdes, so3, device)
+    keyed = _graph_key(batch, sdes, so3, score_model, num_steps, max_t, min_t, device)
+    if keyed is not None:
+        done = _dpm_graphed(keyed[0], keyed[1], batch, score_model, steps, device)
+        if done is not None:
+            return done
+    if not S._HOST_NOISE:
+        return _dpm_loop(batch, score_model, steps, device)
     B = batch.num_graphs
     pos, rot = batch["pos"], batch["node_orientations"]
     for st in steps:

@@ -155,7 +155,7 @@ class StructureModule(nn.Module):
 class _Context:
     """Per-sequence tensors that do not depend on the sample, on t or on the frames."""
 
-    __slots__ = ("key", "lengths", "lmax", "batch", "shared", "mask", "dense_index", "x1d_base", "pair_bias",
+    __slots__ = ("src", "src_versions", "key", "lengths", "lmax", "batch", "shared", "mask", "dense_index", "x1d_base", "pair_bias",
                  "pair_value", "key_bias", "uniform", "tc", "pair_value_packed", "workspace")
 
 
@@ -214,17 +214,31 @@ class DistributionalGraphormer(nn.Module):
         structure_module.py:179,209), cached on the identity of the embedding tensors."""
         single, pair, bidx = ctx_graph["single_embeds"], ctx_graph["pair_embeds"], ctx_graph["batch"]
         known = ctx_graph["pos_is_known"] if "pos_is_known" in ctx_graph else None
-        key = (single.data_ptr(), pair.data_ptr(), bidx.data_ptr(), single._version, pair._version, tuple(single.shape),
-               tuple(pair.shape), None if known is None else (known.data_ptr(), known._version), self._weights_version(),
-               self.precision)
-        if self._ctx is not None and self._ctx.key == key:
-            return self._ctx
+        edges = ctx_graph["edge_index"] if "edge_index" in ctx_graph else None
+        src = (single, pair, bidx, known, edges)
+        versions = tuple(None if a is None else a._version for a in src)
+        key = (self._weights_version(), self.precision, self.x1d_proj[1].weight.data_ptr())
+        c = self._ctx
+        if c is not None and c.key == key:
+            # The cache owns references to the tensors it was built from, so neither an address nor an id can be
+            # recycled under it.  Fast path: the very same tensor objects, unmodified.  Otherwise (a fresh Batch of the
+            # same sequence, sample.py:223 builds one per call) compare by VALUE, exactly, once.
+            if versions == c.src_versions and all(a is b for a, b in zip(src, c.src)):
+                return c
+            held_intact = c.src_versions == tuple(None if a is None else a._version for a in c.src)
+            if (held_intact and not torch.cuda.is_current_stream_capturing()
+                    and all((a is None) == (b is None) for a, b in zip(src, c.src))
+                    and all(a is None or (a.shape == b.shape and a.dtype == b.dtype and a.device == b.device and torch.equal(a, b))
+                            for a, b in zip(src, c.src))):
+                c.src, c.src_versions = src, versions
+                return c
         dev = single.device
         lengths = batch_lengths(ctx_graph)
         B, lmax = len(lengths), max(lengths)
         uniform = all(n == lmax for n in lengths)
         c = _Context()
         c.key, c.lengths, c.lmax, c.batch, c.uniform = key, lengths, lmax, B, uniform
+        c.src, c.src_versions = src, versions
         n_tot = sum(lengths)
         if uniform:
             c.dense_index, mask = None, torch.ones(B, lmax, dtype=torch.bool, device=dev)

@@ -43,12 +43,23 @@ def _guard(t):
     return torch.cuda.device(t.device)
 
 
+_replayed_launches = 0
+
+
 def launch_count() -> int:
-    return int(L.lib().se3_launch_count())
+    """Kernels of libse3diff_b200 launched by this thread (direct launches + launches replayed through CUDA graphs)."""
+    return int(L.lib().se3_launch_count()) + _replayed_launches
 
 
 def launch_count_reset() -> None:
+    global _replayed_launches
+    _replayed_launches = 0
     L.lib().se3_launch_count_reset()
+
+
+def count_replayed_launches(n: int) -> None:
+    global _replayed_launches
+    _replayed_launches += int(n)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -376,12 +387,12 @@ def ipa_head_major_perm(heads: int, dk: int, device=None) -> torch.Tensor:
     """Row permutation of the fused projection weight [q | k | v | q_pt | k_pt | v_pt] (block-major, the reference's
     parameter order) into head-major order: head h owns the contiguous record [q dk | k dk | v dk | qp 12 | kp 12 | vp 24]."""
     hd = heads * dk
-    ar = lambda n: torch.arange(n, device=device)
+    ar = lambda n: torch.arange(n)           # built on the host: 6*H tiny device launches otherwise
     idx = []
     for h in range(heads):
         idx += [h * dk + ar(dk), hd + h * dk + ar(dk), 2 * hd + h * dk + ar(dk), 3 * hd + h * 12 + ar(12),
                 3 * hd + 12 * heads + h * 12 + ar(12), 3 * hd + 24 * heads + h * 24 + ar(24)]
-    return torch.cat(idx)
+    return torch.cat(idx).to(device) if device is not None else torch.cat(idx)
 
 
 def ipa_shape(batch: int, length: int, heads: int, dk: int, pair_batch: int, head_major: bool) -> L.IpaShape:

@@ -111,10 +111,18 @@ def kernel_rooflines(step_fn, L: int, B: int):
     sampling step is the IPA attention kernel; its tensor-eligible algorithmic work is
     4608 * L^2 flop per sample per launch (QK^T + P.V scalar/point/pair)."""
     pk = measured_peaks()
-    with _Hook("ipa_attention_fwd") as h, _Hook("ipa_attention_tc_fwd") as h2:
-        step_fn()
-        ms, n = h.mean_ms()
-        ms2, n2 = h2.mean_ms()
+    prev = os.environ.get("SE3DIFF_B200_CUDA_GRAPH")
+    os.environ["SE3DIFF_B200_CUDA_GRAPH"] = "0"      # the event hooks live in the eager launch path
+    try:
+        with _Hook("ipa_attention_fwd") as h, _Hook("ipa_attention_tc_fwd") as h2:
+            step_fn()
+            ms, n = h.mean_ms()
+            ms2, n2 = h2.mean_ms()
+    finally:
+        if prev is None:
+            os.environ.pop("SE3DIFF_B200_CUDA_GRAPH", None)
+        else:
+            os.environ["SE3DIFF_B200_CUDA_GRAPH"] = prev
     edition = "fp32 SIMT"
     if n2 > n:
         ms, n, edition = ms2, n2, "tcgen05 two-pass"
