@@ -250,10 +250,15 @@ int se3_ipa_attention_fwd(const float* proj, const float* rot, const float* tran
                           float scalar_weight, float* out, const se3_ipa_shape* h_shape, int flags,
                           se3_stream_t stream);
 
-/* Tensor-core edition of the same operator (tcgen05.mma + TMEM, bf16 operands, fp32 accumulation): two
- * passes, see se3diff_b200/csrc/ipa_tc.cu.  Requirements: dk = 16, shared pair tensors (pair_batch = 1),
- * L <= 256, head-major projection rows (off_q..off_vp = 0,16,32,48,60,72 and all head strides 96).  Differences
- * from se3_ipa_attention_fwd:
+/* Tensor-core edition of the same operator (tcgen05.mma + TMEM, bf16 operands, fp32 accumulation): two passes, see
+ * se3diff_b200/csrc/ipa_tc.cu.  Requirements: dk = 16, 4 / 8 points, shared pair tensors (pair_batch = 1), L <= 256.
+ * The projection (structure_module.py:131-135) is delivered as TWO head-major matrices, which the bf16 score network
+ * produces with two GEMMs over row-permuted slices of the fused projection weight:
+ *   scalars_bf16 : bf16 [B*L][scalar_stride], head h owns elements [h*48, h*48+48) = q 16 | k 16 | v 16; the q block
+ *                  must already carry the factor scalar_weight * log2(e) (folded into the weight rows by the caller).
+ *                  Each 16-byte piece is one chunk of a UMMA operand and is copied verbatim (cp.async), no conversion.
+ *   points       : fp32 [B*L][point_stride], head h owns [h*48, h*48+48) = q_pts 12 | k_pts 12 | v_pts 24 (local frame)
+ * Other differences from se3_ipa_attention_fwd:
  *   pair_bias_packed  : TRANSPOSED bf16 [H][L (key j)][round_up(L,8) (query i)] = pair_weight*pair_bias(x2d), zero padded;
  *                       the (head, query-tile) slab is fetched by TMA into shared memory
  *   pair_value_packed : bf16 [L][H][Lp/8][16][8] with Lp = round_up(L,16): pair_value[i, j, h*16+c] stored at
@@ -262,12 +267,14 @@ int se3_ipa_attention_fwd(const float* proj, const float* rot, const float* tran
  *   out               : fp32 or bf16 (out_is_bf16) concat layout
  *   p_workspace / inv_workspace : scratch of the sizes reported by se3_ipa_tc_workspace_bytes (un-normalised probabilities,
  *                       bf16 in UMMA tile layout [H][L][round_up(B,128)/128][Lp/8][128][8], and 1/rowsum fp32
- *                       [H][L][round_up(B,128)]) */
+ *                       [H][L][round_up(B,128)])
+ * Of h_shape only batch, len, heads, dk, pq, pv, pair_batch are read. */
 int64_t se3_ipa_tc_workspace_bytes(const se3_ipa_shape* h_shape, int64_t* p_bytes, int64_t* inv_bytes);
-int se3_ipa_attention_tc_fwd(const float* proj, const float* rot, const float* trans, const void* pair_bias_packed,
-                             const void* pair_value_packed, const float* key_bias, const float* head_weight,
-                             float scalar_weight, void* out, int out_is_bf16, void* p_workspace, float* inv_workspace,
-                             const se3_ipa_shape* h_shape, se3_stream_t stream);
+int se3_ipa_attention_tc_fwd(const void* scalars_bf16, int64_t scalar_stride, const float* points, int64_t point_stride,
+                             const float* rot, const float* trans, const void* pair_bias_packed,
+                             const void* pair_value_packed, const float* key_bias, const float* head_weight, void* out,
+                             int out_is_bf16, void* p_workspace, float* inv_workspace, const se3_ipa_shape* h_shape,
+                             se3_stream_t stream);
 
 /* Fused residual update + pre-LayerNorm of the next block (bf16 throughput mode of the score network):
  *   x[rows,dim] += y[rows,dim] + bias[dim]      (y, bias optional: NULL skips the update; structure_module.py:247-248)

@@ -47,3 +47,11 @@ def ref(proj, rot, trans, pair_bias, pair_value, hw, B, Lm, dt=torch.float64):
     return torch.cat([o_s, o_pl.reshape(B, Lm, -1), o_pair, o_n], -1).reshape(B * Lm, -1)
 
 
+
+
+def split(proj):
+    """(bf16 scalar records with pre-scaled q, fp32 point records) of se3_ipa_attention_tc_fwd."""
+    rows_s, rows_p, qpos = (i.to(proj.device) for i in ops.ipa_split_perms(H, dk))
+    sc = proj[:, rows_s].clone()
+    sc[:, qpos] *= (1 / math.sqrt(3 * dk)) * 1.4426950408889634
+    return sc.to(torch.bfloat16).contiguous(), proj[:, rows_p].contiguous()

@@ -2,13 +2,14 @@
 import sys, os, math, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
-from debug_ipa_tc_common import make, head_major, ops, dev, H
+from debug_ipa_tc_common import make, head_major, split, ops, dev, H
 from se3diff_b200 import _lib
 B, Lm = 256, 84
 proj, rot, trans, pb, pv, hw, shape = make(B, Lm)
-ws = ops.ipa_tc_workspace(shape, dev); pvp = ops.ipa_tc_pack_pair_value(pv, H); pbt = ops.ipa_tc_pack_pair_bias(pb.permute(0, 2, 3, 1)); proj_hm, shape_hm = head_major(proj, shape)
+ws = ops.ipa_tc_workspace(shape, dev); pvp = ops.ipa_tc_pack_pair_value(pv, H); pbt = ops.ipa_tc_pack_pair_bias(pb.permute(0, 2, 3, 1))
 out = torch.empty(B * Lm, 2048, dtype=torch.bfloat16, device=dev)
-run = lambda: ops.ipa_attention_tc_fwd(proj_hm, rot, trans, pbt, pvp, None, hw, 1 / math.sqrt(48), shape_hm, ws, out=out)
+sc_, pt_ = split(proj)
+run = lambda: ops.ipa_attention_tc_fwd(sc_, pt_, rot, trans, pbt, pvp, None, hw, shape, ws, out=out)
 for _ in range(3): run()
 buf = torch.zeros(B * H * 16, dtype=torch.int64, device=dev)
 lib = _lib.lib(); lib.se3_debug_set_phase_buffer.argtypes = [C.c_void_p]; lib.se3_debug_set_phase_buffer.restype = None

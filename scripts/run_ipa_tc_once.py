@@ -2,12 +2,13 @@
 import sys, os, math
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
-from debug_ipa_tc_common import make, head_major, ops, dev, H
+from debug_ipa_tc_common import make, head_major, split, ops, dev, H
 B, Lm = int(os.environ.get("IPA_B", 256)), int(os.environ.get("IPA_L", 84))
 proj, rot, trans, pb, pv, hw, shape = make(B, Lm)
-ws = ops.ipa_tc_workspace(shape, dev); pvp = ops.ipa_tc_pack_pair_value(pv, H); pbt = ops.ipa_tc_pack_pair_bias(pb.permute(0, 2, 3, 1)); proj_hm, shape_hm = head_major(proj, shape)
+ws = ops.ipa_tc_workspace(shape, dev); pvp = ops.ipa_tc_pack_pair_value(pv, H); pbt = ops.ipa_tc_pack_pair_bias(pb.permute(0, 2, 3, 1))
 out = torch.empty(B * Lm, 2048, dtype=torch.bfloat16, device=dev)
+sc_, pt_ = split(proj)
 for _ in range(3):
-    ops.ipa_attention_tc_fwd(proj_hm, rot, trans, pbt, pvp, None, hw, 1 / math.sqrt(48), shape_hm, ws, out=out)
+    ops.ipa_attention_tc_fwd(sc_, pt_, rot, trans, pbt, pvp, None, hw, shape, ws, out=out)
 torch.cuda.synchronize()
 print("ok", float(out.float().abs().mean()))

@@ -9,8 +9,9 @@
 //   SIMT   one thread per TMEM lane (= query row): S += head_w * sum_p |Qp_i - Kp_j| + pair_bias + key_bias
 //          (the un-squared norm of structure_module.py:170 is not a contraction: 128 sqrt per (i,j), MUFU),
 //          logits parked back in TMEM, row max, P = exp2(l - max) -> bf16 -> shared memory (A operand of
-//          MMA 2) and -> global P[h][i][b][Lp] for pass 2, 1/rowsum -> inv[h][i][b]
-//   MMA 2  O[128 x 64] = P.V                       accumulator reuses the TMEM columns of S
+//          MMA 2) and -> global P[h][i][b][Lp] for pass 2
+//   MMA 2  O[128 x 80] = P.[V | 1]                 accumulator reuses the TMEM columns of S; the ones column gives the row
+//          sum of the rounded probabilities -> 1/rowsum -> inv[h][i][b]
 //   SIMT   normalise, undo the re-centring, inverse frame R_i^T(. - T_i), norms; writes the scalar | point |
 //          norm columns of the concat layout (structure_module.py:216)
 // Pass 2, one CTA per (128-sample tile, query i, head h):
@@ -23,6 +24,8 @@
 #include <math_constants.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -31,15 +34,11 @@ using namespace se3;
 namespace {
 
 constexpr int DK = 16, PQ = 4, PV = 8;
-constexpr int NV = DK + 2 * 3 * PV;  // 64 columns of the value operand
+constexpr int NV = 80;  // value operand columns: v 16 | v_pt hi 24 | v_pt lo 24 | ones 1 | 15 x zero (N % 16 == 0)
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-
-template <typename T> __device__ __forceinline__ T to_out(float v);
-template <> __device__ __forceinline__ float to_out<float>(float v) { return v; }
-template <> __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 // N contiguous outputs (N % 8 == 0, destination 16-byte aligned) as 128-bit stores
 template <int N> __device__ __forceinline__ void store_vec(float* dst, const float (&v)[N]) {
@@ -55,11 +54,11 @@ template <int N> __device__ __forceinline__ void store_vec(__nv_bfloat16* dst, c
 
 struct Pass1Smem {
     uint8_t *q, *k, *vt, *p;
-    float *kp, *kb, *frm, *qp;
+    float *kp, *kb, *frm;
 };
-// Shared-memory plan of pass 1.  The P operand (written in the second half of the kernel) can overlay everything
-// that is dead by then -- the bias slab, the key points, the key bias and the K operand -- when those fit into
-// its 256*Lp bytes (`alias`): 40.5 KB per CTA at Lp = 96, i.e. 5 resident CTAs per SM instead of 4.
+// Shared-memory plan of pass 1.  The P operand (written in the second half of the kernel) overlays everything that
+// is dead by then -- the raw point records / bias slab, the key points, the key bias and the K operand -- when those
+// fit into its 256*Lp bytes (`alias`).
 __host__ __device__ inline uint32_t bias_slab_bytes(int L) {
     const int lpi = (L + 7) & ~7;
     return (uint32_t)((L * (lpi < 128 ? lpi : 128) * 2 + 15) & ~15);
@@ -69,33 +68,39 @@ __host__ __device__ inline uint32_t pass1_front_bytes(int L) {   // bias slab an
     return bias_slab_bytes(L) > raw ? bias_slab_bytes(L) : raw;
 }
 __host__ __device__ inline bool pass1_can_alias(int L, int Lp) { return pass1_front_bytes(L) + (uint32_t)Lp * (48 + 4 + 32) <= (uint32_t)Lp * 256; }
-__host__ __device__ inline size_t pass1_frames_bytes(int L) { return (size_t)L * 16 * 4 + 128 * 12 * 4; }  // frames [L][16] | qp [128][12]
 __host__ __device__ inline size_t pass1_smem_bytes(int L, int Lp) {
-    return (pass1_can_alias(L, Lp) ? (size_t)Lp * (128 + 256) + 4096 : (size_t)Lp * (128 + 256 + 48 + 4 + 32) + 4096) + pass1_frames_bytes(L);
+    return (size_t)Lp * (NV * 2 + 256) + 4096 + (pass1_can_alias(L, Lp) ? 0 : (size_t)Lp * (48 + 4 + 32)) + (((size_t)L * 48 + 15) & ~(size_t)15);
 }
 __device__ __forceinline__ Pass1Smem carve1(uint8_t* base, int L, int Lp) {
     Pass1Smem s;
-    s.vt = base;                                 // [Lp/8][8][8][8] bf16, MN-major value operand
-    s.q = s.vt + (size_t)Lp * 128;               // [2][128][16 B]
-    s.p = s.q + 4096;                            // [Lp/8][128][16 B]; the bias slab lives at its start until pass B
+    s.vt = base;                                 // [Lp/8][NV/8][8][8] bf16, MN-major value operand
+    s.q = s.vt + (size_t)Lp * (NV * 2);          // [2][128][16 B]
+    s.p = s.q + 4096;                            // [Lp/8][128][16 B]; raw points, then the bias slab, live at its start until pass B
     uint8_t* rest = pass1_can_alias(L, Lp) ? s.p + pass1_front_bytes(L) : s.p + (size_t)Lp * 256;
-    s.kp = reinterpret_cast<float*>(rest);       // [Lp][12] fp32
+    s.kp = reinterpret_cast<float*>(rest);       // [Lp/2][12][2] fp32: negated global key points, interleaved by key pair
     s.kb = s.kp + Lp * 12;                       // [Lp]
     s.k = reinterpret_cast<uint8_t*>(s.kb + Lp); // [2][Lp][16 B]
     uint8_t* tail = pass1_can_alias(L, Lp) ? s.p + (size_t)Lp * 256 : s.k + (size_t)Lp * 32;
-    s.qp = reinterpret_cast<float*>(tail);       // [128][12] global-frame query points of the tile
-    s.frm = s.qp + 128 * 12;                     // [L][16]: R rows padded to 4 floats | T
+    s.frm = reinterpret_cast<float*>(tail);      // rotations [L][9] then translations [L][3], as they lie in global memory
     return s;
+}
+
+// global = R.local + T for one point
+__device__ __forceinline__ void to_global(const float (&R)[9], const float (&T)[3], float x, float y, float z, float& gx, float& gy, float& gz) {
+    gx = R[0] * x + R[1] * y + R[2] * z + T[0];
+    gy = R[3] * x + R[4] * y + R[5] * z + T[1];
+    gz = R[6] * x + R[7] * y + R[8] * z + T[2];
 }
 
 template <typename OutT>
 __global__ void __launch_bounds__(128, 4)
-k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, const float* __restrict__ trans,
-               const __nv_bfloat16* __restrict__ pair_bias_t, const float* __restrict__ key_bias, const float* __restrict__ head_weight,
-               float scalar_weight, OutT* __restrict__ out, __nv_bfloat16* __restrict__ pbuf, float* __restrict__ inv_sum,
-               const se3_ipa_shape sh, int Lp, int Bpad, int tmem_cols, long long* __restrict__ dbg) {
+k_ipa_tc_pass1(const __nv_bfloat16* __restrict__ scal, int scal_stride, const float* __restrict__ pts, int pts_stride,
+               const float* __restrict__ rot, const float* __restrict__ trans, const __nv_bfloat16* __restrict__ pair_bias_t,
+               const float* __restrict__ key_bias, const float* __restrict__ head_weight, OutT* __restrict__ out,
+               __nv_bfloat16* __restrict__ pbuf, float* __restrict__ inv_sum, const se3_ipa_shape sh, int Lp, int Bpad, int tmem_cols,
+               long long* __restrict__ dbg) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ uint64_t bar, bar_bias;
+    __shared__ uint64_t bar, bar_bias, bar_in;
     // optional phase timestamps: 16 clock64 slots per CTA, written by thread 0 (scripts/ipa_phase_times.py)
 #define SE3_STAMP(k) do { if (dbg && threadIdx.x == 0) dbg[(((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (k)] = clock64(); } while (0)
     SE3_STAMP(0);
@@ -113,160 +118,169 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
     const int Lpi = (L + 7) & ~7;                         // row pitch of the transposed bias matrix
     const int ncol = min(128, Lpi - q0);                  // multiple of 8 -> 16-byte rows
     const __nv_bfloat16* s_bias = reinterpret_cast<const __nv_bfloat16*>(s.p);
-    const bool late_alloc = (tmem_cols & 1) != 0;   // experiment switch folded into the column count
-    tmem_cols &= ~1;
-    if (!late_alloc && warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)tmem_cols);
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)tmem_cols);
     SE3_STAMP(8);
-    if (tid == 0) {
-        tc::mbar_init(&bar, 1);
-        tc::mbar_init(&bar_bias, 1);
-        tc::mbar_fence_init();
+    // ---- staging: everything is an asynchronous copy -------------------------------------------------------------
+    // points : fp32 records [qp 12 | kp 12 | vp 24] of this head, one 192-byte TMA bulk copy per residue, parked raw in
+    //          the (still unused) P region;  frames: the sample's [L][9] and [L][3] blocks, two bulk copies.  Warp 0
+    //          issues them and is the only one to touch their mbarrier before the CTA barrier below.
+    // scalars: bf16 head-major records [q 16 | k 16 | v 16] (q already carries scalar_weight * log2 e) = six 16-byte
+    //          pieces per residue that ARE chunks of the UMMA operands: copied verbatim by warps 1-3 (cp.async), each
+    //          thread owning one fixed piece column and walking residues with a constant stride (no div/mod in the loop)
+    float* s_raw = reinterpret_cast<float*>(s.p);          // [L][48] raw local points
+    float* s_rot = s.frm;
+    float* s_trn = s.frm + L * 9;
+    if (warp == 0) {
+        if (tid == 0) {
+            tc::mbar_init(&bar, 1);
+            tc::mbar_init(&bar_bias, 1);
+            tc::mbar_init(&bar_in, 1);
+            tc::mbar_fence_init();
+        }
+        __syncwarp();
+        const float* rsrc = rot + (int64_t)b * L * 9;
+        const float* tsrc = trans + (int64_t)b * L * 3;
+        const bool bulk_frames = ((L & 3) == 0) && ((reinterpret_cast<uintptr_t>(rot) | reinterpret_cast<uintptr_t>(trans)) & 15) == 0;
+        if (tid == 0) {
+            tc::mbar_expect_tx(&bar_in, (uint32_t)(L * 192 + (bulk_frames ? L * 48 : 0)));
+            if (bulk_frames) {
+                tc::tma_bulk_g2s(s_rot, rsrc, (uint32_t)(L * 36), &bar_in);
+                tc::tma_bulk_g2s(s_trn, tsrc, (uint32_t)(L * 12), &bar_in);
+            }
+        }
+        __syncwarp();
+        const float* g = pts + ((int64_t)b * L + tid) * pts_stride + h * 48;
+        for (int row = tid; row < L; row += 32, g += (int64_t)32 * pts_stride) tc::tma_bulk_g2s(s_raw + row * 48, g, 192u, &bar_in);
+        if (!bulk_frames) {                                // unaligned sample block: 4-byte asynchronous copies
+            for (int idx = tid; idx < L * 9; idx += 32) tc::cp_async4(s_rot + idx, rsrc + idx);
+            for (int idx = tid; idx < L * 3; idx += 32) tc::cp_async4(s_trn + idx, tsrc + idx);
+        }
+    } else {
+        const int t = tid - 32, r0 = t / 6, pc = t - r0 * 6, blk = pc >> 1, half = pc & 1;
+        const uint32_t dbase = blk == 0 ? tc::smem_u32(s.q) + (uint32_t)(half * 2048 - q0 * 16)
+                             : blk == 1 ? tc::smem_u32(s.k) + (uint32_t)(half * Lp * 16) : tc::smem_u32(s.vt) + (uint32_t)(half * 128);
+        const char* g = reinterpret_cast<const char*>(scal + ((int64_t)b * L + r0) * scal_stride + h * 48) + pc * 16;
+        const int64_t gstep = (int64_t)16 * scal_stride * 2;
+        for (int row = r0; row < L; row += 16, g += gstep) {
+            const uint32_t off = blk == 2 ? (uint32_t)((row >> 3) * (NV * 16) + (row & 7) * 16) : (uint32_t)row * 16u;
+            if (blk != 0 || (unsigned)(row - q0) < 128u) tc::cp_async16_s(dbase + off, g);
+        }
     }
-
-    // ---- cooperative staging ---------------------------------------------------------------------------------
-    // The projection rows are HEAD-MAJOR: head h of residue j owns one contiguous 384-byte record
-    // [q 16 | k 16 | v 16 | qp 12 | kp 12 | vp 24] fp32.  The whole (b, h) slab is fetched as 24 float4 per residue with
-    // consecutive lanes on consecutive 16-byte pieces (3 full lines per residue: ~4x fewer L1 wavefronts than
-    // per-block strided loads, which bounded this phase), 8 independent loads in flight per thread.  Scalar pieces are
-    // converted and written straight into the UMMA operands; point pieces are parked raw in the (still unused) P
-    // region and transformed to the global frame after the barrier that also publishes the frames.
-    const float sc = scalar_weight * kLog2e;
-    float* s_raw = reinterpret_cast<float*>(s.p);          // [L][48] raw local points (qp 12 | kp 12 | vp 24)
+    tc::cp_async_commit();
+    for (int j = tid; j < Lp; j += 128) s.kb[j] = (j < L) ? (key_bias ? key_bias[(int64_t)b * L + j] * kLog2e : 0.f) : -CUDART_INF_F;
+    // zero padding: key rows L..Lp of K and V^T, query rows beyond the sequence end
+    for (int idx = tid; idx < (Lp - L) * (2 + NV / 8); idx += 128) {
+        const int row = L + idx / (2 + NV / 8), piece = idx % (2 + NV / 8);
+        if (piece < 2) *reinterpret_cast<uint4*>(s.k + ((size_t)piece * Lp + row) * 16) = make_uint4(0, 0, 0, 0);
+        else *reinterpret_cast<uint4*>(s.vt + (size_t)(row >> 3) * (NV * 16) + (size_t)(piece - 2) * 128 + (size_t)(row & 7) * 16) = make_uint4(0, 0, 0, 0);
+    }
     {
-        const float* slab = proj + (int64_t)b * L * sh.proj_stride + h * 96;
-        const int nunits = L * 12;                         // 12 float4 of scalars + 12 float4 of points per residue
-        for (int base = 0; base < nunits; base += 128 * 4) {
-            float4 sv[4], pv4[4];
-            int rows[4], cs[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {                  // 8 independent 16-byte loads in flight per thread
-                const int idx = base + u * 128 + tid;
-                rows[u] = idx / 12;
-                cs[u] = idx - rows[u] * 12;
-                sv[u] = pv4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (idx < nunits) {
-                    const float4* rec = reinterpret_cast<const float4*>(slab + (int64_t)rows[u] * sh.proj_stride);
-                    sv[u] = __ldg(rec + cs[u]);
-                    pv4[u] = __ldg(rec + 12 + cs[u]);
-                }
-            }
-            if (base == 0) {                               // frames: contiguous [L,9] / [L,3] blocks, coalesced
-                for (int idx = tid; idx < L * 9; idx += 128) {       // frames as [L][R row0 | row1 | row2 | T], 4 floats each
-                    const int j = idx / 9, e = idx - j * 9;
-                    s.frm[j * 16 + (e / 3) * 4 + (e % 3)] = __ldg(rot + (int64_t)b * L * 9 + idx);
-                }
-                for (int idx = tid; idx < L * 3; idx += 128) s.frm[(idx / 3) * 16 + 12 + (idx % 3)] = __ldg(trans + (int64_t)b * L * 3 + idx);
-                for (int j = tid; j < Lp; j += 128) s.kb[j] = (j < L) ? (key_bias ? key_bias[(int64_t)b * L + j] * kLog2e : 0.f) : -CUDART_INF_F;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int idx = base + u * 128 + tid, row = rows[u], c4 = cs[u];
-                if (idx < nunits) {
-                    *reinterpret_cast<float4*>(s_raw + row * 48 + c4 * 4) = pv4[u];
-                    // branch-free routing of the scalar piece: block 0 = q (scaled, tile rows only), 1 = k, 2 = v
-                    const int blk = c4 >> 2, qt = c4 & 3, r = row - q0;
-                    const float f = blk == 0 ? sc : 1.0f;
-                    uint8_t* dq = s.q + ((size_t)(qt >> 1) * 128 + (r & 127)) * 16;
-                    uint8_t* dk = s.k + ((size_t)(qt >> 1) * Lp + row) * 16;
-                    uint8_t* dv = s.vt + (size_t)(row >> 3) * (NV * 16) + (size_t)(qt >> 1) * 128 + (size_t)(row & 7) * 16;
-                    uint8_t* dst = (blk == 0 ? dq : (blk == 1 ? dk : dv)) + (qt & 1) * 8;
-                    if (blk != 0 || (r >= 0 && r < 128))
-                        *reinterpret_cast<uint2*>(dst) = make_uint2(tc::pack_bf16(sv[u].x * f, sv[u].y * f), tc::pack_bf16(sv[u].z * f, sv[u].w * f));
-                }
-            }
-        }
-        // zero padding: key rows L..Lp of K and V^T, query rows beyond the sequence end
-        for (int idx = tid; idx < (Lp - L) * 10; idx += 128) {
-            const int row = L + idx / 10, piece = idx % 10;
-            if (piece < 2) *reinterpret_cast<uint4*>(s.k + ((size_t)piece * Lp + row) * 16) = make_uint4(0, 0, 0, 0);
-            else *reinterpret_cast<uint4*>(s.vt + (size_t)(row >> 3) * (NV * 16) + (size_t)(piece - 2) * 128 + (size_t)(row & 7) * 16) = make_uint4(0, 0, 0, 0);
-        }
         const int nq = min(128, L - q0);
         for (int idx = tid; idx < (128 - nq) * 2; idx += 128)
             *reinterpret_cast<uint4*>(s.q + ((size_t)(idx & 1) * 128 + nq + (idx >> 1)) * 16) = make_uint4(0, 0, 0, 0);
     }
     SE3_STAMP(9);
+    tc::cp_async_wait<0>();
+    if (warp == 0) tc::mbar_wait(&bar_in, 0);
     SE3_STAMP(10);
-    __syncthreads();   // frames and raw points are in shared memory
+    __syncthreads();   // frames, raw points and the scalar operands are in shared memory
     SE3_STAMP(11);
-    const float cx = s.frm[12], cy = s.frm[13], cz = s.frm[14];
-    {
-        const int p4 = tid & 3, p8 = tid & 7;
-#pragma unroll 4
-        for (int row = tid >> 2; row < Lp; row += 32) {          // key points -> global frame, negated, pair-interleaved
-            float g[3] = {0.f, 0.f, 0.f};
-            if (row < L) {
-                const float* pl = s_raw + row * 48 + 12 + p4 * 3;
-                const float4* F4 = reinterpret_cast<const float4*>(s.frm + row * 16);
-                const float4 r0 = F4[0], r1 = F4[1], r2 = F4[2], tt = F4[3];
-                const float x = pl[0], y = pl[1], z = pl[2];
-                g[0] = r0.x * x + r0.y * y + r0.z * z + tt.x; g[1] = r1.x * x + r1.y * y + r1.z * z + tt.y; g[2] = r2.x * x + r2.y * y + r2.z * z + tt.z;
-            }
-            float* dstp = s.kp + (size_t)(row >> 1) * 24 + (row & 1) + p4 * 6;
-            dstp[0] = -g[0]; dstp[2] = -g[1]; dstp[4] = -g[2];
-        }
+
+    // ---- local -> global frame, one thread per residue -------------------------------------------------------------
+    // key points  : negated, interleaved by key pair ([pair][component][2]) so that pass A forms q + (-k) for two keys
+    //               with one packed add; lanes 2m / 2m+1 swap halves by shuffle and each writes 12 contiguous floats
+    // value points: re-centred on the sample's first residue, split hi + lo bf16 (the fp32 aggregation demanded by
+    //               structure_module.py:193-196 keeps ~16 mantissa bits), written as whole 16-byte operand chunks
+    // ones column : channel 64 of V is 1 for real keys, so MMA 2 also returns the row sum of the ROUNDED probabilities
+    const float cx = s_trn[0], cy = s_trn[1], cz = s_trn[2];
+    for (int base = 0; base < Lp; base += 128) {
+        if (base + warp * 32 >= Lp) break;                 // warp-uniform: the shuffles below need whole warps
+        const int row = base + tid;
+        float nk[12];
 #pragma unroll
-        for (int row = tid >> 2; row < 128; row += 32) {         // query points of the tile -> s.qp[row][12]
-            float g[3] = {0.f, 0.f, 0.f};
-            const int qi = q0 + row;
-            if (qi < L) {
-                const float* pl = s_raw + qi * 48 + p4 * 3;
-                const float4* F4 = reinterpret_cast<const float4*>(s.frm + qi * 16);
-                const float4 r0 = F4[0], r1 = F4[1], r2 = F4[2], tt = F4[3];
-                const float x = pl[0], y = pl[1], z = pl[2];
-                g[0] = r0.x * x + r0.y * y + r0.z * z + tt.x; g[1] = r1.x * x + r1.y * y + r1.z * z + tt.y; g[2] = r2.x * x + r2.y * y + r2.z * z + tt.z;
-            }
-            s.qp[row * 12 + p4 * 3] = g[0]; s.qp[row * 12 + p4 * 3 + 1] = g[1]; s.qp[row * 12 + p4 * 3 + 2] = g[2];
-        }
-#pragma unroll 4
-        for (int row = tid >> 3; row < Lp; row += 16) {          // value points: re-centred, split hi + lo bf16
-            __nv_bfloat16 hi[3], lo[3];
+        for (int c = 0; c < 12; ++c) nk[c] = 0.f;
+        if (row < L) {
+            float R[9], T[3];
 #pragma unroll
-            for (int r = 0; r < 3; ++r) hi[r] = lo[r] = __float2bfloat16_rn(0.f);
-            if (row < L) {
-                const float* pl = s_raw + row * 48 + 24 + p8 * 3;
-                const float4* F4 = reinterpret_cast<const float4*>(s.frm + row * 16);
-                const float4 r0 = F4[0], r1 = F4[1], r2 = F4[2], tt = F4[3];
-                const float x = pl[0], y = pl[1], z = pl[2];
-                const float gv[3] = {r0.x * x + r0.y * y + r0.z * z + (tt.x - cx), r1.x * x + r1.y * y + r1.z * z + (tt.y - cy),
-                                     r2.x * x + r2.y * y + r2.z * z + (tt.z - cz)};
+            for (int c = 0; c < 9; ++c) R[c] = s_rot[row * 9 + c];
 #pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    hi[r] = __float2bfloat16_rn(gv[r]);
-                    lo[r] = __float2bfloat16_rn(gv[r] - __bfloat162float(hi[r]));
+            for (int c = 0; c < 3; ++c) T[c] = s_trn[row * 3 + c];
+            const float4* raw4 = reinterpret_cast<const float4*>(s_raw + row * 48);
+            {
+                const float4 a = raw4[3], bb = raw4[4], c = raw4[5];
+                const float l[12] = {a.x, a.y, a.z, a.w, bb.x, bb.y, bb.z, bb.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    float gx, gy, gz;
+                    to_global(R, T, l[3 * p], l[3 * p + 1], l[3 * p + 2], gx, gy, gz);
+                    nk[3 * p] = -gx; nk[3 * p + 1] = -gy; nk[3 * p + 2] = -gz;
                 }
             }
-            __nv_bfloat16* col = reinterpret_cast<__nv_bfloat16*>(s.vt + (size_t)(row >> 3) * (NV * 16) + (size_t)(row & 7) * 16);
+            T[0] -= cx; T[1] -= cy; T[2] -= cz;
+            uint32_t hi[12], lo[12];
+            float gv[24];
+            {
+                float l[24];
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const int ch = DK + p8 * 3 + r, cl = DK + 3 * PV + p8 * 3 + r;   // channel c: group c/8 (128 B apart), c%8 in the piece
-                col[(ch >> 3) * 64 + (ch & 7)] = hi[r];
-                col[(cl >> 3) * 64 + (cl & 7)] = lo[r];
+                for (int c6 = 0; c6 < 6; ++c6) {
+                    const float4 v = raw4[6 + c6];
+                    l[4 * c6] = v.x; l[4 * c6 + 1] = v.y; l[4 * c6 + 2] = v.z; l[4 * c6 + 3] = v.w;
+                }
+#pragma unroll
+                for (int p = 0; p < 8; ++p) to_global(R, T, l[3 * p], l[3 * p + 1], l[3 * p + 2], gv[3 * p], gv[3 * p + 1], gv[3 * p + 2]);
+            }
+#pragma unroll
+            for (int c = 0; c < 12; ++c) {
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(gv[2 * c], gv[2 * c + 1]);
+                hi[c] = *reinterpret_cast<const uint32_t*>(&hh);
+                lo[c] = tc::pack_bf16(gv[2 * c] - __bfloat162float(hh.x), gv[2 * c + 1] - __bfloat162float(hh.y));
+            }
+            uint8_t* col = s.vt + (size_t)(row >> 3) * (NV * 16) + (size_t)(row & 7) * 16;   // chunk g of this row at + g*128
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                *reinterpret_cast<uint4*>(col + (2 + g) * 128) = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+                *reinterpret_cast<uint4*>(col + (5 + g) * 128) = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+            }
+            *reinterpret_cast<uint4*>(col + 8 * 128) = make_uint4(0x00003F80u, 0, 0, 0);     // bf16 1.0 in channel 64
+            *reinterpret_cast<uint4*>(col + 9 * 128) = make_uint4(0, 0, 0, 0);
+        }
+        {
+            const bool odd = tid & 1;
+            float mine[6], recv[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                mine[c] = odd ? nk[c + 6] : nk[c];
+                recv[c] = __shfl_xor_sync(0xffffffffu, odd ? nk[c] : nk[c + 6], 1);
+            }
+            if (row < Lp) {
+                float4* dst = reinterpret_cast<float4*>(s.kp + (size_t)(row >> 1) * 24 + (odd ? 12 : 0));
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    dst[c] = odd ? make_float4(recv[2 * c], mine[2 * c], recv[2 * c + 1], mine[2 * c + 1])
+                                 : make_float4(mine[2 * c], recv[2 * c], mine[2 * c + 1], recv[2 * c + 1]);
             }
         }
     }
+    float qp[12], Ri[9], Ti[3];
+    {
+        const int qi = row_ok ? i : 0;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) Ri[c] = s_rot[qi * 9 + c];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Ti[c] = s_trn[qi * 3 + c];
+        const float4* raw4 = reinterpret_cast<const float4*>(s_raw + qi * 48);
+        const float4 a = raw4[0], bb = raw4[1], c = raw4[2];
+        const float l[12] = {a.x, a.y, a.z, a.w, bb.x, bb.y, bb.z, bb.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int p = 0; p < 4; ++p) to_global(Ri, Ti, l[3 * p], l[3 * p + 1], l[3 * p + 2], qp[3 * p], qp[3 * p + 1], qp[3 * p + 2]);
+    }
     SE3_STAMP(12);
     SE3_STAMP(1);
-    // TMEM is claimed only now: staging of this CTA overlapped with the tensor-memory phase of its neighbours
-    if (late_alloc && warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)tmem_cols);
     tc::fence_async_smem();
     tc::fence_before();
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem = tmem_slot;
-    float qp[12], Ri[9], Ti[3];
-    {
-        const int qi = row_ok ? i : 0;
-#pragma unroll
-        for (int c4 = 0; c4 < 3; ++c4) {
-            const float4 v = reinterpret_cast<const float4*>(s.qp + tid * 12)[c4];
-            qp[c4 * 4] = v.x; qp[c4 * 4 + 1] = v.y; qp[c4 * 4 + 2] = v.z; qp[c4 * 4 + 3] = v.w;
-        }
-        const float4* F4 = reinterpret_cast<const float4*>(s.frm + qi * 16);
-        const float4 r0 = F4[0], r1 = F4[1], r2 = F4[2], tt = F4[3];
-        Ri[0] = r0.x; Ri[1] = r0.y; Ri[2] = r0.z; Ri[3] = r1.x; Ri[4] = r1.y; Ri[5] = r1.z; Ri[6] = r2.x; Ri[7] = r2.y; Ri[8] = r2.z;
-        Ti[0] = tt.x; Ti[1] = tt.y; Ti[2] = tt.z;
-    }
 
     // ---- MMA 1: S = Q.K^T -----------------------------------------------------------------------------------
     if (tid == 0) {
@@ -288,7 +302,7 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
 
     const int nchunk = Lp / 16;
     const uint32_t lane_base = (uint32_t)warp * 32;
-    float inv = 0.f, m = -CUDART_INF_F;
+    float m = -CUDART_INF_F;
     tc::mbar_wait(&bar_bias, 0);
     if (warp_ok) {
         // ---- pass A: logits (log2 domain) -> TMEM, row max -------------------------------------------------
@@ -300,13 +314,18 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
 #pragma unroll
         for (int k = 0; k < 12; ++k) q2[k] = make_float2(qp[k], qp[k]);
         const float2 hw2 = make_float2(hw, hw), l2e2 = make_float2(kLog2e, kLog2e);
-        for (int c = 0; c < nchunk; ++c) {
+        auto chunk = [&](const int c, auto partial_tag) {
+            constexpr bool kPartial = decltype(partial_tag)::value;   // the last chunk when L % 16 != 0: skip padding keys
             uint32_t r[16];
             tc::tmem_ld16(tc::tmem_addr(tmem, lane_base, c * 16), r);
             tc::tmem_wait_ld();
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int j = c * 16 + 2 * u;
+                if (kPartial && j >= L) {                  // padding keys (warp-uniform): no distance work
+                    r[2 * u] = r[2 * u + 1] = __float_as_uint(-CUDART_INF_F);
+                    continue;
+                }
                 const float4* kp4 = reinterpret_cast<const float4*>(s.kp + j * 12);   // pair block: 24 floats
                 float2 ds = make_float2(0.f, 0.f);
 #pragma unroll
@@ -325,8 +344,8 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
                     d2 = __ffma2_rn(dz, dz, d2);
                     ds = __fadd2_rn(ds, make_float2(fast_sqrt(d2.x), fast_sqrt(d2.y)));
                 }
-                const float pb0 = (j < L) ? __bfloat162float(bias_col[j * ncol]) : 0.f;
-                const float pb1 = (j + 1 < L) ? __bfloat162float(bias_col[(j + 1) * ncol]) : 0.f;
+                const float pb0 = __bfloat162float(bias_col[j * ncol]);
+                const float pb1 = (!kPartial || j + 1 < L) ? __bfloat162float(bias_col[(j + 1) * ncol]) : 0.f;
                 const float2 kb2 = *reinterpret_cast<const float2*>(s.kb + j);
                 float2 l2 = __ffma2_rn(hw2, ds, make_float2(__uint_as_float(r[2 * u]), __uint_as_float(r[2 * u + 1])));
                 l2 = __fadd2_rn(__ffma2_rn(make_float2(pb0, pb1), l2e2, l2), kb2);
@@ -335,7 +354,10 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
                 r[2 * u + 1] = __float_as_uint(l2.y);
             }
             tc::tmem_st16(tc::tmem_addr(tmem, lane_base, c * 16), r);
-        }
+        };
+        const int nfull = L / 16;
+        for (int c = 0; c < nfull; ++c) chunk(c, std::false_type{});
+        if (nfull < nchunk) chunk(nfull, std::true_type{});
         tc::tmem_wait_st();
         if (m == -CUDART_INF_F) m = 0.f;
     }
@@ -343,7 +365,6 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
     SE3_STAMP(3);
     if (warp_ok) {
         // ---- pass B: P = exp2(l - m) -> bf16 -> smem (A operand) + global (pass 2) ------------------------------
-        float sum = 0.f;
         // P tile of (h, i, b/128) in UMMA layout: [j/8][b%128][j%8]
         uint8_t* ptile = reinterpret_cast<uint8_t*>(pbuf) + ((((int64_t)h * L + (row_ok ? i : 0)) * (Bpad / 128) + (b >> 7)) * Lp) * 256 + (size_t)(b & 127) * 16;
         for (int c = 0; c < nchunk; ++c) {
@@ -353,9 +374,7 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const float p0 = fast_ex2(__uint_as_float(r[2 * u]) - m), p1 = fast_ex2(__uint_as_float(r[2 * u + 1]) - m);
-                const __nv_bfloat162 v = __floats2bfloat162_rn(p0, p1);
-                sum += __bfloat162float(v.x) + __bfloat162float(v.y);
-                pk[u] = *reinterpret_cast<const uint32_t*>(&v);
+                pk[u] = tc::pack_bf16(p0, p1);
             }
             const uint4 lo = make_uint4(pk[0], pk[1], pk[2], pk[3]), hi = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             *reinterpret_cast<uint4*>(s.p + ((size_t)(2 * c) * 128 + tid) * 16) = lo;
@@ -365,8 +384,6 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
                 *reinterpret_cast<uint4*>(ptile + (size_t)(2 * c + 1) * 2048) = hi;
             }
         }
-        inv = 1.0f / sum;
-        if (row_ok) inv_sum[((int64_t)h * L + i) * Bpad + b] = inv;
     }
     tc::fence_async_smem();
     tc::fence_before();
@@ -397,6 +414,10 @@ k_ipa_tc_pass1(const float* __restrict__ proj, const float* __restrict__ rot, co
             for (int u = 0; u < 16; ++u) o[c * 16 + u] = __uint_as_float(r[u]);
         }
         if (row_ok) {
+            // column 64 = sum_j P_ij * 1 over the ROUNDED probabilities: the weights the tensor core applied sum to one
+            // exactly, which the translation-covariant point aggregate needs
+            const float inv = 1.0f / o[64];
+            inv_sum[((int64_t)h * L + i) * Bpad + b] = inv;
             const int HD = H * DK;
             OutT* orow = out + ((int64_t)b * L + i) * (int64_t)(2 * HD + 4 * H * PV);
             float sc[DK], pl[3 * PV], nr[PV];
@@ -483,26 +504,24 @@ k_ipa_tc_pass2(const __nv_bfloat16* __restrict__ pbuf, const float* __restrict__
 long long* g_phase_dbg = nullptr;  // set by se3_debug_set_phase_buffer
 
 template <typename OutT>
-int launch_tc(const float* proj, const float* rot, const float* trans, const __nv_bfloat16* pair_bias, const __nv_bfloat16* pvc,
-              const float* key_bias, const float* head_weight, float scalar_weight, OutT* out, __nv_bfloat16* pbuf, float* inv_sum,
-              const se3_ipa_shape& sh, int Lp, int Bpad, cudaStream_t st) {
+int launch_tc(const __nv_bfloat16* scal, int scal_stride, const float* pts, int pts_stride, const float* rot, const float* trans,
+              const __nv_bfloat16* pair_bias, const __nv_bfloat16* pvc, const float* key_bias, const float* head_weight, OutT* out,
+              __nv_bfloat16* pbuf, float* inv_sum, const se3_ipa_shape& sh, int Lp, int Bpad, cudaStream_t st) {
     const int L = sh.len;
-    int cols = 64;
+    int cols = 128;                                        // S needs Lp columns, the second accumulator NV = 80
     while (cols < Lp) cols *= 2;
     size_t smem1 = pass1_smem_bytes(L, Lp);
     {   // tensor memory (512 columns per SM) allows 512/cols resident CTAs; a CTA that is resident but blocked in
         // tcgen05.alloc only steals issue slots, so shared memory is padded to admit exactly that many
-        static const int pad = getenv("SE3_IPA_NO_PAD") ? 0 : 1;
         const size_t per_cta = (size_t)(227 * 1024) / (size_t)(512 / cols) - 1024;
         const size_t floor_bytes = (size_t)(227 * 1024) / (size_t)(512 / cols + 1) + 1;
-        if (pad && smem1 < floor_bytes && floor_bytes <= per_cta) smem1 = floor_bytes;
+        if (smem1 < floor_bytes && floor_bytes <= per_cta) smem1 = floor_bytes;
     }
     auto k1 = k_ipa_tc_pass1<OutT>;
     cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
     if (e != cudaSuccess) { set_error("ipa_tc pass1 smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
     dim3 g1((L + 127) / 128, sh.heads, sh.batch);
-    static const int late = getenv("SE3_IPA_LATE_ALLOC") ? atoi(getenv("SE3_IPA_LATE_ALLOC")) : 0;
-    k1<<<g1, 128, smem1, st>>>(proj, rot, trans, pair_bias, key_bias, head_weight, scalar_weight, out, pbuf, inv_sum, sh, Lp, Bpad, cols | late,
+    k1<<<g1, 128, smem1, st>>>(scal, scal_stride, pts, pts_stride, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, Lp, Bpad, cols,
                                g_phase_dbg);
     count_launch();
     int rc = check_launch("se3_ipa_attention_tc_fwd(pass 1)");
@@ -533,30 +552,33 @@ int64_t se3_ipa_tc_workspace_bytes(const se3_ipa_shape* h_shape, int64_t* p_byte
     return pb + ib;
 }
 
-int se3_ipa_attention_tc_fwd(const float* proj, const float* rot, const float* trans, const void* pair_bias_packed,
-                             const void* pair_value_packed, const float* key_bias, const float* head_weight, float scalar_weight,
-                             void* out, int out_is_bf16, void* p_workspace, float* inv_workspace, const se3_ipa_shape* h_shape,
-                             se3_stream_t stream) {
+int se3_ipa_attention_tc_fwd(const void* scalars_bf16, int64_t scalar_stride, const float* points, int64_t point_stride,
+                             const float* rot, const float* trans, const void* pair_bias_packed, const void* pair_value_packed,
+                             const float* key_bias, const float* head_weight, void* out, int out_is_bf16, void* p_workspace,
+                             float* inv_workspace, const se3_ipa_shape* h_shape, se3_stream_t stream) {
     SE3_REQUIRE(h_shape, "null shape");
     const se3_ipa_shape& sh = *h_shape;
     if (sh.batch == 0 || sh.len == 0) return SE3_OK;
-    SE3_REQUIRE(proj && rot && trans && pair_bias_packed && pair_value_packed && head_weight && out && p_workspace && inv_workspace, "null pointer");
+    SE3_REQUIRE(scalars_bf16 && points && rot && trans && pair_bias_packed && pair_value_packed && head_weight && out && p_workspace && inv_workspace,
+                "null pointer");
     if (sh.dk != DK || sh.pq != PQ || sh.pv != PV || sh.pair_batch != 1 || sh.len > 256 || sh.heads > 65535 || sh.batch > 65535) {
-        set_error("se3_ipa_attention_tc_fwd: needs dk=16, 4/8 points, shared pair tensors, L <= 256 "
-                  "(got dk=%d L=%d H=%d pair_batch=%d); use se3_ipa_attention_fwd", sh.dk, sh.len, sh.heads, sh.pair_batch);
+        set_error("se3_ipa_attention_tc_fwd: needs dk=16, 4/8 points, shared pair tensors, L <= 256 (got dk=%d L=%d H=%d pair_batch=%d); "
+                  "use se3_ipa_attention_fwd", sh.dk, sh.len, sh.heads, sh.pair_batch);
         return SE3_EUNSUPPORTED;
     }
-    SE3_REQUIRE(sh.off_q == 0 && sh.off_k == 16 && sh.off_v == 32 && sh.off_qp == 48 && sh.off_kp == 60 && sh.off_vp == 72 &&
-                sh.hs_scalar == 96 && sh.hs_point == 96 && sh.hs_vpoint == 96,
-                "the tensor-core kernel needs head-major projection rows: [h][q16|k16|v16|qp12|kp12|vp24]");
-    SE3_REQUIRE(sh.proj_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(proj) & 15) == 0, "projection matrix must be 16-byte aligned");
+    SE3_REQUIRE(scalar_stride >= (int64_t)sh.heads * 48 && scalar_stride % 8 == 0 && scalar_stride < (1ll << 28) &&
+                (reinterpret_cast<uintptr_t>(scalars_bf16) & 15) == 0, "scalar records: bf16 [rows][>= H*48], stride a multiple of 8, 16-byte aligned");
+    SE3_REQUIRE(point_stride >= (int64_t)sh.heads * 48 && point_stride % 4 == 0 && point_stride < (1ll << 28) &&
+                (reinterpret_cast<uintptr_t>(points) & 15) == 0, "point records: fp32 [rows][>= H*48], stride a multiple of 4, 16-byte aligned");
     const int Lp = (sh.len + 15) / 16 * 16, Bpad = (sh.batch + 127) / 128 * 128;
     cudaStream_t st = (cudaStream_t)stream;
     if (out_is_bf16)
-        return launch_tc<__nv_bfloat16>(proj, rot, trans, (const __nv_bfloat16*)pair_bias_packed, (const __nv_bfloat16*)pair_value_packed, key_bias, head_weight,
-                                        scalar_weight, (__nv_bfloat16*)out, (__nv_bfloat16*)p_workspace, inv_workspace, sh, Lp, Bpad, st);
-    return launch_tc<float>(proj, rot, trans, (const __nv_bfloat16*)pair_bias_packed, (const __nv_bfloat16*)pair_value_packed, key_bias, head_weight, scalar_weight,
-                            (float*)out, (__nv_bfloat16*)p_workspace, inv_workspace, sh, Lp, Bpad, st);
+        return launch_tc<__nv_bfloat16>((const __nv_bfloat16*)scalars_bf16, (int)scalar_stride, points, (int)point_stride, rot, trans,
+                                        (const __nv_bfloat16*)pair_bias_packed, (const __nv_bfloat16*)pair_value_packed, key_bias, head_weight,
+                                        (__nv_bfloat16*)out, (__nv_bfloat16*)p_workspace, inv_workspace, sh, Lp, Bpad, st);
+    return launch_tc<float>((const __nv_bfloat16*)scalars_bf16, (int)scalar_stride, points, (int)point_stride, rot, trans,
+                            (const __nv_bfloat16*)pair_bias_packed, (const __nv_bfloat16*)pair_value_packed, key_bias, head_weight, (float*)out,
+                            (__nv_bfloat16*)p_workspace, inv_workspace, sh, Lp, Bpad, st);
 }
 
 }  // extern "C"

@@ -191,9 +191,15 @@ class DistributionalGraphormer(nn.Module):
             for lyr in self.st_module.encoder.layers:
                 a = lyr.attn
                 w_proj = a.fused_projection_weight().detach()
+                split = {}
                 if dtype != torch.float32 and a.d_k == 16:       # bf16 mode: head-major records for the tensor-core attention
+                    rows_s, rows_p, qpos = (i.to(w_proj.device) for i in ops.ipa_split_perms(a.n_head, a.d_k))
+                    w_s = w_proj[rows_s].float()
+                    w_s[qpos] *= a.scalar_weight * 1.4426950408889634      # q carries scalar_weight * log2 e (exp2 softmax)
+                    split = dict(w_proj_s=w_s.to(dtype).contiguous(), w_proj_p=w_proj[rows_p].to(dtype).contiguous())
                     w_proj = w_proj[ops.ipa_head_major_perm(a.n_head, a.d_k, w_proj.device)]
                 layers.append(dict(
+                    **split,
                     w_proj=w_proj.to(dtype).contiguous(),
                     w_out=a.fc_out.weight.detach().to(dtype).contiguous(),
                     w_ff0=lyr.ffn.ff[0].weight.detach().to(dtype).contiguous(),
@@ -328,9 +334,6 @@ class DistributionalGraphormer(nn.Module):
         return y if bias is None else y + bias
 
     def _attention(self, proj, R, T, c, lw, lyr, n, shape, flags):
-        if c.tc:
-            return ops.ipa_attention_tc_fwd(proj, R, T, c.pair_bias[n], c.pair_value_packed[n], c.key_bias, lw["head_w"],
-                                            lyr.attn.scalar_weight, shape, c.workspace)
         return ops.ipa_attention_fwd(proj, R, T, c.pair_bias[n], c.pair_value[n], c.key_bias, lw["head_w"],
                                      lyr.attn.scalar_weight, shape, flags)
 
@@ -363,7 +366,11 @@ class DistributionalGraphormer(nn.Module):
         for n, lyr in enumerate(self.st_module.encoder.layers):
             lw = w["layers"][n]
             h1 = ops.residual_layernorm(x, y, bias, lyr.norm1.weight, lyr.norm1.bias, lyr.norm1.eps)
-            feat = self._attention(mm(h1, lw["w_proj"]), R, T, c, lw, lyr, n, shape, flags)
+            if c.tc:    # two GEMMs: bf16 scalar records that are copied verbatim into the MMA operands, fp32 point records
+                feat = ops.ipa_attention_tc_fwd(torch.mm(h1, lw["w_proj_s"].t()), mm(h1, lw["w_proj_p"]), R, T, c.pair_bias[n],
+                                                      c.pair_value_packed[n], c.key_bias, lw["head_w"], shape, c.workspace)
+            else:
+                feat = self._attention(mm(h1, lw["w_proj"]), R, T, c, lw, lyr, n, shape, flags)
             if feat.dtype != torch.bfloat16:
                 feat = feat.to(torch.bfloat16)
             y, bias = mm(feat, lw["w_out"]), lyr.attn.fc_out.bias

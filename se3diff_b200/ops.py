@@ -437,22 +437,37 @@ def ipa_tc_workspace(shape: L.IpaShape, device) -> tuple[torch.Tensor, torch.Ten
     return (torch.empty(pb.value // 2, dtype=torch.bfloat16, device=device), torch.empty(ib.value // 4, dtype=torch.float32, device=device))
 
 
-def ipa_attention_tc_fwd(proj, rot, trans, pair_bias_packed, pair_value_packed, key_bias, head_weight, scalar_weight: float,
-                         shape: L.IpaShape, workspace, out_dtype=torch.bfloat16, out=None):
-    """Tensor-core edition (tcgen05/TMEM) of SAAttention.forward between the projections and fc_out."""
-    proj, rot, trans = _dev(proj, name="proj"), _dev(rot, name="rot"), _dev(trans, name="trans")
+def ipa_split_perms(heads: int, dk: int = 16):
+    """Row index sets of the fused projection weight [q | k | v | q_pt | k_pt | v_pt] (structure_module.py:131-135) for the
+    split layout of se3_ipa_attention_tc_fwd: (scalar rows, point rows, positions of the q rows inside the first)."""
+    hd = heads * dk
+    ar = torch.arange
+    sc, pt, qpos = [], [], []
+    for h in range(heads):
+        qpos.append(h * 3 * dk + ar(dk))
+        sc += [h * dk + ar(dk), hd + h * dk + ar(dk), 2 * hd + h * dk + ar(dk)]
+        pt += [3 * hd + h * 12 + ar(12), 3 * hd + 12 * heads + h * 12 + ar(12), 3 * hd + 24 * heads + h * 24 + ar(24)]
+    return torch.cat(sc), torch.cat(pt), torch.cat(qpos)
+
+
+def ipa_attention_tc_fwd(scalars, points, rot, trans, pair_bias_packed, pair_value_packed, key_bias, head_weight,
+                               shape: L.IpaShape, workspace, out_dtype=torch.bfloat16, out=None):
+    """Tensor-core edition (tcgen05/TMEM) of SAAttention.forward between the projections and fc_out, fed by the split
+    projections: bf16 scalar records with pre-scaled q, fp32 point records (see ipa_split_perms)."""
+    scalars = _dev(scalars, torch.bfloat16, "scalars")
+    points, rot, trans = _dev(points, name="points"), _dev(rot, name="rot"), _dev(trans, name="trans")
     pair_bias = _dev(pair_bias_packed, torch.bfloat16, "pair_bias_packed")
     pvp = _dev(pair_value_packed, torch.bfloat16, "pair_value_packed")
     key_bias = None if key_bias is None else _dev(key_bias, name="key_bias")
     head_weight = _dev(head_weight, name="head_weight")
-    width = shape.heads * (2 * shape.dk + 4 * shape.pv)
     if out is None:
-        out = torch.empty(shape.batch * shape.len, width, dtype=out_dtype, device=proj.device)
+        out = torch.empty(shape.batch * shape.len, shape.heads * (2 * shape.dk + 4 * shape.pv), dtype=out_dtype, device=points.device)
     pws, iws = workspace
-    with _guard(proj):
-        L.check(L.lib().se3_ipa_attention_tc_fwd(_p(proj), _p(rot), _p(trans), _p(pair_bias), _p(pvp), _p(key_bias), _p(head_weight),
-                                                 float(scalar_weight), _p(out), int(out.dtype == torch.bfloat16), _p(pws), _p(iws),
-                                                 C.byref(shape), _stream(proj)), "se3_ipa_attention_tc_fwd")
+    with _guard(points):
+        L.check(L.lib().se3_ipa_attention_tc_fwd(_p(scalars), scalars.shape[-1], _p(points), points.shape[-1], _p(rot), _p(trans),
+                                                       _p(pair_bias), _p(pvp), _p(key_bias), _p(head_weight), _p(out),
+                                                       int(out.dtype == torch.bfloat16), _p(pws), _p(iws), C.byref(shape), _stream(points)),
+                "se3_ipa_attention_tc_fwd")
     return out
 
 
