@@ -17,7 +17,7 @@ lib.se3_debug_set_phase_buffer(C.c_void_p(buf.data_ptr())); run(); torch.cuda.sy
 t = buf.view(-1, 16).double().cpu()
 st = t[:, [0, 8, 9, 10, 11, 12, 1]]
 ds = st[:, 1:] - st[:, :-1]
-print('staging detail:', {n: round(v) for n, v in zip(['alloc', 'frames+kb issue', 'kv batch loads+stores', 'barrier', 'point transforms', 'q tile'], ds.mean(0).tolist())})
+print('staging detail:', {n: round(v) for n, v in zip(['alloc', 'TMA issue + key bias', 'cp.async wait', 'CTA barrier + TMA landing', 'frame transforms', 'fences'], ds.mean(0).tolist())})
 t = t[:, :8]
 d = t[:, 1:] - t[:, :-1]
 names = ["staging(+alloc)", "sync+MMA1+wait", "passA(+bias wait)", "passB", "sync+MMA2+wait", "epilogue", "dealloc"]

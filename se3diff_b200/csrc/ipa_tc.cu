@@ -21,6 +21,7 @@
 //   (16 x Lp bf16) are two contiguous blocks fetched with TMA bulk copies (cp.async.bulk -> UBLKCP) that
 //   signal an mbarrier; D[128 x 16] accumulates in TMEM.  pair_value is therefore read once per 128 samples
 //   instead of once per sample (3.7 GB -> 30 MB per layer at B=256, L=84).
+#include <cuda.h>
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -34,7 +35,8 @@ using namespace se3;
 namespace {
 
 constexpr int DK = 16, PQ = 4, PV = 8;
-constexpr int NV = 80;  // value operand columns: v 16 | v_pt hi 24 | v_pt lo 24 | ones 1 | 15 x zero (N % 16 == 0)
+constexpr int NV = 80;   // accumulator columns of the second product: v 16 | v_pt hi 24 | v_pt lo 24 | ones 1 | 15 x zero
+constexpr int NVP = 64;  // ... of which the point operand (hi | lo | ones | zero) is a separate N = 64 MMA
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -53,7 +55,7 @@ template <int N> __device__ __forceinline__ void store_vec(__nv_bfloat16* dst, c
 }
 
 struct Pass1Smem {
-    uint8_t *q, *k, *vt, *p;
+    uint8_t *q, *k, *vs, *vp, *p;
     float *kp, *kb, *frm;
 };
 // Shared-memory plan of pass 1.  The P operand (written in the second half of the kernel) overlays everything that
@@ -65,22 +67,24 @@ __host__ __device__ inline uint32_t bias_slab_bytes(int L) {
 }
 __host__ __device__ inline uint32_t pass1_front_bytes(int L) {   // bias slab and (earlier) the raw local points share it
     const uint32_t raw = (uint32_t)L * 48 * 4;
-    return bias_slab_bytes(L) > raw ? bias_slab_bytes(L) : raw;
+    const uint32_t m = bias_slab_bytes(L) > raw ? bias_slab_bytes(L) : raw;
+    return (m + 127u) & ~127u;
 }
 __host__ __device__ inline bool pass1_can_alias(int L, int Lp) { return pass1_front_bytes(L) + (uint32_t)Lp * (48 + 4 + 32) <= (uint32_t)Lp * 256; }
 __host__ __device__ inline size_t pass1_smem_bytes(int L, int Lp) {
-    return (size_t)Lp * (NV * 2 + 256) + 4096 + (pass1_can_alias(L, Lp) ? 0 : (size_t)Lp * (48 + 4 + 32)) + (((size_t)L * 48 + 15) & ~(size_t)15);
+    return (size_t)Lp * (32 + NVP * 2 + 256) + 4096 + (pass1_can_alias(L, Lp) ? 0 : (size_t)Lp * (48 + 4 + 32)) + (((size_t)L * 48 + 15) & ~(size_t)15);
 }
 __device__ __forceinline__ Pass1Smem carve1(uint8_t* base, int L, int Lp) {
     Pass1Smem s;
-    s.vt = base;                                 // [Lp/8][NV/8][8][8] bf16, MN-major value operand
-    s.q = s.vt + (size_t)Lp * (NV * 2);          // [2][128][16 B]
+    s.vp = base;                                 // [Lp/8][NVP/8][8][8] bf16, MN-major point-value operand
+    s.vs = s.vp + (size_t)Lp * (NVP * 2);        // [2][Lp][16 B] scalar values as they arrive (MN-major through the descriptor strides)
+    s.q = s.vs + (size_t)Lp * 32;                // [2][128][16 B]
     s.p = s.q + 4096;                            // [Lp/8][128][16 B]; raw points, then the bias slab, live at its start until pass B
     uint8_t* rest = pass1_can_alias(L, Lp) ? s.p + pass1_front_bytes(L) : s.p + (size_t)Lp * 256;
-    s.kp = reinterpret_cast<float*>(rest);       // [Lp/2][12][2] fp32: negated global key points, interleaved by key pair
+    s.k = rest;                                  // [2][Lp][16 B]
+    s.kp = reinterpret_cast<float*>(s.k + (size_t)Lp * 32);   // [Lp/2][12][2] fp32: negated global key points, interleaved by key pair
     s.kb = s.kp + Lp * 12;                       // [Lp]
-    s.k = reinterpret_cast<uint8_t*>(s.kb + Lp); // [2][Lp][16 B]
-    uint8_t* tail = pass1_can_alias(L, Lp) ? s.p + (size_t)Lp * 256 : s.k + (size_t)Lp * 32;
+    uint8_t* tail = pass1_can_alias(L, Lp) ? s.p + (size_t)Lp * 256 : reinterpret_cast<uint8_t*>(s.kb + Lp);
     s.frm = reinterpret_cast<float*>(tail);      // rotations [L][9] then translations [L][3], as they lie in global memory
     return s;
 }
@@ -94,7 +98,7 @@ __device__ __forceinline__ void to_global(const float (&R)[9], const float (&T)[
 
 template <typename OutT>
 __global__ void __launch_bounds__(128, 4)
-k_ipa_tc_pass1(const __nv_bfloat16* __restrict__ scal, int scal_stride, const float* __restrict__ pts, int pts_stride,
+k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_pts,
                const float* __restrict__ rot, const float* __restrict__ trans, const __nv_bfloat16* __restrict__ pair_bias_t,
                const float* __restrict__ key_bias, const float* __restrict__ head_weight, OutT* __restrict__ out,
                __nv_bfloat16* __restrict__ pbuf, float* __restrict__ inv_sum, const se3_ipa_shape sh, int Lp, int Bpad, int tmem_cols,
@@ -120,70 +124,50 @@ k_ipa_tc_pass1(const __nv_bfloat16* __restrict__ scal, int scal_stride, const fl
     const __nv_bfloat16* s_bias = reinterpret_cast<const __nv_bfloat16*>(s.p);
     if (warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)tmem_cols);
     SE3_STAMP(8);
-    // ---- staging: everything is an asynchronous copy -------------------------------------------------------------
-    // points : fp32 records [qp 12 | kp 12 | vp 24] of this head, one 192-byte TMA bulk copy per residue, parked raw in
-    //          the (still unused) P region;  frames: the sample's [L][9] and [L][3] blocks, two bulk copies.  Warp 0
-    //          issues them and is the only one to touch their mbarrier before the CTA barrier below.
-    // scalars: bf16 head-major records [q 16 | k 16 | v 16] (q already carries scalar_weight * log2 e) = six 16-byte
-    //          pieces per residue that ARE chunks of the UMMA operands: copied verbatim by warps 1-3 (cp.async), each
-    //          thread owning one fixed piece column and walking residues with a constant stride (no div/mod in the loop)
+    // ---- staging: six TMA tile copies + two bulk copies, issued by one thread -------------------------------------
+    // scalars: bf16 head-major records [q 16 | k 16 | v 16] (q already carries scalar_weight * log2 e).  A 16-byte wide,
+    //          R-row box of the 2-D tensor map lands as [R][16 B]: exactly one K-chunk of a UMMA operand, so q, k and v
+    //          go from global memory into their operand tiles with no thread touching them.  Rows past the end of the
+    //          matrix are zero-filled by the TMA unit; rows past this sample's L hold the next sample's (finite)
+    //          values, which only ever meet logits forced to -inf / probabilities that are exactly zero.
+    // points : fp32 records [qp 12 | kp 12 | vp 24] of this head, one [L][192 B] box, parked raw in the (still unused) P region
+    // frames : the sample's [L][9] and [L][3] blocks, two 1-D bulk copies
     float* s_raw = reinterpret_cast<float*>(s.p);          // [L][48] raw local points
     float* s_rot = s.frm;
     float* s_trn = s.frm + L * 9;
-    if (warp == 0) {
-        if (tid == 0) {
-            tc::mbar_init(&bar, 1);
-            tc::mbar_init(&bar_bias, 1);
-            tc::mbar_init(&bar_in, 1);
-            tc::mbar_fence_init();
+    const float* rsrc = rot + (int64_t)b * L * 9;
+    const float* tsrc = trans + (int64_t)b * L * 3;
+    const bool bulk_frames = ((L & 3) == 0) && ((reinterpret_cast<uintptr_t>(rot) | reinterpret_cast<uintptr_t>(trans)) & 15) == 0;
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::mbar_init(&bar_bias, 1);
+        tc::mbar_init(&bar_in, 1);
+        tc::mbar_fence_init();
+        const int row0 = b * L;
+        tc::mbar_expect_tx(&bar_in, (uint32_t)(4096 + Lp * 64 + L * 192 + (bulk_frames ? L * 48 : 0)));
+        tc::tma_tile_2d_g2s(s_raw, &map_pts, h * 48, row0, &bar_in);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            tc::tma_tile_2d_g2s(s.k + (size_t)half * Lp * 16, &map_kv, h * 48 + 16 + half * 8, row0, &bar_in);
+            tc::tma_tile_2d_g2s(s.q + (size_t)half * 2048, &map_q, h * 48 + half * 8, row0 + q0, &bar_in);
+            tc::tma_tile_2d_g2s(s.vs + (size_t)half * Lp * 16, &map_kv, h * 48 + 32 + half * 8, row0, &bar_in);
         }
-        __syncwarp();
-        const float* rsrc = rot + (int64_t)b * L * 9;
-        const float* tsrc = trans + (int64_t)b * L * 3;
-        const bool bulk_frames = ((L & 3) == 0) && ((reinterpret_cast<uintptr_t>(rot) | reinterpret_cast<uintptr_t>(trans)) & 15) == 0;
-        if (tid == 0) {
-            tc::mbar_expect_tx(&bar_in, (uint32_t)(L * 192 + (bulk_frames ? L * 48 : 0)));
-            if (bulk_frames) {
-                tc::tma_bulk_g2s(s_rot, rsrc, (uint32_t)(L * 36), &bar_in);
-                tc::tma_bulk_g2s(s_trn, tsrc, (uint32_t)(L * 12), &bar_in);
-            }
-        }
-        __syncwarp();
-        const float* g = pts + ((int64_t)b * L + tid) * pts_stride + h * 48;
-        for (int row = tid; row < L; row += 32, g += (int64_t)32 * pts_stride) tc::tma_bulk_g2s(s_raw + row * 48, g, 192u, &bar_in);
-        if (!bulk_frames) {                                // unaligned sample block: 4-byte asynchronous copies
-            for (int idx = tid; idx < L * 9; idx += 32) tc::cp_async4(s_rot + idx, rsrc + idx);
-            for (int idx = tid; idx < L * 3; idx += 32) tc::cp_async4(s_trn + idx, tsrc + idx);
-        }
-    } else {
-        const int t = tid - 32, r0 = t / 6, pc = t - r0 * 6, blk = pc >> 1, half = pc & 1;
-        const uint32_t dbase = blk == 0 ? tc::smem_u32(s.q) + (uint32_t)(half * 2048 - q0 * 16)
-                             : blk == 1 ? tc::smem_u32(s.k) + (uint32_t)(half * Lp * 16) : tc::smem_u32(s.vt) + (uint32_t)(half * 128);
-        const char* g = reinterpret_cast<const char*>(scal + ((int64_t)b * L + r0) * scal_stride + h * 48) + pc * 16;
-        const int64_t gstep = (int64_t)16 * scal_stride * 2;
-        for (int row = r0; row < L; row += 16, g += gstep) {
-            const uint32_t off = blk == 2 ? (uint32_t)((row >> 3) * (NV * 16) + (row & 7) * 16) : (uint32_t)row * 16u;
-            if (blk != 0 || (unsigned)(row - q0) < 128u) tc::cp_async16_s(dbase + off, g);
+        if (bulk_frames) {
+            tc::tma_bulk_g2s(s_rot, rsrc, (uint32_t)(L * 36), &bar_in);
+            tc::tma_bulk_g2s(s_trn, tsrc, (uint32_t)(L * 12), &bar_in);
         }
     }
-    tc::cp_async_commit();
+    if (!bulk_frames) {                                    // unaligned sample block: 4-byte asynchronous copies
+        for (int idx = tid; idx < L * 9; idx += 128) tc::cp_async4(s_rot + idx, rsrc + idx);
+        for (int idx = tid; idx < L * 3; idx += 128) tc::cp_async4(s_trn + idx, tsrc + idx);
+        tc::cp_async_commit();
+    }
     for (int j = tid; j < Lp; j += 128) s.kb[j] = (j < L) ? (key_bias ? key_bias[(int64_t)b * L + j] * kLog2e : 0.f) : -CUDART_INF_F;
-    // zero padding: key rows L..Lp of K and V^T, query rows beyond the sequence end
-    for (int idx = tid; idx < (Lp - L) * (2 + NV / 8); idx += 128) {
-        const int row = L + idx / (2 + NV / 8), piece = idx % (2 + NV / 8);
-        if (piece < 2) *reinterpret_cast<uint4*>(s.k + ((size_t)piece * Lp + row) * 16) = make_uint4(0, 0, 0, 0);
-        else *reinterpret_cast<uint4*>(s.vt + (size_t)(row >> 3) * (NV * 16) + (size_t)(piece - 2) * 128 + (size_t)(row & 7) * 16) = make_uint4(0, 0, 0, 0);
-    }
-    {
-        const int nq = min(128, L - q0);
-        for (int idx = tid; idx < (128 - nq) * 2; idx += 128)
-            *reinterpret_cast<uint4*>(s.q + ((size_t)(idx & 1) * 128 + nq + (idx >> 1)) * 16) = make_uint4(0, 0, 0, 0);
-    }
     SE3_STAMP(9);
     tc::cp_async_wait<0>();
-    if (warp == 0) tc::mbar_wait(&bar_in, 0);
+    __syncthreads();   // the barrier is initialised (and the fallback frame copies are done)
     SE3_STAMP(10);
-    __syncthreads();   // frames, raw points and the scalar operands are in shared memory
+    tc::mbar_wait(&bar_in, 0);   // frames, raw points and the scalar operands are in shared memory
     SE3_STAMP(11);
 
     // ---- local -> global frame, one thread per residue -------------------------------------------------------------
@@ -235,14 +219,18 @@ k_ipa_tc_pass1(const __nv_bfloat16* __restrict__ scal, int scal_stride, const fl
                 hi[c] = *reinterpret_cast<const uint32_t*>(&hh);
                 lo[c] = tc::pack_bf16(gv[2 * c] - __bfloat162float(hh.x), gv[2 * c + 1] - __bfloat162float(hh.y));
             }
-            uint8_t* col = s.vt + (size_t)(row >> 3) * (NV * 16) + (size_t)(row & 7) * 16;   // chunk g of this row at + g*128
+            uint8_t* col = s.vp + (size_t)(row >> 3) * (NVP * 16) + (size_t)(row & 7) * 16;   // chunk g of this row at + g*128
 #pragma unroll
             for (int g = 0; g < 3; ++g) {
-                *reinterpret_cast<uint4*>(col + (2 + g) * 128) = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
-                *reinterpret_cast<uint4*>(col + (5 + g) * 128) = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+                *reinterpret_cast<uint4*>(col + g * 128) = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+                *reinterpret_cast<uint4*>(col + (3 + g) * 128) = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
             }
-            *reinterpret_cast<uint4*>(col + 8 * 128) = make_uint4(0x00003F80u, 0, 0, 0);     // bf16 1.0 in channel 64
-            *reinterpret_cast<uint4*>(col + 9 * 128) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(col + 6 * 128) = make_uint4(0x00003F80u, 0, 0, 0);     // bf16 1.0 in channel 48 of the point operand
+            *reinterpret_cast<uint4*>(col + 7 * 128) = make_uint4(0, 0, 0, 0);
+        } else if (row < Lp) {                             // padding keys: the point operand must be exactly zero
+            uint8_t* col = s.vp + (size_t)(row >> 3) * (NVP * 16) + (size_t)(row & 7) * 16;
+#pragma unroll
+            for (int g = 0; g < NVP / 8; ++g) *reinterpret_cast<uint4*>(col + g * 128) = make_uint4(0, 0, 0, 0);
         }
         {
             const bool odd = tid & 1;
@@ -393,10 +381,14 @@ k_ipa_tc_pass1(const __nv_bfloat16* __restrict__ scal, int scal_stride, const fl
     SE3_STAMP(4);
     // ---- MMA 2: O = P.V (accumulator overwrites the consumed S columns) -------------------------------------------
     if (tid == 0) {
-        const uint32_t idesc = tc::make_idesc_bf16(128, NV, /*b_mn_major=*/true);
-        for (int ks = 0; ks < nchunk; ++ks)
-            tc::mma_bf16(tmem, tc::make_desc_kstep(tc::smem_u32(s.p), 128, ks),
-                         tc::make_desc_raw(tc::smem_u32(s.vt) + (uint32_t)ks * 2u * NV * 16u, /*K-group*/ NV * 16u, /*MN-group*/ 128u), idesc, ks > 0);
+        // two MN-major B operands: the scalar values as TMA delivered them ([channel group][key][16 B]: 8 keys = 128 B apart,
+        // channel groups Lp*16 B apart) -> columns 0..15; the point operand ([key group][channel group][8][8]) -> columns 16..79
+        const uint32_t idesc_s = tc::make_idesc_bf16(128, DK, /*b_mn_major=*/true), idesc_p = tc::make_idesc_bf16(128, NVP, /*b_mn_major=*/true);
+        for (int ks = 0; ks < nchunk; ++ks) {
+            const uint64_t a_desc = tc::make_desc_kstep(tc::smem_u32(s.p), 128, ks);
+            tc::mma_bf16(tmem, a_desc, tc::make_desc_raw(tc::smem_u32(s.vs) + (uint32_t)ks * 256u, /*K-group*/ 128u, /*MN-group*/ (uint32_t)Lp * 16u), idesc_s, ks > 0);
+            tc::mma_bf16(tmem + DK, a_desc, tc::make_desc_raw(tc::smem_u32(s.vp) + (uint32_t)ks * 2u * NVP * 16u, /*K-group*/ NVP * 16u, /*MN-group*/ 128u), idesc_p, ks > 0);
+        }
         tc::mma_commit(&bar);
     }
     tc::mbar_wait(&bar, 1);
@@ -503,6 +495,31 @@ k_ipa_tc_pass2(const __nv_bfloat16* __restrict__ pbuf, const float* __restrict__
 
 long long* g_phase_dbg = nullptr;  // set by se3_debug_set_phase_buffer
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+// row-major [rows][cols] matrix with a row pitch; box = box_cols x box_rows elements, dense in shared memory
+int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems,
+                uint32_t box_cols, uint32_t box_rows, const char* what) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SE3_ECUDA; }
+    const cuuint64_t dims[2] = {cols, rows}, strides[1] = {pitch_elems * (uint64_t)elem_bytes};
+    const cuuint32_t box[2] = {box_cols, box_rows}, estr[2] = {1, 1};
+    const CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("tensor map for %s: cuTensorMapEncodeTiled failed with %d", what, (int)r); return SE3_ECUDA; }
+    return SE3_OK;
+}
+
 template <typename OutT>
 int launch_tc(const __nv_bfloat16* scal, int scal_stride, const float* pts, int pts_stride, const float* rot, const float* trans,
               const __nv_bfloat16* pair_bias, const __nv_bfloat16* pvc, const float* key_bias, const float* head_weight, OutT* out,
@@ -517,11 +534,17 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const float* pts, int 
         const size_t floor_bytes = (size_t)(227 * 1024) / (size_t)(512 / cols + 1) + 1;
         if (smem1 < floor_bytes && floor_bytes <= per_cta) smem1 = floor_bytes;
     }
+    // tensor maps: 16-byte wide boxes of the scalar records (one UMMA K-chunk each), 192-byte wide boxes of the point records
+    CUtensorMap map_q, map_kv, map_pts;
+    const uint64_t rows = (uint64_t)sh.batch * L, width = (uint64_t)sh.heads * 48;
+    if (int rc = make_map_2d(&map_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, scal, width, rows, (uint64_t)scal_stride, 8, 128, "q tiles")) return rc;
+    if (int rc = make_map_2d(&map_kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, scal, width, rows, (uint64_t)scal_stride, 8, (uint32_t)Lp, "k / v tiles")) return rc;
+    if (int rc = make_map_2d(&map_pts, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pts, width, rows, (uint64_t)pts_stride, 48, (uint32_t)L, "point records")) return rc;
     auto k1 = k_ipa_tc_pass1<OutT>;
     cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
     if (e != cudaSuccess) { set_error("ipa_tc pass1 smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
     dim3 g1((L + 127) / 128, sh.heads, sh.batch);
-    k1<<<g1, 128, smem1, st>>>(scal, scal_stride, pts, pts_stride, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, Lp, Bpad, cols,
+    k1<<<g1, 128, smem1, st>>>(map_q, map_kv, map_pts, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, Lp, Bpad, cols,
                                g_phase_dbg);
     count_launch();
     int rc = check_launch("se3_ipa_attention_tc_fwd(pass 1)");

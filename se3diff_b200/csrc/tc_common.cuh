@@ -101,6 +101,15 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
                  :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// TMA 2-D tiled copy global -> shared through a tensor map (SASS: UTMALDG); coordinates are (inner element, row)
+__device__ __forceinline__ void tma_tile_2d_g2s(void* smem_dst, const void* tensor_map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(smem_u32(smem_dst)), "l"(tensor_map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_descriptor(const void* tensor_map) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(tensor_map) : "memory");
+}
+
 // ---- misc ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
