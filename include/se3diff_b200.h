@@ -99,6 +99,11 @@ int se3_frame_update_em(const float* rot, const float* pos, const float* m_rot, 
                         float* rot_out, float* pos_out, float* dw_rot, float* dw_pos, int64_t n,
                         const se3_em_scalars* h_scalars, se3_stream_t stream);
 
+/* The rotation half alone, for samplers whose state is a bare [n,3,3] rotation (the se3diff toy: se3diff/train.py:54-70,
+ * se3diff/finetune.py:33-56).  The pos_* members of the scalars are ignored.  u_rot, dw_rot optional. */
+int se3_so3_update_em(const float* rot, const float* m_rot, const float* u_rot, const float* z_rot, float* rot_out,
+                      float* dw_rot, int64_t n, const se3_em_scalars* h_scalars, se3_stream_t stream);
+
 typedef struct se3_dpm_scalars {
     float pos_std_t;      /* sigma_t = sqrt(1-alpha_t^2)              denoiser.py:677          */
     float pos_c_x_mid;    /* alpha_lambda/alpha_t                     denoiser.py:700          */

@@ -10,7 +10,9 @@ the GPU box, where the reference tree does not exist.  Only data is committed, n
 """
 from __future__ import annotations
 
+import math
 import os
+import sys
 
 import numpy as np
 import torch
@@ -312,12 +314,74 @@ def analytic_denoise(ns):
     np.savez_compressed(os.path.join(OUT, "analytic_denoise.npz"), **_np(out))
 
 
+def toy(ns):
+    """The SO(3)-only toy layer (se3diff/*): ScoreNet forward, mixture sampling / pdf / responsibilities, the DSM loss,
+    reverse diffusion with and without control, and the fine-tune loss with its gradient -- all from the unmodified
+    reference with recorded seeds, small SO(3) tables."""
+    import contextlib
+    import io
+
+    M, T, FT = ns.toy_models, ns.toy_train, ns.toy_finetune
+    torch.manual_seed(61)
+    net = M.ScoreNet()
+    torch.manual_seed(62)
+    ctrl = M.ScoreNet()
+    with torch.no_grad():
+        for p in ctrl.parameters():
+            p.mul_(0.2)
+    sde = M.DiGMixSO3SDE(**SMALL_SDE)
+    g = torch.Generator().manual_seed(63)
+    K = 3
+    mus = ns.so3_sde.rotvec_to_rotmat(torch.randn(K, 3, generator=g))
+    sigmas = torch.tensor([0.1, 0.3, 0.8])
+    weights = torch.tensor([0.5, 0.3, 0.2])
+    h_stars = torch.tensor([0.2, 0.3, 0.5])
+    save = {"net::" + k: v for k, v in net.state_dict().items()}
+    save.update({"ctrl::" + k: v for k, v in ctrl.state_dict().items()})
+    save.update(mus=mus, sigmas=sigmas, weights=weights, h_stars=h_stars)
+    # ScoreNet forward on generic + adversarial rotations
+    v = torch.randn(40, 3, generator=g)
+    v[:4] *= 1e-4
+    v[4:8] = v[4:8] / v[4:8].norm(dim=-1, keepdim=True) * (math.pi - 1e-3)
+    x = ns.so3_sde.rotvec_to_rotmat(v)
+    t = torch.rand(40, generator=g)
+    with torch.no_grad():
+        save.update(fw_x=x, fw_t=t, fw_out=net(x, t))
+        om, pdf = T.igso3_mixture_marginal_pdf(mus, sigmas, weights, l_max=200, num_points=64)
+        save.update(mix_omega=om, mix_pdf=pdf)
+        x0 = ns.so3_sde.rotvec_to_rotmat(torch.randn(24, 3, generator=g))
+        save.update(assign_x0=x0, assign_hs=FT.assign_igso3(x0, mus, sigmas, weights, l_max=200))
+        torch.manual_seed(64)
+        save.update(mixsample_seed=64, mixsample=sde.sample_multiple_igso3(mus, sigmas, weights, 32))
+    torch.manual_seed(65)
+    loss = T.compute_train_loss(sde, net, mus, sigmas, weights, batch_size=64)
+    grads = torch.autograd.grad(loss, [p for p in net.parameters() if p.requires_grad])
+    save.update(train_seed=65, train_loss=loss.detach(), train_grad_norms=torch.stack([gr.norm() for gr in grads]))
+    torch.manual_seed(66)
+    xs, ts = T.reverse_diffusion(sde, net, device="cpu", batch_size=16, num_steps=8)
+    save.update(rev_seed=66, rev_xs=xs, rev_ts=ts)
+    torch.manual_seed(67)
+    xs, ts, us, dWs = FT.reverse_finetune_diffusion(sde, net, ctrl, device="cpu", batch_size=16, num_steps=6)
+    save.update(revft_seed=67, revft_xs=xs, revft_us=us, revft_dWs=dWs)
+    torch.manual_seed(68)
+    with contextlib.redirect_stdout(io.StringIO()):      # ppft.compute_ev_loss prints its arguments
+        loss = FT.compute_finetune_loss(sde, net, ctrl, mus, sigmas, h_stars, device="cpu", batch_size=16, num_steps=6, l_max=200)
+    grads = torch.autograd.grad(loss, [p for p in ctrl.parameters() if p.requires_grad])
+    save.update(ft_seed=68, ft_loss=loss.detach(), ft_grad_norms=torch.stack([gr.norm() for gr in grads]),
+                ft_grad_last=grads[-1])
+    np.savez_compressed(os.path.join(OUT, "toy.npz"), **_np(save))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_harness.load()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    for fn in (so3_maps, igso3_series, so3_tables, schedules, score_model_tiny, score_model_small, trajectories,
-               analytic_denoise):
+    every = (so3_maps, igso3_series, so3_tables, schedules, score_model_tiny, score_model_small, trajectories,
+             analytic_denoise, toy)
+    only = set(sys.argv[1:])                      # e.g. `python -m oracle.gen_golden toy` regenerates one file
+    for fn in every:
+        if only and fn.__name__ not in only:
+            continue
         print("golden:", fn.__name__, flush=True)
         fn(ns)
     print({f: os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT))})

@@ -39,10 +39,11 @@ def load():
         structure_module=structure_module, Batch=Batch, root=REF_ROOT,
     )
     try:
+        import se3diff.finetune as toy_finetune
         import se3diff.models as toy_models
         import se3diff.train as toy_train
 
-        ns.toy_models, ns.toy_train = toy_models, toy_train
+        ns.toy_models, ns.toy_train, ns.toy_finetune = toy_models, toy_train, toy_finetune
     except Exception:  # ppft etc. are optional for the goldens
         pass
     return ns

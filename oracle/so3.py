@@ -26,8 +26,11 @@ def hat(v: torch.Tensor) -> torch.Tensor:
 
 
 def vee(m: torch.Tensor) -> torch.Tensor:
-    """skew matrix -> vector (m21, m02, m10) (so3_sde.py:708-722)."""
-    return torch.stack([m[..., 2, 1], m[..., 0, 2], m[..., 1, 0]], -1)
+    """skew matrix -> vector (m21, m02, m10) (so3_sde.py:708-722).  Filled into zeros_like(m[..., 0]) as the reference does:
+    for permuted inputs that keeps the input's stride order, which decides the summation order of the norm taken next."""
+    v = torch.zeros_like(m[..., 0])
+    v[..., 0], v[..., 1], v[..., 2] = m[..., 2, 1], m[..., 0, 2], m[..., 1, 0]
+    return v
 
 
 def rotvec_to_rotmat(v: torch.Tensor, tol: float = 1e-7) -> torch.Tensor:

@@ -52,6 +52,7 @@ SIGNATURES = {
     "se3_so3_geodesic": [f32p, f32p, f32, f32p, i64, f32, vp],
     "se3_so3_from_quat": [f32p, f32p, f32p, i64, f32, vp],
     "se3_frame_update_em": [f32p] * 12 + [i64, C.POINTER(EmScalars), vp],
+    "se3_so3_update_em": [f32p] * 6 + [i64, C.POINTER(EmScalars), vp],
     "se3_frame_update_dpm_mid": [f32p] * 6 + [i64, C.POINTER(DpmScalars), vp],
     "se3_frame_update_dpm_final": [f32p] * 7 + [i64, C.POINTER(DpmScalars), vp],
     "se3_frame_heun_churn": [f32p] * 6 + [i64, C.POINTER(HeunScalars), vp],

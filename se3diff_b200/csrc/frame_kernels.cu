@@ -105,6 +105,42 @@ k_em(const float* __restrict__ rot, const float* __restrict__ pos, const float* 
     }
 }
 
+// SO(3)-only Euler-Maruyama step: the rotation half of k_em, for samplers whose state is a bare rotation
+// (se3diff/train.py:54-70, se3diff/finetune.py:33-56 call EulerMaruyamaPredictor.update_given_score on [B,3,3]).
+template <bool HAS_U, bool OUT_DW>
+__global__ void __launch_bounds__(kTile)
+k_em_so3(const float* __restrict__ rot, const float* __restrict__ m_rot, const float* __restrict__ u_rot, const float* __restrict__ z_rot,
+         float* __restrict__ rot_out, float* __restrict__ dw_rot, int64_t n, const se3_em_scalars c) {
+    __shared__ __align__(16) float s_rot[kTile * 9];
+    __shared__ __align__(16) float s_v[HAS_U ? 3 : 2][kTile * 3];  // m_rot, z_rot, [u_rot]
+    const int64_t first = (int64_t)blockIdx.x * kTile;
+    const int count = (int)min((int64_t)kTile, n - first);
+    tile_load<9>(rot, s_rot, first, count);
+    tile_load<3>(m_rot, s_v[0], first, count);
+    tile_load<3>(z_rot, s_v[1], first, count);
+    if (HAS_U) tile_load<3>(u_rot, s_v[2], first, count);
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < count) {
+        float r[9], mean[9], out[9];
+        ld9(s_rot, t, r);
+        const Vec3 mr = ld3(s_v[0], t), zr = ld3(s_v[1], t);
+        Vec3 ur = {0, 0, 0};
+        if (HAS_U) ur = ld3(s_v[2], t);
+        const float w = c.score_weight, g = c.rot_g, nsd = c.noise_weight * c.sqrt_abs_dt;
+        const Vec3 sr = {mr.x * c.rot_scale, mr.y * c.rot_scale, mr.z * c.rot_scale};
+        const Vec3 dr = {rot_drift(g, sr.x, w, HAS_U, ur.x), rot_drift(g, sr.y, w, HAS_U, ur.y), rot_drift(g, sr.z, w, HAS_U, ur.z)};
+        const Vec3 dwr = {nsd * zr.x, nsd * zr.y, nsd * zr.z};
+        apply_rotvec(r, {dr.x * c.dt, dr.y * c.dt, dr.z * c.dt}, c.tol, mean);
+        apply_rotvec(mean, {g * dwr.x, g * dwr.y, g * dwr.z}, c.tol, out);
+        st9(s_rot, t, out);
+        if (OUT_DW) st3(s_v[1], t, dwr);
+    }
+    __syncthreads();
+    tile_store<9>(rot_out, s_rot, first, count);
+    if (OUT_DW) tile_store<3>(dw_rot, s_v[1], first, count);
+}
+
 // ---------------------------------------------------------------------------------------------
 // DPM-Solver-2 (denoiser.py:676-762)
 // ---------------------------------------------------------------------------------------------
@@ -339,6 +375,22 @@ int se3_frame_update_em(const float* rot, const float* pos, const float* m_rot, 
     else k_em<false, false><<<grid_for(n), kTile, 0, st>>>(EM_ARGS);
 #undef EM_ARGS
     SE3_LAUNCH_CHECK("se3_frame_update_em");
+}
+
+int se3_so3_update_em(const float* rot, const float* m_rot, const float* u_rot, const float* z_rot, float* rot_out, float* dw_rot,
+                      int64_t n, const se3_em_scalars* h, se3_stream_t stream) {
+    SE3_REQUIRE(n >= 0 && h, "negative n or null scalars");
+    if (n == 0) return SE3_OK;
+    SE3_REQUIRE(rot && m_rot && z_rot && rot_out, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool has_u = u_rot != nullptr, out_dw = dw_rot != nullptr;
+#define EM_ARGS rot, m_rot, u_rot, z_rot, rot_out, dw_rot, n, *h
+    if (has_u && out_dw) k_em_so3<true, true><<<grid_for(n), kTile, 0, st>>>(EM_ARGS);
+    else if (has_u) k_em_so3<true, false><<<grid_for(n), kTile, 0, st>>>(EM_ARGS);
+    else if (out_dw) k_em_so3<false, true><<<grid_for(n), kTile, 0, st>>>(EM_ARGS);
+    else k_em_so3<false, false><<<grid_for(n), kTile, 0, st>>>(EM_ARGS);
+#undef EM_ARGS
+    SE3_LAUNCH_CHECK("se3_so3_update_em");
 }
 
 int se3_frame_update_dpm_mid(const float* rot, const float* pos, const float* m_rot, const float* m_pos,

@@ -191,6 +191,19 @@ def frame_update_em(rot, pos, m_rot, m_pos, z_rot, z_pos, scalars: L.EmScalars, 
     return rot_out, pos_out, dw_rot, dw_pos
 
 
+def so3_update_em(rot, m_rot, z_rot, scalars: L.EmScalars, u_rot=None, want_dw=False, rot_out=None):
+    """The rotation half of the Euler-Maruyama step alone, on bare [n,3,3] rotations (se3diff/train.py:54-70)."""
+    rot = _dev(rot, name="rot")
+    n = rot.numel() // 9
+    m_rot, z_rot, u_rot = _vec(m_rot, n, "m_rot"), _vec(z_rot, n, "z_rot"), _vec(u_rot, n, "u_rot")
+    rot_out = torch.empty_like(rot) if rot_out is None else rot_out
+    dw = torch.empty(n, 3, dtype=torch.float32, device=rot.device) if want_dw else None
+    with _guard(rot):
+        L.check(L.lib().se3_so3_update_em(_p(rot), _p(m_rot), _p(u_rot), _p(z_rot), _p(rot_out), _p(dw), n, C.byref(scalars),
+                                          _stream(rot)), "se3_so3_update_em")
+    return rot_out, dw
+
+
 def frame_update_dpm_mid(rot, pos, m_rot, m_pos, scalars: L.DpmScalars, rot_out=None, pos_out=None):
     rot, pos, n = _chk_frames(rot, pos)
     m_rot, m_pos = _vec(m_rot, n, "m_rot"), _vec(m_pos, n, "m_pos")

@@ -433,3 +433,10 @@ def noise_rand(shape, device):
     if _HOST_NOISE:
         return torch.rand(*shape).to(device)
     return torch.rand(*shape, device=device)
+
+
+def noise_multinomial(weights: torch.Tensor, num_samples: int) -> torch.Tensor:
+    """torch.multinomial(weights, n, replacement=True) on the noise source of the current mode."""
+    if _HOST_NOISE:
+        return torch.multinomial(weights.cpu(), num_samples, replacement=True).to(weights.device)
+    return torch.multinomial(weights, num_samples, replacement=True)

@@ -706,3 +706,54 @@ def test_context_cache_is_keyed_by_value_not_address():
     m = fresh.eval().to(DEV)
     assert torch.equal(other, run(T(g["single"]) * 1.5, [p * 0.5 for p in pairs]))
     assert not torch.equal(other, a1)
+
+
+def test_toy_layer_vs_reference_golden():
+    """se3diff_b200.so3_toy (the mirror of se3diff/{models,train,finetune}.py) against outputs of the unmodified reference,
+    fed the same CPU noise stream."""
+    from oracle.gen_golden import SMALL_SDE
+    from se3diff_b200 import sdes as S
+    from se3diff_b200 import so3_toy as toy
+
+    g = load_golden("toy.npz")
+    tab = oso3.SO3Tables(**SMALL_SDE)
+    sde = toy.DiGMixSO3SDE(**SMALL_SDE)
+    sde.igso3.cdf_igso3.copy_(tab.cdf_igso3)
+    sde.uso3.cdf_igso3.copy_(tab.cdf_uso3)
+    sde.score_function.score_scaling.copy_(tab.score_scaling)
+    sde = sde.to(DEV)
+    net, ctrl = toy.ScoreNet(), toy.ScoreNet()
+    net.load_state_dict(_sd(g, "net::"))
+    ctrl.load_state_dict(_sd(g, "ctrl::"))
+    net, ctrl = net.to(DEV), ctrl.to(DEV)
+    mus, sigmas, weights, h_stars = (T(g[k]).to(DEV) for k in ("mus", "sigmas", "weights", "h_stars"))
+    with torch.no_grad():
+        assert rel_err(net(T(g["fw_x"]).to(DEV), T(g["fw_t"]).to(DEV)), T(g["fw_out"]), floor=0.05) <= 2e-4
+        om, pdf = toy.igso3_mixture_marginal_pdf(mus, sigmas, weights, l_max=200, num_points=64)
+        assert torch.equal(om.cpu(), T(g["mix_omega"])) and rel_err(pdf, T(g["mix_pdf"]), floor=1e-2) <= 1e-4
+        hs = toy.assign_igso3(T(g["assign_x0"]).to(DEV), mus, sigmas, weights, l_max=200)
+        # responsibilities of ~1e-5 come from series values that are pure fp32 cancellation noise in the reference itself
+        # (sum of 200 alternating terms of size ~1e2 clamped at zero); they are compared at that noise level
+        assert (hs.cpu() - T(g["assign_hs"])).abs().max() <= 5e-4
+    with S.host_noise():
+        with torch.no_grad():
+            torch.manual_seed(int(g["mixsample_seed"]))
+            assert rel_err(sde.sample_multiple_igso3(mus, sigmas, weights, 32), T(g["mixsample"]), floor=0.1) <= 1e-5
+        torch.manual_seed(int(g["train_seed"]))
+        loss = toy.compute_train_loss(sde, net, mus, sigmas, weights, device=DEV, batch_size=64)
+        assert abs(loss.item() - float(g["train_loss"])) <= 1e-3 * abs(float(g["train_loss"]))
+        grads = torch.autograd.grad(loss, [p for p in net.parameters() if p.requires_grad])
+        assert rel_err(torch.stack([x.norm() for x in grads]), T(g["train_grad_norms"]), floor=1e-3) <= 2e-3
+        torch.manual_seed(int(g["rev_seed"]))
+        xs, ts = toy.reverse_diffusion(sde, net, device=DEV, batch_size=16, num_steps=8)
+        assert torch.equal(ts.cpu(), T(g["rev_ts"])) and rel_err(xs, T(g["rev_xs"]), floor=0.1) <= TRAJ_TOL
+        torch.manual_seed(int(g["revft_seed"]))
+        xs, ts, us, dWs = toy.reverse_finetune_diffusion(sde, net, ctrl, device=DEV, batch_size=16, num_steps=6)
+        assert rel_err(xs, T(g["revft_xs"]), floor=0.1) <= TRAJ_TOL and rel_err(us, T(g["revft_us"]), floor=0.05) <= TRAJ_TOL
+        assert torch.equal(dWs.cpu(), T(g["revft_dWs"]))
+        torch.manual_seed(int(g["ft_seed"]))
+        loss = toy.compute_finetune_loss(sde, net, ctrl, mus, sigmas, h_stars, device=DEV, batch_size=16, num_steps=6, l_max=200)
+        ref = float(g["ft_loss"])
+        assert abs(loss.item() - ref) <= 5e-3 * max(abs(ref), 1e-3)
+        grads = torch.autograd.grad(loss, [p for p in ctrl.parameters() if p.requires_grad])
+        assert rel_err(grads[-1], T(g["ft_grad_last"]), floor=float(np.abs(g["ft_grad_last"]).max()) * 0.1) <= 2e-2

@@ -260,3 +260,39 @@ def test_analytic_score_moments():
     assert torch.allclose(r.mean(dim=0), torch.eye(3), atol=1e-1)
     assert torch.allclose(r.std(dim=0), torch.zeros(3, 3), atol=1e-1)
     assert abs(float(g["dpm_pos_mean"]) - x0_mean.item()) < 0.5 and abs(float(g["heun_pos_std"]) - 4.3) < 0.5
+
+
+def test_toy_layer_bit_exact():
+    """oracle/toy.py vs the unmodified se3diff/{models,train,finetune}.py (+ bioemu/ppft.py) on recorded seeds."""
+    from oracle import toy
+    from oracle.gen_golden import SMALL_SDE
+
+    g = load_golden("toy.npz")
+    tab = so3.SO3Tables(**SMALL_SDE)
+    net = toy.ScoreNetOracle(_sd(g, "net::"))
+    ctrl = toy.ScoreNetOracle(_sd(g, "ctrl::"))
+    mus, sigmas, weights, h_stars = T(g["mus"]), T(g["sigmas"]), T(g["weights"]), T(g["h_stars"])
+    with torch.no_grad():
+        assert torch.equal(net(T(g["fw_x"]), T(g["fw_t"])), T(g["fw_out"]))
+        om, pdf = toy.igso3_mixture_marginal_pdf(mus, sigmas, weights, l_max=200, num_points=64)
+        assert torch.equal(om, T(g["mix_omega"])) and torch.equal(pdf, T(g["mix_pdf"]))
+        assert torch.equal(toy.assign_igso3(T(g["assign_x0"]), mus, sigmas, weights, l_max=200), T(g["assign_hs"]))
+        torch.manual_seed(int(g["mixsample_seed"]))
+        assert torch.equal(toy.sample_multiple_igso3(tab, mus, sigmas, weights, 32), T(g["mixsample"]))
+    torch.manual_seed(int(g["train_seed"]))
+    loss = toy.compute_train_loss(tab, net, mus, sigmas, weights, batch_size=64)
+    assert torch.equal(loss.detach(), T(g["train_loss"]))
+    grads = torch.autograd.grad(loss, net.parameters())
+    assert torch.allclose(torch.stack([x.norm() for x in grads]), T(g["train_grad_norms"]), rtol=1e-5, atol=1e-8)
+    torch.manual_seed(int(g["rev_seed"]))
+    xs, ts = toy.reverse_diffusion(tab, net, 16, 8)
+    assert torch.equal(xs, T(g["rev_xs"])) and torch.equal(ts, T(g["rev_ts"]))
+    torch.manual_seed(int(g["revft_seed"]))
+    xs, ts, us, dWs = toy.reverse_diffusion(tab, net, 16, 6, finetune_model=ctrl)
+    assert torch.equal(xs, T(g["revft_xs"])) and torch.equal(us, T(g["revft_us"])) and torch.equal(dWs, T(g["revft_dWs"]))
+    torch.manual_seed(int(g["ft_seed"]))
+    loss = toy.compute_finetune_loss(tab, net, ctrl, mus, sigmas, h_stars, batch_size=16, num_steps=6, l_max=200)
+    assert torch.equal(loss.detach(), T(g["ft_loss"]))
+    grads = torch.autograd.grad(loss, ctrl.parameters())
+    assert torch.allclose(torch.stack([x.norm() for x in grads]), T(g["ft_grad_norms"]), rtol=1e-4, atol=1e-9)
+    assert torch.allclose(grads[-1], T(g["ft_grad_last"]), rtol=1e-4, atol=1e-9)
