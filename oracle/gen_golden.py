@@ -282,6 +282,13 @@ def trajectories(ns):
                     emft_us_pos=o.us_batch["pos"], emft_us_rot=o.us_batch["node_orientations"],
                     emft_dWs_pos=o.dWs_batch["pos"], emft_dWs_rot=o.dWs_batch["node_orientations"],
                     emft_timesteps=o.timesteps, emft_seed=54, emft_steps=6)
+        torch.manual_seed(55)
+        o = D.heun_denoiser_finetune(batch=mk(), sdes=sdes, score_model=m, finetune_model=fm, num_steps=5, noise=0.5, **kw)
+        # every entry of o.batches is the same in-place-mutated object (denoiser.py:518,596): only the final state is meaningful
+        save.update(heunft_pos=o.batches[-1].pos, heunft_rot=o.batches[-1].node_orientations,
+                    heunft_us_pos=o.us_batch["pos"], heunft_us_rot=o.us_batch["node_orientations"],
+                    heunft_dWs_pos=o.dWs_batch["pos"], heunft_dWs_rot=o.dWs_batch["node_orientations"],
+                    heunft_aliased=int(all(bb is o.batches[0] for bb in o.batches)), heunft_seed=55, heunft_steps=5)
     np.savez_compressed(os.path.join(OUT, "trajectories.npz"), **_np(save))
 
 

@@ -202,6 +202,62 @@ def heun(score_fn, lengths, r3, so3, num_steps, max_t, min_t, noise, fields=FIEL
     return x["pos"], x["node_orientations"]
 
 
+def heun_finetune(score_fn, finetune_fn, lengths, r3, so3, num_steps, max_t, min_t, noise, fields=FIELDS_YAML):
+    """heun_denoiser_finetune (denoiser.py:462-620): the Heun step with the control in every drift, plus the Brownian
+    increment of the equivalent Euler-Maruyama step traced back per field.  The reference appends ONE in-place-mutated
+    batch object to `batches` every step (denoiser.py:518,564,588,596), so all its stored batches alias the final state;
+    this restatement returns per-step snapshots and the tests compare the last one."""
+    b = len(lengths)
+    bi = torch.repeat_interleave(torch.arange(b), torch.tensor(lengths))
+    pos, rot = _prior(int(sum(lengths)), r3, so3, fields)
+    ts = torch.linspace(max_t, min_t, num_steps + 1)
+    dts = torch.diff(ts)
+    kinds = {"pos": "pos", "node_orientations": "rot"}
+    pred = {f: EM(kinds[f], r3, so3, 0.0) for f in fields}
+    nois = {f: EM(kinds[f], r3, so3, 1.0) for f in fields}
+    x = {"pos": pos, "node_orientations": rot}
+    path_pos, path_rot, us, dWs = [pos], [rot], defaultdict(list), defaultdict(list)
+
+    def both(fn, xx, t):
+        a, c = fn(xx["pos"], xx["node_orientations"], t)
+        return {"pos": a, "node_orientations": c}
+
+    for i in range(num_steps):
+        t = torch.full((b,), ts[i].item())
+        t_next = t + dts[i]
+        churn = i > 0 and 0.0 < t[0] < 1.0
+        t_hat = t - noise * dts[i] if churn else t
+        xh = {f: nois[f].forward_step(x[f], t, (t_hat - t)[0], bi)[0] for f in fields}
+        sc_h = both(lambda p, r, tt: get_score(score_fn, p, r, tt, bi, r3, so3), xh, t_hat)
+        u_h = both(finetune_fn, xh, t_hat)
+        x_prev = dict(x)
+        if churn:
+            sc = both(lambda p, r, tt: get_score(score_fn, p, r, tt, bi, r3, so3), x, t)
+            u = both(finetune_fn, x, t)
+        else:
+            sc, u = sc_h, u_h
+        dh = {f: pred[f].drift_diffusion(xh[f], t_hat, sc_h[f], bi, u_h[f])[0] for f in fields}
+        x = {}
+        for f in fields:
+            x[f] = pred[f].update(xh[f], (t_next - t_hat)[0], dh[f], 0.0)[1]
+        if t_next[0] > 0.0:
+            sc_n = both(lambda p, r, tt: get_score(score_fn, p, r, tt, bi, r3, so3), x, t_next)
+            u_n = both(finetune_fn, x, t_next)
+            avg = {}
+            for f in fields:
+                dn = pred[f].drift_diffusion(x[f], t_next, sc_n[f], bi, u_n[f])[0]
+                avg[f] = (dn + dh[f]) / 2
+            for f in fields:
+                x[f] = pred[f].update(xh[f], (t_next - t_hat)[0], avg[f], 0.0)[1]
+        path_pos.append(x["pos"])
+        path_rot.append(x["node_orientations"])
+        for f in fields:
+            dW = nois[f].traceback(x[f], x_prev[f], t, dts[i], sc[f], bi, u[f])
+            us[f].append(_dense(u[f], bi, lengths))
+            dWs[f].append(_dense(dW, bi, lengths))
+    return Path(path_pos, path_rot, ts, {f: torch.stack(us[f]) for f in fields}, {f: torch.stack(dWs[f]) for f in fields})
+
+
 def dpm_solver(score_fn, lengths, r3, so3, num_steps, max_t, min_t, init=None, trace=None):
     """denoiser.py:634-764 (DPM-Solver-2 on pos, midpoint/extrapolated exp-map step on rot)."""
     assert max_t < 1.0

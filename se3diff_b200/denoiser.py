@@ -243,17 +243,65 @@ def euler_maruyama_predictor_finetune(*, batch, sdes, score_model, finetune_mode
     return _em_loop(batch, sdes, score_model, finetune_model, num_steps, max_t, min_t, device)
 
 
+def _get_score(batch, sdes, score_model, t):
+    """Score-model output -> scores (denoiser.py:169-203)."""
+    bi = batch["batch"]
+    out = score_model(batch, t)
+    rot = out["node_orientations"] * sdes["node_orientations"].get_score_scaling(t, batch_idx=bi).unsqueeze(-1)
+    _, std = sdes["pos"].marginal_prob(x=torch.ones_like(out["pos"]), t=t, batch_idx=bi)
+    return {"node_orientations": rot, "pos": out["pos"] / std}
+
+
+def _heun_finetune_loop(batch, sdes, score_model, finetune_model, num_steps, max_t, min_t, noise, device):
+    """Rollout for the fine-tune objective: 3 score + 3 control evaluations per churned step, so the SDE algebra (composed
+    here from the per-field predictor, i.e. the so3 / elementwise kernels) is a vanishing share; every random draw of the
+    reference happens in the same order (the deterministic updates consume `randn_like` too, denoiser.py:80)."""
+    ts, dts = schedule.timesteps(max_t, min_t, num_steps)
+    ts_dev, dts_dev = ts.to(device), dts.to(device)
+    fields = _fields(sdes)
+    pred = {f: EulerMaruyamaPredictor(corruption=sdes[f], noise_weight=0.0) for f in fields}
+    nois = {f: EulerMaruyamaPredictor(corruption=sdes[f], noise_weight=1.0) for f in fields}
+    bi, B = batch["batch"], batch.num_graphs
+    lengths = batch_lengths(batch)
+    batches, us, dWs = [batch], defaultdict(list), defaultdict(list)
+    for i in range(num_steps):
+        t = _t(float(ts[i]), B, device)
+        t_next = t + dts_dev[i]
+        churn = i > 0 and 0.0 < float(ts[i]) < 1.0
+        t_hat = t - noise * dts_dev[i] if churn else t
+        hat = batch.replace(**{f: nois[f].forward_sde_step(x=batch[f], t=t, dt=(t_hat - t)[0], batch_idx=bi)[0] for f in fields})
+        sc_h, u_h = _get_score(hat, sdes, score_model, t_hat), finetune_model(hat, t_hat)
+        if churn:
+            sc, u = _get_score(batch, sdes, score_model, t), finetune_model(batch, t)
+        else:
+            sc, u = sc_h, u_h
+        dh = {f: pred[f].reverse_drift_and_diffusion(x=hat[f], t=t_hat, score=sc_h[f], finetune_score=u_h[f], batch_idx=bi)[0] for f in fields}
+        step = (t_next - t_hat)[0]
+        new = batch.replace(**{f: pred[f].update_given_drift_and_diffusion(x=hat[f], dt=step, drift=dh[f], diffusion=0.0)[1] for f in fields})
+        if float(t_next[0]) > 0.0:
+            sc_n, u_n = _get_score(new, sdes, score_model, t_next), finetune_model(new, t_next)
+            avg = {f: (pred[f].reverse_drift_and_diffusion(x=new[f], t=t_next, score=sc_n[f], finetune_score=u_n[f], batch_idx=bi)[0]
+                       + dh[f]) / 2 for f in fields}
+            new = batch.replace(**{f: pred[f].update_given_drift_and_diffusion(x=hat[f], dt=step, drift=avg[f], diffusion=0.0)[1] for f in fields})
+        for f in fields:
+            dW = nois[f].traceback_brownian_motion(x_next=new[f], x=batch[f], t=t, dt=dts_dev[i], score=sc[f], finetune_score=u[f],
+                                                   batch_idx=bi)
+            us[f].append(_dense(u[f], batch, lengths))
+            dWs[f].append(_dense(dW, batch, lengths))
+        batch = new
+        batches.append(batch)
+    return DenoisedSDEPath(batches=batches, timesteps=ts_dev, us_batch={f: torch.stack(us[f], dim=0) for f in fields},
+                           dWs_batch={f: torch.stack(dWs[f], dim=0) for f in fields})
+
+
 def _heun_loop(batch, sdes, score_model, finetune_model, num_steps, max_t, min_t, noise, device):
     batch, device, so3, (score_model, finetune_model) = _prepare(batch, sdes, score_model, device, (finetune_model,))
     steps = schedule.heun_schedule(sdes["pos"], so3, num_steps, max_t, min_t, noise)
     batch = _prior(batch, sdes, so3, device)
     B = batch.num_graphs
     fields = _fields(sdes)
-    record = finetune_model is not None
-    if record:
-        raise NotImplementedError(
-            "heun_denoiser_finetune: the reference implementation stores aliases of one in-place-mutated batch "
-            "(denoiser.py:518,564,588,596) and is not used by finetune.sh; use euler_maruyama_predictor_finetune")
+    if finetune_model is not None:
+        return _heun_finetune_loop(batch, sdes, score_model, finetune_model, num_steps, max_t, min_t, noise, device)
     n = batch["pos"].shape[0]
 
     def draws():
@@ -288,7 +336,12 @@ def heun_denoiser(*, batch, sdes, score_model, num_steps: int, max_t: float, min
 @torch.no_grad()
 def heun_denoiser_finetune(*, batch, sdes, score_model, finetune_model, num_steps: int, max_t: float, min_t: float,
                            noise: float, device=None):
-    """denoiser.py:464-620 -- see `_heun_loop` for why this raises."""
+    """denoiser.py:464-620: Heun with the control in every drift; returns the path with dense `us`, `dWs` [T, B, L, 3].
+
+    One deliberate difference: the reference appends the SAME in-place-mutated batch object every step
+    (denoiser.py:518, 564, 588, 596), so all entries of its `batches` alias the final state; here `batches[i]` is the
+    state after step i (what `finetune.py:338-393` needs to re-evaluate the control).  `batches[-1]`, `us_batch`,
+    `dWs_batch` and `timesteps` equal the reference's."""
     return _heun_loop(batch, sdes, score_model, finetune_model, num_steps, max_t, min_t, noise, device)
 
 
@@ -336,6 +389,8 @@ class EulerMaruyamaPredictor:
 
     def traceback_brownian_motion(self, *, x_next, x, t, dt, score, finetune_score=None, batch_idx=None):
         drift, diffusion = self.reverse_drift_and_diffusion(x=x, t=t, score=score, finetune_score=finetune_score, batch_idx=batch_idx)
+        if S._HOST_NOISE:   # the reference obtains the mean through update_given_drift_and_diffusion (denoiser.py:152-157),
+            torch.randn(*drift.shape)   # which draws a randn_like(drift) it then discards: keep the stream aligned
         if isinstance(self.corruption, S.SO3SDE):
             mean = ops.so3_compose_rotvec(x, drift * dt, self.corruption.tol)
             return ops.so3_rel_log(mean, x_next) / diffusion

@@ -583,6 +583,19 @@ def test_em_and_heun_trajectories_vs_reference_golden():
     assert torch.equal(path.dWs_batch["pos"].cpu(), T(g["emft_dWs_pos"]))
     assert torch.equal(path.dWs_batch["node_orientations"].cpu(), T(g["emft_dWs_rot"]))
     assert torch.equal(path.timesteps.cpu(), T(g["emft_timesteps"]))
+    # Heun fine-tune variant (denoiser.py:462-620): final state, controls and traced-back Brownian increments
+    with S.host_noise():
+        torch.manual_seed(int(g["heunft_seed"]))
+        path = shortcuts.heun_denoiser_finetune(batch=batch, sdes=sdes, score_model=m, finetune_model=fm, noise=0.5,
+                                                num_steps=int(g["heunft_steps"]), max_t=0.99, min_t=0.001, device=DEV)
+    assert len(path.batches) == int(g["heunft_steps"]) + 1 and not torch.equal(path.batches[0]["pos"], path.batches[-1]["pos"])
+    assert rel_err(path.batches[-1]["pos"], T(g["heunft_pos"])) <= TRAJ_TOL
+    assert rel_err(path.batches[-1]["node_orientations"], T(g["heunft_rot"])) <= TRAJ_TOL
+    assert rel_err(path.us_batch["pos"], T(g["heunft_us_pos"]), floor=0.1) <= TRAJ_TOL
+    assert rel_err(path.us_batch["node_orientations"], T(g["heunft_us_rot"]), floor=0.1) <= TRAJ_TOL
+    # traced-back increments divide a small difference by g(t): compared at the scale of a unit normal increment
+    assert rel_err(path.dWs_batch["pos"], T(g["heunft_dWs_pos"]), floor=0.1) <= 5 * TRAJ_TOL
+    assert rel_err(path.dWs_batch["node_orientations"], T(g["heunft_dWs_rot"]), floor=0.1) <= 5 * TRAJ_TOL
 
 
 def test_analytic_score_moments_on_gpu():

@@ -233,6 +233,13 @@ def test_sampler_trajectories_bit_exact():
         assert torch.equal(path.dWs["pos"], T(g["emft_dWs_pos"]))
         assert torch.equal(path.dWs["node_orientations"], T(g["emft_dWs_rot"]))
         assert torch.equal(path.timesteps, T(g["emft_timesteps"]))
+        # Heun fine-tune variant: the reference's `batches` all alias its final state (recorded in the fixture)
+        assert int(g["heunft_aliased"]) == 1
+        torch.manual_seed(int(g["heunft_seed"]))
+        path = samplers.heun_finetune(m, fm, lengths, r3, tab, int(g["heunft_steps"]), 0.99, 0.001, 0.5)
+        assert torch.equal(path.pos[-1], T(g["heunft_pos"])) and torch.equal(path.rot[-1], T(g["heunft_rot"]))
+        assert torch.equal(path.us["pos"], T(g["heunft_us_pos"])) and torch.equal(path.us["node_orientations"], T(g["heunft_us_rot"]))
+        assert torch.equal(path.dWs["pos"], T(g["heunft_dWs_pos"])) and torch.equal(path.dWs["node_orientations"], T(g["heunft_dWs_rot"]))
 
 
 def test_analytic_score_moments():
