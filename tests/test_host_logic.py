@@ -161,3 +161,45 @@ def test_samplers_refuse_cpu():
     with pytest.raises(RuntimeError):
         shortcuts.dpm_solver(batch=b, sdes={"pos": shortcuts.CosineVPSDE(), "node_orientations": None},
                              score_model=lambda x, t: x, num_steps=2, max_t=0.99, min_t=0.001, device="cpu")
+
+
+def test_batch_assembly_and_result_format(tmp_path):
+    """sampling_io: the graph of sample.py:143-183, the npz naming / resume rule of utils.py:13-28 and the batch loop of
+    sample.py:288-308, driven with a stub denoiser (the real ones need a GPU)."""
+    import numpy as np
+
+    from se3diff_b200 import sampling_io as sio
+
+    L, seq = 7, "ACDEFGH"
+    g = torch.Generator().manual_seed(0)
+    single, pair = torch.randn(L, 384, generator=g), torch.randn(L, L, 128, generator=g)
+    np.save(tmp_path / "single.npy", single.numpy())
+    cg = sio.generate_chemgraph(sequence=seq, single_embeds=tmp_path / "single.npy", pair_embeds=pair.numpy())
+    assert cg.pair_embeds.shape == (L * L, 128) and torch.equal(cg.pair_embeds[2 * L + 3], pair[2, 3])
+    assert torch.equal(cg.edge_index[:, 2 * L + 3], torch.tensor([2, 3])) and torch.isnan(cg.pos).all()
+    with pytest.raises(ValueError):
+        sio.generate_chemgraph(sequence=seq + "A", single_embeds=single, pair_embeds=pair)
+    assert sio.format_npz_samples_filename(30, 10) == "batch_0000030_0000040.npz"
+
+    calls = []
+
+    def stub_denoiser(*, batch, sdes, score_model, device=None):
+        calls.append((batch.num_graphs, torch.initial_seed()))
+        n = batch["pos"].shape[0]
+        return batch.replace(pos=torch.randn(n, 3), node_orientations=torch.eye(3).expand(n, 3, 3).clone())
+
+    out = tmp_path / "samples"
+    kw = dict(sequence=seq, chemgraph=cg, output_dir=out, bundle=(None, None, stub_denoiser), batch_size=4)
+    first = sio.sample_to_dir(num_samples=6, **kw)
+    assert [p.name for p in first] == ["batch_0000000_0000004.npz", "batch_0000004_0000006.npz"]
+    assert calls == [(4, 0), (2, 4)]                       # batch sizes and per-batch seeds = global sample offsets
+    assert sio.count_samples_in_output_dir(out) == 6
+    second = sio.sample_to_dir(num_samples=11, **kw)       # resume: only the missing 5
+    assert [p.name for p in second] == ["batch_0000006_0000010.npz", "batch_0000010_0000011.npz"]
+    z = np.load(second[0])
+    assert set(z.files) == {"pos", "node_orientations", "sequence"} and z["pos"].shape == (4, L, 3)
+    assert z["node_orientations"].shape == (4, L, 3, 3) and z["sequence"].item() == seq and z["pos"].dtype == np.float32
+    pos, rot = sio.load_samples(out, seq)
+    assert pos.shape == (11, L, 3) and rot.shape == (11, L, 3, 3)
+    torch.manual_seed(4)
+    assert torch.equal(pos[4:6], torch.randn(2 * L, 3).view(2, L, 3))   # batch seeded with its offset (sample.py:298-306)
