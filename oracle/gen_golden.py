@@ -236,6 +236,15 @@ def score_model_small(ns):
     save.update(lengths=np.asarray(lengths), single=torch.cat(single), pair=torch.cat([p.reshape(-1, 128) for p in pair]),
                 in_pos=pos, in_rot=rot, known=known, t=t, out_pos_known=o1["pos"], out_rot_known=o1["node_orientations"],
                 out_pos=o2["pos"], out_rot=o2["node_orientations"], cfg_json=np.asarray(yaml.safe_dump(SMALL_MODEL)))
+    # gradients of a fixed linear functional of the outputs (the differentiable forward the fine-tune step needs, finetune.py:338-393)
+    wp, wr = torch.randn(N, 3, generator=g), torch.randn(N, 3, generator=g)
+    o3 = m(ref_harness.make_batch(ns, single, pair, lengths, pos, rot, extra={"pos_is_known": known}), t)
+    loss = (o3["pos"] * wp).sum() + (o3["node_orientations"] * wr).sum()
+    named = [(k, p) for k, p in m.named_parameters() if p.requires_grad]
+    grads = torch.autograd.grad(loss, [p for _, p in named])
+    save.update(grad_wp=wp, grad_wr=wr, grad_loss=loss.detach(), grad_names=np.asarray([k for k, _ in named]),
+                grad_norms=torch.stack([gr.norm() for gr in grads]),
+                **{"grad::" + k: gr for (k, _), gr in zip(named, grads) if gr.numel() <= 4096})
     np.savez_compressed(os.path.join(OUT, "score_model_small.npz"), **_np(save))
 
 

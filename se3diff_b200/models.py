@@ -16,12 +16,14 @@ The forward pass is re-designed for the GPU (DESIGN.md section "score model"):
     concat) is ONE hand-written kernel (se3_ipa_attention_fwd);
   * GEMMs / LayerNorms go through torch (cuBLAS), in fp32 ("fp32" precision, the parity mode) or
     with bf16 operands and fp32 accumulation ("bf16", the throughput mode).
-Dropout is never applied here: the path is inference (reference parity is defined in eval mode,
-SURVEY.md section 0); a model in training mode with dropout > 0 raises instead of silently differing.
+The kernel path is inference: no dropout, no gradients (reference parity is defined in eval mode).
+A forward that must be differentiated or that applies dropout (the small fine-tune control model) takes
+`_forward_torch`, the same network as torch autograd expressions.
 """
 from __future__ import annotations
 
 import math
+import warnings
 
 import torch
 import torch.nn.functional as F
@@ -387,13 +389,79 @@ class DistributionalGraphormer(nn.Module):
             outs.append(F.linear(hh, w3, seq[3].bias))
         return outs
 
-    @torch.no_grad()
     def forward(self, x, node_orientations, batch_index, t, context):
         """x [N,3] positions, node_orientations [N,3,3] ROTATIONS (not inverse: the reference transposes
-        twice, models.py:369 and structure_module.py:125-127), t [num_graphs] already scaled by 1000."""
-        if self.training and self.dropout_p > 0:
-            raise RuntimeError("se3diff_b200 score model is inference-only: call .eval() (reference parity is defined "
-                               "with dropout off)")
+        twice, models.py:369 and structure_module.py:125-127), t [num_graphs] already scaled by 1000.
+
+        Inference (no gradient wanted, dropout off) runs on this library's kernels.  A forward that has to be
+        differentiated (the fine-tune control inside `_chunk_update`, finetune.py:338-393) or that applies dropout
+        (`finetune_model.train()`, finetune.py:594) is evaluated as torch autograd expressions instead."""
+        needs_autograd = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if needs_autograd or (self.training and self.dropout_p > 0):
+            if not needs_autograd and not getattr(self, "_warned_train", False):
+                self._warned_train = True
+                warnings.warn("se3diff_b200 score model is in training mode with dropout > 0: evaluating the torch (dropout) path; "
+                              "call .eval() to sample on the CUDA kernel path", stacklevel=3)
+            return self._forward_torch(x, node_orientations, t, context)
+        with torch.no_grad():
+            return self._forward_kernels(x, node_orientations, t, context)
+
+    def _forward_torch(self, x, node_orientations, t, context):
+        """The same network (models.py:217-315, structure_module.py:109-287) written with differentiable torch operations
+        on dense [B, L, .] tensors; dropout modules are honoured.  Index / mask bookkeeping comes from the context cache."""
+        c = self._context(context)
+        B, Lm = c.batch, c.lmax
+        dev = x.device
+        single_d = self._to_dense(context["single_embeds"].float(), c)
+        pair_d = self._dense_pairs(context, context["pair_embeds"].float(), c, dev)
+        if c.shared:
+            single_d, pair_d = single_d[:1], pair_d[:1]
+        x1d = self.x1d_proj(single_d) + self.step_emb(t.float()[:B])[:, None]                       # [B, L, D]
+        bucket = self.rp_proj.bucket_table(Lm).to(dev)
+        x2d = self.x2d_proj(pair_d) + self.rp_proj.relative_attention_bias(bucket)[None]             # [Bp, L, L, dp]
+        T = self._to_dense(x.float(), c)                                                             # [B, L, 3]
+        R = self._to_dense(node_orientations.float(), c)                                             # [B, L, 3, 3]
+        bias = None if c.key_bias is None else c.key_bias[:, None, None, :]                          # additive key mask
+        for lyr in self.st_module.encoder.layers:
+            x1d = x1d + self._ipa_torch(lyr.attn, lyr.norm1(x1d), x2d, T, R, bias)
+            x1d = x1d + lyr.ffn.ff(lyr.norm2(x1d))
+        T_eps, IR_eps = self.st_module.diff_head.fc_t(x1d), self.st_module.diff_head.fc_eps(x1d)
+        T_out = torch.matmul(R, T_eps.unsqueeze(-1)).squeeze(-1).reshape(B * Lm, 3)                  # models.py:305
+        IR_eps = IR_eps.reshape(B * Lm, 3)
+        if c.dense_index is None:
+            return T_out, IR_eps
+        return T_out[c.dense_index], IR_eps[c.dense_index]
+
+    @staticmethod
+    def _ipa_torch(a: SAAttention, x1d, x2d, T, R, bias):
+        """SAAttention.forward (structure_module.py:109-220) with autograd; `x2d` may carry a leading 1 (shared context)."""
+        B, Lm, H = x1d.shape[0], x1d.shape[1], a.n_head
+        q = a.scalar_query(x1d).view(B, Lm, H, -1)
+        k = a.scalar_key(x1d).view(B, Lm, H, -1)
+        v = a.scalar_value(x1d).view(B, Lm, H, -1)
+
+        def to_global(p):                                          # apply_affine: R p + T per residue
+            return torch.matmul(R[:, :, None, None], p.unsqueeze(-1)).squeeze(-1) + T[:, :, None, None]
+
+        qp = to_global(a.point_query(x1d).view(B, Lm, H, -1, 3))
+        kp = to_global(a.point_key(x1d).view(B, Lm, H, -1, 3))
+        vp = to_global(a.point_value(x1d).view(B, Lm, H, -1, 3))
+        logits = torch.einsum("bihc,bjhc->bhij", q * a.scalar_weight, k)
+        dist = torch.norm(qp.unsqueeze(2) - kp.unsqueeze(1), dim=-1).sum(dim=-1)                    # [B, i, j, H], un-squared (:170)
+        head_w = -0.5 * a.point_weight * F.softplus(a.trained_point_weight)
+        logits = logits + (head_w * dist).permute(0, 3, 1, 2) + a.pair_weight * a.pair_bias(x2d).permute(0, 3, 1, 2)
+        if bias is not None:
+            logits = logits + bias
+        attn = torch.softmax(logits, dim=-1)
+        o_s = torch.einsum("bhij,bjhc->bihc", attn, v).reshape(B, Lm, -1)
+        o_pg = torch.einsum("bhij,bjhcp->bihcp", attn, vp)
+        o_pl = torch.matmul(R.transpose(-1, -2)[:, :, None, None], (o_pg - T[:, :, None, None]).unsqueeze(-1)).squeeze(-1)
+        o_n = torch.norm(o_pl, dim=-1).reshape(B, Lm, -1)
+        v_pair = a.pair_value(x2d).view(x2d.shape[0], Lm, Lm, H, -1).expand(B, -1, -1, -1, -1)
+        o_pair = torch.einsum("bhij,bijhc->bihc", attn, v_pair).reshape(B, Lm, -1)
+        return a.dropout(a.fc_out(torch.cat([o_s, o_pl.reshape(B, Lm, -1), o_pair, o_n], dim=-1)))
+
+    def _forward_kernels(self, x, node_orientations, t, context):
         c = self._context(context)
         w = self._layer_weights(torch.float32 if self.precision == "fp32" else torch.bfloat16)
         B, Lm, D = c.batch, c.lmax, self.d_model

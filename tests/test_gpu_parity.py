@@ -19,6 +19,14 @@ T = torch.from_numpy
 DEV = "cuda"
 
 
+@pytest.fixture(autouse=True)
+def _inference_mode_by_default():
+    """The kernel path is the inference path: a score model called with gradients enabled and trainable parameters takes
+    the torch autograd forward instead.  Tests of that path (and of the toy losses) enable gradients explicitly."""
+    with torch.no_grad():
+        yield
+
+
 def rel_err(a, b, floor=1.0):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return ((a - b).abs() / (b.abs().clamp_min(floor))).max().item()
@@ -753,9 +761,10 @@ def test_toy_layer_vs_reference_golden():
             torch.manual_seed(int(g["mixsample_seed"]))
             assert rel_err(sde.sample_multiple_igso3(mus, sigmas, weights, 32), T(g["mixsample"]), floor=0.1) <= 1e-5
         torch.manual_seed(int(g["train_seed"]))
-        loss = toy.compute_train_loss(sde, net, mus, sigmas, weights, device=DEV, batch_size=64)
+        with torch.enable_grad():
+            loss = toy.compute_train_loss(sde, net, mus, sigmas, weights, device=DEV, batch_size=64)
+            grads = torch.autograd.grad(loss, [p for p in net.parameters() if p.requires_grad])
         assert abs(loss.item() - float(g["train_loss"])) <= 1e-3 * abs(float(g["train_loss"]))
-        grads = torch.autograd.grad(loss, [p for p in net.parameters() if p.requires_grad])
         assert rel_err(torch.stack([x.norm() for x in grads]), T(g["train_grad_norms"]), floor=1e-3) <= 2e-3
         torch.manual_seed(int(g["rev_seed"]))
         xs, ts = toy.reverse_diffusion(sde, net, device=DEV, batch_size=16, num_steps=8)
@@ -765,10 +774,11 @@ def test_toy_layer_vs_reference_golden():
         assert rel_err(xs, T(g["revft_xs"]), floor=0.1) <= TRAJ_TOL and rel_err(us, T(g["revft_us"]), floor=0.05) <= TRAJ_TOL
         assert torch.equal(dWs.cpu(), T(g["revft_dWs"]))
         torch.manual_seed(int(g["ft_seed"]))
-        loss = toy.compute_finetune_loss(sde, net, ctrl, mus, sigmas, h_stars, device=DEV, batch_size=16, num_steps=6, l_max=200)
+        with torch.enable_grad():
+            loss = toy.compute_finetune_loss(sde, net, ctrl, mus, sigmas, h_stars, device=DEV, batch_size=16, num_steps=6, l_max=200)
+            grads = torch.autograd.grad(loss, [p for p in ctrl.parameters() if p.requires_grad])
         ref = float(g["ft_loss"])
         assert abs(loss.item() - ref) <= 5e-3 * max(abs(ref), 1e-3)
-        grads = torch.autograd.grad(loss, [p for p in ctrl.parameters() if p.requires_grad])
         assert rel_err(grads[-1], T(g["ft_grad_last"]), floor=float(np.abs(g["ft_grad_last"]).max()) * 0.1) <= 2e-2
 
 
@@ -793,3 +803,43 @@ def test_sample_to_dir_runs_the_real_sampler(tmp_path):
     assert pa.shape == (7, L, 3) and torch.equal(pa, pb) and torch.equal(ra, rb)
     eye = torch.eye(3).expand(7, L, 3, 3)
     assert (ra.transpose(-1, -2) @ ra - eye).abs().max() < 1e-4 and torch.isfinite(pa).all()
+
+
+def test_differentiable_forward_matches_reference_outputs_and_gradients():
+    """The torch-autograd forward (taken when a gradient is wanted, finetune.py:338-393) against the reference: outputs on
+    the ragged / masked golden and the gradient of a fixed linear functional with respect to every parameter."""
+    from se3diff_b200.models import DiGConditionalScoreModel
+
+    g = load_golden("score_model_small.npz")
+    cfg = yaml.safe_load(str(g["cfg_json"]))
+    lengths = g["lengths"].tolist()
+    m = DiGConditionalScoreModel(**cfg)
+    m.load_state_dict(_sd(g, "sd::"))
+    m = m.eval().to(DEV)
+    pairs = _pairs(T(g["pair"]), lengths)
+    bk = _make_batch(T(g["single"]), pairs, lengths, T(g["in_pos"]), T(g["in_rot"]), extra={"pos_is_known": T(g["known"])}).to(DEV)
+    torch.set_grad_enabled(True)                           # grad mode + trainable parameters -> autograd path
+    out = m(bk, T(g["t"]).to(DEV))
+    assert out["pos"].requires_grad
+    assert rel_err(out["pos"], T(g["out_pos_known"]), floor=0.1) <= MODEL_TOL
+    assert rel_err(out["node_orientations"], T(g["out_rot_known"]), floor=0.1) <= MODEL_TOL
+    loss = (out["pos"] * T(g["grad_wp"]).to(DEV)).sum() + (out["node_orientations"] * T(g["grad_wr"]).to(DEV)).sum()
+    assert abs(loss.item() - float(g["grad_loss"])) <= 1e-3 * abs(float(g["grad_loss"]))
+    named = dict(m.named_parameters())
+    names = [str(n) for n in g["grad_names"]]
+    grads = torch.autograd.grad(loss, [named[n] for n in names])
+    norms = torch.stack([x.norm() for x in grads]).cpu()
+    assert rel_err(norms, T(g["grad_norms"]), floor=float(g["grad_norms"].max()) * 1e-3) <= 2e-3
+    for n, x in zip(names, grads):
+        if "grad::" + n in g:
+            ref = T(g["grad::" + n])
+            assert rel_err(x, ref, floor=float(ref.abs().max()) * 0.05 + 1e-9) <= 2e-2, n
+    # the kernel path and the autograd path agree with each other
+    with torch.no_grad():
+        out_k = m(bk, T(g["t"]).to(DEV))
+    assert rel_err(out_k["pos"], out["pos"], floor=0.1) <= MODEL_TOL
+    # training mode applies dropout: finite, and different from the eval output
+    m.train()
+    with torch.no_grad():
+        out_t = m(bk, T(g["t"]).to(DEV))
+    assert torch.isfinite(out_t["pos"]).all() and not torch.equal(out_t["pos"], out_k["pos"])
