@@ -288,6 +288,12 @@ int se3_ipa_attention_tc_fwd(const void* scalars_bf16, int64_t scalar_stride, co
 int se3_residual_layernorm(float* x, const float* y, const float* bias, const float* gamma, const float* beta, float eps,
                            void* out, int out_is_bf16, int64_t rows, int dim, se3_stream_t stream);
 
+/* Folded-state indicator of the fine-tune objective (observables/folding_stability.py:52-81, called at finetune.py:452 on
+ * the last batch of the rollout): dRMSD of every sample's C-alpha distance matrix to the reference's,
+ * p = clamp(sigmoid(k (dRMSD - d_0)), tol, 1 - tol).  coords [batch, len, 3], ref_coords [len, 3] (nm); drmsd optional. */
+int se3_folded_proportion(const float* coords, const float* ref_coords, float* p_folded, float* drmsd, int64_t batch, int len,
+                          float k, float d_0, float tol, se3_stream_t stream);
+
 /* tcgen05 self-test: d[128,n] fp32 = a[128,k] . b[n,k]^T with bf16 operands, through the operand staging,
  * UMMA descriptors, TMEM allocation and mbarrier completion the attention kernels use. */
 int se3_debug_umma_gemm(const void* a_bf16, const void* b_bf16, float* d, int n, int k, se3_stream_t stream);

@@ -388,12 +388,78 @@ def toy(ns):
     np.savez_compressed(os.path.join(OUT, "toy.npz"), **_np(save))
 
 
+def finetune_step(ns):
+    """The fine-tune step (finetune.py:338-393 `_chunk_update`, observables/folding_stability.py:52-101) from the reference's
+    own function bodies (executed in memory: their modules need hydra / mdtraj / Bio to import) on a reference rollout."""
+    import contextlib
+    import io
+    from collections import defaultdict
+
+    import torch.nn.functional as F
+    from torch_geometric.utils import to_dense_batch
+
+    import bioemu.ppft as ppft
+
+    fs = ref_harness.extract_functions("bioemu/src/bioemu/observables/folding_stability.py",
+                                       ["compute_folded_proportion", "compute_dG", "compute_folded_proportion_from_dG"],
+                                       {"torch": torch, "F": F, "K_BOLTZMANN": 0.001987203599772605})
+    ft = ref_harness.extract_functions("bioemu/src/bioemu/finetune.py", ["_chunk_update"], {
+        "torch": torch, "defaultdict": defaultdict, "to_dense_batch": to_dense_batch, "ChemGraph": ns.chemgraph.ChemGraph,
+        "DiGConditionalScoreModel": ns.models.DiGConditionalScoreModel, "DeviceLikeType": object,
+        "compute_int_dws": ppft.compute_int_dws, "compute_int_u_u_dt": ppft.compute_int_u_u_dt,
+        "compute_ev_loss": ppft.compute_ev_loss, "compute_kl_loss": ppft.compute_kl_loss})
+    m, fm = _small_model(ns, 41), _small_model(ns, 42)
+    with torch.no_grad():
+        for p in fm.parameters():
+            p.mul_(0.3)
+    g = torch.Generator().manual_seed(43)                   # the sequence of the `trajectories` fixture
+    L, B, T = 11, 4, 6
+    single = [torch.randn(L, 384, generator=g)] * B
+    pair = [torch.randn(L, L, 128, generator=g)] * B
+    so3 = ns.so3_sde.DiGSO3SDE(**SMALL_SDE)
+    sdes = {"node_orientations": so3, "pos": ns.sde_lib.CosineVPSDE(s=0.008)}
+    with torch.no_grad():
+        torch.manual_seed(71)
+        path = ns.denoiser.euler_maruyama_predictor_finetune(batch=ref_harness.make_batch(ns, single, pair, [L] * B), sdes=sdes, score_model=m,
+                                                             finetune_model=fm, num_steps=T, max_t=0.99, min_t=0.001, device="cpu")
+    batches, timesteps, us_sg, dWs = path
+    fields = list(sdes.keys())
+    # observable: random-weight frames live at the 100-nm scale, so the sigmoid is given a matching width / threshold
+    gg = torch.Generator().manual_seed(72)
+    ref_coords = torch.randn(L, 3, generator=gg) * 40.0
+    coords = to_dense_batch(batches[-1].pos, batches[-1].batch)[0]
+    k_, d0_ = -0.02, 120.0
+    p_folded = fs["compute_folded_proportion"](coords, ref_coords, k_, d0_, 1e-7)
+    hs = p_folded.unsqueeze(-1)
+    h_stars = torch.tensor([0.6])
+    dts = torch.diff(timesteps)
+    int_sg = sum(ppft.compute_int_u_u_dt(us=us_sg[f].flatten(-2, -1), dts=dts) for f in fields)
+    fm.zero_grad()
+    micro = 4
+    with contextlib.redirect_stdout(io.StringIO()):
+        for lo in range(0, T, micro):
+            hi = min(lo + micro, T)
+            ft["_chunk_update"](batches=batches[lo:hi], timesteps=timesteps[lo:hi], dts=dts[lo:hi], dWs_batch={f: dWs[f][lo:hi] for f in fields},
+                                int_u_u_dt_sg=int_sg, hs=hs, h_stars=h_stars, finetune_model=fm, fields=fields, batch_size=B, device="cpu",
+                                lambda_=0.1, tol=1e-7)
+        ws = torch.ones_like(int_sg)
+        val = ppft.compute_ev_loss(ws=ws, hs=hs, h_stars=h_stars, from_int_dws=False, use_stab=False, tol=1e-7) + 0.1 * ppft.compute_kl_loss(
+            ws=ws, int_u_u_dt=int_sg, int_u_u_dt_sg=int_sg, from_int_dws=False, use_rloo=False)
+    named = [(k, p) for k, p in fm.named_parameters() if p.grad is not None]
+    save = dict(L=L, B=B, T=T, seed=71, micro=micro, k=k_, d_0=d0_, ref_coords=ref_coords, coords=coords, p_folded=p_folded,
+                dG=fs["compute_dG"](p_folded), p_from_dG=fs["compute_folded_proportion_from_dG"](torch.tensor([-1.0, 0.0, 2.5])),
+                h_stars=h_stars, val_loss=val.detach(), final_pos=batches[-1].pos, grad_names=np.asarray([k for k, _ in named]),
+                grad_norms=torch.stack([p.grad.norm() for _, p in named]),
+                **{"grad::" + k: p.grad for k, p in named if p.numel() <= 4096})
+    np.savez_compressed(os.path.join(OUT, "finetune_step.npz"), **_np(save))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_harness.load()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     every = (so3_maps, igso3_series, so3_tables, schedules, score_model_tiny, score_model_small, trajectories,
-             analytic_denoise, toy)
+             analytic_denoise, toy, finetune_step)
     only = set(sys.argv[1:])                      # e.g. `python -m oracle.gen_golden toy` regenerates one file
     for fn in every:
         if only and fn.__name__ not in only:

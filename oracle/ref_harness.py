@@ -72,3 +72,21 @@ def make_batch(ns, single, pair, lengths, pos=None, rot=None, extra=None):
         graphs.append(ns.chemgraph.ChemGraph(**kw))
         o += n
     return ns.Batch.from_data_list(graphs)
+
+
+def extract_functions(rel_path: str, names, namespace: dict) -> dict:
+    """Executes the named top-level function definitions of a reference file, verbatim and in memory, inside `namespace`
+    -- for modules whose import chain needs packages that are absent here (hydra, mdtraj, Bio): the function bodies still
+    are the reference's own code.  Returns the namespace."""
+    import ast
+
+    path = os.path.join(REF_ROOT, rel_path)
+    tree = ast.parse(open(path).read(), filename=path)
+    picked = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    missing = set(names) - {n.name for n in picked}
+    if missing:
+        raise RuntimeError(f"{rel_path}: functions not found: {sorted(missing)}")
+    for n in picked:
+        n.decorator_list = []
+    exec(compile(ast.Module(body=picked, type_ignores=[]), path, "exec"), namespace)
+    return namespace

@@ -24,6 +24,7 @@ SOURCES = {
     "tc_selftest.cu": [],
     "ipa_tc.cu": [],
     "fused_rows.cu": [],
+    "observables.cu": [],
 }
 
 

@@ -484,6 +484,20 @@ def ipa_attention_tc_fwd(scalars, points, rot, trans, pair_bias_packed, pair_val
     return out
 
 
+def folded_proportion(coords: torch.Tensor, ref_coords: torch.Tensor, k: float = -24.0, d_0: float = 0.4, tol: float = 1e-7,
+                      want_drmsd: bool = False):
+    """compute_folded_proportion (observables/folding_stability.py:52-81): coords [B, L, 3], ref_coords [L, 3] -> p [B]."""
+    c, r = _dev(coords, name="coords"), _dev(ref_coords, name="ref_coords")
+    if c.dim() != 3 or c.shape[-1] != 3 or tuple(r.shape) != (c.shape[1], 3):
+        raise ValueError(f"coords [B, L, 3] and ref_coords [L, 3] expected, got {tuple(c.shape)} and {tuple(r.shape)}")
+    p = torch.empty(c.shape[0], dtype=torch.float32, device=c.device)
+    d = torch.empty_like(p) if want_drmsd else None
+    with _guard(c):
+        L.check(L.lib().se3_folded_proportion(_p(c), _p(r), _p(p), _p(d), c.shape[0], c.shape[1], float(k), float(d_0), float(tol),
+                                              _stream(c)), "se3_folded_proportion")
+    return (p, d) if want_drmsd else p
+
+
 def residual_layernorm(x, y, bias, gamma, beta, eps: float, out_dtype=torch.bfloat16):
     """x += y + bias (in place, skipped when y is None); returns LayerNorm(x) in `out_dtype`."""
     if x.dtype != torch.float32 or not x.is_contiguous():

@@ -843,3 +843,45 @@ def test_differentiable_forward_matches_reference_outputs_and_gradients():
     with torch.no_grad():
         out_t = m(bk, T(g["t"]).to(DEV))
     assert torch.isfinite(out_t["pos"]).all() and not torch.equal(out_t["pos"], out_k["pos"])
+
+
+def test_finetune_step_vs_reference_function_bodies():
+    """Rollout -> observable -> chunked loss + backward (finetune.py:291-514) against gradients produced by the reference's
+    own `_chunk_update`, ppft functionals and folding-stability formulas (tests/golden/finetune_step.npz)."""
+    from se3diff_b200 import finetune_step as FS
+    from se3diff_b200 import ops, shortcuts
+
+    g, m, fm, sdes, _, S = _traj_setup()
+    f = load_golden("finetune_step.npz")
+    L, B, steps = int(f["L"]), int(f["B"]), int(f["T"])
+    k, d_0 = float(f["k"]), float(f["d_0"])
+    # observable
+    p, d = ops.folded_proportion(T(f["coords"]).to(DEV), T(f["ref_coords"]).to(DEV), k, d_0, want_drmsd=True)
+    assert rel_err(p, T(f["p_folded"]), floor=0.05) <= 1e-3
+    assert abs(FS.compute_dG(p).item() - float(f["dG"])) <= 1e-3 * max(abs(float(f["dG"])), 0.1)
+    assert torch.allclose(FS.compute_folded_proportion_from_dG(torch.tensor([-1.0, 0.0, 2.5])), T(f["p_from_dG"]), rtol=1e-6)
+    # rollout on the CUDA path with the reference's noise stream
+    nan = float("nan")
+    batch = _make_batch(T(g["single"]).repeat(B, 1), [T(g["pair"])] * B, [L] * B, torch.full((B * L, 3), nan), torch.full((B * L, 3, 3), nan))
+    m, fm = m.to(DEV), fm.to(DEV)
+    with S.host_noise():
+        torch.manual_seed(int(f["seed"]))
+        path = shortcuts.euler_maruyama_predictor_finetune(batch=batch, sdes=sdes, score_model=m, finetune_model=fm, num_steps=steps,
+                                                           max_t=0.99, min_t=0.001, device=DEV)
+    assert rel_err(path.batches[-1]["pos"], T(f["final_pos"])) <= TRAJ_TOL
+    # loss + gradient of the control model
+    bundle = FS.FinetuneBundle(sdes, m, fm, None, FS.FoldingStability(k=k, d_0=d_0, ref_coords=T(f["ref_coords"]).to(DEV)))
+    fm.zero_grad()
+    loss = FS.compute_finetune_loss(sequence="A" * L, h_stars=T(f["h_stars"]), finetune_bundle=bundle, denoised_sde_path=path, batch_size=B,
+                                    device=DEV, for_grad=True, micro_batch_size=int(f["micro"]))
+    assert abs(loss.item() - float(f["val_loss"])) <= 2e-3 * abs(float(f["val_loss"]))
+    named = dict(fm.named_parameters())
+    names = [str(n) for n in f["grad_names"]]
+    norms = torch.stack([named[n].grad.norm() for n in names]).cpu()
+    assert rel_err(norms, T(f["grad_norms"]), floor=float(f["grad_norms"].max()) * 1e-2) <= 2e-2
+    for n in names:
+        if "grad::" + n in f:
+            ref = T(f["grad::" + n])
+            assert rel_err(named[n].grad, ref, floor=float(ref.abs().max()) * 0.1 + 1e-12) <= 5e-2, n
+    with pytest.raises(ValueError):
+        FS.compute_finetune_loss(sequence="A" * L, h_stars=T(f["h_stars"]), finetune_bundle=bundle, denoised_sde_path=path, batch_size=1)
