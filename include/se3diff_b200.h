@@ -294,6 +294,17 @@ int se3_residual_layernorm(float* x, const float* y, const float* bias, const fl
 int se3_folded_proportion(const float* coords, const float* ref_coords, float* p_folded, float* drmsd, int64_t batch, int len,
                           float k, float d_0, float tol, se3_stream_t stream);
 
+/* Backbone atoms from frames (get_atom37_from_frames / compute_backbone / _adjust_oxygen_pos, convert_chemgraph.py:139-293):
+ * pos [batch, len, 3] in Angstrom, rot [batch, len, 3, 3], aatype [len] (openfold order ARNDCQEGHILKMFPSTWYV), pos_is_known
+ * [len] bytes or NULL -> atoms [batch, len, 5, 3] = N, CA, C, CB, O (the first five slots of the atom37 layout; glycine CB
+ * is exactly zero, i.e. masked out by the reference's `any(pos != 0)` rule). */
+int se3_backbone_atoms(const float* pos, const float* rot, const int32_t* aatype, const uint8_t* pos_is_known, float* atoms,
+                       int64_t batch, int len, se3_stream_t stream);
+/* The three statistics of the physicality filter (_filter_unphysical_traj_masks, convert_chemgraph.py:296-345) per sample:
+ * out [batch, 3] = max sequential CA-CA distance, max sequential C-N distance, min heavy-atom distance between residues at
+ * least three apart, in the unit of `atoms` ([batch, len, 5, 3] as written by se3_backbone_atoms). */
+int se3_physicality(const float* atoms, const int32_t* aatype, float* out, int64_t batch, int len, se3_stream_t stream);
+
 /* tcgen05 self-test: d[128,n] fp32 = a[128,k] . b[n,k]^T with bf16 operands, through the operand staging,
  * UMMA descriptors, TMEM allocation and mbarrier completion the attention kernels use. */
 int se3_debug_umma_gemm(const void* a_bf16, const void* b_bf16, float* d, int n, int k, se3_stream_t stream);

@@ -454,12 +454,34 @@ def finetune_step(ns):
     np.savez_compressed(os.path.join(OUT, "finetune_step.npz"), **_np(save))
 
 
+def backbone(ns):
+    """Frames -> atom37 (convert_chemgraph.py:17-293) from the reference's own function bodies (the module itself needs mdtraj
+    / modelcif to import), on a random-walk chain whose sequence holds all twenty residue types."""
+    from bioemu.openfold.np import residue_constants
+    from bioemu.openfold.utils.rigid_utils import Rigid, Rotation
+
+    cc = ref_harness.extract_functions("bioemu/src/bioemu/convert_chemgraph.py",
+                                       ["_torsion_angles_to_frames", "frames_to_atom14_pos", "compute_backbone", "_adjust_oxygen_pos",
+                                        "get_atom37_from_frames"],
+                                       {"torch": torch, "residue_constants": residue_constants, "Rigid": Rigid, "Rotation": Rotation,
+                                        "C_O_BOND_LENGTH": 1.23})
+    seq = "ARNDCQEGHILKMFPSTWYVGGAPX"
+    g = torch.Generator().manual_seed(81)
+    L = len(seq)
+    steps = torch.randn(L, 3, generator=g)
+    pos = torch.cumsum(3.8 * steps / steps.norm(dim=-1, keepdim=True), dim=0)      # Angstrom, CA spacing 3.8
+    rot = ns.so3_sde.rotvec_to_rotmat(torch.randn(L, 3, generator=g))
+    atom37, mask, aatype = cc["get_atom37_from_frames"](pos.clone(), rot.clone(), seq)
+    np.savez_compressed(os.path.join(OUT, "backbone.npz"), **_np(dict(sequence=np.asarray(seq), pos=pos, rot=rot, atom37=atom37,
+                                                                       mask=mask, aatype=aatype)))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_harness.load()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     every = (so3_maps, igso3_series, so3_tables, schedules, score_model_tiny, score_model_small, trajectories,
-             analytic_denoise, toy, finetune_step)
+             analytic_denoise, toy, finetune_step, backbone)
     only = set(sys.argv[1:])                      # e.g. `python -m oracle.gen_golden toy` regenerates one file
     for fn in every:
         if only and fn.__name__ not in only:

@@ -71,6 +71,8 @@ SIGNATURES = {
     "se3_ipa_tc_workspace_bytes": [C.POINTER(IpaShape), C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
     "se3_ipa_attention_tc_fwd": [vp, i64, f32p, i64, f32p, f32p, vp, vp, f32p, f32p, vp, i32, vp, f32p, C.POINTER(IpaShape), vp],
     "se3_folded_proportion": [f32p, f32p, f32p, f32p, i64, i32, f32, f32, f32, vp],
+    "se3_backbone_atoms": [f32p, f32p, vp, vp, f32p, i64, i32, vp],
+    "se3_physicality": [f32p, vp, f32p, i64, i32, vp],
     "se3_residual_layernorm": [f32p] * 5 + [f32, vp, i32, i64, i32, vp],
     "se3_debug_umma_gemm": [vp, vp, f32p, i32, i32, vp],
     "se3_last_error": [],

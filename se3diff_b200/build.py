@@ -25,6 +25,7 @@ SOURCES = {
     "ipa_tc.cu": [],
     "fused_rows.cu": [],
     "observables.cu": [],
+    "backbone.cu": [],
 }
 
 

@@ -498,6 +498,32 @@ def folded_proportion(coords: torch.Tensor, ref_coords: torch.Tensor, k: float =
     return (p, d) if want_drmsd else p
 
 
+def backbone_atoms(pos: torch.Tensor, rot: torch.Tensor, aatype: torch.Tensor, pos_is_known: torch.Tensor | None = None) -> torch.Tensor:
+    """pos [B, L, 3] (Angstrom), rot [B, L, 3, 3], aatype [L] -> atoms [B, L, 5, 3] = N, CA, C, CB, O (convert_chemgraph.py:139-293)."""
+    pos, rot = _dev(pos, name="pos"), _dev(rot, name="rot")
+    if pos.dim() != 3 or tuple(rot.shape) != tuple(pos.shape[:2]) + (3, 3):
+        raise ValueError(f"pos [B, L, 3] and rot [B, L, 3, 3] expected, got {tuple(pos.shape)} and {tuple(rot.shape)}")
+    aa = _dev(aatype, torch.int32, "aatype")
+    if aa.numel() != pos.shape[1] or int(aa.max()) > 19 or int(aa.min()) < 0:
+        raise ValueError("aatype must hold one residue type in [0, 19] per residue")
+    known = None if pos_is_known is None else _dev(pos_is_known.to(torch.uint8), torch.uint8, "pos_is_known")
+    out = torch.empty(pos.shape[0], pos.shape[1], 5, 3, dtype=torch.float32, device=pos.device)
+    with _guard(pos):
+        L.check(L.lib().se3_backbone_atoms(_p(pos), _p(rot), _p(aa), _p(known), _p(out), pos.shape[0], pos.shape[1], _stream(pos)),
+                "se3_backbone_atoms")
+    return out
+
+
+def physicality(atoms: torch.Tensor, aatype: torch.Tensor) -> torch.Tensor:
+    """atoms [B, L, 5, 3] -> [B, 3]: max sequential CA-CA, max sequential C-N, min heavy-atom distance between residues >= 3 apart."""
+    atoms = _dev(atoms, name="atoms")
+    aa = _dev(aatype, torch.int32, "aatype")
+    out = torch.empty(atoms.shape[0], 3, dtype=torch.float32, device=atoms.device)
+    with _guard(atoms):
+        L.check(L.lib().se3_physicality(_p(atoms), _p(aa), _p(out), atoms.shape[0], atoms.shape[1], _stream(atoms)), "se3_physicality")
+    return out
+
+
 def residual_layernorm(x, y, bias, gamma, beta, eps: float, out_dtype=torch.bfloat16):
     """x += y + bias (in place, skipped when y is None); returns LayerNorm(x) in `out_dtype`."""
     if x.dtype != torch.float32 or not x.is_contiguous():

@@ -885,3 +885,36 @@ def test_finetune_step_vs_reference_function_bodies():
             assert rel_err(named[n].grad, ref, floor=float(ref.abs().max()) * 0.1 + 1e-12) <= 5e-2, n
     with pytest.raises(ValueError):
         FS.compute_finetune_loss(sequence="A" * L, h_stars=T(f["h_stars"]), finetune_bundle=bundle, denoised_sde_path=path, batch_size=1)
+
+
+def test_backbone_atoms_and_physicality_filter():
+    """f4: get_atom37_from_frames against the reference's own function bodies (tests/golden/backbone.npz); the physicality
+    statistics against the numpy restatement of the documented mdtraj criteria and against constructed known answers."""
+    from oracle import backbone as ob
+    from se3diff_b200 import backbone as bb
+    from se3diff_b200 import ops
+
+    g = load_golden("backbone.npz")
+    seq = str(g["sequence"])
+    pos, rot = T(g["pos"]).to(DEV), T(g["rot"]).to(DEV)
+    atom37, mask, aatype = bb.get_atom37_from_frames(pos, rot, seq)
+    assert torch.equal(aatype.cpu(), T(g["aatype"])) and torch.equal(mask.cpu(), T(g["mask"]))
+    assert (atom37.cpu() - T(g["atom37"])).abs().max() <= 2e-5 * max(1.0, float(np.abs(g["atom37"]).max()))
+    # batched, with the statistics checked against brute force
+    gen = torch.Generator().manual_seed(5)
+    B, L = 6, len(seq)
+    steps = torch.randn(B, L, 3, generator=gen)
+    pos_b = torch.cumsum(3.8 * steps / steps.norm(dim=-1, keepdim=True), dim=1)
+    pos_b[2, 10:] += torch.tensor([3.0, 0.0, 0.0])            # sample 2: one CA-CA bond stretched beyond 4.5 A
+    pos_b[4, 20] = pos_b[4, 3] + 0.3                          # sample 4: residues 3 and 20 on top of each other
+    rot_b = ops.so3_exp(torch.randn(B * L, 3, generator=gen).to(DEV)).view(B, L, 3, 3)
+    atoms = bb.backbone_atoms_batch(pos_b.to(DEV), rot_b, seq)
+    assert (atoms[0] - bb.get_atom37_from_frames(pos_b[0].to(DEV), rot_b[0], seq)[0][:, :5]).abs().max() == 0
+    stats = ops.physicality(atoms, bb.sequence_to_aatype(seq, DEV)).cpu().double()
+    ref = torch.from_numpy(ob.physicality_statistics(atoms.cpu().numpy(), bb.sequence_to_aatype(seq).numpy()))
+    assert (stats - ref).abs().max() <= 1e-4
+    ca_ok, cn_ok, clash_ok = bb.filter_unphysical_masks(pos_b.to(DEV) * 0.1, rot_b, seq)
+    assert not bool(ca_ok[2]) and not bool(clash_ok[4])
+    xyz, keep = bb.backbone_trajectory(pos_b.to(DEV) * 0.1, rot_b, seq, filter_samples=False)
+    assert xyz.shape == (B, 5 * L - seq.count("G"), 3) and keep.tolist() == list(range(B))
+    assert xyz.mean(dim=1).abs().max() < 0.5                    # centred on the CA centroid, in nm
