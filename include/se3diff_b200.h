@@ -204,14 +204,17 @@ int se3_igso3_build_score_scaling(const float* sigma_grid, int num_sigma, const 
  *             both NULL => in-kernel Philox4x32-10 keyed by (seed, element index)
  *   x       : optional [n,3,3]; NULL => out = Exp(axis*omega)
  *   angle_out optional [n]
- *   cdf_index: optional search index built by se3_igso3_build_cdf_index (same row order as cdf); NULL => binary
+ *   cdf_index: optional guide records built by se3_igso3_build_cdf_index (same row order as cdf); NULL => binary
  *             search.  Either way the angle index equals the reference's `sum(cdf < u)` exactly. */
 int se3_igso3_sample(const float* sigma, const float* sigma_grid, int num_sigma, const float* cdf,
                      const float* omega_grid, int num_omega, const float* normals, const float* u,
                      uint64_t seed, const float* x, float* out, float* angle_out, int64_t n, float tol,
                      const float* cdf_index, se3_stream_t stream);
-/* Blocked search index over the CDF rows (fan-out 8: one 32-byte sector per level, 4 sector reads per lookup
- * instead of 11 scattered probes); index is [num_rows, 584] fp32, num_omega <= 2048. */
+/* Guide records over the CDF rows: [0,1) is cut into G = 2^k >= num_omega/2 bins and each (row, bin) owns one aligned
+ * 32-byte record {lo | hi << 16, cdf[lo-1 .. lo+5]} with lo/hi = lower_bound(row, bin edges): a lookup reads ONE L2
+ * sector (binary search inside [lo, hi] only for flat stretches of the CDF) instead of 11 scattered probes.
+ * index: se3_igso3_cdf_index_floats(num_rows, num_omega) floats, 32-byte aligned; num_omega <= 65535. */
+int64_t se3_igso3_cdf_index_floats(int num_rows, int num_omega);
 int se3_igso3_build_cdf_index(const float* cdf, int num_rows, int num_omega, float* index, se3_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

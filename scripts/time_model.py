@@ -15,6 +15,7 @@ graph = ChemGraph(pos=torch.randn(L, 3), node_orientations=torch.eye(3).repeat(L
 batch = Batch.from_data_list([graph] * B).to(dev)
 batch = batch.replace(pos=torch.randn(B * L, 3, device=dev), node_orientations=ops.so3_exp(torch.randn(B * L, 3, device=dev)))
 t = torch.full((B,), 0.5, device=dev)
+torch.set_grad_enabled(False)   # the kernel path is inference only (a forward that needs gradients takes the autograd path)
 for _ in range(3): out = model(batch, t)
 torch.cuda.synchronize()
 def timeit(fn, n=20):

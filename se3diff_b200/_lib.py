@@ -6,7 +6,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libse3diff_b200.so")
+LIB_PATH = os.environ.get("SE3DIFF_B200_LIB") or os.path.join(_HERE, "_lib", "libse3diff_b200.so")   # override: developer experiments only
 _lock = threading.Lock()
 _lib = None
 
@@ -67,6 +67,7 @@ SIGNATURES = {
     "se3_igso3_build_score_scaling": [f32p, i32, f64p, i32, i32, f64, f32p, vp],
     "se3_igso3_sample": [f32p, f32p, i32, f32p, f32p, i32, f32p, f32p, u64, f32p, f32p, f32p, i64, f32, f32p, vp],
     "se3_igso3_build_cdf_index": [f32p, i32, i32, f32p, vp],
+    "se3_igso3_cdf_index_floats": [i32, i32],
     "se3_ipa_attention_fwd": [f32p] * 7 + [f32, f32p, C.POINTER(IpaShape), i32, vp],
     "se3_ipa_tc_workspace_bytes": [C.POINTER(IpaShape), C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
     "se3_ipa_attention_tc_fwd": [vp, i64, f32p, i64, f32p, f32p, vp, vp, f32p, f32p, vp, i32, vp, f32p, C.POINTER(IpaShape), vp],
@@ -80,7 +81,7 @@ SIGNATURES = {
     "se3_launch_count": [],
     "se3_launch_count_reset": [],
 }
-_RESTYPES = {"se3_ipa_tc_workspace_bytes": C.c_int64, "se3_last_error": C.c_char_p, "se3_launch_count": C.c_int64, "se3_launch_count_reset": None}
+_RESTYPES = {"se3_ipa_tc_workspace_bytes": C.c_int64, "se3_igso3_cdf_index_floats": C.c_int64, "se3_last_error": C.c_char_p, "se3_launch_count": C.c_int64, "se3_launch_count_reset": None}
 
 
 class Se3LibraryError(RuntimeError):

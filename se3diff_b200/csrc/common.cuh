@@ -44,6 +44,27 @@ __device__ __forceinline__ void tile_load(const T* __restrict__ g, T* __restrict
     }
 }
 
+// Asynchronous edition (cp.async, no register staging): the copy is in flight while the thread does independent work;
+// tile_load_wait() before the __syncthreads() that publishes the tile.
+template <int W, typename T>
+__device__ __forceinline__ void tile_load_async(const T* __restrict__ g, T* __restrict__ s, int64_t first, int count) {
+    const T* src = g + first * W;
+    constexpr int kPerVec = 16 / sizeof(T);
+    if (count == kTile && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (kTile * W) % kPerVec == 0) {
+        constexpr int nvec = kTile * W / kPerVec;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s);
+#pragma unroll
+        for (int i = threadIdx.x; i < nvec; i += kTile)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + (uint32_t)i * 16u), "l"(reinterpret_cast<const float4*>(src) + i) : "memory");
+    } else {
+        for (int i = threadIdx.x; i < count * W; i += kTile) s[i] = src[i];
+    }
+}
+__device__ __forceinline__ void tile_load_wait() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 template <int W, typename T>
 __device__ __forceinline__ void tile_store(T* __restrict__ g, const T* __restrict__ s, int64_t first, int count) {
     T* dst = g + first * W;

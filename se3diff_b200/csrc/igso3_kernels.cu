@@ -251,47 +251,84 @@ __device__ __forceinline__ int lower_bound_geometric(const float* __restrict__ a
     const float a0 = __ldg(a), a1 = __ldg(a + n - 1);
     if (!(v > a0)) return 0;
     if (v > a1) return n;
-    int k = (int)ceilf(__logf(v / a0) / __logf(a1 / a0) * (float)(n - 1));
+    // the guess may be off by one or two slots (approximate log2 / division); the two loops below make it exact
+    int k = (int)ceilf(__fdividef(__log2f(v) - __log2f(a0), __log2f(a1) - __log2f(a0)) * (float)(n - 1));
     k = min(max(k, 0), n - 1);
     while (k > 0 && !(__ldg(a + k - 1) < v)) --k;      // a[k-1] >= v: answer is further left
     while (k < n && __ldg(a + k) < v) ++k;             // a[k] < v: answer is further right
     return k;
 }
 
-// Blocked search index over a CDF row (fan-out 8, 4 levels, rows of up to 2048 entries): every level is ONE aligned
-// 32-byte sector holding 8 separators, so a lookup costs 4 sector reads instead of the 11 scattered probes of a
-// binary search -- the sampling kernel is bound by L2 sector traffic, not by arithmetic.
-//   level 0: cdf[256(m+1)-1]                     m = 0..7      [8]
-//   level 1: cdf[256 c0 + 32(m+1)-1]                           [8][8]
-//   level 2: cdf[256 c0 + 32 c1 + 4(m+1)-1]                    [64][8]
-//   level 3: cdf[256 c0 + 32 c1 + 4 c2 + 0..3]  (the row itself)
-// Entries past the row end are +inf.  The result is exactly lower_bound(row, u).
-constexpr int kIndexPitch = 8 + 64 + 512;   // floats per row
+// Guide records over a CDF row: the unit interval is cut into G = 2^k bins (G ~ n/2) and bin g of a row owns ONE aligned
+// 32-byte record
+//     word 0    : lo | hi << 16,  lo = lower_bound(row, g/G), hi = lower_bound(row, (g+1)/G)
+//     words 1..7: cdf[lo-1 .. lo+5]  (+inf past the row end; word 1 is unused when lo == 0)
+// For u in [g/G, (g+1)/G) the answer of lower_bound(row, u) lies in [lo, hi]; when hi - lo <= 5 (the usual case: a
+// bin holds ~2 grid points) the record also contains both CDF values the interpolation needs, so one lookup costs ONE
+// L2 sector instead of the 11 scattered probes of a binary search -- the sampling kernel is bound by L2 sector traffic,
+// not by arithmetic.  Longer runs (flat stretches of the CDF) fall back to a binary search inside [lo, hi].  u * G and
+// g / G are exact in fp32 (power-of-two scaling), so the result is exactly lower_bound(row, u) = sum(cdf < u).
+__host__ __device__ inline int guide_bins(int n) {   // smallest power of two >= n/2, within [8, 4096]: n = 2000 -> 1024
+    int g = 8;
+    while (g < (n + 1) / 2 && g < 4096) g *= 2;
+    return g;
+}
 
-__global__ void k_build_cdf_index(const float* __restrict__ cdf, int rows, int n, float* __restrict__ index) {
+__global__ void k_build_cdf_index(const float* __restrict__ cdf, int rows, int n, int G, float* __restrict__ index) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)rows * kIndexPitch) return;
-    const int row = (int)(t / kIndexPitch), e = (int)(t - (int64_t)row * kIndexPitch);
-    int src;
-    if (e < 8) src = 256 * (e + 1) - 1;
-    else if (e < 72) { const int c0 = (e - 8) >> 3, m = (e - 8) & 7; src = 256 * c0 + 32 * (m + 1) - 1; }
-    else { const int blk = (e - 72) >> 3, m = (e - 72) & 7; src = 32 * blk + 4 * (m + 1) - 1; }
-    index[t] = src < n ? cdf[(int64_t)row * n + src] : __int_as_float(0x7f800000);
+    if (t >= (int64_t)rows * G) return;
+    const int row = (int)(t / G), g = (int)(t - (int64_t)row * G);
+    const float* c = cdf + (int64_t)row * n;
+    const int lo = lower_bound(c, n, (float)g / (float)G);
+    const int hi = g + 1 < G ? lower_bound(c, n, (float)(g + 1) / (float)G) : n;
+    float4 a, b;
+    const float inf = __int_as_float(0x7f800000);
+    auto at = [&](int k) { const int i = lo - 1 + k; return (i >= 0 && i < n) ? c[i] : inf; };
+    a.x = __uint_as_float((uint32_t)lo | ((uint32_t)hi << 16));
+    a.y = at(0); a.z = at(1); a.w = at(2);
+    b.x = at(3); b.y = at(4); b.z = at(5); b.w = at(6);
+    float4* dst = reinterpret_cast<float4*>(index + t * 8);
+    dst[0] = a;
+    dst[1] = b;
 }
 
-__device__ __forceinline__ int count_less8(const float* __restrict__ node, float v) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(node)), b = __ldg(reinterpret_cast<const float4*>(node) + 1);
-    return (a.x < v) + (a.y < v) + (a.z < v) + (a.w < v) + (b.x < v) + (b.y < v) + (b.z < v) + (b.w < v);
-}
-__device__ __forceinline__ int lower_bound_indexed(const float* __restrict__ row, const float* __restrict__ idx, int n, float v) {
-    const int c0 = min(count_less8(idx, v), 7);
-    const int c1 = min(count_less8(idx + 8 + c0 * 8, v), 7);
-    const int c2 = min(count_less8(idx + 72 + (c0 * 8 + c1) * 8, v), 7);
-    const int base = 256 * c0 + 32 * c1 + 4 * c2;
-    int c3 = 0;
+// lower_bound(row, u) through the guide records, also returning cdf[max(stop-1,0)] and cdf[min(stop,n-1)] (the two values
+// the reference interpolates between, so3_sde.py:1268-1281) with `stop` already clipped to n-1
+__device__ __forceinline__ int lookup_guided(const float* __restrict__ row, const float* __restrict__ rec_row, int n, int G, float u,
+                                             float& c0, float& c1) {
+    int lo = 0, hi = n;
+    if (u >= 0.0f && u < 1.0f) {
+        const int g = min((int)(u * (float)G), G - 1);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(rec_row + (int64_t)g * 8)), b = __ldg(reinterpret_cast<const float4*>(rec_row + (int64_t)g * 8) + 1);
+        const uint32_t w = __float_as_uint(a.x);
+        lo = (int)(w & 0xffffu); hi = (int)(w >> 16);
+        if (hi - lo <= 5) {
+            const float v[7] = {a.y, a.z, a.w, b.x, b.y, b.z, b.w};   // cdf[lo-1+k]
+            // p[k] = "cdf[lo+k] < u" is monotone in k (sorted row), cnt = number of true ones; the two values the
+            // interpolation needs are v[cnt] (= cdf[stop-1]) and v[cnt+1] (= cdf[stop]): nested selects on the predicates
+            bool p[5];
 #pragma unroll
-    for (int m = 0; m < 4; ++m) c3 += (base + m < n && __ldg(row + base + m) < v) ? 1 : 0;
-    return min(base + c3, n);
+            for (int k = 0; k < 5; ++k) p[k] = (k < hi - lo) && (v[1 + k] < u);
+            const int cnt = (int)p[0] + (int)p[1] + (int)p[2] + (int)p[3] + (int)p[4];
+            const int stop = lo + cnt;
+            if (stop < n) {                              // (stop == n: u above the whole row -> generic path below)
+                float lo_v = v[0], hi_v = v[1];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) { lo_v = p[k] ? v[k + 1] : lo_v; hi_v = p[k] ? v[k + 2] : hi_v; }
+                c1 = hi_v;
+                c0 = stop > 0 ? lo_v : hi_v;             // start = max(stop - 1, 0)
+                return stop;
+            }
+        }
+    }
+    while (lo < hi) {                                    // long run (or u outside [0,1)): bounded binary search
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(row + mid) < u) lo = mid + 1; else hi = mid;
+    }
+    int stop = lo < n ? lo : n - 1;
+    const int start = stop > 0 ? stop - 1 : 0;
+    c0 = __ldg(row + start); c1 = __ldg(row + stop);
+    return stop;
 }
 
 __device__ __forceinline__ uint32_t mulhilo(uint32_t a, uint32_t b, uint32_t* hi) {
@@ -318,52 +355,63 @@ __global__ void __launch_bounds__(kTile)
 k_sample(const float* __restrict__ sigma, const float* __restrict__ sigma_grid, int num_sigma, const float* __restrict__ cdf,
          const float* __restrict__ omega_grid, int num_omega, const float* __restrict__ normals, const float* __restrict__ u,
          uint64_t seed, const float* __restrict__ x, float* __restrict__ out, float* __restrict__ angle_out, int64_t n,
-         float tol, const float* __restrict__ cdf_index) {
+         float tol, const float* __restrict__ cdf_index, int guide_bins_n) {
     __shared__ __align__(16) float s_rot[kTile * 9];
     __shared__ __align__(16) float s_nrm[kTile * 3];
     const int64_t first = (int64_t)blockIdx.x * kTile;
     const int count = (int)min((int64_t)kTile, n - first);
-    if (x) tile_load<9>(x, s_rot, first, count);
-    if (normals) tile_load<3>(normals, s_nrm, first, count);
-    __syncthreads();
+    // three independent fetches per rotation -- the operand tiles, (sigma, u), and the guide record that depends on (sigma, u)
+    // -- are put in flight together: the tiles by cp.async, so the table lookup proceeds under them
+    if (x) tile_load_async<9>(x, s_rot, first, count);
+    if (normals) tile_load_async<3>(normals, s_nrm, first, count);
     const int t = threadIdx.x;
+    const int64_t e = first + t;
+    int stop = 0;
+    float c0 = 0.f, c1 = 0.f, sg = 0.f, uu = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
     if (t < count) {
-        const int64_t e = first + t;
-        float nx, ny, nz, uu;
         if (normals) {
-            nx = s_nrm[t * 3]; ny = s_nrm[t * 3 + 1]; nz = s_nrm[t * 3 + 2];
             uu = u[e];
         } else {
             uint32_t r[4], r2[4];
             philox(seed, (uint64_t)e, 0u, r);
             philox(seed, (uint64_t)e, 1u, r2);
             const float a0 = sqrtf(-2.0f * logf(1.0f - u01(r[0]))), a1 = sqrtf(-2.0f * logf(1.0f - u01(r[2])));
-            float s0, c0, s1, c1;
-            sincospif(2.0f * u01(r[1]), &s0, &c0);
-            sincospif(2.0f * u01(r[3]), &s1, &c1);
-            nx = a0 * c0; ny = a0 * s0; nz = a1 * c1;
+            float s0, cs0, s1, cs1;
+            sincospif(2.0f * u01(r[1]), &s0, &cs0);
+            sincospif(2.0f * u01(r[3]), &s1, &cs1);
+            nx = a0 * cs0; ny = a0 * s0; nz = a1 * cs1;
             uu = u01(r2[0]);
             (void)s1;
         }
         int row = 0;
-        float sg = 0.f;
         if (sigma) {
             sg = sigma[e];
             row = lower_bound_geometric(sigma_grid, num_sigma, sg);  // torch.bucketize(sigma, sigma_grid)
             row = row < num_sigma ? row : num_sigma - 1;   // the reference would raise (so3_sde.py:1633)
         }
         const float* c = cdf + (int64_t)row * num_omega;
-        int stop = cdf_index ? lower_bound_indexed(c, cdf_index + (int64_t)row * kIndexPitch, num_omega, uu) : lower_bound(c, num_omega, uu);
-        stop = stop < num_omega ? stop : num_omega - 1;
+        if (cdf_index) {
+            stop = lookup_guided(c, cdf_index + (int64_t)row * guide_bins_n * 8, num_omega, guide_bins_n, uu, c0, c1);
+        } else {
+            stop = lower_bound(c, num_omega, uu);
+            stop = stop < num_omega ? stop : num_omega - 1;
+            c0 = __ldg(c + (stop > 0 ? stop - 1 : 0)); c1 = __ldg(c + stop);
+        }
+    }
+    tile_load_wait();
+    __syncthreads();
+    if (t < count) {
+        if (normals) { nx = s_nrm[t * 3]; ny = s_nrm[t * 3 + 1]; nz = s_nrm[t * 3 + 2]; }
         const int start = stop > 0 ? stop - 1 : 0;
-        const float c0 = __ldg(c + start), c1 = __ldg(c + stop);
         const float delta = fmaxf(c1 - c0, tol);
         float w = (uu - c0) / delta;
         w = fminf(fmaxf(w, 0.0f), 1.0f);
         const float o0 = __ldg(omega_grid + start), o1 = __ldg(omega_grid + stop);
         // torch.lerp (CPU/CUDA kernels): w < 0.5 ? a + w*(b-a) : b - (b-a)*(1-w)
         const float diff = o1 - o0;
-        float ang = w < 0.5f ? o0 + w * diff : o1 - diff * (1.0f - w);
+        // ATen contracts both branches into one FMA (CPU: vec::fmadd in lerp_vec / -mfma scalar code; CUDA: nvcc -fmad), and this
+        // translation unit is built with -fmad=false, so the FMAs are spelled out
+        float ang = w < 0.5f ? fmaf(w, diff, o0) : fmaf(-diff, 1.0f - w, o1);
         if (sigma && sg < tol) ang = 0.0f;  // SampleIGSO3._process_angles
         const float nn = sqrtf(nx * nx + ny * ny + nz * nz);
         float v[3] = {(nx / nn) * ang, (ny / nn) * ang, (nz / nn) * ang};
@@ -463,11 +511,18 @@ int se3_igso3_build_score_scaling(const float* sigma_grid, int num_sigma, const 
     return table_launch(1, sigma_grid, num_sigma, omega_pts, n_pts, l_max, tol, 0, score_scaling, (cudaStream_t)stream);
 }
 
+int64_t se3_igso3_cdf_index_floats(int num_rows, int num_omega) {
+    if (num_rows < 1 || num_omega < 1 || num_omega > 65535) return SE3_EINVAL;
+    return (int64_t)num_rows * guide_bins(num_omega) * 8;
+}
+
 int se3_igso3_build_cdf_index(const float* cdf, int num_rows, int num_omega, float* index, se3_stream_t stream) {
     SE3_REQUIRE(cdf && index && num_rows >= 1 && num_omega >= 1, "bad argument");
-    SE3_REQUIRE(num_omega <= 2048, "the blocked index covers rows of up to 2048 entries");
-    const int64_t total = (int64_t)num_rows * kIndexPitch;
-    k_build_cdf_index<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(cdf, num_rows, num_omega, index);
+    SE3_REQUIRE(num_omega <= 65535, "the guide records hold 16-bit grid indices");
+    SE3_REQUIRE((reinterpret_cast<uintptr_t>(index) & 31) == 0, "index must be 32-byte aligned");
+    const int G = guide_bins(num_omega);
+    const int64_t total = (int64_t)num_rows * G;
+    k_build_cdf_index<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(cdf, num_rows, num_omega, G, index);
     SE3_LAUNCH_CHECK("se3_igso3_build_cdf_index");
 }
 
@@ -480,7 +535,8 @@ int se3_igso3_sample(const float* sigma, const float* sigma_grid, int num_sigma,
     SE3_REQUIRE(!sigma || (sigma_grid && num_sigma >= 1), "sigma given without sigma_grid");
     SE3_REQUIRE((normals == nullptr) == (u == nullptr), "normals and u must be given together");
     k_sample<<<(unsigned)((n + kTile - 1) / kTile), kTile, 0, (cudaStream_t)stream>>>(sigma, sigma_grid, num_sigma, cdf, omega_grid,
-                                                                                    num_omega, normals, u, seed, x, out, angle_out, n, tol, num_omega <= 2048 ? cdf_index : nullptr);
+                                                                                    num_omega, normals, u, seed, x, out, angle_out, n, tol, num_omega <= 65535 ? cdf_index : nullptr,
+                                                                                    guide_bins(num_omega));
     SE3_LAUNCH_CHECK("se3_igso3_sample");
 }
 

@@ -332,14 +332,14 @@ def igso3_build_score_scaling(sigma_grid: torch.Tensor, omega_pts: torch.Tensor,
     return out
 
 
-CDF_INDEX_PITCH = 584
-
-
 def igso3_build_cdf_index(cdf: torch.Tensor) -> torch.Tensor:
-    """Blocked fan-out-8 search index over the CDF rows (one 32-byte sector per level); [rows, 584] fp32."""
+    """Guide records over the CDF rows (one 32-byte record per (row, bin of [0,1)): a lookup is one L2 sector); flat fp32."""
     cdf = _dev(cdf, name="cdf")
     rows, n = cdf.shape
-    out = torch.empty(rows, CDF_INDEX_PITCH, dtype=torch.float32, device=cdf.device)
+    count = int(L.lib().se3_igso3_cdf_index_floats(rows, n))
+    if count < 0:
+        raise ValueError(f"igso3_build_cdf_index: unsupported table shape {tuple(cdf.shape)}")
+    out = torch.empty(count, dtype=torch.float32, device=cdf.device)
     with _guard(cdf):
         L.check(L.lib().se3_igso3_build_cdf_index(_p(cdf), rows, n, _p(out), _stream(cdf)), "se3_igso3_build_cdf_index")
     return out

@@ -250,7 +250,7 @@ class BaseSampleSO3(nn.Module):
         # search index over the CDF rows, rebuilt whenever the table buffer is replaced, moved or written to
         key = (self.cdf_igso3.data_ptr(), self.cdf_igso3._version)
         if getattr(self, "_index_key", None) != key:
-            self._cdf_index = ops.igso3_build_cdf_index(self.cdf_igso3) if self.cdf_igso3.shape[1] <= 2048 else None
+            self._cdf_index = ops.igso3_build_cdf_index(self.cdf_igso3) if self.cdf_igso3.shape[1] <= 65535 else None
             self._index_key = key
         out = ops.igso3_sample(self.cdf_igso3, self.omega_grid, n * m, sigma=sig, cdf_index=self._cdf_index,
                                sigma_grid=None if self._uniform else self.sigma_grid, normals=normals.reshape(-1, 3),

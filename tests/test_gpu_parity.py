@@ -387,6 +387,58 @@ def test_igso3_sampling_vs_oracle_golden():
     assert torch.equal(big, big2), "Philox stream must be reproducible"
 
 
+def test_igso3_guide_records_equal_binary_search():
+    """The guide-record lookup (one 32-byte record per (sigma row, bin of [0,1))) must return exactly the index and the
+    interpolated angle of the plain lower_bound = the reference's `sum(cdf < u)` (so3_sde.py:1262-1281): full-size table
+    (1000 x 2000, config.yaml:23-35), random rows, and adversarial uniforms -- 0, denormal-small, every bin edge +- 1 ulp,
+    exact CDF entries +- 1 ulp, 1 - 2^-24."""
+    from se3diff_b200 import ops
+
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    sig_grid = 0.02 * (2.33 / 0.02) ** torch.linspace(0.001, 1.0, 1000, device=DEV)
+    om = torch.linspace(0.0, 1, 2001, device=DEV, dtype=torch.float64) ** 3 * math.pi
+    cdf = ops.igso3_build_cdf(sig_grid, om, 2000)
+    omg = om[1:].float()
+    idx = ops.igso3_build_cdf_index(cdf)
+    assert idx.numel() == 1000 * 1024 * 8
+    n = 1 << 20
+    rows = torch.randint(0, 1000, (n,), generator=gen, device=DEV)
+    u = torch.rand(n, generator=gen, device=DEV)
+    edges = torch.arange(0, 1025, device=DEV, dtype=torch.float32) / 1024
+    k = n // 8
+    u[:k] = edges[torch.randint(0, 1024, (k,), generator=gen, device=DEV)]
+    u[k:2 * k] = torch.nextafter(edges[torch.randint(1, 1025, (k,), generator=gen, device=DEV)], torch.tensor(0.0, device=DEV))
+    u[2 * k:3 * k] = torch.nextafter(edges[torch.randint(0, 1024, (k,), generator=gen, device=DEV)], torch.tensor(2.0, device=DEV))
+    ent = cdf[rows[3 * k:6 * k], torch.randint(0, 2000, (3 * k,), generator=gen, device=DEV)]
+    u[3 * k:4 * k] = ent[:k]
+    u[4 * k:5 * k] = torch.nextafter(ent[k:2 * k], torch.tensor(0.0, device=DEV))
+    u[5 * k:6 * k] = torch.nextafter(ent[2 * k:], torch.tensor(2.0, device=DEV))
+    u[6 * k] = 0.0
+    u[6 * k + 1] = 1e-45
+    u[6 * k + 2] = 1.0 - 2.0 ** -24
+    u = u.clamp_(0.0, 1.0 - 2.0 ** -24)
+    sigma = sig_grid[rows]                      # bucketize(sigma_grid[r]) == r
+    nrm = torch.randn(n, 3, generator=gen, device=DEV)
+    r_idx, a_idx = ops.igso3_sample(cdf, omg, n, sigma=sigma, sigma_grid=sig_grid, normals=nrm, u=u, want_angle=True, cdf_index=idx)
+    r_bin, a_bin = ops.igso3_sample(cdf, omg, n, sigma=sigma, sigma_grid=sig_grid, normals=nrm, u=u, want_angle=True)
+    assert torch.equal(a_idx, a_bin) and torch.equal(r_idx, r_bin)
+    # and against torch's own count on a slice (the reference's formulation)
+    sel = torch.cat([torch.arange(j * k, j * k + 2048, device=DEV) for j in range(8)])   # 2048 of each kind of uniform
+    cdf_c, omg_c, rows_c, u_c = cdf.cpu(), omg.cpu(), rows[sel].cpu(), u[sel].cpu()
+    stop = (cdf_c[rows_c] < u_c[:, None]).sum(-1).clamp_(max=1999)
+    start = (stop - 1).clamp_(min=0)
+    c0, c1 = cdf_c[rows_c, start], cdf_c[rows_c, stop]
+    w = ((u_c - c0) / (c1 - c0).clamp_(min=1e-7)).clamp_(0, 1)
+    ang = torch.lerp(omg_c[start], omg_c[stop], w)
+    assert torch.equal(a_idx[sel].cpu(), ang)
+    # the uniform-SO(3) table (one row) through the same records
+    cu = cdf[-1:].contiguous()
+    iu = ops.igso3_build_cdf_index(cu)
+    _, au = ops.igso3_sample(cu, omg, n, normals=nrm, u=u, want_angle=True, cdf_index=iu)
+    _, ab = ops.igso3_sample(cu, omg, n, normals=nrm, u=u, want_angle=True)
+    assert torch.equal(au, ab)
+
+
 # ------------------------------------------------------------------------------------------------
 # K4 + score model
 # ------------------------------------------------------------------------------------------------
