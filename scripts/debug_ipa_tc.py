@@ -5,7 +5,7 @@ import torch
 from debug_ipa_tc_common import make, head_major, split, ref, ops, dev, H
 
 names = [("scalar", 0, 512), ("point", 512, 1280), ("pair", 1280, 1792), ("norm", 1792, 2048)]
-for B, Lm, scale in ((3, 84, 1.5), (2, 56, 1.5), (130, 20, 1.5), (2, 200, 1.5), (2, 84, 100.0)):
+for B, Lm, scale in ((3, 84, 1.5), (2, 56, 1.5), (130, 20, 1.5), (2, 200, 1.5), (2, 84, 100.0), (2, 256, 1.5), (2, 257, 1.5), (3, 300, 1.5), (2, 384, 1.5), (2, 512, 1.5), (1, 500, 100.0)):
     proj, rot, trans, pb, pv, hw, shape = make(B, Lm, seed=Lm, pos_scale=scale)
     r64 = ref(proj, rot, trans, pb, pv, hw, B, Lm)
     ws = ops.ipa_tc_workspace(shape, dev)

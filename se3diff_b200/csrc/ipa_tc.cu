@@ -14,6 +14,10 @@
 //          sum of the rounded probabilities -> 1/rowsum -> inv[h][i][b]
 //   SIMT   normalise, undo the re-centring, inverse frame R_i^T(. - T_i), norms; writes the scalar | point |
 //          norm columns of the concat layout (structure_module.py:216)
+// Sequences of 257..512 residues ("split" edition of pass 1): the keys of one (sample, head, query tile) are divided between the
+// two CTAs of a thread-block cluster, each running the schedule above on its half.  They exchange the row maxima through
+// distributed shared memory before the probabilities are formed (so both halves of P carry the same scale and pass 2 is
+// unchanged), and rank 1 hands its partial O = P.[V | 1] to rank 0 the same way for the common epilogue.
 // Pass 2, one CTA per (128-sample tile, query i, head h):
 //   out_pair[b, i, h, :] = sum_j P[h,i,b,j] * pair_value[i,j,h,:]   (structure_module.py:209-213)
 //   as a tensor-core GEMM with the SAMPLE index as M.  Pass 1 writes P directly in the UMMA operand layout
@@ -42,6 +46,20 @@ constexpr float kLog2e = 1.4426950408889634f;
 __device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
+// thread-block cluster primitives (split edition)
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_peer_f32(const float* own_smem_ptr, uint32_t peer_rank) {   // same variable in the peer CTA
+    uint32_t a = tc::smem_u32(own_smem_ptr), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(peer_rank));
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
+}
+
 // N contiguous outputs (N % 8 == 0, destination 16-byte aligned) as 128-bit stores
 template <int N> __device__ __forceinline__ void store_vec(float* dst, const float (&v)[N]) {
 #pragma unroll
@@ -61,31 +79,33 @@ struct Pass1Smem {
 // Shared-memory plan of pass 1.  The P operand (written in the second half of the kernel) overlays everything that
 // is dead by then -- the raw point records / bias slab, the key points, the key bias and the K operand -- when those
 // fit into its 256*Lp bytes (`alias`).
-__host__ __device__ inline uint32_t bias_slab_bytes(int L) {
+// L = sequence length (query side), LK = key rows staged by the CTA (= L, or the cluster rank's share in the split edition),
+// Lp = LK rounded up to 16
+__host__ __device__ inline uint32_t bias_slab_bytes(int L, int LK) {
     const int lpi = (L + 7) & ~7;
-    return (uint32_t)((L * (lpi < 128 ? lpi : 128) * 2 + 15) & ~15);
+    return (uint32_t)((LK * (lpi < 128 ? lpi : 128) * 2 + 15) & ~15);
 }
-__host__ __device__ inline uint32_t pass1_front_bytes(int L) {   // bias slab and (earlier) the raw local points share it
-    const uint32_t raw = (uint32_t)L * 48 * 4;
-    const uint32_t m = bias_slab_bytes(L) > raw ? bias_slab_bytes(L) : raw;
+__host__ __device__ inline uint32_t pass1_front_bytes(int L, int LK) {   // bias slab and (earlier) the raw local points share it
+    const uint32_t raw = (uint32_t)LK * 48 * 4;
+    const uint32_t m = bias_slab_bytes(L, LK) > raw ? bias_slab_bytes(L, LK) : raw;
     return (m + 127u) & ~127u;
 }
-__host__ __device__ inline bool pass1_can_alias(int L, int Lp) { return pass1_front_bytes(L) + (uint32_t)Lp * (48 + 4 + 32) <= (uint32_t)Lp * 256; }
-__host__ __device__ inline size_t pass1_smem_bytes(int L, int Lp) {
-    return (size_t)Lp * (32 + NVP * 2 + 256) + 4096 + (pass1_can_alias(L, Lp) ? 0 : (size_t)Lp * (48 + 4 + 32)) + (((size_t)L * 48 + 15) & ~(size_t)15);
+__host__ __device__ inline bool pass1_can_alias(int L, int LK, int Lp) { return pass1_front_bytes(L, LK) + (uint32_t)Lp * (48 + 4 + 32) <= (uint32_t)Lp * 256; }
+__host__ __device__ inline size_t pass1_smem_bytes(int L, int LK, int Lp) {
+    return (size_t)Lp * (32 + NVP * 2 + 256) + 4096 + (pass1_can_alias(L, LK, Lp) ? 0 : (size_t)Lp * (48 + 4 + 32)) + (((size_t)LK * 48 + 15) & ~(size_t)15);
 }
-__device__ __forceinline__ Pass1Smem carve1(uint8_t* base, int L, int Lp) {
+__device__ __forceinline__ Pass1Smem carve1(uint8_t* base, int L, int LK, int Lp) {
     Pass1Smem s;
     s.vp = base;                                 // [Lp/8][NVP/8][8][8] bf16, MN-major point-value operand
     s.vs = s.vp + (size_t)Lp * (NVP * 2);        // [2][Lp][16 B] scalar values as they arrive (MN-major through the descriptor strides)
     s.q = s.vs + (size_t)Lp * 32;                // [2][128][16 B]
     s.p = s.q + 4096;                            // [Lp/8][128][16 B]; raw points, then the bias slab, live at its start until pass B
-    uint8_t* rest = pass1_can_alias(L, Lp) ? s.p + pass1_front_bytes(L) : s.p + (size_t)Lp * 256;
+    uint8_t* rest = pass1_can_alias(L, LK, Lp) ? s.p + pass1_front_bytes(L, LK) : s.p + (size_t)Lp * 256;
     s.k = rest;                                  // [2][Lp][16 B]
     s.kp = reinterpret_cast<float*>(s.k + (size_t)Lp * 32);   // [Lp/2][12][2] fp32: negated global key points, interleaved by key pair
     s.kb = s.kp + Lp * 12;                       // [Lp]
-    uint8_t* tail = pass1_can_alias(L, Lp) ? s.p + (size_t)Lp * 256 : reinterpret_cast<uint8_t*>(s.kb + Lp);
-    s.frm = reinterpret_cast<float*>(tail);      // rotations [L][9] then translations [L][3], as they lie in global memory
+    uint8_t* tail = pass1_can_alias(L, LK, Lp) ? s.p + (size_t)Lp * 256 : reinterpret_cast<uint8_t*>(s.kb + Lp);
+    s.frm = reinterpret_cast<float*>(tail);      // rotations [LK][9] then translations [LK][3], as they lie in global memory
     return s;
 }
 
@@ -96,22 +116,31 @@ __device__ __forceinline__ void to_global(const float (&R)[9], const float (&T)[
     gz = R[6] * x + R[7] * y + R[8] * z + T[2];
 }
 
-template <typename OutT>
-__global__ void __launch_bounds__(128, 4)
+// kSplit = false: one CTA per (sample, head, query tile), all keys (L <= 256).   LpB = LpT = L rounded up to 16.
+// kSplit = true : a cluster of two CTAs per (sample, head, query tile); rank 0 takes keys [0, LpB), rank 1 keys [LpB, LpT)
+//                 (LpB = half of LpT rounded up to 16 = rows of every staging buffer; blockIdx.x = 2 * tile + rank).
+template <typename OutT, bool kSplit>
+__global__ void __launch_bounds__(128, kSplit ? 1 : 4)
 k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_pts,
                const float* __restrict__ rot, const float* __restrict__ trans, const __nv_bfloat16* __restrict__ pair_bias_t,
                const float* __restrict__ key_bias, const float* __restrict__ head_weight, OutT* __restrict__ out,
-               __nv_bfloat16* __restrict__ pbuf, float* __restrict__ inv_sum, const se3_ipa_shape sh, int Lp, int Bpad, int tmem_cols,
-               long long* __restrict__ dbg) {
+               __nv_bfloat16* __restrict__ pbuf, float* __restrict__ inv_sum, const se3_ipa_shape sh, int LpB, int LpT, int Bpad, int tmem_cols,
+               const float* __restrict__ pts, int pts_stride, long long* __restrict__ dbg) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t bar, bar_bias, bar_in;
+    __shared__ float s_xmax[kSplit ? 128 : 1];             // row maxima offered to the peer CTA (split edition)
     // optional phase timestamps: 16 clock64 slots per CTA, written by thread 0 (scripts/ipa_phase_times.py)
 #define SE3_STAMP(k) do { if (dbg && threadIdx.x == 0) dbg[(((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (k)] = clock64(); } while (0)
     SE3_STAMP(0);
     __shared__ uint32_t tmem_slot;
     const int L = sh.len, H = sh.heads;
-    const Pass1Smem s = carve1(smem_raw, L, Lp);
-    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
+    const uint32_t rank = kSplit ? cluster_ctarank() : 0u;
+    const int k0 = kSplit ? (int)rank * LpB : 0;                      // first key of this CTA
+    const int Lp = kSplit ? (rank ? LpT - LpB : LpB) : LpB;           // its keys, padded to 16 ...
+    const int LK = kSplit ? min(L - k0, Lp) : L;                      // ... of which real
+    const int LKbox = kSplit ? LpB : L;                               // rows of the staged point records
+    const Pass1Smem s = carve1(smem_raw, L, LKbox, LpB);
+    const int b = blockIdx.z, h = blockIdx.y, q0 = (kSplit ? blockIdx.x >> 1 : blockIdx.x) * 128;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int i = q0 + tid;
     const bool row_ok = i < L;
@@ -131,12 +160,12 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     //          matrix are zero-filled by the TMA unit; rows past this sample's L hold the next sample's (finite)
     //          values, which only ever meet logits forced to -inf / probabilities that are exactly zero.
     // points : fp32 records [qp 12 | kp 12 | vp 24] of this head, one [L][192 B] box, parked raw in the (still unused) P region
-    // frames : the sample's [L][9] and [L][3] blocks, two 1-D bulk copies
-    float* s_raw = reinterpret_cast<float*>(s.p);          // [L][48] raw local points
+    // frames : the [LK][9] and [LK][3] blocks of this CTA's key residues, two 1-D bulk copies
+    float* s_raw = reinterpret_cast<float*>(s.p);          // [LKbox][48] raw local points
     float* s_rot = s.frm;
-    float* s_trn = s.frm + L * 9;
-    const float* rsrc = rot + (int64_t)b * L * 9;
-    const float* tsrc = trans + (int64_t)b * L * 3;
+    float* s_trn = s.frm + LK * 9;
+    const float* rsrc = rot + ((int64_t)b * L + k0) * 9;
+    const float* tsrc = trans + ((int64_t)b * L + k0) * 3;
     const bool bulk_frames = ((L & 3) == 0) && ((reinterpret_cast<uintptr_t>(rot) | reinterpret_cast<uintptr_t>(trans)) & 15) == 0;
     if (tid == 0) {
         tc::mbar_init(&bar, 1);
@@ -144,25 +173,25 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         tc::mbar_init(&bar_in, 1);
         tc::mbar_fence_init();
         const int row0 = b * L;
-        tc::mbar_expect_tx(&bar_in, (uint32_t)(4096 + Lp * 64 + L * 192 + (bulk_frames ? L * 48 : 0)));
-        tc::tma_tile_2d_g2s(s_raw, &map_pts, h * 48, row0, &bar_in);
+        tc::mbar_expect_tx(&bar_in, (uint32_t)(4096 + LpB * 64 + LKbox * 192 + (bulk_frames ? LK * 48 : 0)));
+        tc::tma_tile_2d_g2s(s_raw, &map_pts, h * 48, row0 + k0, &bar_in);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            tc::tma_tile_2d_g2s(s.k + (size_t)half * Lp * 16, &map_kv, h * 48 + 16 + half * 8, row0, &bar_in);
+            tc::tma_tile_2d_g2s(s.k + (size_t)half * LpB * 16, &map_kv, h * 48 + 16 + half * 8, row0 + k0, &bar_in);
             tc::tma_tile_2d_g2s(s.q + (size_t)half * 2048, &map_q, h * 48 + half * 8, row0 + q0, &bar_in);
-            tc::tma_tile_2d_g2s(s.vs + (size_t)half * Lp * 16, &map_kv, h * 48 + 32 + half * 8, row0, &bar_in);
+            tc::tma_tile_2d_g2s(s.vs + (size_t)half * LpB * 16, &map_kv, h * 48 + 32 + half * 8, row0 + k0, &bar_in);
         }
         if (bulk_frames) {
-            tc::tma_bulk_g2s(s_rot, rsrc, (uint32_t)(L * 36), &bar_in);
-            tc::tma_bulk_g2s(s_trn, tsrc, (uint32_t)(L * 12), &bar_in);
+            tc::tma_bulk_g2s(s_rot, rsrc, (uint32_t)(LK * 36), &bar_in);
+            tc::tma_bulk_g2s(s_trn, tsrc, (uint32_t)(LK * 12), &bar_in);
         }
     }
     if (!bulk_frames) {                                    // unaligned sample block: 4-byte asynchronous copies
-        for (int idx = tid; idx < L * 9; idx += 128) tc::cp_async4(s_rot + idx, rsrc + idx);
-        for (int idx = tid; idx < L * 3; idx += 128) tc::cp_async4(s_trn + idx, tsrc + idx);
+        for (int idx = tid; idx < LK * 9; idx += 128) tc::cp_async4(s_rot + idx, rsrc + idx);
+        for (int idx = tid; idx < LK * 3; idx += 128) tc::cp_async4(s_trn + idx, tsrc + idx);
         tc::cp_async_commit();
     }
-    for (int j = tid; j < Lp; j += 128) s.kb[j] = (j < L) ? (key_bias ? key_bias[(int64_t)b * L + j] * kLog2e : 0.f) : -CUDART_INF_F;
+    for (int j = tid; j < Lp; j += 128) s.kb[j] = (j < LK) ? (key_bias ? key_bias[(int64_t)b * L + k0 + j] * kLog2e : 0.f) : -CUDART_INF_F;
     SE3_STAMP(9);
     tc::cp_async_wait<0>();
     __syncthreads();   // the barrier is initialised (and the fallback frame copies are done)
@@ -176,14 +205,15 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     // value points: re-centred on the sample's first residue, split hi + lo bf16 (the fp32 aggregation demanded by
     //               structure_module.py:193-196 keeps ~16 mantissa bits), written as whole 16-byte operand chunks
     // ones column : channel 64 of V is 1 for real keys, so MMA 2 also returns the row sum of the ROUNDED probabilities
-    const float cx = s_trn[0], cy = s_trn[1], cz = s_trn[2];
+    const float* t0 = kSplit ? trans + (int64_t)b * L * 3 : s_trn;     // the sample's first residue (rank 1 does not stage it)
+    const float cx = t0[0], cy = t0[1], cz = t0[2];
     for (int base = 0; base < Lp; base += 128) {
         if (base + warp * 32 >= Lp) break;                 // warp-uniform: the shuffles below need whole warps
         const int row = base + tid;
         float nk[12];
 #pragma unroll
         for (int c = 0; c < 12; ++c) nk[c] = 0.f;
-        if (row < L) {
+        if (row < LK) {
             float R[9], T[3];
 #pragma unroll
             for (int c = 0; c < 9; ++c) R[c] = s_rot[row * 9 + c];
@@ -251,12 +281,15 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
     float qp[12], Ri[9], Ti[3];
     {
+        // the thread's own query residue: from the staged blocks, or (split edition: the CTA stages key residues only) from global
         const int qi = row_ok ? i : 0;
+        const float* qrot = kSplit ? rot + ((int64_t)b * L + qi) * 9 : s_rot + qi * 9;
+        const float* qtrn = kSplit ? trans + ((int64_t)b * L + qi) * 3 : s_trn + qi * 3;
 #pragma unroll
-        for (int c = 0; c < 9; ++c) Ri[c] = s_rot[qi * 9 + c];
+        for (int c = 0; c < 9; ++c) Ri[c] = qrot[c];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) Ti[c] = s_trn[qi * 3 + c];
-        const float4* raw4 = reinterpret_cast<const float4*>(s_raw + qi * 48);
+        for (int c = 0; c < 3; ++c) Ti[c] = qtrn[c];
+        const float4* raw4 = reinterpret_cast<const float4*>(kSplit ? pts + ((int64_t)b * L + qi) * pts_stride + h * 48 : s_raw + qi * 48);
         const float4 a = raw4[0], bb = raw4[1], c = raw4[2];
         const float l[12] = {a.x, a.y, a.z, a.w, bb.x, bb.y, bb.z, bb.w, c.x, c.y, c.z, c.w};
 #pragma unroll
@@ -273,14 +306,14 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     // ---- MMA 1: S = Q.K^T -----------------------------------------------------------------------------------
     if (tid == 0) {
         // the raw-point area is dead: fetch the pair-bias slab into it (TMA), it lands while the MMA runs
-        const __nv_bfloat16* src = pair_bias_t + (int64_t)h * L * Lpi + q0;
-        tc::mbar_expect_tx(&bar_bias, (uint32_t)(L * ncol * 2));
+        const __nv_bfloat16* src = pair_bias_t + ((int64_t)h * L + k0) * Lpi + q0;
+        tc::mbar_expect_tx(&bar_bias, (uint32_t)(LK * ncol * 2));
         if (ncol == Lpi) {
-            tc::tma_bulk_g2s(s.p, src, (uint32_t)(L * ncol * 2), &bar_bias);
+            tc::tma_bulk_g2s(s.p, src, (uint32_t)(LK * ncol * 2), &bar_bias);
         } else {
-            for (int j = 0; j < L; ++j) tc::tma_bulk_g2s(s.p + (size_t)j * ncol * 2, src + (int64_t)j * Lpi, (uint32_t)(ncol * 2), &bar_bias);
+            for (int j = 0; j < LK; ++j) tc::tma_bulk_g2s(s.p + (size_t)j * ncol * 2, src + (int64_t)j * Lpi, (uint32_t)(ncol * 2), &bar_bias);
         }
-        tc::mma_bf16(tmem, tc::make_desc(tc::smem_u32(s.q), 128), tc::make_desc(tc::smem_u32(s.k), (uint32_t)Lp),
+        tc::mma_bf16(tmem, tc::make_desc(tc::smem_u32(s.q), 128), tc::make_desc(tc::smem_u32(s.k), (uint32_t)LpB),
                      tc::make_idesc_bf16(128, Lp), false);
         tc::mma_commit(&bar);
     }
@@ -310,7 +343,7 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int j = c * 16 + 2 * u;
-                if (kPartial && j >= L) {                  // padding keys (warp-uniform): no distance work
+                if (kPartial && j >= LK) {                 // padding keys (warp-uniform): no distance work
                     r[2 * u] = r[2 * u + 1] = __float_as_uint(-CUDART_INF_F);
                     continue;
                 }
@@ -333,7 +366,7 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     ds = __fadd2_rn(ds, make_float2(fast_sqrt(d2.x), fast_sqrt(d2.y)));
                 }
                 const float pb0 = __bfloat162float(bias_col[j * ncol]);
-                const float pb1 = (!kPartial || j + 1 < L) ? __bfloat162float(bias_col[(j + 1) * ncol]) : 0.f;
+                const float pb1 = (!kPartial || j + 1 < LK) ? __bfloat162float(bias_col[(j + 1) * ncol]) : 0.f;
                 const float2 kb2 = *reinterpret_cast<const float2*>(s.kb + j);
                 float2 l2 = __ffma2_rn(hw2, ds, make_float2(__uint_as_float(r[2 * u]), __uint_as_float(r[2 * u + 1])));
                 l2 = __fadd2_rn(__ffma2_rn(make_float2(pb0, pb1), l2e2, l2), kb2);
@@ -343,18 +376,25 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             }
             tc::tmem_st16(tc::tmem_addr(tmem, lane_base, c * 16), r);
         };
-        const int nfull = L / 16;
+        const int nfull = LK / 16;
         for (int c = 0; c < nfull; ++c) chunk(c, std::false_type{});
         if (nfull < nchunk) chunk(nfull, std::true_type{});
         tc::tmem_wait_st();
-        if (m == -CUDART_INF_F) m = 0.f;
     }
+    if constexpr (kSplit) {
+        // the two key halves must form their probabilities against the same row maximum: swap maxima through DSMEM
+        s_xmax[tid] = m;
+        cluster_sync();
+        m = fmaxf(m, ld_peer_f32(&s_xmax[tid], rank ^ 1u));
+    }
+    if (m == -CUDART_INF_F) m = 0.f;
     __syncthreads();  // every warp is done with the bias tile: its shared memory becomes the P operand
     SE3_STAMP(3);
     if (warp_ok) {
         // ---- pass B: P = exp2(l - m) -> bf16 -> smem (A operand) + global (pass 2) ------------------------------
         // P tile of (h, i, b/128) in UMMA layout: [j/8][b%128][j%8]
-        uint8_t* ptile = reinterpret_cast<uint8_t*>(pbuf) + ((((int64_t)h * L + (row_ok ? i : 0)) * (Bpad / 128) + (b >> 7)) * Lp) * 256 + (size_t)(b & 127) * 16;
+        uint8_t* ptile = reinterpret_cast<uint8_t*>(pbuf) + ((((int64_t)h * L + (row_ok ? i : 0)) * (Bpad / 128) + (b >> 7)) * LpT) * 256 + (size_t)(b & 127) * 16 +
+                         (size_t)(k0 >> 3) * 2048;
         for (int c = 0; c < nchunk; ++c) {
             uint32_t r[16], pk[8];
             tc::tmem_ld16(tc::tmem_addr(tmem, lane_base, c * 16), r);
@@ -386,7 +426,7 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const uint32_t idesc_s = tc::make_idesc_bf16(128, DK, /*b_mn_major=*/true), idesc_p = tc::make_idesc_bf16(128, NVP, /*b_mn_major=*/true);
         for (int ks = 0; ks < nchunk; ++ks) {
             const uint64_t a_desc = tc::make_desc_kstep(tc::smem_u32(s.p), 128, ks);
-            tc::mma_bf16(tmem, a_desc, tc::make_desc_raw(tc::smem_u32(s.vs) + (uint32_t)ks * 256u, /*K-group*/ 128u, /*MN-group*/ (uint32_t)Lp * 16u), idesc_s, ks > 0);
+            tc::mma_bf16(tmem, a_desc, tc::make_desc_raw(tc::smem_u32(s.vs) + (uint32_t)ks * 256u, /*K-group*/ 128u, /*MN-group*/ (uint32_t)LpB * 16u), idesc_s, ks > 0);
             tc::mma_bf16(tmem + DK, a_desc, tc::make_desc_raw(tc::smem_u32(s.vp) + (uint32_t)ks * 2u * NVP * 16u, /*K-group*/ NVP * 16u, /*MN-group*/ 128u), idesc_p, ks > 0);
         }
         tc::mma_commit(&bar);
@@ -395,8 +435,7 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     tc::fence_after();
     SE3_STAMP(5);
 
-    if (warp_ok) {
-        float o[NV];
+    auto load_acc = [&](float (&o)[NV]) {
 #pragma unroll
         for (int c = 0; c < NV / 16; ++c) {
             uint32_t r[16];
@@ -405,6 +444,8 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #pragma unroll
             for (int u = 0; u < 16; ++u) o[c * 16 + u] = __uint_as_float(r[u]);
         }
+    };
+    auto finish = [&](const float (&o)[NV]) {
         if (row_ok) {
             // column 64 = sum_j P_ij * 1 over the ROUNDED probabilities: the weights the tensor core applied sum to one
             // exactly, which the translation-covariant point aggregate needs
@@ -428,6 +469,33 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             store_vec<DK>(orow + h * DK, sc);
             store_vec<3 * PV>(orow + HD + h * PV * 3, pl);
             store_vec<PV>(orow + 2 * HD + 3 * H * PV + h * PV, nr);
+        }
+    };
+    if constexpr (kSplit) {
+        // rank 1 parks its partial accumulator (65 live columns: v 16 | points hi 24 | lo 24 | row sum) in its dead P operand,
+        // [column][row] so that both the stores and rank 0's DSMEM loads are conflict-free; rank 0 adds and finishes the rows
+        constexpr int kLive = 65;
+        float* s_xo = reinterpret_cast<float*>(s.p);
+        if (rank == 1 && warp_ok) {
+            float o[NV];
+            load_acc(o);
+#pragma unroll
+            for (int c = 0; c < kLive; ++c) s_xo[c * 128 + tid] = o[c];
+        }
+        cluster_sync();
+        if (rank == 0 && warp_ok) {
+            float o[NV];
+            load_acc(o);
+#pragma unroll
+            for (int c = 0; c < kLive; ++c) o[c] += ld_peer_f32(&s_xo[c * 128 + tid], 1u);
+            finish(o);
+        }
+        cluster_sync();   // rank 1's shared memory must outlive rank 0's loads
+    } else {
+        if (warp_ok) {
+            float o[NV];
+            load_acc(o);
+            finish(o);
         }
     }
     tc::fence_before();
@@ -525,11 +593,14 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const float* pts, int 
               const __nv_bfloat16* pair_bias, const __nv_bfloat16* pvc, const float* key_bias, const float* head_weight, OutT* out,
               __nv_bfloat16* pbuf, float* inv_sum, const se3_ipa_shape& sh, int Lp, int Bpad, cudaStream_t st) {
     const int L = sh.len;
-    int cols = 128;                                        // S needs Lp columns, the second accumulator NV = 80
-    while (cols < Lp) cols *= 2;
-    size_t smem1 = pass1_smem_bytes(L, Lp);
-    {   // tensor memory (512 columns per SM) allows 512/cols resident CTAs; a CTA that is resident but blocked in
-        // tcgen05.alloc only steals issue slots, so shared memory is padded to admit exactly that many
+    const bool split = Lp > 256;                           // keys divided between the two CTAs of a cluster
+    const int LpB = split ? ((Lp / 2 + 15) & ~15) : Lp;    // key rows per CTA (rank 1 of a split gets Lp - LpB)
+    const int LKbox = split ? LpB : L;
+    int cols = 128;                                        // S needs LpB columns, the second accumulator NV = 80
+    while (cols < LpB) cols *= 2;
+    size_t smem1 = pass1_smem_bytes(L, LKbox, LpB);
+    if (!split) {   // tensor memory (512 columns per SM) allows 512/cols resident CTAs; a CTA that is resident but blocked in
+                    // tcgen05.alloc only steals issue slots, so shared memory is padded to admit exactly that many
         const size_t per_cta = (size_t)(227 * 1024) / (size_t)(512 / cols) - 1024;
         const size_t floor_bytes = (size_t)(227 * 1024) / (size_t)(512 / cols + 1) + 1;
         if (smem1 < floor_bytes && floor_bytes <= per_cta) smem1 = floor_bytes;
@@ -538,14 +609,37 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const float* pts, int 
     CUtensorMap map_q, map_kv, map_pts;
     const uint64_t rows = (uint64_t)sh.batch * L, width = (uint64_t)sh.heads * 48;
     if (int rc = make_map_2d(&map_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, scal, width, rows, (uint64_t)scal_stride, 8, 128, "q tiles")) return rc;
-    if (int rc = make_map_2d(&map_kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, scal, width, rows, (uint64_t)scal_stride, 8, (uint32_t)Lp, "k / v tiles")) return rc;
-    if (int rc = make_map_2d(&map_pts, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pts, width, rows, (uint64_t)pts_stride, 48, (uint32_t)L, "point records")) return rc;
-    auto k1 = k_ipa_tc_pass1<OutT>;
-    cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-    if (e != cudaSuccess) { set_error("ipa_tc pass1 smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
-    dim3 g1((L + 127) / 128, sh.heads, sh.batch);
-    k1<<<g1, 128, smem1, st>>>(map_q, map_kv, map_pts, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, Lp, Bpad, cols,
-                               g_phase_dbg);
+    if (int rc = make_map_2d(&map_kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, scal, width, rows, (uint64_t)scal_stride, 8, (uint32_t)LpB, "k / v tiles")) return rc;
+    if (int rc = make_map_2d(&map_pts, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pts, width, rows, (uint64_t)pts_stride, 48, (uint32_t)LKbox, "point records")) return rc;
+    const int ntile = (L + 127) / 128;
+    cudaError_t e;
+    if (!split) {
+        auto k1 = k_ipa_tc_pass1<OutT, false>;
+        e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        if (e != cudaSuccess) { set_error("ipa_tc pass1 smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
+        dim3 g1(ntile, sh.heads, sh.batch);
+        k1<<<g1, 128, smem1, st>>>(map_q, map_kv, map_pts, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad, cols,
+                                   pts, pts_stride, g_phase_dbg);
+    } else {
+        auto k1 = k_ipa_tc_pass1<OutT, true>;
+        e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        if (e != cudaSuccess) { set_error("ipa_tc pass1 (split) smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * ntile, sh.heads, sh.batch);
+        cfg.blockDim = dim3(128, 1, 1);
+        cfg.dynamicSmemBytes = smem1;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, k1, map_q, map_kv, map_pts, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad, cols,
+                               pts, pts_stride, (long long*)nullptr);
+        if (e != cudaSuccess) { set_error("ipa_tc pass1 (split) launch: %s", cudaGetErrorString(e)); return SE3_ECUDA; }
+    }
     count_launch();
     int rc = check_launch("se3_ipa_attention_tc_fwd(pass 1)");
     if (rc) return rc;
@@ -584,8 +678,8 @@ int se3_ipa_attention_tc_fwd(const void* scalars_bf16, int64_t scalar_stride, co
     if (sh.batch == 0 || sh.len == 0) return SE3_OK;
     SE3_REQUIRE(scalars_bf16 && points && rot && trans && pair_bias_packed && pair_value_packed && head_weight && out && p_workspace && inv_workspace,
                 "null pointer");
-    if (sh.dk != DK || sh.pq != PQ || sh.pv != PV || sh.pair_batch != 1 || sh.len > 256 || sh.heads > 65535 || sh.batch > 65535) {
-        set_error("se3_ipa_attention_tc_fwd: needs dk=16, 4/8 points, shared pair tensors, L <= 256 (got dk=%d L=%d H=%d pair_batch=%d); "
+    if (sh.dk != DK || sh.pq != PQ || sh.pv != PV || sh.pair_batch != 1 || sh.len > 512 || sh.heads > 65535 || sh.batch > 65535) {
+        set_error("se3_ipa_attention_tc_fwd: needs dk=16, 4/8 points, shared pair tensors, L <= 512 (got dk=%d L=%d H=%d pair_batch=%d); "
                   "use se3_ipa_attention_fwd", sh.dk, sh.len, sh.heads, sh.pair_batch);
         return SE3_EUNSUPPORTED;
     }

@@ -419,7 +419,7 @@ def ipa_shape(batch: int, length: int, heads: int, dk: int, pair_batch: int, hea
 
 
 def ipa_tc_supported(shape: L.IpaShape) -> bool:
-    return shape.dk == 16 and shape.pq == 4 and shape.pv == 8 and shape.pair_batch == 1 and shape.len <= 256
+    return shape.dk == 16 and shape.pq == 4 and shape.pv == 8 and shape.pair_batch == 1 and shape.len <= 512
 
 
 def ipa_tc_pack_pair_value(pair_value: torch.Tensor, heads: int) -> torch.Tensor:

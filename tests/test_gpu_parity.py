@@ -686,6 +686,61 @@ def test_analytic_score_moments_on_gpu():
         assert torch.allclose(out.node_orientations.std(dim=0), torch.zeros(3, 3, device=DEV), atol=1e-1)
 
 
+@pytest.mark.parametrize("B,L,scale", [(3, 84, 1.5), (130, 20, 1.5), (2, 57, 1.5), (2, 200, 1.5), (2, 84, 100.0), (2, 256, 1.5),
+                                       (2, 257, 1.5), (3, 300, 1.5), (2, 512, 1.5), (1, 500, 100.0)])
+def test_ipa_tensor_core_operator_vs_fp64(B, L, scale):
+    """se3_ipa_attention_tc_fwd (tcgen05 two-pass; L > 256: keys split over a 2-CTA cluster) against an fp64 evaluation of
+    SAAttention.forward between the projections and fc_out (structure_module.py:131-216) on the same bf16-rounded
+    scalar operands.  Stated tolerance: 1.5e-2 of max(1, |block|max) per output block (bf16 probabilities, 2^-9 relative)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    from debug_ipa_tc_common import H, make, ref, split
+    from se3diff_b200 import ops
+
+    proj, rot, trans, pb, pv, hw, shape = make(B, L, seed=L, pos_scale=scale)
+    assert ops.ipa_tc_supported(shape)
+    want = ref(proj, rot, trans, pb, pv, hw, B, L)
+    ws = ops.ipa_tc_workspace(shape, DEV)
+    pvp, pbt = ops.ipa_tc_pack_pair_value(pv, H), ops.ipa_tc_pack_pair_bias(pb.permute(0, 2, 3, 1))
+    sc, pt = split(proj)
+    for odt in (torch.float32, torch.bfloat16):
+        got = ops.ipa_attention_tc_fwd(sc, pt, rot, trans, pbt, pvp, None, hw, shape, ws, out_dtype=odt)
+        assert torch.isfinite(got).all()
+        for name, a, b in (("scalar", 0, 512), ("point", 512, 1280), ("pair", 1280, 1792), ("norm", 1792, 2048)):
+            err = (got[:, a:b].double() - want[:, a:b]).abs().max().item()
+            ref_max = max(1.0, want[:, a:b].abs().max().item())
+            assert err <= 1.5e-2 * ref_max * (2.0 if odt == torch.bfloat16 else 1.0), (name, odt, err, ref_max)
+
+
+def test_bf16_forward_long_sequence_uses_split_attention():
+    """L = 300 (> 256): bf16 mode must stay on the tensor-core attention (cluster-split keys) and agree with the fp32 parity
+    path of the same model to the bf16 level (2 layers, B = 2, physical-scale frames)."""
+    from se3diff_b200.models import DiGConditionalScoreModel
+
+    torch.manual_seed(0)
+    m = DiGConditionalScoreModel(num_layers=2).eval().to(DEV)
+    L, B = 300, 2
+    g = torch.Generator().manual_seed(9)
+    single, pair = torch.randn(L, 384, generator=g), torch.randn(L, L, 128, generator=g)
+    pos = torch.randn(B * L, 3, generator=g) * 1.5
+    from se3diff_b200 import ops
+    rot = ops.so3_exp(torch.randn(B * L, 3, generator=g).to(DEV)).cpu()
+    batch = _make_batch(single.repeat(B, 1), [pair] * B, [L] * B, pos, rot).to(DEV)
+    t = torch.full((B,), 0.4, device=DEV)
+    outs = {}
+    with torch.no_grad():
+        for prec in ("fp32", "bf16"):
+            m.set_precision(prec)
+            o = m(batch, t)
+            outs[prec] = (o["pos"].double().cpu(), o["node_orientations"].double().cpu())
+    assert m.model_nn._ctx.tc, "bf16 mode must run the tensor-core attention path at L = 300"
+    for k in range(2):
+        a, b = outs["fp32"][k], outs["bf16"][k]
+        assert torch.isfinite(b).all()
+        assert (a - b).abs().max() <= 3e-2 * max(1.0, a.abs().max().item()), ((a - b).abs().max(), a.abs().max())
+
+
 def test_bf16_mode_ca_rmsd_tolerance():
     """north_star: "bf16 attention within a stated tolerance on final C-alpha RMSD".  Full-width model (4 layers),
     L = 56, B = 4, 25 dpm steps, identical prior and schedule in fp32 (parity mode) and bf16 (tcgen05 attention,
