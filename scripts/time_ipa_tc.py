@@ -17,3 +17,9 @@ e0.record()
 for _ in range(n): run()
 e1.record(); torch.cuda.synchronize()
 print(f"{os.environ.get('SE3DIFF_B200_LIB', 'default')}: B={B} L={Lm}: {e0.elapsed_time(e1) / n * 1e3:.1f} us per call (pass 1 + pass 2), checksum {float(out.float().abs().mean()):.6f}")
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(3): run()
+    torch.cuda.synchronize()
+for r in sorted(prof.key_averages(), key=lambda r: -r.device_time_total)[:3]:
+    print(f"   {r.device_time_total / r.count:9.1f} us  {r.key[:90]}")

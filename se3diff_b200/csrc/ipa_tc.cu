@@ -52,6 +52,11 @@ __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void st_peer_f32(float* own_smem_ptr, uint32_t peer_rank, float v) {   // same variable in the peer CTA
+    uint32_t a = tc::smem_u32(own_smem_ptr), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(peer_rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" :: "r"(ra), "f"(v) : "memory");
+}
 __device__ __forceinline__ float ld_peer_f32(const float* own_smem_ptr, uint32_t peer_rank) {   // same variable in the peer CTA
     uint32_t a = tc::smem_u32(own_smem_ptr), ra;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(peer_rank));
@@ -119,16 +124,21 @@ __device__ __forceinline__ void to_global(const float (&R)[9], const float (&T)[
 // kSplit = false: one CTA per (sample, head, query tile), all keys (L <= 256).   LpB = LpT = L rounded up to 16.
 // kSplit = true : a cluster of two CTAs per (sample, head, query tile); rank 0 takes keys [0, LpB), rank 1 keys [LpB, LpT)
 //                 (LpB = half of LpT rounded up to 16 = rows of every staging buffer; blockIdx.x = 2 * tile + rank).
-template <typename OutT, bool kSplit>
-__global__ void __launch_bounds__(128, kSplit ? 1 : 4)
+// kWide (always with kSplit, and alone for 129..256 key rows, where shared memory admits one CTA per SM anyway): 256 threads;
+//                 warps w and w + 4 share a TMEM lane quadrant (= 32 query rows) and take one half of the key columns each.
+template <typename OutT, bool kSplit, bool kWide>
+__global__ void __launch_bounds__(kWide ? 256 : 128, kWide ? 1 : 4)
 k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_pts,
-               const float* __restrict__ rot, const float* __restrict__ trans, const __nv_bfloat16* __restrict__ pair_bias_t,
+               const __grid_constant__ CUtensorMap map_bias, const __grid_constant__ CUtensorMap map_p, const float* __restrict__ rot, const float* __restrict__ trans, const __nv_bfloat16* __restrict__ pair_bias_t,
                const float* __restrict__ key_bias, const float* __restrict__ head_weight, OutT* __restrict__ out,
                __nv_bfloat16* __restrict__ pbuf, float* __restrict__ inv_sum, const se3_ipa_shape sh, int LpB, int LpT, int Bpad, int tmem_cols,
                const float* __restrict__ pts, int pts_stride, long long* __restrict__ dbg) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t bar, bar_bias, bar_in;
     __shared__ float s_xmax[kSplit ? 128 : 1];             // row maxima offered to the peer CTA (split edition)
+    __shared__ float s_hmax[kWide ? 256 : 1];              // row maxima of the two key-column halves (wide edition)
+    static_assert(kWide || !kSplit, "the split edition runs 256 threads");
+    constexpr int kThreads = kWide ? 256 : 128;
     // optional phase timestamps: 16 clock64 slots per CTA, written by thread 0 (scripts/ipa_phase_times.py)
 #define SE3_STAMP(k) do { if (dbg && threadIdx.x == 0) dbg[(((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (k)] = clock64(); } while (0)
     SE3_STAMP(0);
@@ -142,14 +152,18 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const Pass1Smem s = carve1(smem_raw, L, LKbox, LpB);
     const int b = blockIdx.z, h = blockIdx.y, q0 = (kSplit ? blockIdx.x >> 1 : blockIdx.x) * 128;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int i = q0 + tid;
+    const int qrow = kWide ? (tid & 127) : tid;            // query row of the tile = TMEM lane
+    const int khalf = kWide ? (tid >> 7) : 0;              // which half of the key columns this thread walks in passes A and B
+    const int i = q0 + qrow;
     const bool row_ok = i < L;
-    const bool warp_ok = q0 + warp * 32 < L;
+    const bool warp_ok = q0 + (warp & 3) * 32 < L;
 
     // pair-bias tile of this (head, query tile): bf16 [L keys][ncol queries], fetched by TMA into the region that
     // later holds P (P is only written after every warp has finished the logit pass)
     const int Lpi = (L + 7) & ~7;                         // row pitch of the transposed bias matrix
-    const int ncol = min(128, Lpi - q0);                  // multiple of 8 -> 16-byte rows
+    // L <= 128: the whole [L][Lpi] matrix of the head, one bulk copy.  Longer sequences: a [keys][128 queries] box of the 2-D
+    // tensor map (columns past the matrix edge are zero-filled), slab pitch 128
+    const int ncol = Lpi <= 128 ? Lpi : 128;              // multiple of 8 -> 16-byte rows
     const __nv_bfloat16* s_bias = reinterpret_cast<const __nv_bfloat16*>(s.p);
     if (warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)tmem_cols);
     SE3_STAMP(8);
@@ -187,11 +201,11 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
     }
     if (!bulk_frames) {                                    // unaligned sample block: 4-byte asynchronous copies
-        for (int idx = tid; idx < LK * 9; idx += 128) tc::cp_async4(s_rot + idx, rsrc + idx);
-        for (int idx = tid; idx < LK * 3; idx += 128) tc::cp_async4(s_trn + idx, tsrc + idx);
+        for (int idx = tid; idx < LK * 9; idx += kThreads) tc::cp_async4(s_rot + idx, rsrc + idx);
+        for (int idx = tid; idx < LK * 3; idx += kThreads) tc::cp_async4(s_trn + idx, tsrc + idx);
         tc::cp_async_commit();
     }
-    for (int j = tid; j < Lp; j += 128) s.kb[j] = (j < LK) ? (key_bias ? key_bias[(int64_t)b * L + k0 + j] * kLog2e : 0.f) : -CUDART_INF_F;
+    for (int j = tid; j < Lp; j += kThreads) s.kb[j] = (j < LK) ? (key_bias ? key_bias[(int64_t)b * L + k0 + j] * kLog2e : 0.f) : -CUDART_INF_F;
     SE3_STAMP(9);
     tc::cp_async_wait<0>();
     __syncthreads();   // the barrier is initialised (and the fallback frame copies are done)
@@ -207,7 +221,7 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     // ones column : channel 64 of V is 1 for real keys, so MMA 2 also returns the row sum of the ROUNDED probabilities
     const float* t0 = kSplit ? trans + (int64_t)b * L * 3 : s_trn;     // the sample's first residue (rank 1 does not stage it)
     const float cx = t0[0], cy = t0[1], cz = t0[2];
-    for (int base = 0; base < Lp; base += 128) {
+    for (int base = 0; base < Lp; base += kThreads) {
         if (base + warp * 32 >= Lp) break;                 // warp-uniform: the shuffles below need whole warps
         const int row = base + tid;
         float nk[12];
@@ -307,11 +321,12 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     if (tid == 0) {
         // the raw-point area is dead: fetch the pair-bias slab into it (TMA), it lands while the MMA runs
         const __nv_bfloat16* src = pair_bias_t + ((int64_t)h * L + k0) * Lpi + q0;
-        tc::mbar_expect_tx(&bar_bias, (uint32_t)(LK * ncol * 2));
         if (ncol == Lpi) {
+            tc::mbar_expect_tx(&bar_bias, (uint32_t)(LK * ncol * 2));
             tc::tma_bulk_g2s(s.p, src, (uint32_t)(LK * ncol * 2), &bar_bias);
-        } else {
-            for (int j = 0; j < LK; ++j) tc::tma_bulk_g2s(s.p + (size_t)j * ncol * 2, src + (int64_t)j * Lpi, (uint32_t)(ncol * 2), &bar_bias);
+        } else {   // one tile copy (a loop of per-key 256-byte bulk copies issued by this thread was measured at ~25k cycles)
+            tc::mbar_expect_tx(&bar_bias, (uint32_t)(LKbox * 128 * 2));
+            tc::tma_tile_2d_g2s(s.p, &map_bias, q0, h * L + k0, &bar_bias);
         }
         tc::mma_bf16(tmem, tc::make_desc(tc::smem_u32(s.q), 128), tc::make_desc(tc::smem_u32(s.k), (uint32_t)LpB),
                      tc::make_idesc_bf16(128, Lp), false);
@@ -322,13 +337,15 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     SE3_STAMP(2);
 
     const int nchunk = Lp / 16;
-    const uint32_t lane_base = (uint32_t)warp * 32;
+    const uint32_t lane_base = (uint32_t)(warp & 3) * 32;
     float m = -CUDART_INF_F;
+    // 16-key column chunks of this thread: all of them, or one half each for the two threads of a row (wide edition)
+    const int c_begin = khalf ? (nchunk + 1) / 2 : 0, c_end = (kWide && !khalf) ? (nchunk + 1) / 2 : nchunk;
     tc::mbar_wait(&bar_bias, 0);
     if (warp_ok) {
         // ---- pass A: logits (log2 domain) -> TMEM, row max -------------------------------------------------
         const float hw = head_weight[h] * kLog2e;
-        const __nv_bfloat16* bias_col = s_bias + min(tid, ncol - 1);   // [j][query]: conflict-free 2-byte LDS
+        const __nv_bfloat16* bias_col = s_bias + min(qrow, ncol - 1);   // [j][query]: conflict-free 2-byte LDS
         // Packed fp32x2 arithmetic (FADD2/FMUL2/FFMA2, sm_100): two keys per instruction.  The key points are staged
         // NEGATED and interleaved by key pair ([pair][component][2]) so that q + (-k) is a single packed add.
         float2 q2[12];
@@ -377,25 +394,31 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             tc::tmem_st16(tc::tmem_addr(tmem, lane_base, c * 16), r);
         };
         const int nfull = LK / 16;
-        for (int c = 0; c < nfull; ++c) chunk(c, std::false_type{});
-        if (nfull < nchunk) chunk(nfull, std::true_type{});
+        for (int c = c_begin; c < c_end; ++c) {
+            if (c < nfull) chunk(c, std::false_type{}); else chunk(c, std::true_type{});
+        }
         tc::tmem_wait_st();
+    }
+    if constexpr (kWide) {
+        // the two column halves of a row were walked by different threads
+        s_hmax[tid] = m;
+        __syncthreads();
+        m = fmaxf(s_hmax[qrow], s_hmax[128 + qrow]);
     }
     if constexpr (kSplit) {
         // the two key halves must form their probabilities against the same row maximum: swap maxima through DSMEM
-        s_xmax[tid] = m;
+        if (khalf == 0) s_xmax[qrow] = m;
         cluster_sync();
-        m = fmaxf(m, ld_peer_f32(&s_xmax[tid], rank ^ 1u));
+        m = fmaxf(m, ld_peer_f32(&s_xmax[qrow], rank ^ 1u));
     }
     if (m == -CUDART_INF_F) m = 0.f;
     __syncthreads();  // every warp is done with the bias tile: its shared memory becomes the P operand
     SE3_STAMP(3);
     if (warp_ok) {
         // ---- pass B: P = exp2(l - m) -> bf16 -> smem (A operand) + global (pass 2) ------------------------------
-        // P tile of (h, i, b/128) in UMMA layout: [j/8][b%128][j%8]
-        uint8_t* ptile = reinterpret_cast<uint8_t*>(pbuf) + ((((int64_t)h * L + (row_ok ? i : 0)) * (Bpad / 128) + (b >> 7)) * LpT) * 256 + (size_t)(b & 127) * 16 +
-                         (size_t)(k0 >> 3) * 2048;
-        for (int c = 0; c < nchunk; ++c) {
+        // the tile goes to the probability workspace by ONE TMA tensor store after the barrier below (per-thread 16-byte stores
+        // to 2048-byte-strided addresses cost 32 LSU wavefronts each and half-filled every L2 sector)
+        for (int c = c_begin; c < c_end; ++c) {
             uint32_t r[16], pk[8];
             tc::tmem_ld16(tc::tmem_addr(tmem, lane_base, c * 16), r);
             tc::tmem_wait_ld();
@@ -405,12 +428,8 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 pk[u] = tc::pack_bf16(p0, p1);
             }
             const uint4 lo = make_uint4(pk[0], pk[1], pk[2], pk[3]), hi = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            *reinterpret_cast<uint4*>(s.p + ((size_t)(2 * c) * 128 + tid) * 16) = lo;
-            *reinterpret_cast<uint4*>(s.p + ((size_t)(2 * c + 1) * 128 + tid) * 16) = hi;
-            if (row_ok) {
-                *reinterpret_cast<uint4*>(ptile + (size_t)(2 * c) * 2048) = lo;
-                *reinterpret_cast<uint4*>(ptile + (size_t)(2 * c + 1) * 2048) = hi;
-            }
+            *reinterpret_cast<uint4*>(s.p + ((size_t)(2 * c) * 128 + qrow) * 16) = lo;
+            *reinterpret_cast<uint4*>(s.p + ((size_t)(2 * c + 1) * 128 + qrow) * 16) = hi;
         }
     }
     tc::fence_async_smem();
@@ -421,6 +440,9 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     SE3_STAMP(4);
     // ---- MMA 2: O = P.V (accumulator overwrites the consumed S columns) -------------------------------------------
     if (tid == 0) {
+        // P workspace [h][b/128][i][j/8][b%128][j%8] seen as a 5-D tensor (j%8, i, j/8, b%128, h*nbt + b/128): the shared
+        // operand tile [j/8][row][8] is one box; rows past L and key groups past LpT/8 are clipped by the TMA unit
+        tc::tma_tile_5d_s2g(&map_p, s.p, 0, q0, k0 >> 3, b & 127, h * (Bpad >> 7) + (b >> 7));
         // two MN-major B operands: the scalar values as TMA delivered them ([channel group][key][16 B]: 8 keys = 128 B apart,
         // channel groups Lp*16 B apart) -> columns 0..15; the point operand ([key group][channel group][8][8]) -> columns 16..79
         const uint32_t idesc_s = tc::make_idesc_bf16(128, DK, /*b_mn_major=*/true), idesc_p = tc::make_idesc_bf16(128, NVP, /*b_mn_major=*/true);
@@ -471,28 +493,29 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             store_vec<PV>(orow + 2 * HD + 3 * H * PV + h * PV, nr);
         }
     };
+    if (tid == 0) tc::tma_store_wait_read();   // the P tile has left shared memory (reused below / released at exit)
     if constexpr (kSplit) {
-        // rank 1 parks its partial accumulator (65 live columns: v 16 | points hi 24 | lo 24 | row sum) in its dead P operand,
-        // [column][row] so that both the stores and rank 0's DSMEM loads are conflict-free; rank 0 adds and finishes the rows
+        // rank 1 pushes its partial accumulator (65 live columns: v 16 | points hi 24 | lo 24 | row sum) into rank 0's dead P
+        // operand through DSMEM, [column][row] (conflict-free on both sides); rank 0 adds and finishes the rows
         constexpr int kLive = 65;
         float* s_xo = reinterpret_cast<float*>(s.p);
-        if (rank == 1 && warp_ok) {
+        cluster_sync();   // rank 0's P operand is dead: its second product is complete and its tile store has read it
+        if (rank == 1 && warp_ok && khalf == 0) {
             float o[NV];
             load_acc(o);
 #pragma unroll
-            for (int c = 0; c < kLive; ++c) s_xo[c * 128 + tid] = o[c];
+            for (int c = 0; c < kLive; ++c) st_peer_f32(&s_xo[c * 128 + qrow], 0u, o[c]);
         }
-        cluster_sync();
-        if (rank == 0 && warp_ok) {
+        cluster_sync();   // the pushed values are visible to rank 0
+        if (rank == 0 && warp_ok && khalf == 0) {
             float o[NV];
             load_acc(o);
 #pragma unroll
-            for (int c = 0; c < kLive; ++c) o[c] += ld_peer_f32(&s_xo[c * 128 + tid], 1u);
+            for (int c = 0; c < kLive; ++c) o[c] += s_xo[c * 128 + qrow];
             finish(o);
         }
-        cluster_sync();   // rank 1's shared memory must outlive rank 0's loads
     } else {
-        if (warp_ok) {
+        if (warp_ok && khalf == 0) {
             float o[NV];
             load_acc(o);
             finish(o);
@@ -527,7 +550,7 @@ k_ipa_tc_pass2(const __nv_bfloat16* __restrict__ pbuf, const float* __restrict__
         tc::mbar_fence_init();
         // TMA: both operand tiles are contiguous in global memory and already in the UMMA layout
         tc::mbar_expect_tx(&bar_tma, a_bytes + b_bytes);
-        tc::tma_bulk_g2s(sA, reinterpret_cast<const uint8_t*>(pbuf) + (((int64_t)h * L + i) * (Bpad / 128) + bt) * (int64_t)a_bytes, a_bytes, &bar_tma);
+        tc::tma_bulk_g2s(sA, reinterpret_cast<const uint8_t*>(pbuf) + (((int64_t)h * (Bpad / 128) + bt) * L + i) * (int64_t)a_bytes, a_bytes, &bar_tma);
         tc::tma_bulk_g2s(sB, reinterpret_cast<const uint8_t*>(pvc) + ((int64_t)i * H + h) * (int64_t)b_bytes, b_bytes, &bar_tma);
     }
     const int b = bt * 128 + tid;
@@ -606,27 +629,46 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const float* pts, int 
         if (smem1 < floor_bytes && floor_bytes <= per_cta) smem1 = floor_bytes;
     }
     // tensor maps: 16-byte wide boxes of the scalar records (one UMMA K-chunk each), 192-byte wide boxes of the point records
-    CUtensorMap map_q, map_kv, map_pts;
+    CUtensorMap map_q, map_kv, map_pts, map_bias, map_p;
     const uint64_t rows = (uint64_t)sh.batch * L, width = (uint64_t)sh.heads * 48;
     if (int rc = make_map_2d(&map_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, scal, width, rows, (uint64_t)scal_stride, 8, 128, "q tiles")) return rc;
     if (int rc = make_map_2d(&map_kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, scal, width, rows, (uint64_t)scal_stride, 8, (uint32_t)LpB, "k / v tiles")) return rc;
     if (int rc = make_map_2d(&map_pts, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pts, width, rows, (uint64_t)pts_stride, 48, (uint32_t)LKbox, "point records")) return rc;
+    {   // probability workspace [h][b/128][i][j/8][b%128][j%8] as (j%8, i, j/8, b%128, h*nbt + b/128); box = one operand tile
+        EncodeTiledFn fn = encode_tiled_fn();
+        if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SE3_ECUDA; }
+        const uint64_t tile = (uint64_t)Lp * 256;          // bytes of one (h, b/128, i) tile
+        const cuuint64_t dims[5] = {8, (cuuint64_t)L, (cuuint64_t)(Lp / 8), 128, (cuuint64_t)sh.heads * (uint64_t)(Bpad / 128)};
+        const cuuint64_t strides[4] = {tile, 2048, 16, tile * (uint64_t)L};
+        const cuuint32_t box[5] = {8, 128, (cuuint32_t)(LpB / 8), 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+        const CUresult r = fn(&map_p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, pbuf, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("tensor map for the probability workspace: cuTensorMapEncodeTiled failed with %d", (int)r); return SE3_ECUDA; }
+    }
     const int ntile = (L + 127) / 128;
+    const int Lpi = (L + 7) & ~7;
+    if (Lpi > 128) {
+        if (int rc = make_map_2d(&map_bias, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pair_bias, (uint64_t)Lpi, (uint64_t)sh.heads * L, (uint64_t)Lpi, 128,
+                                 (uint32_t)LKbox, "pair-bias slabs")) return rc;
+    } else {
+        map_bias = map_q;                                  // unused by the kernel for L <= 128
+    }
     cudaError_t e;
     if (!split) {
-        auto k1 = k_ipa_tc_pass1<OutT, false>;
+        const bool wide = LpB > 128;                       // one CTA per SM by shared memory anyway: give it eight warps
+        auto k1 = wide ? k_ipa_tc_pass1<OutT, false, true> : k_ipa_tc_pass1<OutT, false, false>;
         e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e != cudaSuccess) { set_error("ipa_tc pass1 smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
         dim3 g1(ntile, sh.heads, sh.batch);
-        k1<<<g1, 128, smem1, st>>>(map_q, map_kv, map_pts, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad, cols,
-                                   pts, pts_stride, g_phase_dbg);
+        k1<<<g1, wide ? 256 : 128, smem1, st>>>(map_q, map_kv, map_pts, map_bias, map_p, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad,
+                                                cols, pts, pts_stride, g_phase_dbg);
     } else {
-        auto k1 = k_ipa_tc_pass1<OutT, true>;
+        auto k1 = k_ipa_tc_pass1<OutT, true, true>;
         e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e != cudaSuccess) { set_error("ipa_tc pass1 (split) smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * ntile, sh.heads, sh.batch);
-        cfg.blockDim = dim3(128, 1, 1);
+        cfg.blockDim = dim3(256, 1, 1);
         cfg.dynamicSmemBytes = smem1;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -636,8 +678,8 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const float* pts, int 
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, k1, map_q, map_kv, map_pts, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad, cols,
-                               pts, pts_stride, (long long*)nullptr);
+        e = cudaLaunchKernelEx(&cfg, k1, map_q, map_kv, map_pts, map_bias, map_p, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad, cols,
+                               pts, pts_stride, g_phase_dbg);
         if (e != cudaSuccess) { set_error("ipa_tc pass1 (split) launch: %s", cudaGetErrorString(e)); return SE3_ECUDA; }
     }
     count_launch();

@@ -106,6 +106,14 @@ __device__ __forceinline__ void tma_tile_2d_g2s(void* smem_dst, const void* tens
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  :: "r"(smem_u32(smem_dst)), "l"(tensor_map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
+// TMA 5-D tiled store shared -> global through a tensor map (bulk async-group completion); the shared tile is dense in box order
+__device__ __forceinline__ void tma_tile_5d_s2g(const void* tensor_map, const void* smem_src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
+                 :: "l"(tensor_map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(smem_src)) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the issuing thread's bulk stores have finished READING shared memory (the source may be overwritten / the CTA may exit)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_descriptor(const void* tensor_map) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(tensor_map) : "memory");
 }
