@@ -4,14 +4,15 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 from debug_ipa_tc_common import make, head_major, split, ops, dev, H
 from se3diff_b200 import _lib
-B, Lm = 256, 84
+B, Lm = int(os.environ.get('IPA_B', 256)), int(os.environ.get('IPA_L', 84))
+n_cta = B * H * ((Lm + 127) // 128) * (2 if Lm > 256 else 1)
 proj, rot, trans, pb, pv, hw, shape = make(B, Lm)
 ws = ops.ipa_tc_workspace(shape, dev); pvp = ops.ipa_tc_pack_pair_value(pv, H); pbt = ops.ipa_tc_pack_pair_bias(pb.permute(0, 2, 3, 1))
 out = torch.empty(B * Lm, 2048, dtype=torch.bfloat16, device=dev)
 sc_, pt_ = split(proj)
 run = lambda: ops.ipa_attention_tc_fwd(sc_, pt_, rot, trans, pbt, pvp, None, hw, shape, ws, out=out)
 for _ in range(3): run()
-buf = torch.zeros(B * H * 16, dtype=torch.int64, device=dev)
+buf = torch.zeros(n_cta * 16, dtype=torch.int64, device=dev)
 lib = _lib.lib(); lib.se3_debug_set_phase_buffer.argtypes = [C.c_void_p]; lib.se3_debug_set_phase_buffer.restype = None
 lib.se3_debug_set_phase_buffer(C.c_void_p(buf.data_ptr())); run(); torch.cuda.synchronize(); lib.se3_debug_set_phase_buffer(None)
 t = buf.view(-1, 16).double().cpu()

@@ -79,7 +79,7 @@ template <int N> __device__ __forceinline__ void store_vec(__nv_bfloat16* dst, c
 
 struct Pass1Smem {
     uint8_t *q, *k, *vs, *vp, *p;
-    float *kp, *kb, *frm;
+    float *kp, *kb, *frm, *raw, *xo;
 };
 // Shared-memory plan of pass 1.  The P operand (written in the second half of the kernel) overlays everything that
 // is dead by then -- the raw point records / bias slab, the key points, the key bias and the K operand -- when those
@@ -96,10 +96,15 @@ __host__ __device__ inline uint32_t pass1_front_bytes(int L, int LK) {   // bias
     return (m + 127u) & ~127u;
 }
 __host__ __device__ inline bool pass1_can_alias(int L, int LK, int Lp) { return pass1_front_bytes(L, LK) + (uint32_t)Lp * (48 + 4 + 32) <= (uint32_t)Lp * 256; }
-__host__ __device__ inline size_t pass1_smem_bytes(int L, int LK, int Lp) {
-    return (size_t)Lp * (32 + NVP * 2 + 256) + 4096 + (pass1_can_alias(L, LK, Lp) ? 0 : (size_t)Lp * (48 + 4 + 32)) + (((size_t)LK * 48 + 15) & ~(size_t)15);
+// The 256-thread editions (one CTA per SM) walk several items per CTA and prefetch the next item's inputs while the current
+// item's probability tile is still draining from the P region: the raw point records get their own buffer instead of
+// borrowing the front of the P region, and the split edition adds the [65][128] fp32 exchange buffer.
+constexpr size_t kExchangeBytes = 65 * 128 * 4;
+__host__ __device__ inline size_t pass1_smem_bytes(int L, int LK, int Lp, bool wide = false, bool split = false) {
+    const size_t base = (size_t)Lp * (32 + NVP * 2 + 256) + 4096 + (pass1_can_alias(L, LK, Lp) ? 0 : (size_t)Lp * (48 + 4 + 32)) + (((size_t)LK * 48 + 127) & ~(size_t)127);
+    return base + (wide ? (size_t)LK * 192 + 128 : 0) + (split ? kExchangeBytes : 0);
 }
-__device__ __forceinline__ Pass1Smem carve1(uint8_t* base, int L, int LK, int Lp) {
+__device__ __forceinline__ Pass1Smem carve1(uint8_t* base, int L, int LK, int Lp, bool wide = false) {
     Pass1Smem s;
     s.vp = base;                                 // [Lp/8][NVP/8][8][8] bf16, MN-major point-value operand
     s.vs = s.vp + (size_t)Lp * (NVP * 2);        // [2][Lp][16 B] scalar values as they arrive (MN-major through the descriptor strides)
@@ -111,6 +116,10 @@ __device__ __forceinline__ Pass1Smem carve1(uint8_t* base, int L, int LK, int Lp
     s.kb = s.kp + Lp * 12;                       // [Lp]
     uint8_t* tail = pass1_can_alias(L, LK, Lp) ? s.p + (size_t)Lp * 256 : reinterpret_cast<uint8_t*>(s.kb + Lp);
     s.frm = reinterpret_cast<float*>(tail);      // rotations [LK][9] then translations [LK][3], as they lie in global memory
+    // (TMA tile destinations need 128-byte alignment; `tail` is only 64-byte aligned when Lp is an odd multiple of 16)
+    uint8_t* after = base + (((size_t)(tail - base) + (((size_t)LK * 48 + 127) & ~(size_t)127) + 127) & ~(size_t)127);
+    s.raw = wide ? reinterpret_cast<float*>(after) : reinterpret_cast<float*>(s.p);
+    s.xo = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s.raw) + (size_t)LK * 192);   // split edition only
     return s;
 }
 
@@ -139,9 +148,6 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     __shared__ float s_hmax[kWide ? 256 : 1];              // row maxima of the two key-column halves (wide edition)
     static_assert(kWide || !kSplit, "the split edition runs 256 threads");
     constexpr int kThreads = kWide ? 256 : 128;
-    // optional phase timestamps: 16 clock64 slots per CTA, written by thread 0 (scripts/ipa_phase_times.py)
-#define SE3_STAMP(k) do { if (dbg && threadIdx.x == 0) dbg[(((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (k)] = clock64(); } while (0)
-    SE3_STAMP(0);
     __shared__ uint32_t tmem_slot;
     const int L = sh.len, H = sh.heads;
     const uint32_t rank = kSplit ? cluster_ctarank() : 0u;
@@ -149,14 +155,20 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const int Lp = kSplit ? (rank ? LpT - LpB : LpB) : LpB;           // its keys, padded to 16 ...
     const int LK = kSplit ? min(L - k0, Lp) : L;                      // ... of which real
     const int LKbox = kSplit ? LpB : L;                               // rows of the staged point records
-    const Pass1Smem s = carve1(smem_raw, L, LKbox, LpB);
-    const int b = blockIdx.z, h = blockIdx.y, q0 = (kSplit ? blockIdx.x >> 1 : blockIdx.x) * 128;
+    const Pass1Smem s = carve1(smem_raw, L, LKbox, LpB, kWide);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int qrow = kWide ? (tid & 127) : tid;            // query row of the tile = TMEM lane
     const int khalf = kWide ? (tid >> 7) : 0;              // which half of the key columns this thread walks in passes A and B
-    const int i = q0 + qrow;
-    const bool row_ok = i < L;
-    const bool warp_ok = q0 + (warp & 3) * 32 < L;
+    const int ntile = (L + 127) >> 7;
+    // Work items (sample b, head h, query tile).  Narrow edition: one per CTA, from the grid coordinates.  256-thread editions:
+    // item = (b * H + h) * ntile + tile, this CTA (cluster) takes every `item_step`-th one starting at its own index, so that
+    // the CTAs running at any moment work on neighbouring (sample, head) pairs whose record slices share DRAM pages.
+    const int item_step = kWide ? (int)(kSplit ? gridDim.x >> 1 : gridDim.x) : 1;
+    const int item_first = kWide ? (int)(kSplit ? blockIdx.x >> 1 : blockIdx.x) : 0;
+    const int n_items = kWide ? ntile * H * sh.batch : 1;
+    int item = item_first;
+    // optional phase timestamps: 16 clock64 slots per item, written by thread 0 (scripts/ipa_phase_times.py)
+#define SE3_STAMP(k) do { if (dbg && threadIdx.x == 0) dbg[(kWide ? (int64_t)item * (kSplit ? 2 : 1) + (int64_t)rank : ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (k)] = clock64(); } while (0)
 
     // pair-bias tile of this (head, query tile): bf16 [L keys][ncol queries], fetched by TMA into the region that
     // later holds P (P is only written after every warp has finished the logit pass)
@@ -165,52 +177,81 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     // tensor map (columns past the matrix edge are zero-filled), slab pitch 128
     const int ncol = Lpi <= 128 ? Lpi : 128;              // multiple of 8 -> 16-byte rows
     const __nv_bfloat16* s_bias = reinterpret_cast<const __nv_bfloat16*>(s.p);
-    if (warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)tmem_cols);
-    SE3_STAMP(8);
-    // ---- staging: six TMA tile copies + two bulk copies, issued by one thread -------------------------------------
+    // ---- staging: six TMA tile copies + two bulk copies per item, issued by one thread --------------------------------
     // scalars: bf16 head-major records [q 16 | k 16 | v 16] (q already carries scalar_weight * log2 e).  A 16-byte wide,
     //          R-row box of the 2-D tensor map lands as [R][16 B]: exactly one K-chunk of a UMMA operand, so q, k and v
     //          go from global memory into their operand tiles with no thread touching them.  Rows past the end of the
     //          matrix are zero-filled by the TMA unit; rows past this sample's L hold the next sample's (finite)
     //          values, which only ever meet logits forced to -inf / probabilities that are exactly zero.
     // points : fp32 records [qp 12 | kp 12 | vp 24] of this head, one [L][192 B] box, parked raw in the (still unused) P region
+    //          (256-thread editions: in their own buffer)
     // frames : the [LK][9] and [LK][3] blocks of this CTA's key residues, two 1-D bulk copies
-    float* s_raw = reinterpret_cast<float*>(s.p);          // [LKbox][48] raw local points
+    float* s_raw = s.raw;                                  // [LKbox][48] raw local points
     float* s_rot = s.frm;
     float* s_trn = s.frm + LK * 9;
-    const float* rsrc = rot + ((int64_t)b * L + k0) * 9;
-    const float* tsrc = trans + ((int64_t)b * L + k0) * 3;
     const bool bulk_frames = ((L & 3) == 0) && ((reinterpret_cast<uintptr_t>(rot) | reinterpret_cast<uintptr_t>(trans)) & 15) == 0;
+    auto decode = [&](const int it, int& b_, int& h_, int& q0_) {
+        if constexpr (kWide) {
+            const int bh = it / ntile;
+            b_ = bh / H; h_ = bh - b_ * H; q0_ = (it - bh * ntile) * 128;
+        } else {
+            b_ = blockIdx.z; h_ = blockIdx.y; q0_ = blockIdx.x * 128;
+        }
+    };
+    auto issue_loads = [&](const int it) {                 // thread 0 only
+        int b_, h_, q0_;
+        decode(it, b_, h_, q0_);
+        const int row0 = b_ * L;
+        tc::mbar_expect_tx(&bar_in, (uint32_t)(4096 + LpB * 64 + LKbox * 192 + (bulk_frames ? LK * 48 : 0)));
+        tc::tma_tile_2d_g2s(s_raw, &map_pts, h_ * 48, row0 + k0, &bar_in);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            tc::tma_tile_2d_g2s(s.k + (size_t)half * LpB * 16, &map_kv, h_ * 48 + 16 + half * 8, row0 + k0, &bar_in);
+            tc::tma_tile_2d_g2s(s.q + (size_t)half * 2048, &map_q, h_ * 48 + half * 8, row0 + q0_, &bar_in);
+            tc::tma_tile_2d_g2s(s.vs + (size_t)half * LpB * 16, &map_kv, h_ * 48 + 32 + half * 8, row0 + k0, &bar_in);
+        }
+        if (bulk_frames) {
+            tc::tma_bulk_g2s(s_rot, rot + ((int64_t)b_ * L + k0) * 9, (uint32_t)(LK * 36), &bar_in);
+            tc::tma_bulk_g2s(s_trn, trans + ((int64_t)b_ * L + k0) * 3, (uint32_t)(LK * 12), &bar_in);
+        }
+    };
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)tmem_cols);
     if (tid == 0) {
         tc::mbar_init(&bar, 1);
         tc::mbar_init(&bar_bias, 1);
         tc::mbar_init(&bar_in, 1);
         tc::mbar_fence_init();
-        const int row0 = b * L;
-        tc::mbar_expect_tx(&bar_in, (uint32_t)(4096 + LpB * 64 + LKbox * 192 + (bulk_frames ? LK * 48 : 0)));
-        tc::tma_tile_2d_g2s(s_raw, &map_pts, h * 48, row0 + k0, &bar_in);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            tc::tma_tile_2d_g2s(s.k + (size_t)half * LpB * 16, &map_kv, h * 48 + 16 + half * 8, row0 + k0, &bar_in);
-            tc::tma_tile_2d_g2s(s.q + (size_t)half * 2048, &map_q, h * 48 + half * 8, row0 + q0, &bar_in);
-            tc::tma_tile_2d_g2s(s.vs + (size_t)half * LpB * 16, &map_kv, h * 48 + 32 + half * 8, row0 + k0, &bar_in);
-        }
-        if (bulk_frames) {
-            tc::tma_bulk_g2s(s_rot, rsrc, (uint32_t)(LK * 36), &bar_in);
-            tc::tma_bulk_g2s(s_trn, tsrc, (uint32_t)(LK * 12), &bar_in);
-        }
+        if (item < n_items) issue_loads(item);
     }
+    tc::fence_before();
+    __syncthreads();   // the barriers are initialised, the TMEM base address is published
+    tc::fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int nchunk = Lp / 16;
+    const uint32_t lane_base = (uint32_t)(warp & 3) * 32;
+
+  for (uint32_t par = 0; item < n_items; item += item_step, par ^= 1u) {
+    SE3_STAMP(0);
+    int b, h, q0;
+    decode(item, b, h, q0);
+    const int i = q0 + qrow;
+    const bool row_ok = i < L;
+    const bool warp_ok = q0 + (warp & 3) * 32 < L;
     if (!bulk_frames) {                                    // unaligned sample block: 4-byte asynchronous copies
+        const float* rsrc = rot + ((int64_t)b * L + k0) * 9;
+        const float* tsrc = trans + ((int64_t)b * L + k0) * 3;
         for (int idx = tid; idx < LK * 9; idx += kThreads) tc::cp_async4(s_rot + idx, rsrc + idx);
         for (int idx = tid; idx < LK * 3; idx += kThreads) tc::cp_async4(s_trn + idx, tsrc + idx);
         tc::cp_async_commit();
     }
     for (int j = tid; j < Lp; j += kThreads) s.kb[j] = (j < LK) ? (key_bias ? key_bias[(int64_t)b * L + k0 + j] * kLog2e : 0.f) : -CUDART_INF_F;
     SE3_STAMP(9);
-    tc::cp_async_wait<0>();
-    __syncthreads();   // the barrier is initialised (and the fallback frame copies are done)
+    if (!bulk_frames) {
+        tc::cp_async_wait<0>();
+        __syncthreads();   // the fallback frame copies of every thread are done
+    }
     SE3_STAMP(10);
-    tc::mbar_wait(&bar_in, 0);   // frames, raw points and the scalar operands are in shared memory
+    tc::mbar_wait(&bar_in, par);   // frames, raw points and the scalar operands are in shared memory
     SE3_STAMP(11);
 
     // ---- local -> global frame, one thread per residue -------------------------------------------------------------
@@ -315,10 +356,10 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     tc::fence_before();
     __syncthreads();
     tc::fence_after();
-    const uint32_t tmem = tmem_slot;
 
     // ---- MMA 1: S = Q.K^T -----------------------------------------------------------------------------------
     if (tid == 0) {
+        if constexpr (kWide) tc::tma_store_wait_read();   // the previous item's probability tile has left the P region
         // the raw-point area is dead: fetch the pair-bias slab into it (TMA), it lands while the MMA runs
         const __nv_bfloat16* src = pair_bias_t + ((int64_t)h * L + k0) * Lpi + q0;
         if (ncol == Lpi) {
@@ -336,12 +377,10 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     tc::fence_after();
     SE3_STAMP(2);
 
-    const int nchunk = Lp / 16;
-    const uint32_t lane_base = (uint32_t)(warp & 3) * 32;
     float m = -CUDART_INF_F;
     // 16-key column chunks of this thread: all of them, or one half each for the two threads of a row (wide edition)
     const int c_begin = khalf ? (nchunk + 1) / 2 : 0, c_end = (kWide && !khalf) ? (nchunk + 1) / 2 : nchunk;
-    tc::mbar_wait(&bar_bias, 0);
+    tc::mbar_wait(&bar_bias, par);
     if (warp_ok) {
         // ---- pass A: logits (log2 domain) -> TMEM, row max -------------------------------------------------
         const float hw = head_weight[h] * kLog2e;
@@ -456,6 +495,11 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     tc::mbar_wait(&bar, 1);
     tc::fence_after();
     SE3_STAMP(5);
+    if constexpr (kWide) {
+        // both products have consumed their shared-memory operands and the raw points sit in their own buffer: the next item's
+        // copies fly under this item's epilogue and the draining probability tile
+        if (tid == 0 && item + item_step < n_items) issue_loads(item + item_step);
+    }
 
     auto load_acc = [&](float (&o)[NV]) {
 #pragma unroll
@@ -493,13 +537,15 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             store_vec<PV>(orow + 2 * HD + 3 * H * PV + h * PV, nr);
         }
     };
-    if (tid == 0) tc::tma_store_wait_read();   // the P tile has left shared memory (reused below / released at exit)
+    if constexpr (!kWide) {
+        if (tid == 0) tc::tma_store_wait_read();   // the P tile has left shared memory before the CTA exits
+    }
     if constexpr (kSplit) {
         // rank 1 pushes its partial accumulator (65 live columns: v 16 | points hi 24 | lo 24 | row sum) into rank 0's dead P
         // operand through DSMEM, [column][row] (conflict-free on both sides); rank 0 adds and finishes the rows
         constexpr int kLive = 65;
-        float* s_xo = reinterpret_cast<float*>(s.p);
-        cluster_sync();   // rank 0's P operand is dead: its second product is complete and its tile store has read it
+        float* s_xo = s.xo;
+        cluster_sync();   // rank 0 has consumed the exchange buffer of the previous item
         if (rank == 1 && warp_ok && khalf == 0) {
             float o[NV];
             load_acc(o);
@@ -522,10 +568,17 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
     }
     tc::fence_before();
-    __syncthreads();
+    __syncthreads();   // every warp has read its accumulator rows: TMEM and the operand buffers belong to the next item
+    tc::fence_after();
     SE3_STAMP(6);
-    if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)tmem_cols);
     SE3_STAMP(7);
+    if constexpr (!kWide) break;
+  }
+    if constexpr (kWide) {
+        if (tid == 0) tc::tma_store_wait_read();   // the last probability tile has left shared memory before the CTA exits
+        __syncthreads();
+    }
+    if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)tmem_cols);
 #undef SE3_STAMP
 }
 
@@ -621,7 +674,8 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const float* pts, int 
     const int LKbox = split ? LpB : L;
     int cols = 128;                                        // S needs LpB columns, the second accumulator NV = 80
     while (cols < LpB) cols *= 2;
-    size_t smem1 = pass1_smem_bytes(L, LKbox, LpB);
+    const bool wide = split || LpB > 128;                  // one CTA per SM by shared memory anyway: eight warps, several items per CTA
+    size_t smem1 = pass1_smem_bytes(L, LKbox, LpB, wide, split);
     if (!split) {   // tensor memory (512 columns per SM) allows 512/cols resident CTAs; a CTA that is resident but blocked in
                     // tcgen05.alloc only steals issue slots, so shared memory is padded to admit exactly that many
         const size_t per_cta = (size_t)(227 * 1024) / (size_t)(512 / cols) - 1024;
@@ -654,12 +708,14 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const float* pts, int 
         map_bias = map_q;                                  // unused by the kernel for L <= 128
     }
     cudaError_t e;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    const int n_items = ntile * sh.heads * sh.batch;
     if (!split) {
-        const bool wide = LpB > 128;                       // one CTA per SM by shared memory anyway: give it eight warps
         auto k1 = wide ? k_ipa_tc_pass1<OutT, false, true> : k_ipa_tc_pass1<OutT, false, false>;
         e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e != cudaSuccess) { set_error("ipa_tc pass1 smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
-        dim3 g1(ntile, sh.heads, sh.batch);
+        const dim3 g1 = wide ? dim3((unsigned)(n_items < sms ? n_items : sms), 1, 1) : dim3(ntile, sh.heads, sh.batch);
         k1<<<g1, wide ? 256 : 128, smem1, st>>>(map_q, map_kv, map_pts, map_bias, map_p, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad,
                                                 cols, pts, pts_stride, g_phase_dbg);
     } else {
@@ -667,7 +723,7 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const float* pts, int 
         e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e != cudaSuccess) { set_error("ipa_tc pass1 (split) smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * ntile, sh.heads, sh.batch);
+        cfg.gridDim = dim3(2 * (sms / 2), 1, 1);
         cfg.blockDim = dim3(256, 1, 1);
         cfg.dynamicSmemBytes = smem1;
         cfg.stream = st;
@@ -678,6 +734,11 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const float* pts, int 
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
+        // persistent clusters: as many as can be co-resident (both CTAs of a cluster need SMs of one GPC)
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, k1, &cfg) != cudaSuccess || ncl < 1) { (void)cudaGetLastError(); ncl = sms / 2; }
+        if (ncl > n_items) ncl = n_items;
+        cfg.gridDim = dim3(2 * ncl, 1, 1);
         e = cudaLaunchKernelEx(&cfg, k1, map_q, map_kv, map_pts, map_bias, map_p, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad, cols,
                                pts, pts_stride, g_phase_dbg);
         if (e != cudaSuccess) { set_error("ipa_tc pass1 (split) launch: %s", cudaGetErrorString(e)); return SE3_ECUDA; }
