@@ -455,8 +455,12 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     SE3_STAMP(3);
     if (warp_ok) {
         // ---- pass B: P = exp2(l - m) -> bf16 -> smem (A operand) + global (pass 2) ------------------------------
-        // the tile goes to the probability workspace by ONE TMA tensor store after the barrier below (per-thread 16-byte stores
-        // to 2048-byte-strided addresses cost 32 LSU wavefronts each and half-filled every L2 sector)
+        // Probability workspace [h][b/128][i][j/8][b%128][j%8] (pass 2 reads the [128 samples][LpT] tile of a (h, i) as one block).
+        // 256-thread editions: the tile leaves by ONE 5-D TMA tensor store after the barrier below -- per-thread 16-byte stores to
+        // 2048-byte-strided addresses stretched this loop from 2.6k to 12k cycles there.  Narrow edition (four CTAs per SM hide
+        // each other's store latency): per-thread stores; the tensor store measured the same there.
+        uint8_t* ptile = reinterpret_cast<uint8_t*>(pbuf) + ((((int64_t)h * (Bpad / 128) + (b >> 7)) * L + (row_ok ? i : 0)) * LpT) * 256 +
+                         (size_t)(b & 127) * 16 + (size_t)(k0 >> 3) * 2048;
         for (int c = c_begin; c < c_end; ++c) {
             uint32_t r[16], pk[8];
             tc::tmem_ld16(tc::tmem_addr(tmem, lane_base, c * 16), r);
@@ -469,6 +473,12 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             const uint4 lo = make_uint4(pk[0], pk[1], pk[2], pk[3]), hi = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             *reinterpret_cast<uint4*>(s.p + ((size_t)(2 * c) * 128 + qrow) * 16) = lo;
             *reinterpret_cast<uint4*>(s.p + ((size_t)(2 * c + 1) * 128 + qrow) * 16) = hi;
+            if constexpr (!kWide) {
+                if (row_ok) {
+                    *reinterpret_cast<uint4*>(ptile + (size_t)(2 * c) * 2048) = lo;
+                    *reinterpret_cast<uint4*>(ptile + (size_t)(2 * c + 1) * 2048) = hi;
+                }
+            }
         }
     }
     tc::fence_async_smem();
@@ -481,7 +491,7 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     if (tid == 0) {
         // P workspace [h][b/128][i][j/8][b%128][j%8] seen as a 5-D tensor (j%8, i, j/8, b%128, h*nbt + b/128): the shared
         // operand tile [j/8][row][8] is one box; rows past L and key groups past LpT/8 are clipped by the TMA unit
-        tc::tma_tile_5d_s2g(&map_p, s.p, 0, q0, k0 >> 3, b & 127, h * (Bpad >> 7) + (b >> 7));
+        if constexpr (kWide) tc::tma_tile_5d_s2g(&map_p, s.p, 0, q0, k0 >> 3, b & 127, h * (Bpad >> 7) + (b >> 7));
         // two MN-major B operands: the scalar values as TMA delivered them ([channel group][key][16 B]: 8 keys = 128 B apart,
         // channel groups Lp*16 B apart) -> columns 0..15; the point operand ([key group][channel group][8][8]) -> columns 16..79
         const uint32_t idesc_s = tc::make_idesc_bf16(128, DK, /*b_mn_major=*/true), idesc_p = tc::make_idesc_bf16(128, NVP, /*b_mn_major=*/true);
@@ -537,9 +547,6 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             store_vec<PV>(orow + 2 * HD + 3 * H * PV + h * PV, nr);
         }
     };
-    if constexpr (!kWide) {
-        if (tid == 0) tc::tma_store_wait_read();   // the P tile has left shared memory before the CTA exits
-    }
     if constexpr (kSplit) {
         // rank 1 pushes its partial accumulator (65 live columns: v 16 | points hi 24 | lo 24 | row sum) into rank 0's dead P
         // operand through DSMEM, [column][row] (conflict-free on both sides); rank 0 adds and finishes the rows
