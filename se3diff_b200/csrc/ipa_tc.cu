@@ -138,7 +138,7 @@ __device__ __forceinline__ void to_global(const float (&R)[9], const float (&T)[
 template <typename OutT, bool kSplit, bool kWide>
 __global__ void __launch_bounds__(kWide ? 256 : 128, kWide ? 1 : 4)
 k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_pts,
-               const __grid_constant__ CUtensorMap map_bias, const __grid_constant__ CUtensorMap map_p, const float* __restrict__ rot, const float* __restrict__ trans, const __nv_bfloat16* __restrict__ pair_bias_t,
+               const __grid_constant__ CUtensorMap map_bias, const float* __restrict__ rot, const float* __restrict__ trans, const __nv_bfloat16* __restrict__ pair_bias_t,
                const float* __restrict__ key_bias, const float* __restrict__ head_weight, OutT* __restrict__ out,
                __nv_bfloat16* __restrict__ pbuf, float* __restrict__ inv_sum, const se3_ipa_shape sh, int LpB, int LpT, int Bpad, int tmem_cols,
                const float* __restrict__ pts, int pts_stride, long long* __restrict__ dbg) {
@@ -359,7 +359,6 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
     // ---- MMA 1: S = Q.K^T -----------------------------------------------------------------------------------
     if (tid == 0) {
-        if constexpr (kWide) tc::tma_store_wait_read();   // the previous item's probability tile has left the P region
         // the raw-point area is dead: fetch the pair-bias slab into it (TMA), it lands while the MMA runs
         const __nv_bfloat16* src = pair_bias_t + ((int64_t)h * L + k0) * Lpi + q0;
         if (ncol == Lpi) {
@@ -455,12 +454,11 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     SE3_STAMP(3);
     if (warp_ok) {
         // ---- pass B: P = exp2(l - m) -> bf16 -> smem (A operand) + global (pass 2) ------------------------------
-        // Probability workspace [h][b/128][i][j/8][b%128][j%8] (pass 2 reads the [128 samples][LpT] tile of a (h, i) as one block).
-        // 256-thread editions: the tile leaves by ONE 5-D TMA tensor store after the barrier below -- per-thread 16-byte stores to
-        // 2048-byte-strided addresses stretched this loop from 2.6k to 12k cycles there.  Narrow edition (four CTAs per SM hide
-        // each other's store latency): per-thread stores; the tensor store measured the same there.
-        uint8_t* ptile = reinterpret_cast<uint8_t*>(pbuf) + ((((int64_t)h * (Bpad / 128) + (b >> 7)) * L + (row_ok ? i : 0)) * LpT) * 256 +
-                         (size_t)(b & 127) * 16 + (size_t)(k0 >> 3) * 2048;
+        // Probability workspace: row-major [h][i][b][LpT] bf16 -- per (head, query) a [samples][keys] matrix that pass 2 fetches
+        // as 128-sample x 64-key swizzled TMA boxes.  This thread owns row (h, i, b): every 16-key chunk is ONE aligned 32-byte
+        // store, i.e. whole L2 sectors (the earlier [j/8][b%128][8] operand layout scattered 16-byte half-sectors 2 KB apart:
+        // 2x DRAM write amplification and a 9k-cycle drain per 128 x 256 tile, by per-thread stores and by a TMA tensor store alike).
+        uint8_t* prow = reinterpret_cast<uint8_t*>(pbuf) + ((((int64_t)h * L + (row_ok ? i : 0)) * Bpad + b) * LpT + k0) * 2;
         for (int c = c_begin; c < c_end; ++c) {
             uint32_t r[16], pk[8];
             tc::tmem_ld16(tc::tmem_addr(tmem, lane_base, c * 16), r);
@@ -473,12 +471,9 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             const uint4 lo = make_uint4(pk[0], pk[1], pk[2], pk[3]), hi = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             *reinterpret_cast<uint4*>(s.p + ((size_t)(2 * c) * 128 + qrow) * 16) = lo;
             *reinterpret_cast<uint4*>(s.p + ((size_t)(2 * c + 1) * 128 + qrow) * 16) = hi;
-            if constexpr (!kWide) {
-                if (row_ok) {
-                    *reinterpret_cast<uint4*>(ptile + (size_t)(2 * c) * 2048) = lo;
-                    *reinterpret_cast<uint4*>(ptile + (size_t)(2 * c + 1) * 2048) = hi;
-                }
-            }
+            if (row_ok)
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                             :: "l"(prow + (size_t)c * 32), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
         }
     }
     tc::fence_async_smem();
@@ -489,9 +484,6 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     SE3_STAMP(4);
     // ---- MMA 2: O = P.V (accumulator overwrites the consumed S columns) -------------------------------------------
     if (tid == 0) {
-        // P workspace [h][b/128][i][j/8][b%128][j%8] seen as a 5-D tensor (j%8, i, j/8, b%128, h*nbt + b/128): the shared
-        // operand tile [j/8][row][8] is one box; rows past L and key groups past LpT/8 are clipped by the TMA unit
-        if constexpr (kWide) tc::tma_tile_5d_s2g(&map_p, s.p, 0, q0, k0 >> 3, b & 127, h * (Bpad >> 7) + (b >> 7));
         // two MN-major B operands: the scalar values as TMA delivered them ([channel group][key][16 B]: 8 keys = 128 B apart,
         // channel groups Lp*16 B apart) -> columns 0..15; the point operand ([key group][channel group][8][8]) -> columns 16..79
         const uint32_t idesc_s = tc::make_idesc_bf16(128, DK, /*b_mn_major=*/true), idesc_p = tc::make_idesc_bf16(128, NVP, /*b_mn_major=*/true);
@@ -581,10 +573,6 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     SE3_STAMP(7);
     if constexpr (!kWide) break;
   }
-    if constexpr (kWide) {
-        if (tid == 0) tc::tma_store_wait_read();   // the last probability tile has left shared memory before the CTA exits
-        __syncthreads();
-    }
     if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)tmem_cols);
 #undef SE3_STAMP
 }
@@ -592,25 +580,28 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 // ---------------------------------------------------------------------------------------------------------------
 template <typename OutT>
 __global__ void __launch_bounds__(128)
-k_ipa_tc_pass2(const __nv_bfloat16* __restrict__ pbuf, const float* __restrict__ inv_sum, const __nv_bfloat16* __restrict__ pvc,
+k_ipa_tc_pass2(const __grid_constant__ CUtensorMap map_p, const float* __restrict__ inv_sum, const __nv_bfloat16* __restrict__ pvc,
                OutT* __restrict__ out, const se3_ipa_shape sh, int Lp, int Bpad) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t bar_tma, bar_mma;
     __shared__ uint32_t tmem_slot;
     const int L = sh.len, H = sh.heads, B = sh.batch;
     const int bt = blockIdx.x, i = blockIdx.y, h = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t a_bytes = (uint32_t)Lp * 256u, b_bytes = (uint32_t)Lp * 32u;
-    uint8_t* sA = smem_raw;
-    uint8_t* sB = smem_raw + a_bytes;
+    // A = probabilities of (h, i): rows = 128 samples, K = keys, fetched from the row-major workspace as 64-key boxes in the
+    // 128-byte-swizzle operand layout (16 KB each, keys past LpT zero-filled by the TMA unit); B = pre-packed pair values
+    const int nblk = (Lp + 63) >> 6;
+    const uint32_t a_bytes = (uint32_t)nblk * 16384u, b_bytes = (uint32_t)Lp * 32u;
+    uint8_t* sA = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // the swizzle pattern is tied to 1024-byte alignment
+    uint8_t* sB = sA + a_bytes;
     if (warp == 0) tc::tmem_alloc(&tmem_slot, 32);
     if (tid == 0) {
         tc::mbar_init(&bar_tma, 1);
         tc::mbar_init(&bar_mma, 1);
         tc::mbar_fence_init();
-        // TMA: both operand tiles are contiguous in global memory and already in the UMMA layout
         tc::mbar_expect_tx(&bar_tma, a_bytes + b_bytes);
-        tc::tma_bulk_g2s(sA, reinterpret_cast<const uint8_t*>(pbuf) + (((int64_t)h * (Bpad / 128) + bt) * L + i) * (int64_t)a_bytes, a_bytes, &bar_tma);
+        const int row0 = (h * L + i) * Bpad + bt * 128;
+        for (int kb = 0; kb < nblk; ++kb) tc::tma_tile_2d_g2s(sA + (size_t)kb * 16384, &map_p, kb * 64, row0, &bar_tma);
         tc::tma_bulk_g2s(sB, reinterpret_cast<const uint8_t*>(pvc) + ((int64_t)i * H + h) * (int64_t)b_bytes, b_bytes, &bar_tma);
     }
     const int b = bt * 128 + tid;
@@ -624,7 +615,7 @@ k_ipa_tc_pass2(const __nv_bfloat16* __restrict__ pbuf, const float* __restrict__
         const uint32_t idesc = tc::make_idesc_bf16(128, DK);
         const uint32_t a_addr = tc::smem_u32(sA), b_addr = tc::smem_u32(sB);
         for (int ks = 0; ks < Lp / 16; ++ks)
-            tc::mma_bf16(tmem, tc::make_desc_kstep(a_addr, 128, ks), tc::make_desc_kstep(b_addr, DK, ks), idesc, ks > 0);
+            tc::mma_bf16(tmem, tc::make_desc_sw128(a_addr + (uint32_t)(ks >> 2) * 16384u, ks & 3), tc::make_desc_kstep(b_addr, DK, ks), idesc, ks > 0);
         tc::mma_commit(&bar_mma);
     }
     tc::mbar_wait(&bar_mma, 0);
@@ -660,12 +651,12 @@ EncodeTiledFn encode_tiled_fn() {
 }
 // row-major [rows][cols] matrix with a row pitch; box = box_cols x box_rows elements, dense in shared memory
 int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems,
-                uint32_t box_cols, uint32_t box_rows, const char* what) {
+                uint32_t box_cols, uint32_t box_rows, const char* what, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_NONE) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SE3_ECUDA; }
     const cuuint64_t dims[2] = {cols, rows}, strides[1] = {pitch_elems * (uint64_t)elem_bytes};
     const cuuint32_t box[2] = {box_cols, box_rows}, estr[2] = {1, 1};
-    const CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+    const CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("tensor map for %s: cuTensorMapEncodeTiled failed with %d", what, (int)r); return SE3_ECUDA; }
     return SE3_OK;
@@ -695,17 +686,9 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const float* pts, int 
     if (int rc = make_map_2d(&map_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, scal, width, rows, (uint64_t)scal_stride, 8, 128, "q tiles")) return rc;
     if (int rc = make_map_2d(&map_kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, scal, width, rows, (uint64_t)scal_stride, 8, (uint32_t)LpB, "k / v tiles")) return rc;
     if (int rc = make_map_2d(&map_pts, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pts, width, rows, (uint64_t)pts_stride, 48, (uint32_t)LKbox, "point records")) return rc;
-    {   // probability workspace [h][b/128][i][j/8][b%128][j%8] as (j%8, i, j/8, b%128, h*nbt + b/128); box = one operand tile
-        EncodeTiledFn fn = encode_tiled_fn();
-        if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SE3_ECUDA; }
-        const uint64_t tile = (uint64_t)Lp * 256;          // bytes of one (h, b/128, i) tile
-        const cuuint64_t dims[5] = {8, (cuuint64_t)L, (cuuint64_t)(Lp / 8), 128, (cuuint64_t)sh.heads * (uint64_t)(Bpad / 128)};
-        const cuuint64_t strides[4] = {tile, 2048, 16, tile * (uint64_t)L};
-        const cuuint32_t box[5] = {8, 128, (cuuint32_t)(LpB / 8), 1, 1}, estr[5] = {1, 1, 1, 1, 1};
-        const CUresult r = fn(&map_p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, pbuf, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { set_error("tensor map for the probability workspace: cuTensorMapEncodeTiled failed with %d", (int)r); return SE3_ECUDA; }
-    }
+    // probability workspace: row-major [h][i][b][Lp] = a [heads * L * Bpad][Lp] matrix; pass 2 takes 64-key x 128-sample boxes
+    if (int rc = make_map_2d(&map_p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pbuf, (uint64_t)Lp, (uint64_t)sh.heads * L * Bpad, (uint64_t)Lp, 64, 128,
+                             "probability workspace", CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     const int ntile = (L + 127) / 128;
     const int Lpi = (L + 7) & ~7;
     if (Lpi > 128) {
@@ -723,7 +706,7 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const float* pts, int 
         e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e != cudaSuccess) { set_error("ipa_tc pass1 smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
         const dim3 g1 = wide ? dim3((unsigned)(n_items < sms ? n_items : sms), 1, 1) : dim3(ntile, sh.heads, sh.batch);
-        k1<<<g1, wide ? 256 : 128, smem1, st>>>(map_q, map_kv, map_pts, map_bias, map_p, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad,
+        k1<<<g1, wide ? 256 : 128, smem1, st>>>(map_q, map_kv, map_pts, map_bias, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad,
                                                 cols, pts, pts_stride, g_phase_dbg);
     } else {
         auto k1 = k_ipa_tc_pass1<OutT, true, true>;
@@ -746,19 +729,19 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const float* pts, int 
         if (cudaOccupancyMaxActiveClusters(&ncl, k1, &cfg) != cudaSuccess || ncl < 1) { (void)cudaGetLastError(); ncl = sms / 2; }
         if (ncl > n_items) ncl = n_items;
         cfg.gridDim = dim3(2 * ncl, 1, 1);
-        e = cudaLaunchKernelEx(&cfg, k1, map_q, map_kv, map_pts, map_bias, map_p, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad, cols,
+        e = cudaLaunchKernelEx(&cfg, k1, map_q, map_kv, map_pts, map_bias, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad, cols,
                                pts, pts_stride, g_phase_dbg);
         if (e != cudaSuccess) { set_error("ipa_tc pass1 (split) launch: %s", cudaGetErrorString(e)); return SE3_ECUDA; }
     }
     count_launch();
     int rc = check_launch("se3_ipa_attention_tc_fwd(pass 1)");
     if (rc) return rc;
-    const size_t smem2 = (size_t)Lp * 256 + (size_t)Lp * 32;
+    const size_t smem2 = (size_t)((Lp + 63) / 64) * 16384 + (size_t)Lp * 32 + 1024;   // + slack for the 1024-byte alignment of the swizzled tiles
     auto k2 = k_ipa_tc_pass2<OutT>;
     e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     if (e != cudaSuccess) { set_error("ipa_tc pass2 smem attribute (%zu B): %s", smem2, cudaGetErrorString(e)); return SE3_ECUDA; }
     dim3 g2(Bpad / 128, L, sh.heads);
-    k2<<<g2, 128, smem2, st>>>(pbuf, inv_sum, pvc, out, sh, Lp, Bpad);
+    k2<<<g2, 128, smem2, st>>>(map_p, inv_sum, pvc, out, sh, Lp, Bpad);
     count_launch();
     return check_launch("se3_ipa_attention_tc_fwd(pass 2)");
 }

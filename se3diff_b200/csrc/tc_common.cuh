@@ -31,6 +31,15 @@ __device__ __forceinline__ uint64_t make_desc_raw(uint32_t smem_addr, uint32_t l
 __device__ __forceinline__ uint64_t make_desc_kstep(uint32_t smem_base, uint32_t rows, int ks) {
     return make_desc(smem_base + (uint32_t)ks * 2u * rows * 16u, rows);
 }
+// K-major operand tile in the 128-byte-swizzle layout (what a TMA box of 64 bf16 x R rows with CU_TENSOR_MAP_SWIZZLE_128B
+// writes: row r at r * 128 B, its 16-byte chunk c at position c ^ (r % 8); tile base 1024-byte aligned):
+// SBO (next 8-row group) = 1024 B, LBO unused, layout_type [61,64) = 2.  The K = 16 slice number k of the 64-column
+// block starts 32 * k bytes into the row: the hardware applies the XOR to the address bits, so the slice is selected by
+// adding 32 * k to the start address (as CUTLASS / DeepGEMM advance the descriptor's low word).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t tile_base, int kslice) {
+    const uint32_t addr = tile_base + (uint32_t)kslice * 32u;
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
 // 32-bit instruction descriptor, kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, both K-major,
 // N>>3 [17,23), M>>4 [24,29)
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool b_mn_major = false) {
