@@ -210,6 +210,8 @@ def main():
     # ---- end-to-end timing through the public API with host buffers ----------------------------------------
     h2d = sum(v.numel() * v.element_size() for _, v in host_batch.items() if torch.is_tensor(v))
     d2h = B * L * 12 * 4
+    for w in range(args.warmup):                                             # the host-buffer path has its own cold costs (a second
+        one_step(1500 + rank * B + w, host_batch, False).to("cpu")           # 1 GB device block from cudaMalloc, pinned staging): untimed
     barrier()
     evs = []
     for k in range(args.steps):
