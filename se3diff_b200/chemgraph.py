@@ -97,7 +97,51 @@ class Batch(ChemGraph):
         out = cls(**fields)
         object.__setattr__(out, "_lengths", lengths)
         object.__setattr__(out, "_edges", [int(g["edge_index"].shape[1]) if "edge_index" in g else 0 for g in graphs])
+        if len(graphs) > 1 and all(g is graphs[0] for g in graphs):
+            # B references to ONE graph (sample.py:223 builds its batch exactly so): remember which concatenated tensors are
+            # plain replications of which single-graph tensor, so that `.to(cuda)` ships the graph once (3.9 MB instead of
+            # 988 MB at L = 84, B = 256) and replicates on the device.  Entries: field -> (built tensor, its version, source).
+            rep = {k: (fields[k], fields[k]._version, graphs[0][k]) for k in graphs[0].keys() if torch.is_tensor(graphs[0][k])}
+            object.__setattr__(out, "_replica", (len(graphs), rep))
         return out
+
+    def _replica_source(self, key, value):
+        """The single-graph tensor `value` (field `key`) is B copies of, or None (field replaced / modified / not a replica)."""
+        rep = self.__dict__.get("_replica")
+        if rep is None or not torch.is_tensor(value):
+            return None
+        ent = rep[1].get(key)
+        if ent is None or value is not ent[0] or value._version != ent[1] or value.device.type != "cpu":
+            return None
+        return ent[2]
+
+    def h2d_nbytes(self) -> int:
+        """Bytes `.to(cuda)` copies from the host for this batch."""
+        n = 0
+        for k, v in self._fields.items():
+            if torch.is_tensor(v) and v.device.type == "cpu":
+                src = self._replica_source(k, v)
+                n += (src if src is not None else v).numel() * v.element_size()
+        return n
+
+    def to(self, device, non_blocking: bool = False):
+        dev = torch.device(device)
+        if dev.type != "cuda" or self.__dict__.get("_replica") is None:
+            return super().to(device, non_blocking=non_blocking)
+        B = self.__dict__["_replica"][0]
+        n, e = self.__dict__["_lengths"][0], self.__dict__["_edges"][0]
+        out = {}
+        for k, v in self._fields.items():
+            src = self._replica_source(k, v)
+            if src is None:
+                out[k] = v.to(dev, non_blocking=non_blocking) if torch.is_tensor(v) else v
+                continue
+            one = src.to(dev, non_blocking=non_blocking)
+            if k == "edge_index":
+                out[k] = one.repeat(1, B) + (torch.arange(B, device=dev) * n).repeat_interleave(e)
+            else:
+                out[k] = one.repeat(B, *([1] * (one.dim() - 1)))
+        return self._clone_meta(out)
 
     @property
     def num_graphs(self) -> int:

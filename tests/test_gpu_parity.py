@@ -741,6 +741,24 @@ def test_bf16_forward_long_sequence_uses_split_attention():
         assert (a - b).abs().max() <= 3e-2 * max(1.0, a.abs().max().item()), ((a - b).abs().max(), a.abs().max())
 
 
+def test_batch_to_device_replicates_a_repeated_graph_on_the_device():
+    """Batch.from_data_list([g] * B).to(cuda) ships g once and replicates on the device: every field must equal the plain
+    transfer of the concatenated host tensors, including the offset edge_index."""
+    from se3diff_b200.chemgraph import Batch, ChemGraph, complete_graph_edge_index
+
+    L, B = 7, 5
+    g = ChemGraph(pos=torch.randn(L, 3), node_orientations=torch.randn(L, 3, 3), edge_index=complete_graph_edge_index(L),
+                  single_embeds=torch.randn(L, 4), pair_embeds=torch.randn(L * L, 2))
+    b = Batch.from_data_list([g] * B)
+    d = b.to(DEV)
+    for k, v in b.items():
+        if torch.is_tensor(v):
+            assert d[k].device.type == "cuda" and d[k].dtype == v.dtype and torch.equal(d[k].cpu(), v), k
+    assert d.lengths == b.lengths and d.num_graphs == B
+    d2 = b.replace(pos=torch.zeros(B * L, 3)).to(DEV)
+    assert torch.equal(d2["pos"].cpu(), torch.zeros(B * L, 3)) and torch.equal(d2["pair_embeds"].cpu(), b["pair_embeds"])
+
+
 def test_bf16_mode_ca_rmsd_tolerance():
     """north_star: "bf16 attention within a stated tolerance on final C-alpha RMSD".  Full-width model (4 layers),
     L = 56, B = 4, 25 dpm steps, identical prior and schedule in fp32 (parity mode) and bf16 (tcgen05 attention,

@@ -243,3 +243,26 @@ def test_pdb_ca_parser_on_the_reference_structures():
     assert sh3.shape == (56, 3) and pdz.shape == (84, 3)
     d = (sh3[1:] - sh3[:-1]).norm(dim=-1)
     assert 0.36 < d.min() and d.max() < 0.40        # consecutive C-alpha atoms are 0.38 nm apart
+
+
+def test_batch_of_one_repeated_graph_tracks_replication():
+    """sample.py:223 batches B references to one graph: the batch must know which fields are plain replications (so that the
+    device transfer can ship the graph once), and must forget it for fields that were replaced or written to."""
+    import torch
+    from se3diff_b200.chemgraph import Batch, ChemGraph, complete_graph_edge_index
+
+    L, B = 5, 3
+    g = ChemGraph(pos=torch.randn(L, 3), node_orientations=torch.randn(L, 3, 3), edge_index=complete_graph_edge_index(L),
+                  single_embeds=torch.randn(L, 4), pair_embeds=torch.randn(L * L, 2))
+    full = lambda b: sum(v.numel() * v.element_size() for _, v in b.items() if torch.is_tensor(v))
+    one = sum(v.numel() * v.element_size() for _, v in g.items())
+    b = Batch.from_data_list([g] * B)
+    small = b["batch"].numel() * 8 + b["ptr"].numel() * 8
+    assert b.h2d_nbytes() == one + small < full(b)
+    b2 = b.replace(pos=torch.zeros(B * L, 3))                      # a replaced field travels whole
+    assert b2.h2d_nbytes() == b.h2d_nbytes() + (B - 1) * L * 3 * 4
+    b["single_embeds"].add_(1.0)                                   # so does one that was written to in place
+    assert b.h2d_nbytes() == one + small + (B - 1) * L * 4 * 4
+    distinct = Batch.from_data_list([g, g.replace(pos=torch.randn(L, 3)), g])
+    assert distinct.h2d_nbytes() == full(distinct)
+    assert torch.equal(b.to("cpu")["pair_embeds"], b["pair_embeds"])
