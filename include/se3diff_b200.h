@@ -290,6 +290,13 @@ int se3_ipa_attention_tc_fwd(const void* scalars_bf16, int64_t scalar_stride, co
  * dim in {128, 256, 512, 1024}; all pointers 16-byte aligned. */
 int se3_residual_layernorm(float* x, const float* y, const float* bias, const float* gamma, const float* beta, float eps,
                            void* out, int out_is_bf16, int64_t rows, int dim, se3_stream_t stream);
+/* Tail of a diffusion head, structure_module.py:12-22 (`... Linear(D, D) -> ReLU -> Linear(D, 3)`):
+ * out[r, k] = sum_c relu(y[r, c] + b1[c]) * w3[k, c] + b3[k], k < 3; y [rows, dim] fp32 = the first Linear without its bias,
+ * w3 [3, dim] row-major; dim in {128, 256, 512, 1024}; out [rows, 3] fp32. */
+int se3_bias_relu_project3(const float* y, const float* b1, const float* w3, const float* b3, float* out, int64_t rows, int dim,
+                           se3_stream_t stream);
+/* Exact (erf) GELU of FeedForward (structure_module.py:25-40) on bf16 data, fp32 math; n % 8 == 0; in == out allowed. */
+int se3_gelu_bf16(const void* in, void* out, int64_t n, se3_stream_t stream);
 
 /* Folded-state indicator of the fine-tune objective (observables/folding_stability.py:52-81, called at finetune.py:452 on
  * the last batch of the rollout): dRMSD of every sample's C-alpha distance matrix to the reference's,

@@ -64,6 +64,61 @@ k_residual_layernorm(float* __restrict__ x, const float* __restrict__ y, const f
     }
 }
 
+// Tail of a diffusion head (structure_module.py:12-22: ... Linear(D, D) -> ReLU -> Linear(D, 3)): the second Linear has three
+// output columns, so instead of bias-add, ReLU and a [rows, D] x [D, 3] library GEMM (four passes over the fp32 activations and
+// a 32 x 64-tile SIMT sgemm with 3 useful columns) one warp per row forms out[r, k] = sum_c relu(y[r, c] + b1[c]) * w3[k, c] + b3[k].
+template <int VPL, int K>
+__global__ void __launch_bounds__(256)
+k_bias_relu_project(const float* __restrict__ y, const float* __restrict__ b1, const float* __restrict__ w3, const float* __restrict__ b3,
+                    float* __restrict__ out, int64_t rows) {
+    constexpr int D = 128 * VPL;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    const float4* yr = reinterpret_cast<const float4*>(y + row * D);
+    float acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        const float4 a = __ldg(yr + v * 32 + lane), b = __ldg(reinterpret_cast<const float4*>(b1) + v * 32 + lane);
+        const float h0 = fmaxf(a.x + b.x, 0.f), h1 = fmaxf(a.y + b.y, 0.f), h2 = fmaxf(a.z + b.z, 0.f), h3 = fmaxf(a.w + b.w, 0.f);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(w3 + (int64_t)k * D) + v * 32 + lane);
+            acc[k] += (h0 * w.x + h1 * w.y) + (h2 * w.z + h3 * w.w);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    }
+    if (lane < K) {
+        float r = acc[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) r = (lane == k) ? acc[k] : r;
+        out[row * K + lane] = r + b3[lane];
+    }
+}
+
+// exact (erf) GELU on bf16 rows in place of ATen's elementwise kernel: 128-bit accesses, fp32 math (torch upcasts the same way)
+__global__ void __launch_bounds__(256)
+k_gelu_bf16(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t nvec) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvec) return;
+    const uint4 v = __ldg(in + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float a = __uint_as_float(w[k] << 16), b = __uint_as_float(w[k] & 0xffff0000u);
+        const float ga = 0.5f * a * (1.0f + erff(a * 0.70710678118654752440f)), gb = 0.5f * b * (1.0f + erff(b * 0.70710678118654752440f));
+        r[k] = tc::pack_bf16(ga, gb);
+    }
+    out[i] = make_uint4(r[0], r[1], r[2], r[3]);
+}
+
 template <typename OutT>
 int launch(float* x, const float* y, const float* bias, const float* gamma, const float* beta, float eps, OutT* out, int64_t rows,
            int dim, cudaStream_t st) {
@@ -92,4 +147,35 @@ extern "C" int se3_residual_layernorm(float* x, const float* y, const float* bia
                 "pointers must be 16-byte aligned");
     if (out_is_bf16) return launch<__nv_bfloat16>(x, y, bias, gamma, beta, eps, (__nv_bfloat16*)out, rows, dim, (cudaStream_t)stream);
     return launch<float>(x, y, bias, gamma, beta, eps, (float*)out, rows, dim, (cudaStream_t)stream);
+}
+
+extern "C" int se3_bias_relu_project3(const float* y, const float* b1, const float* w3, const float* b3, float* out, int64_t rows, int dim,
+                                      se3_stream_t stream) {
+    SE3_REQUIRE(rows >= 0, "negative rows");
+    if (rows == 0) return SE3_OK;
+    SE3_REQUIRE(y && b1 && w3 && b3 && out, "null pointer");
+    SE3_REQUIRE(((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(b1) | reinterpret_cast<uintptr_t>(w3)) & 15) == 0,
+                "pointers must be 16-byte aligned");
+    const unsigned grid = (unsigned)((rows * 32 + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dim) {
+        case 128: k_bias_relu_project<1, 3><<<grid, 256, 0, st>>>(y, b1, w3, b3, out, rows); break;
+        case 256: k_bias_relu_project<2, 3><<<grid, 256, 0, st>>>(y, b1, w3, b3, out, rows); break;
+        case 512: k_bias_relu_project<4, 3><<<grid, 256, 0, st>>>(y, b1, w3, b3, out, rows); break;
+        case 1024: k_bias_relu_project<8, 3><<<grid, 256, 0, st>>>(y, b1, w3, b3, out, rows); break;
+        default: set_error("se3_bias_relu_project3: dim must be 128, 256, 512 or 1024 (got %d)", dim); return SE3_EUNSUPPORTED;
+    }
+    count_launch();
+    return check_launch("se3_bias_relu_project3");
+}
+
+extern "C" int se3_gelu_bf16(const void* in, void* out, int64_t n, se3_stream_t stream) {
+    SE3_REQUIRE(n >= 0 && n % 8 == 0, "element count must be a non-negative multiple of 8");
+    if (n == 0) return SE3_OK;
+    SE3_REQUIRE(in && out, "null pointer");
+    SE3_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "pointers must be 16-byte aligned");
+    const int64_t nvec = n / 8;
+    k_gelu_bf16<<<(unsigned)((nvec + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, nvec);
+    count_launch();
+    return check_launch("se3_gelu_bf16");
 }

@@ -377,7 +377,7 @@ class DistributionalGraphormer(nn.Module):
                 feat = feat.to(torch.bfloat16)
             y, bias = mm(feat, lw["w_out"]), lyr.attn.fc_out.bias
             h2 = ops.residual_layernorm(x, y, bias, lyr.norm2.weight, lyr.norm2.bias, lyr.norm2.eps)
-            hid = F.gelu(F.linear(h2, lw["w_ff0"], lw["b_ff0"]))
+            hid = ops.gelu_bf16_(F.linear(h2, lw["w_ff0"], lw["b_ff0"]))
             y, bias = mm(hid, lw["w_ff3"]), lyr.ffn.ff[3].bias
         outs = []
         for name in ("fc_t", "fc_eps"):
@@ -385,8 +385,7 @@ class DistributionalGraphormer(nn.Module):
             w1, w3 = w["heads"][name]
             hh = ops.residual_layernorm(x, y, bias, seq[0].weight, seq[0].bias, seq[0].eps)
             y = bias = None   # the residual update is applied once
-            hh = F.relu(mm(hh, w1) + seq[1].bias)
-            outs.append(F.linear(hh, w3, seq[3].bias))
+            outs.append(ops.bias_relu_project3(mm(hh, w1), seq[1].bias, w3, seq[3].bias))
         return outs
 
     def forward(self, x, node_orientations, batch_index, t, context):

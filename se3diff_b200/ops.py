@@ -539,3 +539,26 @@ def residual_layernorm(x, y, bias, gamma, beta, eps: float, out_dtype=torch.bflo
                                                int(out_dtype == torch.bfloat16), x.numel() // dim, dim, _stream(x)),
                 "se3_residual_layernorm")
     return out
+
+
+def bias_relu_project3(y, b1, w3, b3):
+    """Tail of a diffusion head: relu(y + b1) @ w3.T + b3 with w3 [3, D] (structure_module.py:12-22), one pass over y."""
+    y = _dev(y, name="y")
+    b1, w3, b3 = _dev(b1, name="b1"), _dev(w3, name="w3"), _dev(b3, name="b3")
+    rows, dim = y.shape
+    if w3.shape != (3, dim) or b1.shape != (dim,) or b3.shape != (3,):
+        raise ValueError(f"bias_relu_project3: shapes {tuple(y.shape)}, {tuple(b1.shape)}, {tuple(w3.shape)}, {tuple(b3.shape)}")
+    out = torch.empty(rows, 3, dtype=torch.float32, device=y.device)
+    with _guard(y):
+        L.check(L.lib().se3_bias_relu_project3(_p(y), _p(b1), _p(w3), _p(b3), _p(out), rows, dim, _stream(y)), "se3_bias_relu_project3")
+    return out
+
+
+def gelu_bf16_(x):
+    """Exact (erf) GELU in place on a contiguous bf16 tensor."""
+    x = _dev(x, torch.bfloat16, "x")
+    if x.numel() % 8:
+        raise ValueError("gelu_bf16_: element count must be a multiple of 8")
+    with _guard(x):
+        L.check(L.lib().se3_gelu_bf16(_p(x), _p(x), x.numel(), _stream(x)), "se3_gelu_bf16")
+    return x

@@ -741,6 +741,28 @@ def test_bf16_forward_long_sequence_uses_split_attention():
         assert (a - b).abs().max() <= 3e-2 * max(1.0, a.abs().max().item()), ((a - b).abs().max(), a.abs().max())
 
 
+def test_fused_row_kernels_vs_torch():
+    """se3_bias_relu_project3 (tail of a diffusion head, structure_module.py:12-22) and se3_gelu_bf16 (FeedForward's exact GELU)
+    against the torch expressions they replace in bf16 mode."""
+    from se3diff_b200 import ops
+
+    g = torch.Generator(device=DEV).manual_seed(3)
+    for rows, dim in ((1, 512), (1000, 512), (21504, 512), (77, 128), (5, 1024)):
+        y = torch.randn(rows, dim, generator=g, device=DEV)
+        b1, w3, b3 = torch.randn(dim, generator=g, device=DEV), torch.randn(3, dim, generator=g, device=DEV) / dim ** 0.5, torch.randn(3, generator=g, device=DEV)
+        got = ops.bias_relu_project3(y, b1, w3, b3)
+        want = (torch.relu(y.double() + b1.double()) @ w3.double().t() + b3.double())
+        assert got.shape == (rows, 3) and (got.double() - want).abs().max() <= 2e-5 * max(1.0, want.abs().max().item())
+    x = torch.randn(21504, 1024, generator=g, device=DEV).to(torch.bfloat16) * 3
+    x[0, :8] = torch.tensor([0.0, -0.0, 1e-8, -30.0, 30.0, float("inf"), -float("inf"), 0.5], device=DEV).to(torch.bfloat16)
+    want = torch.nn.functional.gelu(x)
+    got = ops.gelu_bf16_(x.clone())
+    assert torch.equal(got[0, :5], want[0, :5])
+    ok = torch.isfinite(want)
+    assert (got[ok].float() - want[ok].float()).abs().max() <= 2 ** -7 * want[ok].float().abs().max()
+    assert ((got[ok] != want[ok]).float().mean() < 1e-3), "same fp32 formula: at most a few last-bit differences (erff vs ATen erf)"
+
+
 def test_batch_to_device_replicates_a_repeated_graph_on_the_device():
     """Batch.from_data_list([g] * B).to(cuda) ships g once and replicates on the device: every field must equal the plain
     transfer of the concatenated host tensors, including the offset edge_index."""
