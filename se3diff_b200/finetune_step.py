@@ -112,12 +112,23 @@ def _chunk_update(batches, timesteps, dts, dWs_batch, int_u_u_dt_sg, hs, h_stars
     estimator and back-propagate it (gradients accumulate on `finetune_model`)."""
     us = defaultdict(list)
     ts_host = timesteps.detach().cpu()
-    for i, batch in enumerate(batches):
-        t = torch.full((batch_size,), float(ts_host[i]), device=device)
-        u_t = finetune_model(batch, t)
-        lengths = batch_lengths(batch)
+    # One differentiable pass over the whole chunk when the stored states share one context (B copies of one sequence): the
+    # chunk's K control evaluations are independent, so K launch-bound passes of the 0.19 M-parameter model become one of batch
+    # K * B (the reference loops, finetune.py:352-361; equal up to floating-point summation order).
+    stacked = None
+    if hasattr(finetune_model, "forward_stacked") and not (finetune_model.training and getattr(finetune_model.model_nn, "dropout_p", 0) > 0):
+        stacked = finetune_model.forward_stacked(list(batches), timesteps.to(device=device, dtype=torch.float32))
+    if stacked is not None:
+        lengths = batch_lengths(batches[0])
         for f in fields:
-            us[f].append(_dense(u_t[f], batch, lengths))
+            us[f] = [_dense(stacked[f][i], batches[0], lengths) for i in range(len(batches))]
+    else:
+        for i, batch in enumerate(batches):
+            t = torch.full((batch_size,), float(ts_host[i]), device=device)
+            u_t = finetune_model(batch, t)
+            lengths = batch_lengths(batch)
+            for f in fields:
+                us[f].append(_dense(u_t[f], batch, lengths))
     us_flat = {f: torch.stack(us[f], dim=0).flatten(-2, -1) for f in fields}
     dWs_flat = {f: dWs_batch[f].flatten(-2, -1) for f in fields}
     int_dws = sum(pathwise.compute_int_dws(us=us_flat[f], dWs=dWs_flat[f]) for f in fields)

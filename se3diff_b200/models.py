@@ -410,26 +410,47 @@ class DistributionalGraphormer(nn.Module):
         on dense [B, L, .] tensors; dropout modules are honoured.  Index / mask bookkeeping comes from the context cache."""
         c = self._context(context)
         B, Lm = c.batch, c.lmax
-        dev = x.device
+        T = self._to_dense(x.float(), c)                                                             # [B, L, 3]
+        R = self._to_dense(node_orientations.float(), c)                                             # [B, L, 3, 3]
+        T_out, IR_eps = self._forward_torch_dense(c, context, T, R, t.float()[:B])
+        T_out, IR_eps = T_out.reshape(B * Lm, 3), IR_eps.reshape(B * Lm, 3)
+        if c.dense_index is None:
+            return T_out, IR_eps
+        return T_out[c.dense_index], IR_eps[c.dense_index]
+
+    def _forward_torch_dense(self, c, context, T, R, t):
+        """Body of `_forward_torch` on dense frames T [B', L, 3], R [B', L, 3, 3] and per-graph times t [B'].  B' may be a
+        multiple of the context's batch when the context is shared (B copies of one sequence): `forward_stacked`."""
+        Lm, dev = c.lmax, T.device
         single_d = self._to_dense(context["single_embeds"].float(), c)
         pair_d = self._dense_pairs(context, context["pair_embeds"].float(), c, dev)
         if c.shared:
             single_d, pair_d = single_d[:1], pair_d[:1]
-        x1d = self.x1d_proj(single_d) + self.step_emb(t.float()[:B])[:, None]                       # [B, L, D]
+        x1d = self.x1d_proj(single_d) + self.step_emb(t)[:, None]                                    # [B', L, D]
         bucket = self.rp_proj.bucket_table(Lm).to(dev)
         x2d = self.x2d_proj(pair_d) + self.rp_proj.relative_attention_bias(bucket)[None]             # [Bp, L, L, dp]
-        T = self._to_dense(x.float(), c)                                                             # [B, L, 3]
-        R = self._to_dense(node_orientations.float(), c)                                             # [B, L, 3, 3]
         bias = None if c.key_bias is None else c.key_bias[:, None, None, :]                          # additive key mask
         for lyr in self.st_module.encoder.layers:
             x1d = x1d + self._ipa_torch(lyr.attn, lyr.norm1(x1d), x2d, T, R, bias)
             x1d = x1d + lyr.ffn.ff(lyr.norm2(x1d))
         T_eps, IR_eps = self.st_module.diff_head.fc_t(x1d), self.st_module.diff_head.fc_eps(x1d)
-        T_out = torch.matmul(R, T_eps.unsqueeze(-1)).squeeze(-1).reshape(B * Lm, 3)                  # models.py:305
-        IR_eps = IR_eps.reshape(B * Lm, 3)
-        if c.dense_index is None:
-            return T_out, IR_eps
-        return T_out[c.dense_index], IR_eps[c.dense_index]
+        return torch.matmul(R, T_eps.unsqueeze(-1)).squeeze(-1), IR_eps                              # models.py:305
+
+    def forward_stacked(self, xs, node_orientations, ts, context):
+        """K evaluations of the network on the SAME shared context (B copies of one sequence, no masks) as ONE differentiable
+        forward of batch K * B: xs [K, N, 3], node_orientations [K, N, 3, 3], ts [K] (already scaled by 1000).  Samples never
+        interact (attention is within a sample), so this equals K separate calls up to floating-point summation order; it turns
+        the 2 * K launch-bound passes of the small control model in `_chunk_update` (finetune.py:338-393) into two.
+        Returns (pos [K, N, 3], rot [K, N, 3]) or None when the context is not of that kind."""
+        c = self._context(context)
+        if not (c.shared and c.uniform and c.key_bias is None and c.dense_index is None):
+            return None
+        K, B, Lm = xs.shape[0], c.batch, c.lmax
+        T = xs.float().reshape(K * B, Lm, 3)
+        R = node_orientations.float().reshape(K * B, Lm, 3, 3)
+        t = ts.float().reshape(K, 1).expand(K, B).reshape(K * B)
+        T_out, IR_eps = self._forward_torch_dense(c, context, T, R, t)
+        return T_out.reshape(K, B * Lm, 3), IR_eps.reshape(K, B * Lm, 3)
 
     @staticmethod
     def _ipa_torch(a: SAAttention, x1d, x2d, T, R, bias):
@@ -511,3 +532,18 @@ class DiGConditionalScoreModel(nn.Module):
         pos, rot = self.model_nn(x=x["pos"], node_orientations=x["node_orientations"], batch_index=x["batch"],
                                  t=t * 1000, context=context)
         return x.replace(pos=pos, node_orientations=rot)
+
+    def forward_stacked(self, batches, ts: torch.Tensor):
+        """The control on K stored states of one rollout in one differentiable pass (see DistributionalGraphormer.forward_stacked):
+        `batches` K batches of the same B graphs, `ts` [K] diffusion times.  Returns {"pos": [K, N, 3], "node_orientations":
+        [K, N, 3]} or None when the batches do not share one context (then call the model step by step)."""
+        x0 = batches[0]
+        if not x0["pos"].is_cuda or len(batches) < 2:
+            return None
+        for b in batches[1:]:
+            if b["single_embeds"] is not x0["single_embeds"] or b["pair_embeds"] is not x0["pair_embeds"] or b["batch"] is not x0["batch"]:
+                return None
+        context = x0.replace(pos=None, node_orientations=None)
+        out = self.model_nn.forward_stacked(torch.stack([b["pos"] for b in batches]), torch.stack([b["node_orientations"] for b in batches]),
+                                            ts * 1000, context)
+        return None if out is None else {"pos": out[0], "node_orientations": out[1]}
