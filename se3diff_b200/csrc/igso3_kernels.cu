@@ -372,16 +372,19 @@ k_sample(const float* __restrict__ sigma, const float* __restrict__ sigma_grid, 
         if (normals) {
             uu = u[e];
         } else {
-            uint32_t r[4], r2[4];
+            // One Philox4x32-10 block per rotation: a direction uniform on the sphere from two uniforms (z = 2a - 1, phi = 2 pi b) --
+            // the same law as the reference's normalised Gaussian triple (so3_sde.py:1229-1242), which would take four uniforms,
+            // two logarithms and a second block -- and the CDF uniform from the third.  (Bit parity with the reference's torch
+            // generator is the business of the noise-passed-in mode; this mode only has to draw from the same distribution.)
+            uint32_t r[4];
             philox(seed, (uint64_t)e, 0u, r);
-            philox(seed, (uint64_t)e, 1u, r2);
-            const float a0 = sqrtf(-2.0f * logf(1.0f - u01(r[0]))), a1 = sqrtf(-2.0f * logf(1.0f - u01(r[2])));
-            float s0, cs0, s1, cs1;
-            sincospif(2.0f * u01(r[1]), &s0, &cs0);
-            sincospif(2.0f * u01(r[3]), &s1, &cs1);
-            nx = a0 * cs0; ny = a0 * s0; nz = a1 * cs1;
-            uu = u01(r2[0]);
-            (void)s1;
+            const float z = 2.0f * u01(r[0]) - 1.0f;
+            const float rho = sqrtf(fmaxf(1.0f - z * z, 0.0f));
+            float sp, cp;
+            sincospif(2.0f * u01(r[1]), &sp, &cp);
+            nx = rho * cp; ny = rho * sp; nz = z;
+            if (nx == 0.0f && ny == 0.0f && nz == 0.0f) nz = 1.0f;
+            uu = u01(r[2]);
         }
         int row = 0;
         if (sigma) {
