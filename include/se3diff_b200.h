@@ -295,7 +295,8 @@ int se3_residual_layernorm(float* x, const float* y, const float* bias, const fl
  * w3 [3, dim] row-major; dim in {128, 256, 512, 1024}; out [rows, 3] fp32. */
 int se3_bias_relu_project3(const float* y, const float* b1, const float* w3, const float* b3, float* out, int64_t rows, int dim,
                            se3_stream_t stream);
-/* Exact (erf) GELU of FeedForward (structure_module.py:25-40) on bf16 data, fp32 math; n % 8 == 0; in == out allowed. */
+/* erf GELU of FeedForward (structure_module.py:25-40) on bf16 data, fp32 math, erfc by Abramowitz & Stegun 7.1.26
+ * (absolute error 1.5e-7, i.e. below the bf16 output rounding); n % 8 == 0; in == out allowed. */
 int se3_gelu_bf16(const void* in, void* out, int64_t n, se3_stream_t stream);
 
 /* Folded-state indicator of the fine-tune objective (observables/folding_stability.py:52-81, called at finetune.py:452 on
