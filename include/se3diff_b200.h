@@ -285,10 +285,10 @@ int se3_ipa_attention_tc_fwd(const void* scalars_bf16, int64_t scalar_stride, co
                              se3_stream_t stream);
 
 /* Fused residual update + pre-LayerNorm of the next block (bf16 throughput mode of the score network):
- *   x[rows,dim] += y[rows,dim] + bias[dim]      (y, bias optional: NULL skips the update; structure_module.py:247-248)
+ *   x[rows,dim] += y[rows,dim] + bias[dim]      (y fp32 or bf16, bias optional: NULL skips the update; structure_module.py:247-248)
  *   out[rows,dim] = LayerNorm(x; gamma, beta, eps)   written as fp32 or bf16
  * dim in {128, 256, 512, 1024}; all pointers 16-byte aligned. */
-int se3_residual_layernorm(float* x, const float* y, const float* bias, const float* gamma, const float* beta, float eps,
+int se3_residual_layernorm(float* x, const void* y, int y_is_bf16, const float* bias, const float* gamma, const float* beta, float eps,
                            void* out, int out_is_bf16, int64_t rows, int dim, se3_stream_t stream);
 /* Tail of a diffusion head, structure_module.py:12-22 (`... Linear(D, D) -> ReLU -> Linear(D, 3)`):
  * out[r, k] = sum_c relu(y[r, c] + b1[c]) * w3[k, c] + b3[k], k < 3; y [rows, dim] fp32 = the first Linear without its bias,

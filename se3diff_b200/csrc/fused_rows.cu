@@ -11,9 +11,9 @@ using namespace se3;
 
 namespace {
 
-template <int VPL, typename OutT>  // VPL float4 per lane: D = 128 * VPL
+template <int VPL, typename OutT, typename YT>  // VPL float4 per lane: D = 128 * VPL
 __global__ void __launch_bounds__(256)
-k_residual_layernorm(float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ bias,
+k_residual_layernorm(float* __restrict__ x, const YT* __restrict__ y, const float* __restrict__ bias,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps, OutT* __restrict__ out,
                      int64_t rows) {
     constexpr int D = 128 * VPL;
@@ -25,10 +25,15 @@ k_residual_layernorm(float* __restrict__ x, const float* __restrict__ y, const f
 #pragma unroll
     for (int k = 0; k < VPL; ++k) v[k] = xr[k * 32 + lane];
     if (y != nullptr) {
-        const float4* yr = reinterpret_cast<const float4*>(y + row * D);
 #pragma unroll
         for (int k = 0; k < VPL; ++k) {
-            const float4 a = __ldg(yr + k * 32 + lane);
+            float4 a;
+            if constexpr (sizeof(YT) == 2) {                // bf16 sublayer output: 4 values per 8-byte load
+                const uint2 p = __ldg(reinterpret_cast<const uint2*>(y + row * D) + k * 32 + lane);
+                a = make_float4(__uint_as_float(p.x << 16), __uint_as_float(p.x & 0xffff0000u), __uint_as_float(p.y << 16), __uint_as_float(p.y & 0xffff0000u));
+            } else {
+                a = __ldg(reinterpret_cast<const float4*>(y + row * D) + k * 32 + lane);
+            }
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(bias) + k * 32 + lane);
             v[k].x += a.x + b4.x; v[k].y += a.y + b4.y; v[k].z += a.z + b4.z; v[k].w += a.w + b4.w;
@@ -145,15 +150,15 @@ k_gelu_bf16(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t nvec)
     }
 }
 
-template <typename OutT>
-int launch(float* x, const float* y, const float* bias, const float* gamma, const float* beta, float eps, OutT* out, int64_t rows,
+template <typename OutT, typename YT>
+int launch(float* x, const YT* y, const float* bias, const float* gamma, const float* beta, float eps, OutT* out, int64_t rows,
            int dim, cudaStream_t st) {
     const unsigned grid = (unsigned)((rows * 32 + 255) / 256);
     switch (dim / 128) {
-        case 1: k_residual_layernorm<1, OutT><<<grid, 256, 0, st>>>(x, y, bias, gamma, beta, eps, out, rows); break;
-        case 2: k_residual_layernorm<2, OutT><<<grid, 256, 0, st>>>(x, y, bias, gamma, beta, eps, out, rows); break;
-        case 4: k_residual_layernorm<4, OutT><<<grid, 256, 0, st>>>(x, y, bias, gamma, beta, eps, out, rows); break;
-        case 8: k_residual_layernorm<8, OutT><<<grid, 256, 0, st>>>(x, y, bias, gamma, beta, eps, out, rows); break;
+        case 1: k_residual_layernorm<1, OutT, YT><<<grid, 256, 0, st>>>(x, y, bias, gamma, beta, eps, out, rows); break;
+        case 2: k_residual_layernorm<2, OutT, YT><<<grid, 256, 0, st>>>(x, y, bias, gamma, beta, eps, out, rows); break;
+        case 4: k_residual_layernorm<4, OutT, YT><<<grid, 256, 0, st>>>(x, y, bias, gamma, beta, eps, out, rows); break;
+        case 8: k_residual_layernorm<8, OutT, YT><<<grid, 256, 0, st>>>(x, y, bias, gamma, beta, eps, out, rows); break;
         default: set_error("se3_residual_layernorm: dim must be 128, 256, 512 or 1024 (got %d)", dim); return SE3_EUNSUPPORTED;
     }
     count_launch();
@@ -162,7 +167,7 @@ int launch(float* x, const float* y, const float* bias, const float* gamma, cons
 
 }  // namespace
 
-extern "C" int se3_residual_layernorm(float* x, const float* y, const float* bias, const float* gamma, const float* beta, float eps,
+extern "C" int se3_residual_layernorm(float* x, const void* y, int y_is_bf16, const float* bias, const float* gamma, const float* beta, float eps,
                                       void* out, int out_is_bf16, int64_t rows, int dim, se3_stream_t stream) {
     SE3_REQUIRE(rows >= 0, "negative rows");
     if (rows == 0) return SE3_OK;
@@ -171,8 +176,15 @@ extern "C" int se3_residual_layernorm(float* x, const float* y, const float* bia
     SE3_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias) |
                   reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
                 "pointers must be 16-byte aligned");
-    if (out_is_bf16) return launch<__nv_bfloat16>(x, y, bias, gamma, beta, eps, (__nv_bfloat16*)out, rows, dim, (cudaStream_t)stream);
-    return launch<float>(x, y, bias, gamma, beta, eps, (float*)out, rows, dim, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (y_is_bf16) {
+        const __nv_bfloat16* yb = (const __nv_bfloat16*)y;
+        if (out_is_bf16) return launch<__nv_bfloat16, __nv_bfloat16>(x, yb, bias, gamma, beta, eps, (__nv_bfloat16*)out, rows, dim, st);
+        return launch<float, __nv_bfloat16>(x, yb, bias, gamma, beta, eps, (float*)out, rows, dim, st);
+    }
+    const float* yf = (const float*)y;
+    if (out_is_bf16) return launch<__nv_bfloat16, float>(x, yf, bias, gamma, beta, eps, (__nv_bfloat16*)out, rows, dim, st);
+    return launch<float, float>(x, yf, bias, gamma, beta, eps, (float*)out, rows, dim, st);
 }
 
 extern "C" int se3_bias_relu_project3(const float* y, const float* b1, const float* w3, const float* b3, float* out, int64_t rows, int dim,

@@ -364,6 +364,10 @@ class DistributionalGraphormer(nn.Module):
         stays fp32; bias + residual + the next block's LayerNorm + bf16 cast are one kernel
         (se3_residual_layernorm), so activations make one round trip per block."""
         mm = lambda a, wt: torch.mm(a, wt.t(), out_dtype=torch.float32)
+        # the two sublayer outputs per block (fc_out, FFN second Linear) leave their GEMMs as bf16 and are added to the fp32 residual
+        # stream by the fused kernel: -70 us of GEMM epilogue and -27 us of LayerNorm traffic per evaluation for +10 % of the bf16
+        # mode's own deviation (RMSD / Rg 6.8e-4 -> 7.5e-4 in test_bf16_mode_ca_rmsd_tolerance; tolerance 2.5e-3)
+        sub = lambda a, wt: torch.mm(a, wt.t())
         y = bias = None
         for n, lyr in enumerate(self.st_module.encoder.layers):
             lw = w["layers"][n]
@@ -375,10 +379,10 @@ class DistributionalGraphormer(nn.Module):
                 feat = self._attention(mm(h1, lw["w_proj"]), R, T, c, lw, lyr, n, shape, flags)
             if feat.dtype != torch.bfloat16:
                 feat = feat.to(torch.bfloat16)
-            y, bias = mm(feat, lw["w_out"]), lyr.attn.fc_out.bias
+            y, bias = sub(feat, lw["w_out"]), lyr.attn.fc_out.bias
             h2 = ops.residual_layernorm(x, y, bias, lyr.norm2.weight, lyr.norm2.bias, lyr.norm2.eps)
             hid = ops.gelu_bf16_(F.linear(h2, lw["w_ff0"], lw["b_ff0"]))
-            y, bias = mm(hid, lw["w_ff3"]), lyr.ffn.ff[3].bias
+            y, bias = sub(hid, lw["w_ff3"]), lyr.ffn.ff[3].bias
         outs = []
         for name in ("fc_t", "fc_eps"):
             seq = getattr(self.st_module.diff_head, name)

@@ -529,13 +529,13 @@ def residual_layernorm(x, y, bias, gamma, beta, eps: float, out_dtype=torch.bflo
     if x.dtype != torch.float32 or not x.is_contiguous():
         raise ValueError("x must be a contiguous fp32 tensor (it is updated in place)")
     x = _dev(x, name="x")
-    y = None if y is None else _dev(y, name="y")
+    y = None if y is None else _dev(y, torch.bfloat16 if y.dtype == torch.bfloat16 else torch.float32, "y")
     bias = None if bias is None else _dev(bias, name="bias")
     gamma, beta = _dev(gamma, name="gamma"), _dev(beta, name="beta")
     out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
     dim = x.shape[-1]
     with _guard(x):
-        L.check(L.lib().se3_residual_layernorm(_p(x), _p(y), _p(bias), _p(gamma), _p(beta), float(eps), _p(out),
+        L.check(L.lib().se3_residual_layernorm(_p(x), _p(y), int(y is not None and y.dtype == torch.bfloat16), _p(bias), _p(gamma), _p(beta), float(eps), _p(out),
                                                int(out_dtype == torch.bfloat16), x.numel() // dim, dim, _stream(x)),
                 "se3_residual_layernorm")
     return out

@@ -816,6 +816,7 @@ def test_bf16_mode_ca_rmsd_tolerance():
     p16, r16 = outs["bf16"]
     rg = (p32 - p32.mean(dim=1, keepdim=True)).pow(2).sum(-1).mean(-1).sqrt()           # [B]
     rmsd = (p16 - p32).pow(2).sum(-1).mean(-1).sqrt()
+    print("bf16 vs fp32: RMSD / Rg per sample =", (rmsd / rg).tolist(), " max rotation-matrix difference =", (r16 - r32).abs().max().item())
     assert torch.isfinite(p16).all() and (rmsd <= 2.5e-3 * rg).all(), (rmsd, rg)
     assert (r16 - r32).abs().max() <= 5e-2
 
