@@ -686,7 +686,7 @@ def test_analytic_score_moments_on_gpu():
         assert torch.allclose(out.node_orientations.std(dim=0), torch.zeros(3, 3, device=DEV), atol=1e-1)
 
 
-@pytest.mark.parametrize("B,L,scale", [(3, 84, 1.5), (130, 20, 1.5), (2, 57, 1.5), (2, 200, 1.5), (2, 84, 100.0), (2, 256, 1.5),
+@pytest.mark.parametrize("B,L,scale", [(3, 84, 1.5), (130, 20, 1.5), (2, 57, 1.5), (2, 200, 1.5), (300, 131, 1.5), (2, 84, 100.0), (2, 256, 1.5),
                                        (2, 257, 1.5), (3, 300, 1.5), (2, 512, 1.5), (1, 500, 100.0)])
 def test_ipa_tensor_core_operator_vs_fp64(B, L, scale):
     """se3_ipa_attention_tc_fwd (tcgen05 two-pass; L > 256: keys split over a 2-CTA cluster) against an fp64 evaluation of
