@@ -260,7 +260,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD['name']} L={L} B={B}/GPU {S} diffusion steps (2 score evals each), "
+            "config": {"workload": f"{WORKLOAD['name'] if L == WORKLOAD['L'] else 'synthetic-sequence dpm_solver'} L={L} B={B}/GPU {S} diffusion steps (2 score evals each), "
                                    f"bioemu-v1.0 architecture random-init, synthetic embeddings",
                        "step": "one dpm_solver call incl. prior sampling" + (" + NCCL ensemble all_gather" if world > 1 else ""),
                        "l2": "512 MiB buffer written between timed iterations", "parallelism": f"dp{world} (independent samples)"},
