@@ -292,9 +292,10 @@ int se3_residual_layernorm(float* x, const void* y, int y_is_bf16, const float* 
                            void* out, int out_is_bf16, int64_t rows, int dim, se3_stream_t stream);
 /* Tail of a diffusion head, structure_module.py:12-22 (`... Linear(D, D) -> ReLU -> Linear(D, 3)`):
  * out[r, k] = sum_c relu(y[r, c] + b1[c]) * w3[k, c] + b3[k], k < 3; y [rows, dim] fp32 = the first Linear without its bias,
- * w3 [3, dim] row-major; dim in {128, 256, 512, 1024}; out [rows, 3] fp32. */
-int se3_bias_relu_project3(const float* y, const float* b1, const float* w3, const float* b3, float* out, int64_t rows, int dim,
-                           se3_stream_t stream);
+ * w3 [3, dim] row-major; dim in {128, 256, 512, 1024}; out [rows, 3] fp32.  rot: optional [rows, 3, 3] frames -- the result is
+ * rotated into the global frame, out[r] = R_r . out[r] (models.py:305: the translation score); NULL for none. */
+int se3_bias_relu_project3(const float* y, const float* b1, const float* w3, const float* b3, const float* rot, float* out,
+                           int64_t rows, int dim, se3_stream_t stream);
 /* erf GELU of FeedForward (structure_module.py:25-40) on bf16 data, fp32 math, erfc by Abramowitz & Stegun 7.1.26
  * (absolute error 1.5e-7, i.e. below the bf16 output rounding); n % 8 == 0; in == out allowed. */
 int se3_gelu_bf16(const void* in, void* out, int64_t n, se3_stream_t stream);

@@ -75,7 +75,7 @@ SIGNATURES = {
     "se3_backbone_atoms": [f32p, f32p, vp, vp, f32p, i64, i32, vp],
     "se3_physicality": [f32p, vp, f32p, i64, i32, vp],
     "se3_residual_layernorm": [f32p, vp, i32, f32p, f32p, f32p, f32, vp, i32, i64, i32, vp],
-    "se3_bias_relu_project3": [f32p] * 5 + [i64, i32, vp],
+    "se3_bias_relu_project3": [f32p] * 6 + [i64, i32, vp],
     "se3_gelu_bf16": [vp, vp, i64, vp],
     "se3_debug_umma_gemm": [vp, vp, f32p, i32, i32, vp],
     "se3_last_error": [],

@@ -75,7 +75,7 @@ k_residual_layernorm(float* __restrict__ x, const YT* __restrict__ y, const floa
 template <int VPL, int K>
 __global__ void __launch_bounds__(256)
 k_bias_relu_project(const float* __restrict__ y, const float* __restrict__ b1, const float* __restrict__ w3, const float* __restrict__ b3,
-                    float* __restrict__ out, int64_t rows) {
+                    const float* __restrict__ rot, float* __restrict__ out, int64_t rows) {
     constexpr int D = 128 * VPL;
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -100,10 +100,16 @@ k_bias_relu_project(const float* __restrict__ y, const float* __restrict__ b1, c
         for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
     }
     if (lane < K) {
-        float r = acc[0];
+        if (rot != nullptr) {                               // K == 3: out = R_row . (projection + b3), models.py:305
+            static_assert(K == 3, "the frame rotation applies to 3-vectors");
+            const float* R = rot + row * 9 + lane * 3;
+            out[row * 3 + lane] = R[0] * (acc[0] + b3[0]) + R[1] * (acc[1] + b3[1]) + R[2] * (acc[2] + b3[2]);
+        } else {
+            float r = acc[0];
 #pragma unroll
-        for (int k = 1; k < K; ++k) r = (lane == k) ? acc[k] : r;
-        out[row * K + lane] = r + b3[lane];
+            for (int k = 1; k < K; ++k) r = (lane == k) ? acc[k] : r;
+            out[row * K + lane] = r + b3[lane];
+        }
     }
 }
 
@@ -187,8 +193,8 @@ extern "C" int se3_residual_layernorm(float* x, const void* y, int y_is_bf16, co
     return launch<float, float>(x, yf, bias, gamma, beta, eps, (float*)out, rows, dim, st);
 }
 
-extern "C" int se3_bias_relu_project3(const float* y, const float* b1, const float* w3, const float* b3, float* out, int64_t rows, int dim,
-                                      se3_stream_t stream) {
+extern "C" int se3_bias_relu_project3(const float* y, const float* b1, const float* w3, const float* b3, const float* rot, float* out,
+                                      int64_t rows, int dim, se3_stream_t stream) {
     SE3_REQUIRE(rows >= 0, "negative rows");
     if (rows == 0) return SE3_OK;
     SE3_REQUIRE(y && b1 && w3 && b3 && out, "null pointer");
@@ -197,10 +203,10 @@ extern "C" int se3_bias_relu_project3(const float* y, const float* b1, const flo
     const unsigned grid = (unsigned)((rows * 32 + 255) / 256);
     cudaStream_t st = (cudaStream_t)stream;
     switch (dim) {
-        case 128: k_bias_relu_project<1, 3><<<grid, 256, 0, st>>>(y, b1, w3, b3, out, rows); break;
-        case 256: k_bias_relu_project<2, 3><<<grid, 256, 0, st>>>(y, b1, w3, b3, out, rows); break;
-        case 512: k_bias_relu_project<4, 3><<<grid, 256, 0, st>>>(y, b1, w3, b3, out, rows); break;
-        case 1024: k_bias_relu_project<8, 3><<<grid, 256, 0, st>>>(y, b1, w3, b3, out, rows); break;
+        case 128: k_bias_relu_project<1, 3><<<grid, 256, 0, st>>>(y, b1, w3, b3, rot, out, rows); break;
+        case 256: k_bias_relu_project<2, 3><<<grid, 256, 0, st>>>(y, b1, w3, b3, rot, out, rows); break;
+        case 512: k_bias_relu_project<4, 3><<<grid, 256, 0, st>>>(y, b1, w3, b3, rot, out, rows); break;
+        case 1024: k_bias_relu_project<8, 3><<<grid, 256, 0, st>>>(y, b1, w3, b3, rot, out, rows); break;
         default: set_error("se3_bias_relu_project3: dim must be 128, 256, 512 or 1024 (got %d)", dim); return SE3_EUNSUPPORTED;
     }
     count_launch();

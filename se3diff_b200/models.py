@@ -389,7 +389,7 @@ class DistributionalGraphormer(nn.Module):
             w1, w3 = w["heads"][name]
             hh = ops.residual_layernorm(x, y, bias, seq[0].weight, seq[0].bias, seq[0].eps)
             y = bias = None   # the residual update is applied once
-            outs.append(ops.bias_relu_project3(mm(hh, w1), seq[1].bias, w3, seq[3].bias))
+            outs.append(ops.bias_relu_project3(mm(hh, w1), seq[1].bias, w3, seq[3].bias, rot=R if name == "fc_t" else None))
         return outs
 
     def forward(self, x, node_orientations, batch_index, t, context):
@@ -562,10 +562,10 @@ class DistributionalGraphormer(nn.Module):
         flags = ops.IPA_EXACT if self.precision == "fp32" else ops.IPA_FAST_MATH
         fused = self.precision == "bf16" and D % 128 == 0 and D <= 1024
         if fused:
-            T_eps, IR_eps = self._forward_fused(x1d.contiguous(), R, T, c, w, shape, flags)
+            T_out, IR_eps = self._forward_fused(x1d.contiguous(), R, T, c, w, shape, flags)   # the head kernel applies R (models.py:305)
         else:
             T_eps, IR_eps = self._forward_plain(x1d, R, T, c, w, shape, flags)
-        T_out = torch.bmm(R.view(-1, 3, 3), T_eps.unsqueeze(-1)).squeeze(-1)      # models.py:305
+            T_out = torch.bmm(R.view(-1, 3, 3), T_eps.unsqueeze(-1)).squeeze(-1)      # models.py:305
         if c.dense_index is None:
             return T_out, IR_eps
         return T_out[c.dense_index], IR_eps[c.dense_index]

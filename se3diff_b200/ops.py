@@ -541,16 +541,20 @@ def residual_layernorm(x, y, bias, gamma, beta, eps: float, out_dtype=torch.bflo
     return out
 
 
-def bias_relu_project3(y, b1, w3, b3):
-    """Tail of a diffusion head: relu(y + b1) @ w3.T + b3 with w3 [3, D] (structure_module.py:12-22), one pass over y."""
+def bias_relu_project3(y, b1, w3, b3, rot=None):
+    """Tail of a diffusion head: relu(y + b1) @ w3.T + b3 with w3 [3, D] (structure_module.py:12-22), one pass over y;
+    `rot` [rows, 3, 3]: additionally rotate each 3-vector by its residue's frame (models.py:305)."""
     y = _dev(y, name="y")
+    rot = None if rot is None else _dev(rot, name="rot")
+    if rot is not None and rot.numel() != y.shape[0] * 9:
+        raise ValueError("bias_relu_project3: rot must hold one 3x3 matrix per row")
     b1, w3, b3 = _dev(b1, name="b1"), _dev(w3, name="w3"), _dev(b3, name="b3")
     rows, dim = y.shape
     if w3.shape != (3, dim) or b1.shape != (dim,) or b3.shape != (3,):
         raise ValueError(f"bias_relu_project3: shapes {tuple(y.shape)}, {tuple(b1.shape)}, {tuple(w3.shape)}, {tuple(b3.shape)}")
     out = torch.empty(rows, 3, dtype=torch.float32, device=y.device)
     with _guard(y):
-        L.check(L.lib().se3_bias_relu_project3(_p(y), _p(b1), _p(w3), _p(b3), _p(out), rows, dim, _stream(y)), "se3_bias_relu_project3")
+        L.check(L.lib().se3_bias_relu_project3(_p(y), _p(b1), _p(w3), _p(b3), _p(rot), _p(out), rows, dim, _stream(y)), "se3_bias_relu_project3")
     return out
 
 

@@ -753,6 +753,10 @@ def test_fused_row_kernels_vs_torch():
         got = ops.bias_relu_project3(y, b1, w3, b3)
         want = (torch.relu(y.double() + b1.double()) @ w3.double().t() + b3.double())
         assert got.shape == (rows, 3) and (got.double() - want).abs().max() <= 2e-5 * max(1.0, want.abs().max().item())
+        R = ops.so3_exp(torch.randn(rows, 3, generator=g, device=DEV))
+        got_r = ops.bias_relu_project3(y, b1, w3, b3, rot=R)
+        want_r = torch.bmm(R.double(), want.unsqueeze(-1)).squeeze(-1)
+        assert (got_r.double() - want_r).abs().max() <= 2e-5 * max(1.0, want.abs().max().item())
     # GELU: erf from Abramowitz & Stegun 7.1.26 (|erfc error| <= 1.5e-7), evaluated without cancellation on the negative side.
     # Stated tolerance against the exact fp32 erf GELU of the same bf16 input: one bf16 rounding (2^-8 relative) + 2e-6 absolute.
     x = torch.randn(21504, 1024, generator=g, device=DEV).to(torch.bfloat16) * 3
