@@ -265,7 +265,10 @@ int se3_ipa_attention_fwd(const float* proj, const float* rot, const float* tran
  *   scalars_bf16 : bf16 [B*L][scalar_stride], head h owns elements [h*48, h*48+48) = q 16 | k 16 | v 16; the q block
  *                  must already carry the factor scalar_weight * log2(e) (folded into the weight rows by the caller).
  *                  Each 16-byte piece is one chunk of a UMMA operand and is copied verbatim (cp.async), no conversion.
- *   points       : fp32 [B*L][point_stride], head h owns [h*48, h*48+48) = q_pts 12 | k_pts 12 | v_pts 24 (local frame)
+ *   points       : fp32 or bf16 (points_are_bf16) [B*L][point_stride], head h owns [h*48, h*48+48) = q_pts 12 | k_pts 12 |
+ *                  v_pts 24 (local frame).  bf16 records let ONE projection GEMM write scalar and point records side by side
+ *                  (row pitch = scalar_stride = point_stride); their 2^-9 rounding is of the size of the bf16 GEMM-operand
+ *                  rounding the local points already carry
  * Other differences from se3_ipa_attention_fwd:
  *   pair_bias_packed  : TRANSPOSED bf16 [H][L (key j)][round_up(L,8) (query i)] = pair_weight*pair_bias(x2d), zero padded;
  *                       the (head, query-tile) slab is fetched by TMA into shared memory
@@ -274,12 +277,11 @@ int se3_ipa_attention_fwd(const float* proj, const float* rot, const float* tran
  *                       sequence by the caller)
  *   out               : fp32 or bf16 (out_is_bf16) concat layout
  *   p_workspace / inv_workspace : scratch of the sizes reported by se3_ipa_tc_workspace_bytes (un-normalised probabilities,
- *                       bf16 in UMMA tile layout [H][L][round_up(B,128)/128][Lp/8][128][8], and 1/rowsum fp32
- *                       [H][L][round_up(B,128)])
+ *                       bf16 row-major [H][L][round_up(B,128)][Lp], and 1/rowsum fp32 [H][L][round_up(B,128)])
  * Of h_shape only batch, len, heads, dk, pq, pv, pair_batch are read. */
 int64_t se3_ipa_tc_workspace_bytes(const se3_ipa_shape* h_shape, int64_t* p_bytes, int64_t* inv_bytes);
-int se3_ipa_attention_tc_fwd(const void* scalars_bf16, int64_t scalar_stride, const float* points, int64_t point_stride,
-                             const float* rot, const float* trans, const void* pair_bias_packed,
+int se3_ipa_attention_tc_fwd(const void* scalars_bf16, int64_t scalar_stride, const void* points, int points_are_bf16,
+                             int64_t point_stride, const float* rot, const float* trans, const void* pair_bias_packed,
                              const void* pair_value_packed, const float* key_bias, const float* head_weight, void* out,
                              int out_is_bf16, void* p_workspace, float* inv_workspace, const se3_ipa_shape* h_shape,
                              se3_stream_t stream);

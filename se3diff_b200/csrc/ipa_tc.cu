@@ -123,6 +123,28 @@ __device__ __forceinline__ Pass1Smem carve1(uint8_t* base, int L, int LK, int Lp
     return s;
 }
 
+// N consecutive coordinates (N % 4 == 0) of a point record starting at element `first` (a multiple of 4): fp32 records are read
+// as float4, bf16 records (4 values per 8-byte load) are widened
+template <bool kBf16, int N>
+__device__ __forceinline__ void load_coords(const void* row, int first, float (&l)[N]) {
+    if constexpr (kBf16) {
+        const uint2* p = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(row) + first * 2);
+#pragma unroll
+        for (int c = 0; c < N / 4; ++c) {
+            const uint2 v = p[c];
+            l[4 * c] = __uint_as_float(v.x << 16); l[4 * c + 1] = __uint_as_float(v.x & 0xffff0000u);
+            l[4 * c + 2] = __uint_as_float(v.y << 16); l[4 * c + 3] = __uint_as_float(v.y & 0xffff0000u);
+        }
+    } else {
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(row) + first);
+#pragma unroll
+        for (int c = 0; c < N / 4; ++c) {
+            const float4 v = p[c];
+            l[4 * c] = v.x; l[4 * c + 1] = v.y; l[4 * c + 2] = v.z; l[4 * c + 3] = v.w;
+        }
+    }
+}
+
 // global = R.local + T for one point
 __device__ __forceinline__ void to_global(const float (&R)[9], const float (&T)[3], float x, float y, float z, float& gx, float& gy, float& gz) {
     gx = R[0] * x + R[1] * y + R[2] * z + T[0];
@@ -135,13 +157,15 @@ __device__ __forceinline__ void to_global(const float (&R)[9], const float (&T)[
 //                 (LpB = half of LpT rounded up to 16 = rows of every staging buffer; blockIdx.x = 2 * tile + rank).
 // kWide (always with kSplit, and alone for 129..256 key rows, where shared memory admits one CTA per SM anyway): 256 threads;
 //                 warps w and w + 4 share a TMEM lane quadrant (= 32 query rows) and take one half of the key columns each.
-template <typename OutT, bool kSplit, bool kWide>
+// kPtsBf16: the point records are bf16 (one projection GEMM writes scalar and point records side by side) instead of fp32.
+template <typename OutT, bool kSplit, bool kWide, bool kPtsBf16>
 __global__ void __launch_bounds__(kWide ? 256 : 128, kWide ? 1 : 4)
 k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_pts,
                const __grid_constant__ CUtensorMap map_bias, const float* __restrict__ rot, const float* __restrict__ trans, const __nv_bfloat16* __restrict__ pair_bias_t,
                const float* __restrict__ key_bias, const float* __restrict__ head_weight, OutT* __restrict__ out,
                __nv_bfloat16* __restrict__ pbuf, float* __restrict__ inv_sum, const se3_ipa_shape sh, int LpB, int LpT, int Bpad, int tmem_cols,
-               const float* __restrict__ pts, int pts_stride, long long* __restrict__ dbg) {
+               const void* __restrict__ pts, int pts_stride, long long* __restrict__ dbg) {
+    constexpr int kRawRow = kPtsBf16 ? 96 : 192;            // bytes of one staged point record [qp 12 | kp 12 | vp 24]
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t bar, bar_bias, bar_in;
     __shared__ float s_xmax[kSplit ? 128 : 1];             // row maxima offered to the peer CTA (split edition)
@@ -186,7 +210,7 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     // points : fp32 records [qp 12 | kp 12 | vp 24] of this head, one [L][192 B] box, parked raw in the (still unused) P region
     //          (256-thread editions: in their own buffer)
     // frames : the [LK][9] and [LK][3] blocks of this CTA's key residues, two 1-D bulk copies
-    float* s_raw = s.raw;                                  // [LKbox][48] raw local points
+    const uint8_t* s_raw = reinterpret_cast<const uint8_t*>(s.raw);   // [LKbox][48] raw local points
     float* s_rot = s.frm;
     float* s_trn = s.frm + LK * 9;
     const bool bulk_frames = ((L & 3) == 0) && ((reinterpret_cast<uintptr_t>(rot) | reinterpret_cast<uintptr_t>(trans)) & 15) == 0;
@@ -202,8 +226,8 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         int b_, h_, q0_;
         decode(it, b_, h_, q0_);
         const int row0 = b_ * L;
-        tc::mbar_expect_tx(&bar_in, (uint32_t)(4096 + LpB * 64 + LKbox * 192 + (bulk_frames ? LK * 48 : 0)));
-        tc::tma_tile_2d_g2s(s_raw, &map_pts, h_ * 48, row0 + k0, &bar_in);
+        tc::mbar_expect_tx(&bar_in, (uint32_t)(4096 + LpB * 64 + LKbox * kRawRow + (bulk_frames ? LK * 48 : 0)));
+        tc::tma_tile_2d_g2s(s.raw, &map_pts, h_ * 48, row0 + k0, &bar_in);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             tc::tma_tile_2d_g2s(s.k + (size_t)half * LpB * 16, &map_kv, h_ * 48 + 16 + half * 8, row0 + k0, &bar_in);
@@ -274,10 +298,10 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             for (int c = 0; c < 9; ++c) R[c] = s_rot[row * 9 + c];
 #pragma unroll
             for (int c = 0; c < 3; ++c) T[c] = s_trn[row * 3 + c];
-            const float4* raw4 = reinterpret_cast<const float4*>(s_raw + row * 48);
+            const uint8_t* rawrow = s_raw + (size_t)row * kRawRow;
             {
-                const float4 a = raw4[3], bb = raw4[4], c = raw4[5];
-                const float l[12] = {a.x, a.y, a.z, a.w, bb.x, bb.y, bb.z, bb.w, c.x, c.y, c.z, c.w};
+                float l[12];
+                load_coords<kPtsBf16, 12>(rawrow, 12, l);
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
                     float gx, gy, gz;
@@ -290,11 +314,7 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             float gv[24];
             {
                 float l[24];
-#pragma unroll
-                for (int c6 = 0; c6 < 6; ++c6) {
-                    const float4 v = raw4[6 + c6];
-                    l[4 * c6] = v.x; l[4 * c6 + 1] = v.y; l[4 * c6 + 2] = v.z; l[4 * c6 + 3] = v.w;
-                }
+                load_coords<kPtsBf16, 24>(rawrow, 24, l);
 #pragma unroll
                 for (int p = 0; p < 8; ++p) to_global(R, T, l[3 * p], l[3 * p + 1], l[3 * p + 2], gv[3 * p], gv[3 * p + 1], gv[3 * p + 2]);
             }
@@ -344,9 +364,10 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         for (int c = 0; c < 9; ++c) Ri[c] = qrot[c];
 #pragma unroll
         for (int c = 0; c < 3; ++c) Ti[c] = qtrn[c];
-        const float4* raw4 = reinterpret_cast<const float4*>(kSplit ? pts + ((int64_t)b * L + qi) * pts_stride + h * 48 : s_raw + qi * 48);
-        const float4 a = raw4[0], bb = raw4[1], c = raw4[2];
-        const float l[12] = {a.x, a.y, a.z, a.w, bb.x, bb.y, bb.z, bb.w, c.x, c.y, c.z, c.w};
+        const void* qrow = kSplit ? static_cast<const void*>(reinterpret_cast<const uint8_t*>(pts) + (((int64_t)b * L + qi) * pts_stride + h * 48) * (kPtsBf16 ? 2 : 4))
+                                  : static_cast<const void*>(s_raw + (size_t)qi * kRawRow);
+        float l[12];
+        load_coords<kPtsBf16, 12>(qrow, 0, l);
 #pragma unroll
         for (int p = 0; p < 4; ++p) to_global(Ri, Ti, l[3 * p], l[3 * p + 1], l[3 * p + 2], qp[3 * p], qp[3 * p + 1], qp[3 * p + 2]);
     }
@@ -662,8 +683,8 @@ int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const 
     return SE3_OK;
 }
 
-template <typename OutT>
-int launch_tc(const __nv_bfloat16* scal, int scal_stride, const float* pts, int pts_stride, const float* rot, const float* trans,
+template <typename OutT, bool kPtsBf16>
+int launch_tc(const __nv_bfloat16* scal, int scal_stride, const void* pts, int pts_stride, const float* rot, const float* trans,
               const __nv_bfloat16* pair_bias, const __nv_bfloat16* pvc, const float* key_bias, const float* head_weight, OutT* out,
               __nv_bfloat16* pbuf, float* inv_sum, const se3_ipa_shape& sh, int Lp, int Bpad, cudaStream_t st) {
     const int L = sh.len;
@@ -685,7 +706,8 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const float* pts, int 
     const uint64_t rows = (uint64_t)sh.batch * L, width = (uint64_t)sh.heads * 48;
     if (int rc = make_map_2d(&map_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, scal, width, rows, (uint64_t)scal_stride, 8, 128, "q tiles")) return rc;
     if (int rc = make_map_2d(&map_kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, scal, width, rows, (uint64_t)scal_stride, 8, (uint32_t)LpB, "k / v tiles")) return rc;
-    if (int rc = make_map_2d(&map_pts, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pts, width, rows, (uint64_t)pts_stride, 48, (uint32_t)LKbox, "point records")) return rc;
+    if (int rc = make_map_2d(&map_pts, kPtsBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, kPtsBf16 ? 2 : 4, pts, width, rows,
+                             (uint64_t)pts_stride, 48, (uint32_t)LKbox, "point records")) return rc;
     // probability workspace: row-major [h][i][b][Lp] = a [heads * L * Bpad][Lp] matrix; pass 2 takes 64-key x 128-sample boxes
     if (int rc = make_map_2d(&map_p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pbuf, (uint64_t)Lp, (uint64_t)sh.heads * L * Bpad, (uint64_t)Lp, 64, 128,
                              "probability workspace", CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
@@ -702,14 +724,14 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const float* pts, int 
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
     const int n_items = ntile * sh.heads * sh.batch;
     if (!split) {
-        auto k1 = wide ? k_ipa_tc_pass1<OutT, false, true> : k_ipa_tc_pass1<OutT, false, false>;
+        auto k1 = wide ? k_ipa_tc_pass1<OutT, false, true, kPtsBf16> : k_ipa_tc_pass1<OutT, false, false, kPtsBf16>;
         e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e != cudaSuccess) { set_error("ipa_tc pass1 smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
         const dim3 g1 = wide ? dim3((unsigned)(n_items < sms ? n_items : sms), 1, 1) : dim3(ntile, sh.heads, sh.batch);
         k1<<<g1, wide ? 256 : 128, smem1, st>>>(map_q, map_kv, map_pts, map_bias, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad,
                                                 cols, pts, pts_stride, g_phase_dbg);
     } else {
-        auto k1 = k_ipa_tc_pass1<OutT, true, true>;
+        auto k1 = k_ipa_tc_pass1<OutT, true, true, kPtsBf16>;
         e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e != cudaSuccess) { set_error("ipa_tc pass1 (split) smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
         cudaLaunchConfig_t cfg = {};
@@ -762,7 +784,7 @@ int64_t se3_ipa_tc_workspace_bytes(const se3_ipa_shape* h_shape, int64_t* p_byte
     return pb + ib;
 }
 
-int se3_ipa_attention_tc_fwd(const void* scalars_bf16, int64_t scalar_stride, const float* points, int64_t point_stride,
+int se3_ipa_attention_tc_fwd(const void* scalars_bf16, int64_t scalar_stride, const void* points, int points_are_bf16, int64_t point_stride,
                              const float* rot, const float* trans, const void* pair_bias_packed, const void* pair_value_packed,
                              const float* key_bias, const float* head_weight, void* out, int out_is_bf16, void* p_workspace,
                              float* inv_workspace, const se3_ipa_shape* h_shape, se3_stream_t stream) {
@@ -778,17 +800,22 @@ int se3_ipa_attention_tc_fwd(const void* scalars_bf16, int64_t scalar_stride, co
     }
     SE3_REQUIRE(scalar_stride >= (int64_t)sh.heads * 48 && scalar_stride % 8 == 0 && scalar_stride < (1ll << 28) &&
                 (reinterpret_cast<uintptr_t>(scalars_bf16) & 15) == 0, "scalar records: bf16 [rows][>= H*48], stride a multiple of 8, 16-byte aligned");
-    SE3_REQUIRE(point_stride >= (int64_t)sh.heads * 48 && point_stride % 4 == 0 && point_stride < (1ll << 28) &&
-                (reinterpret_cast<uintptr_t>(points) & 15) == 0, "point records: fp32 [rows][>= H*48], stride a multiple of 4, 16-byte aligned");
+    SE3_REQUIRE(point_stride >= (int64_t)sh.heads * 48 && point_stride % (points_are_bf16 ? 8 : 4) == 0 && point_stride < (1ll << 28) &&
+                (reinterpret_cast<uintptr_t>(points) & 15) == 0, "point records: [rows][>= H*48] fp32 (stride % 4) or bf16 (stride % 8), 16-byte aligned");
     const int Lp = (sh.len + 15) / 16 * 16, Bpad = (sh.batch + 127) / 128 * 128;
     cudaStream_t st = (cudaStream_t)stream;
-    if (out_is_bf16)
-        return launch_tc<__nv_bfloat16>((const __nv_bfloat16*)scalars_bf16, (int)scalar_stride, points, (int)point_stride, rot, trans,
-                                        (const __nv_bfloat16*)pair_bias_packed, (const __nv_bfloat16*)pair_value_packed, key_bias, head_weight,
-                                        (__nv_bfloat16*)out, (__nv_bfloat16*)p_workspace, inv_workspace, sh, Lp, Bpad, st);
-    return launch_tc<float>((const __nv_bfloat16*)scalars_bf16, (int)scalar_stride, points, (int)point_stride, rot, trans,
-                            (const __nv_bfloat16*)pair_bias_packed, (const __nv_bfloat16*)pair_value_packed, key_bias, head_weight, (float*)out,
-                            (__nv_bfloat16*)p_workspace, inv_workspace, sh, Lp, Bpad, st);
+    const __nv_bfloat16* sc = (const __nv_bfloat16*)scalars_bf16;
+    const __nv_bfloat16 *pb = (const __nv_bfloat16*)pair_bias_packed, *pv = (const __nv_bfloat16*)pair_value_packed;
+    __nv_bfloat16* pw = (__nv_bfloat16*)p_workspace;
+    const int ss = (int)scalar_stride, ps = (int)point_stride;
+    if (out_is_bf16) {
+        __nv_bfloat16* o = (__nv_bfloat16*)out;
+        return points_are_bf16 ? launch_tc<__nv_bfloat16, true>(sc, ss, points, ps, rot, trans, pb, pv, key_bias, head_weight, o, pw, inv_workspace, sh, Lp, Bpad, st)
+                               : launch_tc<__nv_bfloat16, false>(sc, ss, points, ps, rot, trans, pb, pv, key_bias, head_weight, o, pw, inv_workspace, sh, Lp, Bpad, st);
+    }
+    float* o = (float*)out;
+    return points_are_bf16 ? launch_tc<float, true>(sc, ss, points, ps, rot, trans, pb, pv, key_bias, head_weight, o, pw, inv_workspace, sh, Lp, Bpad, st)
+                           : launch_tc<float, false>(sc, ss, points, ps, rot, trans, pb, pv, key_bias, head_weight, o, pw, inv_workspace, sh, Lp, Bpad, st);
 }
 
 }  // extern "C"

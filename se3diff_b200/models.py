@@ -199,6 +199,7 @@ class DistributionalGraphormer(nn.Module):
                     w_s = w_proj[rows_s].float()
                     w_s[qpos] *= a.scalar_weight * 1.4426950408889634      # q carries scalar_weight * log2 e (exp2 softmax)
                     split = dict(w_proj_s=w_s.to(dtype).contiguous(), w_proj_p=w_proj[rows_p].to(dtype).contiguous())
+                    split["w_proj_sp"] = torch.cat([split["w_proj_s"], split["w_proj_p"]], dim=0).contiguous()   # one GEMM: scalar | point records
                     w_proj = w_proj[ops.ipa_head_major_perm(a.n_head, a.d_k, w_proj.device)]
                 layers.append(dict(
                     **split,
@@ -372,8 +373,12 @@ class DistributionalGraphormer(nn.Module):
         for n, lyr in enumerate(self.st_module.encoder.layers):
             lw = w["layers"][n]
             h1 = ops.residual_layernorm(x, y, bias, lyr.norm1.weight, lyr.norm1.bias, lyr.norm1.eps)
-            if c.tc:    # two GEMMs: bf16 scalar records that are copied verbatim into the MMA operands, fp32 point records
-                feat = ops.ipa_attention_tc_fwd(torch.mm(h1, lw["w_proj_s"].t()), mm(h1, lw["w_proj_p"]), R, T, c.pair_bias[n],
+            if c.tc:    # ONE GEMM writes the bf16 scalar records (copied verbatim into the MMA operands) and the bf16 point records
+                # side by side.  The local points leave a bf16-operand GEMM with ~2^-9 relative error anyway, so storing them in
+                # fp32 (a second GEMM with a 132 MB fp32 epilogue, 46 us against 34 us) bought nothing measurable.
+                sp = torch.mm(h1, lw["w_proj_sp"].t())
+                half = sp.shape[1] // 2
+                feat = ops.ipa_attention_tc_fwd(sp[:, :half], sp[:, half:], R, T, c.pair_bias[n],
                                                       c.pair_value_packed[n], c.key_bias, lw["head_w"], shape, c.workspace)
             else:
                 feat = self._attention(mm(h1, lw["w_proj"]), R, T, c, lw, lyr, n, shape, flags)

@@ -463,12 +463,23 @@ def ipa_split_perms(heads: int, dk: int = 16):
     return torch.cat(sc), torch.cat(pt), torch.cat(qpos)
 
 
+def _rows_view(t, dtype, name):
+    """A 2-D tensor whose rows are contiguous (any row pitch): accepted as is; anything else is made contiguous."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        return _dev(t, dtype, name)
+    if t.dtype == dtype and t.dim() == 2 and t.stride(1) == 1:
+        return t
+    return _dev(t, dtype, name)
+
+
 def ipa_attention_tc_fwd(scalars, points, rot, trans, pair_bias_packed, pair_value_packed, key_bias, head_weight,
                                shape: L.IpaShape, workspace, out_dtype=torch.bfloat16, out=None):
-    """Tensor-core edition (tcgen05/TMEM) of SAAttention.forward between the projections and fc_out, fed by the split
-    projections: bf16 scalar records with pre-scaled q, fp32 point records (see ipa_split_perms)."""
-    scalars = _dev(scalars, torch.bfloat16, "scalars")
-    points, rot, trans = _dev(points, name="points"), _dev(rot, name="rot"), _dev(trans, name="trans")
+    """Tensor-core edition (tcgen05/TMEM) of SAAttention.forward between the projections and fc_out, fed by head-major
+    records: bf16 scalar records with pre-scaled q, and fp32 or bf16 point records (see ipa_split_perms).  Both may be column
+    slices of one projection output (row pitch = that matrix's width)."""
+    scalars = _rows_view(scalars, torch.bfloat16, "scalars")
+    points = _rows_view(points, torch.bfloat16 if points.dtype == torch.bfloat16 else torch.float32, "points")
+    rot, trans = _dev(rot, name="rot"), _dev(trans, name="trans")
     pair_bias = _dev(pair_bias_packed, torch.bfloat16, "pair_bias_packed")
     pvp = _dev(pair_value_packed, torch.bfloat16, "pair_value_packed")
     key_bias = None if key_bias is None else _dev(key_bias, name="key_bias")
@@ -477,8 +488,8 @@ def ipa_attention_tc_fwd(scalars, points, rot, trans, pair_bias_packed, pair_val
         out = torch.empty(shape.batch * shape.len, shape.heads * (2 * shape.dk + 4 * shape.pv), dtype=out_dtype, device=points.device)
     pws, iws = workspace
     with _guard(points):
-        L.check(L.lib().se3_ipa_attention_tc_fwd(_p(scalars), scalars.shape[-1], _p(points), points.shape[-1], _p(rot), _p(trans),
-                                                       _p(pair_bias), _p(pvp), _p(key_bias), _p(head_weight), _p(out),
+        L.check(L.lib().se3_ipa_attention_tc_fwd(_p(scalars), scalars.stride(0), _p(points), int(points.dtype == torch.bfloat16), points.stride(0),
+                                                       _p(rot), _p(trans), _p(pair_bias), _p(pvp), _p(key_bias), _p(head_weight), _p(out),
                                                        int(out.dtype == torch.bfloat16), _p(pws), _p(iws), C.byref(shape), _stream(points)),
                 "se3_ipa_attention_tc_fwd")
     return out

@@ -116,7 +116,9 @@ def kernel_rooflines(step_fn, L: int, B: int, heads: int = 32):
     two roofs HBM is the binding one, so `bound` = "hbm"; the tensor-pipe figure is kept next to it."""
     pk = measured_peaks()
     prev = os.environ.get("SE3DIFF_B200_CUDA_GRAPH")
+    prev_m = os.environ.get("SE3DIFF_B200_MODEL_GRAPH")
     os.environ["SE3DIFF_B200_CUDA_GRAPH"] = "0"      # the event hooks live in the eager launch path
+    os.environ["SE3DIFF_B200_MODEL_GRAPH"] = "0"
     names = ("ipa_attention_fwd", "ipa_attention_tc_fwd")
     hooks = [_Hook(n) for n in names]
     try:
@@ -127,16 +129,17 @@ def kernel_rooflines(step_fn, L: int, B: int, heads: int = 32):
     finally:
         for h in hooks:
             h.__exit__()
-        if prev is None:
-            os.environ.pop("SE3DIFF_B200_CUDA_GRAPH", None)
-        else:
-            os.environ["SE3DIFF_B200_CUDA_GRAPH"] = prev
+        for key, val in (("SE3DIFF_B200_CUDA_GRAPH", prev), ("SE3DIFF_B200_MODEL_GRAPH", prev_m)):
+            if val is None:
+                os.environ.pop(key, None)
+            else:
+                os.environ[key] = val
     name = max(names, key=lambda n: timed[n][1])
     ms, n = timed[name]
     rows, width_out = B * L, heads * (2 * 16 + 4 * 8)
     edition, proj_bytes, out_bytes = {
         "ipa_attention_fwd": ("fp32 SIMT", rows * heads * 96 * 4, rows * width_out * 4),
-        "ipa_attention_tc_fwd": ("tcgen05 two-pass (bf16 scalar + fp32 point projections)", rows * heads * 48 * (2 + 4), rows * width_out * 2),
+        "ipa_attention_tc_fwd": ("tcgen05 two-pass (bf16 scalar and point records from one projection)", rows * heads * 48 * (2 + 2), rows * width_out * 2),
     }[name]
     pair_el = 4 if name == "ipa_attention_fwd" else 2
     nbytes = proj_bytes + rows * 48 + out_bytes + heads * L * L * pair_el + L * L * heads * 16 * pair_el

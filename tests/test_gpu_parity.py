@@ -704,12 +704,17 @@ def test_ipa_tensor_core_operator_vs_fp64(B, L, scale):
     ws = ops.ipa_tc_workspace(shape, DEV)
     pvp, pbt = ops.ipa_tc_pack_pair_value(pv, H), ops.ipa_tc_pack_pair_bias(pb.permute(0, 2, 3, 1))
     sc, pt = split(proj)
-    for odt in (torch.float32, torch.bfloat16):
-        got = ops.ipa_attention_tc_fwd(sc, pt, rot, trans, pbt, pvp, None, hw, shape, ws, out_dtype=odt)
+    both = torch.cat([sc, pt.to(torch.bfloat16)], dim=1)        # what one projection GEMM writes in bf16 mode: scalar | point records
+    want_b = ref(torch.cat([proj[:, :1536], proj[:, 1536:].to(torch.bfloat16).float()], dim=1), rot, trans, pb, pv, hw, B, L)
+    for odt in (torch.float32, torch.bfloat16, "bf16-points"):
+        if odt == "bf16-points":
+            got, odt, want_cmp = ops.ipa_attention_tc_fwd(both[:, :1536], both[:, 1536:], rot, trans, pbt, pvp, None, hw, shape, ws, out_dtype=torch.float32), torch.float32, want_b
+        else:
+            got, want_cmp = ops.ipa_attention_tc_fwd(sc, pt, rot, trans, pbt, pvp, None, hw, shape, ws, out_dtype=odt), want
         assert torch.isfinite(got).all()
         for name, a, b in (("scalar", 0, 512), ("point", 512, 1280), ("pair", 1280, 1792), ("norm", 1792, 2048)):
-            err = (got[:, a:b].double() - want[:, a:b]).abs().max().item()
-            ref_max = max(1.0, want[:, a:b].abs().max().item())
+            err = (got[:, a:b].double() - want_cmp[:, a:b]).abs().max().item()
+            ref_max = max(1.0, want_cmp[:, a:b].abs().max().item())
             assert err <= 1.5e-2 * ref_max * (2.0 if odt == torch.bfloat16 else 1.0), (name, odt, err, ref_max)
 
 
