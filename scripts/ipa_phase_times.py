@@ -10,6 +10,8 @@ proj, rot, trans, pb, pv, hw, shape = make(B, Lm)
 ws = ops.ipa_tc_workspace(shape, dev); pvp = ops.ipa_tc_pack_pair_value(pv, H); pbt = ops.ipa_tc_pack_pair_bias(pb.permute(0, 2, 3, 1))
 out = torch.empty(B * Lm, 2048, dtype=torch.bfloat16, device=dev)
 sc_, pt_ = split(proj)
+both_ = torch.cat([sc_, pt_.to(torch.bfloat16)], dim=1)      # production layout: one projection writes scalar | bf16 point records
+sc_, pt_ = both_[:, :sc_.shape[1]], both_[:, sc_.shape[1]:]
 run = lambda: ops.ipa_attention_tc_fwd(sc_, pt_, rot, trans, pbt, pvp, None, hw, shape, ws, out=out)
 for _ in range(3): run()
 buf = torch.zeros(n_cta * 16, dtype=torch.int64, device=dev)
