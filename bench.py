@@ -107,7 +107,7 @@ def reference_arm(args):
     from oracle.score_model import init_state_dict
 
     L = WORKLOAD["L"]
-    sB, sS = 4, 3
+    sB, sS = 8, 6
     sd = init_state_dict(seed=0)
     total = args.steps + args.warmup
     times, cores = cpu_reference_run(L, sB, sS, sd, None, repeats=total)
@@ -249,7 +249,7 @@ def main():
                 sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
                 tables = dict(omega_grid=so3.igso3.omega_grid.cpu(), cdf_igso3=so3.igso3.cdf_igso3.cpu(),
                               cdf_uso3=so3.uso3.cdf_igso3.cpu(), score_scaling=so3.score_function.score_scaling.cpu())
-                sB, sS = 4, 6
+                sB, sS = 8, 20                                             # ~10-20 s of CPU work on the box's host cores
                 (t_cpu,), cores = cpu_reference_run(L, sB, sS, sd, tables)
                 cpu = {"value": sB * L * sS / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
                        "sample": f"oracle dpm_solver, B={sB} of {B} samples, {sS} of {S} diffusion steps, L={L}, fp32, "
