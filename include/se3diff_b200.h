@@ -258,6 +258,24 @@ int se3_ipa_attention_fwd(const float* proj, const float* rot, const float* tran
                           float scalar_weight, float* out, const se3_ipa_shape* h_shape, int flags,
                           se3_stream_t stream);
 
+/* Gradient of se3_ipa_attention_fwd (SE3_IPA_EXACT) for the fine-tune loss side, where the control model is re-evaluated
+ * with autograd on stored rollout states (finetune.py:338-393 `_chunk_update`; torch autograd of structure_module.py:131-216
+ * in the reference).  Frames (rot, trans) are constants there and receive no gradient.
+ *   out, d_out : the forward result and its incoming gradient, [B*L, H*(2*dk + 4*pv)] fp32
+ *   d_proj     : [B*L, proj_stride] fp32, every column of the q | k | v | q_pt | k_pt | v_pt blocks is written
+ *   p_ws, ds_ws: [B, H, L, L] fp32 each -- the attention probabilities and the logit gradients dS.  They ARE outputs:
+ *                d pair_bias = ds_ws (summed over B when pair_batch = 1), d pair_value[b, i, j, h*dk + c] =
+ *                p_ws[b, h, i, j] * d_out[b*L + i, pair block h, c] (summed over B when pair_batch = 1: a GEMM over the
+ *                samples, left to the caller's BLAS)
+ *   d_hw_rows  : [B*L, H] fp32, per-row partials of d head_weight (sum over rows = the gradient; deterministic)
+ * One CTA per (sample, head) keeps the L keys, the L query records and both L x L matrices in shared memory:
+ * len <= SE3_IPA_BWD_MAX_LEN and (2*len*(2*dk+36) + 2*len*(len|1) + len) * 4 bytes <= 227 KB. */
+#define SE3_IPA_BWD_MAX_LEN 128
+int se3_ipa_attention_bwd(const float* proj, const float* rot, const float* trans, const float* pair_bias,
+                          const float* pair_value, const float* key_bias, const float* head_weight,
+                          float scalar_weight, const float* out, const float* d_out, float* d_proj, float* p_ws,
+                          float* ds_ws, float* d_hw_rows, const se3_ipa_shape* h_shape, se3_stream_t stream);
+
 /* Tensor-core edition of the same operator (tcgen05.mma + TMEM, bf16 operands, fp32 accumulation): two passes, see
  * se3diff_b200/csrc/ipa_tc.cu.  Requirements: dk = 16, 4 / 8 points, shared pair tensors (pair_batch = 1), L <= 256.
  * The projection (structure_module.py:131-135) is delivered as TWO head-major matrices, which the bf16 score network

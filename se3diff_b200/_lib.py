@@ -69,6 +69,7 @@ SIGNATURES = {
     "se3_igso3_build_cdf_index": [f32p, i32, i32, f32p, vp],
     "se3_igso3_cdf_index_floats": [i32, i32],
     "se3_ipa_attention_fwd": [f32p] * 7 + [f32, f32p, C.POINTER(IpaShape), i32, vp],
+    "se3_ipa_attention_bwd": [f32p] * 7 + [f32] + [f32p] * 6 + [C.POINTER(IpaShape), vp],
     "se3_ipa_tc_workspace_bytes": [C.POINTER(IpaShape), C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
     "se3_ipa_attention_tc_fwd": [vp, i64, vp, i32, i64, f32p, f32p, vp, vp, f32p, f32p, vp, i32, vp, f32p, C.POINTER(IpaShape), vp],
     "se3_folded_proportion": [f32p, f32p, f32p, f32p, i64, i32, f32, f32, f32, vp],

@@ -21,6 +21,7 @@ SOURCES = {
     "frame_kernels.cu": ["-fmad=false"],
     "igso3_kernels.cu": ["-fmad=false"],
     "ipa_simt.cu": [],
+    "ipa_bwd.cu": [],
     "tc_selftest.cu": [],
     "ipa_tc.cu": [],
     "fused_rows.cu": [],

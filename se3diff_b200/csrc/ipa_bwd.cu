@@ -1,0 +1,347 @@
+// K4 backward (fp32 SIMT) -- gradient of se3_ipa_attention_fwd (ipa_simt.cu), i.e. of SAAttention.forward between the
+// input projections and fc_out (structure_module.py:131-216), for the fine-tune loss side (finetune.py:338-393: the
+// control model is re-evaluated on stored rollout states with autograd; frames carry no gradient there).
+//
+//   s_ij   = (sw q_i).k_j + hw * sum_p |Qp_i - Kp_j| + pair_bias_hij + key_bias_j          P = softmax_j(s)
+//   o_s    = sum_j P_ij v_j         o_pg = sum_j P_ij Vp_j      o_pl = R_i^T (o_pg - T_i)     o_n = |o_pl|
+//   o_pair = sum_j P_ij z_ij
+// With g_pl = dO_pl + dO_n o_pl/|o_pl|, g_pg = R_i g_pl:
+//   dP_ij - D_i = dO_s.(v_j - o_s) + g_pg.(Vp_j - o_pg) + dO_pair.(z_ij - o_pair)          dS_ij = P_ij (dP_ij - D_i)
+//   dq_i = sw sum_j dS_ij k_j        dk_j = sum_i dS_ij (sw q_i)      dv_j = sum_i P_ij dO_s,i
+//   dQp_i = hw sum_j dS_ij sum_p (Qp_i - Kp_j)/|.|   (dKp_j: minus the same, summed over i)   dVp_j = sum_i P_ij g_pg,i
+//   d hw  = sum_ij dS_ij sum_p |Qp_i - Kp_j|        point gradients return to the local frame through R^T.
+// One CTA per (sample, head), all L <= 128 keys resident.  Phase 1: one thread per QUERY row recomputes the logits and
+// the softmax (rows of P and dS stay in shared memory) and accumulates the query-side gradients; phase 2: one thread per
+// KEY column walks the same two matrices down the rows for the key-side gradients -- no atomics, deterministic.  P and
+// dS also go to global memory (coalesced): the caller reduces them over the samples into the gradients of the shared
+// pair tensors (d pair_bias = sum_b dS; d pair_value[i,j,h,:] = sum_b P_hij dO_pair_i -- a GEMM with K = samples).
+#include <math_constants.h>
+
+#include "common.cuh"
+
+using namespace se3;
+
+namespace {
+
+constexpr int PQ = 4, PV = 8;
+
+template <int DK>
+__global__ void __launch_bounds__(128)
+k_ipa_bwd(const float* __restrict__ proj, const float* __restrict__ rot, const float* __restrict__ trans,
+          const float* __restrict__ pair_bias, const float* __restrict__ pair_value, const float* __restrict__ key_bias,
+          const float* __restrict__ head_weight, float scalar_weight, const float* __restrict__ out,
+          const float* __restrict__ d_out, float* __restrict__ d_proj, float* __restrict__ p_ws, float* __restrict__ ds_ws,
+          float* __restrict__ d_hw_rows, const se3_ipa_shape sh) {
+    constexpr int KW = 2 * DK + 3 * PQ + 3 * PV;                                  // floats per staged record
+    constexpr int O_KS = 0, O_KP = DK, O_VS = DK + 3 * PQ, O_VP = 2 * DK + 3 * PQ;  // key record: k | Kp | v | Vp (global frame)
+    constexpr int O_Q = 0, O_QP = DK, O_GS = DK + 3 * PQ, O_GP = 2 * DK + 3 * PQ;   // query record: sw q | Qp | dO_s | g_pg
+    extern __shared__ __align__(16) float smem[];
+    const int L = sh.len, H = sh.heads, LS = L | 1;                               // odd row pitch: conflict-free both ways
+    float* keys = smem;               // [L][KW]
+    float* qrec = keys + L * KW;      // [L][KW]
+    float* Pm = qrec + L * KW;        // [L][LS]
+    float* Sm = Pm + L * LS;          // [L][LS]
+    float* kbias = Sm + L * LS;       // [L]
+
+    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const bool active = tid < L;
+    const int i = active ? tid : 0;
+    const int pb = sh.pair_batch == 1 ? 0 : b;
+    const int64_t row_i = (int64_t)b * L + i;
+    const float hw = head_weight[h];
+    const int HD = H * DK;
+    const int W = 2 * HD + 4 * H * PV;
+    const int C_S = h * DK, C_P = HD + h * PV * 3, C_Z = HD + 3 * H * PV + h * DK, C_N = 2 * HD + 3 * H * PV + h * PV;
+
+    // ---- phase 0: stage the keys of this (sample, head) in the global frame --------------------------------
+    for (int idx = tid; idx < L * DK; idx += blockDim.x) {
+        const int j = idx / DK, c = idx - j * DK;
+        const float* pr = proj + ((int64_t)b * L + j) * sh.proj_stride;
+        keys[j * KW + O_KS + c] = pr[sh.off_k + h * sh.hs_scalar + c];
+        keys[j * KW + O_VS + c] = pr[sh.off_v + h * sh.hs_scalar + c];
+    }
+    for (int idx = tid; idx < L * (PQ + PV); idx += blockDim.x) {
+        const int j = idx / (PQ + PV), p = idx - j * (PQ + PV);
+        const int64_t rj = (int64_t)b * L + j;
+        const float* pr = proj + rj * sh.proj_stride + (p < PQ ? sh.off_kp + h * sh.hs_point + p * 3 : sh.off_vp + h * sh.hs_vpoint + (p - PQ) * 3);
+        const float x = pr[0], y = pr[1], z = pr[2];
+        const float* R = rot + rj * 9;
+        const float* T = trans + rj * 3;
+        float* dst = keys + j * KW + (p < PQ ? O_KP + p * 3 : O_VP + (p - PQ) * 3);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) dst[r] = ((R[r * 3] * x + R[r * 3 + 1] * y) + R[r * 3 + 2] * z) + T[r];
+    }
+    for (int idx = tid; idx < L; idx += blockDim.x) kbias[idx] = key_bias ? key_bias[(int64_t)b * L + idx] : 0.f;
+
+    // ---- the thread's query row: operands, incoming gradients, D_i ---------------------------------------------
+    float q[DK], qp[3 * PQ], gs[DK], gp[3 * PV], gzp[DK], opg[3 * PV], Ri[9];
+    float Ds = 0.f;                                                    // dO_s.o_s + dO_pair.o_pair
+    if (active) {
+        const float* pr = proj + row_i * sh.proj_stride;
+        const float* o = out + row_i * (int64_t)W;
+        const float* go = d_out + row_i * (int64_t)W;
+        float Ti[3];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Ri[k] = rot[row_i * 9 + k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Ti[k] = trans[row_i * 3 + k];
+#pragma unroll
+        for (int c = 0; c < DK; ++c) {
+            q[c] = pr[sh.off_q + h * sh.hs_scalar + c] * scalar_weight;
+            gs[c] = go[C_S + c];
+            gzp[c] = go[C_Z + c];
+            Ds += gs[c] * o[C_S + c] + gzp[c] * o[C_Z + c];
+        }
+#pragma unroll
+        for (int p = 0; p < PQ; ++p) {
+            const float x = pr[sh.off_qp + h * sh.hs_point + p * 3], y = pr[sh.off_qp + h * sh.hs_point + p * 3 + 1], z = pr[sh.off_qp + h * sh.hs_point + p * 3 + 2];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) qp[p * 3 + r] = ((Ri[r * 3] * x + Ri[r * 3 + 1] * y) + Ri[r * 3 + 2] * z) + Ti[r];
+        }
+#pragma unroll
+        for (int p = 0; p < PV; ++p) {
+            const float lx = o[C_P + p * 3], ly = o[C_P + p * 3 + 1], lz = o[C_P + p * 3 + 2];
+            float gx = go[C_P + p * 3], gy = go[C_P + p * 3 + 1], gz = go[C_P + p * 3 + 2];
+            const float nrm = sqrtf(lx * lx + ly * ly + lz * lz);
+            if (nrm > 0.f) {                                           // torch.norm's backward is 0 at the origin
+                const float sc = go[C_N + p] / nrm;
+                gx += sc * lx; gy += sc * ly; gz += sc * lz;
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                gp[p * 3 + r] = (Ri[r * 3] * gx + Ri[r * 3 + 1] * gy) + Ri[r * 3 + 2] * gz;
+                opg[p * 3 + r] = ((Ri[r * 3] * lx + Ri[r * 3 + 1] * ly) + Ri[r * 3 + 2] * lz) + Ti[r];
+            }
+        }
+        float* qr = qrec + i * KW;
+#pragma unroll
+        for (int c = 0; c < DK; ++c) { qr[O_Q + c] = q[c]; qr[O_GS + c] = gs[c]; }
+#pragma unroll
+        for (int c = 0; c < 3 * PQ; ++c) qr[O_QP + c] = qp[c];
+#pragma unroll
+        for (int c = 0; c < 3 * PV; ++c) qr[O_GP + c] = gp[c];
+    }
+    __syncthreads();
+
+    // ---- phase 1: query rows ----------------------------------------------------------------------------------------
+    if (active) {
+        const float* bias_row = pair_bias + (((int64_t)pb * H + h) * L + i) * L;
+        const float* pv_row = pair_value + (((int64_t)pb * L + i) * L) * (int64_t)HD + h * DK;
+        float* Prow = Pm + i * LS;
+        float* Srow = Sm + i * LS;
+        float m = -CUDART_INF_F;
+        for (int j = 0; j < L; ++j) {                                 // logits (ipa_simt.cu evaluates the same expression)
+            const float4* kr = reinterpret_cast<const float4*>(keys + j * KW);
+            float dot = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < DK / 4; ++c4) {
+                const float4 kv = kr[c4];
+                dot += q[c4 * 4] * kv.x; dot += q[c4 * 4 + 1] * kv.y; dot += q[c4 * 4 + 2] * kv.z; dot += q[c4 * 4 + 3] * kv.w;
+            }
+            float kp[3 * PQ];
+#pragma unroll
+            for (int c4 = 0; c4 < 3; ++c4) {
+                const float4 kv = kr[DK / 4 + c4];
+                kp[c4 * 4] = kv.x; kp[c4 * 4 + 1] = kv.y; kp[c4 * 4 + 2] = kv.z; kp[c4 * 4 + 3] = kv.w;
+            }
+            float dsum = 0.f;
+#pragma unroll
+            for (int p = 0; p < PQ; ++p) {
+                const float dx = qp[p * 3] - kp[p * 3], dy = qp[p * 3 + 1] - kp[p * 3 + 1], dz = qp[p * 3 + 2] - kp[p * 3 + 2];
+                dsum += sqrtf(dx * dx + dy * dy + dz * dz);
+            }
+            const float s = ((dot + hw * dsum) + __ldg(bias_row + j)) + kbias[j];
+            Srow[j] = s;
+            m = fmaxf(m, s);
+        }
+        float l = 0.f;
+        for (int j = 0; j < L; ++j) {
+            const float e = m == -CUDART_INF_F ? 0.f : expf(Srow[j] - m);
+            Prow[j] = e;
+            l += e;
+        }
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+        float dq[DK], dQp[3 * PQ], dhw = 0.f;
+#pragma unroll
+        for (int c = 0; c < DK; ++c) dq[c] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3 * PQ; ++c) dQp[c] = 0.f;
+        for (int j = 0; j < L; ++j) {
+            const float p = Prow[j] * inv;
+            const float4* kr = reinterpret_cast<const float4*>(keys + j * KW);
+            float dP = -Ds;
+#pragma unroll
+            for (int c4 = 0; c4 < DK / 4; ++c4) {
+                const float4 v = kr[O_VS / 4 + c4];
+                dP += gs[c4 * 4] * v.x; dP += gs[c4 * 4 + 1] * v.y; dP += gs[c4 * 4 + 2] * v.z; dP += gs[c4 * 4 + 3] * v.w;
+            }
+#pragma unroll
+            for (int c4 = 0; c4 < 3 * PV / 4; ++c4) {
+                const float4 v = kr[O_VP / 4 + c4];
+                dP += gp[c4 * 4] * (v.x - opg[c4 * 4]); dP += gp[c4 * 4 + 1] * (v.y - opg[c4 * 4 + 1]);
+                dP += gp[c4 * 4 + 2] * (v.z - opg[c4 * 4 + 2]); dP += gp[c4 * 4 + 3] * (v.w - opg[c4 * 4 + 3]);
+            }
+            const float4* zr = reinterpret_cast<const float4*>(pv_row + (int64_t)j * HD);
+#pragma unroll
+            for (int c4 = 0; c4 < DK / 4; ++c4) {
+                const float4 v = __ldg(zr + c4);
+                dP += gzp[c4 * 4] * v.x; dP += gzp[c4 * 4 + 1] * v.y; dP += gzp[c4 * 4 + 2] * v.z; dP += gzp[c4 * 4 + 3] * v.w;
+            }
+            const float ds = p * dP;
+            Prow[j] = p;
+            Srow[j] = ds;
+#pragma unroll
+            for (int c4 = 0; c4 < DK / 4; ++c4) {
+                const float4 kv = kr[O_KS / 4 + c4];
+                dq[c4 * 4] += ds * kv.x; dq[c4 * 4 + 1] += ds * kv.y; dq[c4 * 4 + 2] += ds * kv.z; dq[c4 * 4 + 3] += ds * kv.w;
+            }
+            float kp[3 * PQ];
+#pragma unroll
+            for (int c4 = 0; c4 < 3; ++c4) {
+                const float4 kv = kr[O_KP / 4 + c4];
+                kp[c4 * 4] = kv.x; kp[c4 * 4 + 1] = kv.y; kp[c4 * 4 + 2] = kv.z; kp[c4 * 4 + 3] = kv.w;
+            }
+            float dsum = 0.f;
+            const float hds = hw * ds;
+#pragma unroll
+            for (int pt = 0; pt < PQ; ++pt) {
+                const float dx = qp[pt * 3] - kp[pt * 3], dy = qp[pt * 3 + 1] - kp[pt * 3 + 1], dz = qp[pt * 3 + 2] - kp[pt * 3 + 2];
+                const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+                dsum += d;
+                const float coef = d > 0.f ? hds / d : 0.f;            // torch.norm's backward is 0 at distance 0
+                dQp[pt * 3] += coef * dx; dQp[pt * 3 + 1] += coef * dy; dQp[pt * 3 + 2] += coef * dz;
+            }
+            dhw += ds * dsum;
+        }
+        float* gr = d_proj + row_i * sh.proj_stride;
+#pragma unroll
+        for (int c = 0; c < DK; ++c) gr[sh.off_q + h * sh.hs_scalar + c] = dq[c] * scalar_weight;
+#pragma unroll
+        for (int pt = 0; pt < PQ; ++pt)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)                                 // local = R^T global
+                gr[sh.off_qp + h * sh.hs_point + pt * 3 + c] = (Ri[c] * dQp[pt * 3] + Ri[3 + c] * dQp[pt * 3 + 1]) + Ri[6 + c] * dQp[pt * 3 + 2];
+        d_hw_rows[row_i * H + h] = dhw;
+    }
+    __syncthreads();
+
+    // ---- P and dS of this (sample, head) to global memory, coalesced ---------------------------------------------
+    {
+        float* pg = p_ws + ((int64_t)b * H + h) * L * L;
+        float* sg = ds_ws + ((int64_t)b * H + h) * L * L;
+        for (int idx = tid; idx < L * L; idx += blockDim.x) {
+            const int r = idx / L, c = idx - r * L;
+            pg[idx] = Pm[r * LS + c];
+            sg[idx] = Sm[r * LS + c];
+        }
+    }
+
+    // ---- phase 2: key columns -----------------------------------------------------------------------------------------
+    if (active) {
+        const int j = tid;
+        float kp[3 * PQ], dk[DK], dv[DK], dVp[3 * PV], dKp[3 * PQ];
+#pragma unroll
+        for (int c = 0; c < 3 * PQ; ++c) { kp[c] = keys[j * KW + O_KP + c]; dKp[c] = 0.f; }
+#pragma unroll
+        for (int c = 0; c < DK; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
+#pragma unroll
+        for (int c = 0; c < 3 * PV; ++c) dVp[c] = 0.f;
+        for (int r = 0; r < L; ++r) {
+            const float p = Pm[r * LS + j], ds = Sm[r * LS + j];
+            const float4* qr = reinterpret_cast<const float4*>(qrec + r * KW);
+#pragma unroll
+            for (int c4 = 0; c4 < DK / 4; ++c4) {
+                const float4 v = qr[O_Q / 4 + c4];
+                dk[c4 * 4] += ds * v.x; dk[c4 * 4 + 1] += ds * v.y; dk[c4 * 4 + 2] += ds * v.z; dk[c4 * 4 + 3] += ds * v.w;
+            }
+#pragma unroll
+            for (int c4 = 0; c4 < DK / 4; ++c4) {
+                const float4 v = qr[O_GS / 4 + c4];
+                dv[c4 * 4] += p * v.x; dv[c4 * 4 + 1] += p * v.y; dv[c4 * 4 + 2] += p * v.z; dv[c4 * 4 + 3] += p * v.w;
+            }
+#pragma unroll
+            for (int c4 = 0; c4 < 3 * PV / 4; ++c4) {
+                const float4 v = qr[O_GP / 4 + c4];
+                dVp[c4 * 4] += p * v.x; dVp[c4 * 4 + 1] += p * v.y; dVp[c4 * 4 + 2] += p * v.z; dVp[c4 * 4 + 3] += p * v.w;
+            }
+            float qv[3 * PQ];
+#pragma unroll
+            for (int c4 = 0; c4 < 3; ++c4) {
+                const float4 v = qr[O_QP / 4 + c4];
+                qv[c4 * 4] = v.x; qv[c4 * 4 + 1] = v.y; qv[c4 * 4 + 2] = v.z; qv[c4 * 4 + 3] = v.w;
+            }
+            const float hds = hw * ds;
+#pragma unroll
+            for (int pt = 0; pt < PQ; ++pt) {
+                const float dx = qv[pt * 3] - kp[pt * 3], dy = qv[pt * 3 + 1] - kp[pt * 3 + 1], dz = qv[pt * 3 + 2] - kp[pt * 3 + 2];
+                const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+                const float coef = d > 0.f ? hds / d : 0.f;
+                dKp[pt * 3] -= coef * dx; dKp[pt * 3 + 1] -= coef * dy; dKp[pt * 3 + 2] -= coef * dz;
+            }
+        }
+        // Ri is this thread's own residue (i == j): gradients of the local points are R^T (global gradient)
+        float* gr = d_proj + row_i * sh.proj_stride;
+#pragma unroll
+        for (int c = 0; c < DK; ++c) {
+            gr[sh.off_k + h * sh.hs_scalar + c] = dk[c];
+            gr[sh.off_v + h * sh.hs_scalar + c] = dv[c];
+        }
+#pragma unroll
+        for (int pt = 0; pt < PQ; ++pt)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                gr[sh.off_kp + h * sh.hs_point + pt * 3 + c] = (Ri[c] * dKp[pt * 3] + Ri[3 + c] * dKp[pt * 3 + 1]) + Ri[6 + c] * dKp[pt * 3 + 2];
+#pragma unroll
+        for (int pt = 0; pt < PV; ++pt)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                gr[sh.off_vp + h * sh.hs_vpoint + pt * 3 + c] = (Ri[c] * dVp[pt * 3] + Ri[3 + c] * dVp[pt * 3 + 1]) + Ri[6 + c] * dVp[pt * 3 + 2];
+    }
+}
+
+template <int DK>
+int launch(const float* proj, const float* rot, const float* trans, const float* pair_bias, const float* pair_value,
+           const float* key_bias, const float* head_weight, float scalar_weight, const float* out, const float* d_out,
+           float* d_proj, float* p_ws, float* ds_ws, float* d_hw_rows, const se3_ipa_shape& sh, cudaStream_t st) {
+    constexpr int KW = 2 * DK + 3 * PQ + 3 * PV;
+    const int L = sh.len, LS = L | 1;
+    const int threads = ((L + 31) / 32) * 32;
+    const size_t smem = ((size_t)2 * L * KW + (size_t)2 * L * LS + L) * sizeof(float);
+    auto kern = k_ipa_bwd<DK>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("ipa bwd smem attribute (%zu bytes): %s", smem, cudaGetErrorString(e)); return SE3_ECUDA; }
+    }
+    dim3 grid(sh.heads, sh.batch);
+    kern<<<grid, threads, smem, st>>>(proj, rot, trans, pair_bias, pair_value, key_bias, head_weight, scalar_weight, out, d_out,
+                                      d_proj, p_ws, ds_ws, d_hw_rows, sh);
+    count_launch();
+    return check_launch("se3_ipa_attention_bwd");
+}
+
+}  // namespace
+
+extern "C" int se3_ipa_attention_bwd(const float* proj, const float* rot, const float* trans, const float* pair_bias,
+                                     const float* pair_value, const float* key_bias, const float* head_weight,
+                                     float scalar_weight, const float* out, const float* d_out, float* d_proj, float* p_ws,
+                                     float* ds_ws, float* d_hw_rows, const se3_ipa_shape* h_shape, se3_stream_t stream) {
+    SE3_REQUIRE(h_shape, "null shape");
+    const se3_ipa_shape& sh = *h_shape;
+    SE3_REQUIRE(sh.batch >= 0 && sh.len >= 0 && sh.heads > 0, "bad shape");
+    if (sh.batch == 0 || sh.len == 0) return SE3_OK;
+    SE3_REQUIRE(proj && rot && trans && pair_bias && pair_value && head_weight && out && d_out && d_proj && p_ws && ds_ws && d_hw_rows,
+                "null pointer");
+    SE3_REQUIRE(sh.pq == PQ && sh.pv == PV, "only 4 query/key points and 8 value points (structure_module.py:85-93)");
+    SE3_REQUIRE(sh.pair_batch == 1 || sh.pair_batch == sh.batch, "pair_batch must be 1 or batch");
+    SE3_REQUIRE(sh.len <= SE3_IPA_BWD_MAX_LEN, "se3_ipa_attention_bwd keeps all keys of a (sample, head) in shared memory: len <= 128");
+    SE3_REQUIRE(sh.batch <= 65535, "grid limit");
+    SE3_REQUIRE((reinterpret_cast<uintptr_t>(pair_value) & 15) == 0, "pair_value must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (sh.dk) {
+        case 4: return launch<4>(proj, rot, trans, pair_bias, pair_value, key_bias, head_weight, scalar_weight, out, d_out, d_proj, p_ws, ds_ws, d_hw_rows, sh, st);
+        case 8: return launch<8>(proj, rot, trans, pair_bias, pair_value, key_bias, head_weight, scalar_weight, out, d_out, d_proj, p_ws, ds_ws, d_hw_rows, sh, st);
+        case 16: return launch<16>(proj, rot, trans, pair_bias, pair_value, key_bias, head_weight, scalar_weight, out, d_out, d_proj, p_ws, ds_ws, d_hw_rows, sh, st);
+        case 32: return launch<32>(proj, rot, trans, pair_bias, pair_value, key_bias, head_weight, scalar_weight, out, d_out, d_proj, p_ws, ds_ws, d_hw_rows, sh, st);
+        default: set_error("se3_ipa_attention_bwd: unsupported dk=%d (4, 8, 16, 32)", sh.dk); return SE3_EUNSUPPORTED;
+    }
+}

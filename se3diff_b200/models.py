@@ -23,6 +23,7 @@ A forward that must be differentiated or that applies dropout (the small fine-tu
 from __future__ import annotations
 
 import math
+import os
 import warnings
 
 import torch
@@ -529,6 +530,18 @@ class DistributionalGraphormer(nn.Module):
     def _ipa_torch(a: SAAttention, x1d, x2d, T, R, bias):
         """SAAttention.forward (structure_module.py:109-220) with autograd; `x2d` may carry a leading 1 (shared context)."""
         B, Lm, H = x1d.shape[0], x1d.shape[1], a.n_head
+        head_w = -0.5 * a.point_weight * F.softplus(a.trained_point_weight)
+        shape = ops.ipa_shape(B, Lm, H, a.d_k, x2d.shape[0], head_major=False)
+        if (x1d.is_cuda and x1d.dtype == torch.float32 and not (R.requires_grad or T.requires_grad) and x2d.shape[0] in (1, B)
+                and ops.ipa_bwd_supported(shape) and os.environ.get("SE3DIFF_B200_IPA_BWD", "1") != "0"):
+            # one fused operator with a hand-written backward (ipa_simt.cu / ipa_bwd.cu) instead of the chain of einsums
+            # below, whose autograd graph keeps the [B, L, L, H, 4, 3] point differences alive
+            proj = F.linear(x1d, a.fused_projection_weight()).reshape(B * Lm, -1)
+            pair_b = (a.pair_weight * a.pair_bias(x2d)).permute(0, 3, 1, 2)                          # [Bp, H, L, L]
+            key_b = None if bias is None else bias.expand(B, 1, 1, Lm).reshape(B, Lm).contiguous()
+            feat = ops.IpaAttention.apply(proj, R.reshape(B * Lm, 9).contiguous(), T.reshape(B * Lm, 3).contiguous(), pair_b,
+                                          a.pair_value(x2d), key_b, head_w, a.scalar_weight, shape)
+            return a.dropout(a.fc_out(feat.view(B, Lm, -1)))
         q = a.scalar_query(x1d).view(B, Lm, H, -1)
         k = a.scalar_key(x1d).view(B, Lm, H, -1)
         v = a.scalar_value(x1d).view(B, Lm, H, -1)
@@ -541,7 +554,6 @@ class DistributionalGraphormer(nn.Module):
         vp = to_global(a.point_value(x1d).view(B, Lm, H, -1, 3))
         logits = torch.einsum("bihc,bjhc->bhij", q * a.scalar_weight, k)
         dist = torch.norm(qp.unsqueeze(2) - kp.unsqueeze(1), dim=-1).sum(dim=-1)                    # [B, i, j, H], un-squared (:170)
-        head_w = -0.5 * a.point_weight * F.softplus(a.trained_point_weight)
         logits = logits + (head_w * dist).permute(0, 3, 1, 2) + a.pair_weight * a.pair_bias(x2d).permute(0, 3, 1, 2)
         if bias is not None:
             logits = logits + bias

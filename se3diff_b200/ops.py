@@ -387,6 +387,68 @@ def ipa_attention_fwd(proj, rot, trans, pair_bias, pair_value, key_bias, head_we
     return out
 
 
+def ipa_bwd_supported(shape: L.IpaShape) -> bool:
+    """Shapes se3_ipa_attention_bwd takes: one CTA keeps the keys, the query records and two L x L matrices in shared memory."""
+    n, kw = shape.len, 2 * shape.dk + 36
+    return (shape.dk in (4, 8, 16, 32) and shape.pq == 4 and shape.pv == 8 and 0 < n <= 128 and 0 < shape.batch <= 65535
+            and (2 * n * kw + 2 * n * (n | 1) + n) * 4 <= 227 * 1024)
+
+
+def ipa_attention_bwd(proj, rot, trans, pair_bias, pair_value, key_bias, head_weight, scalar_weight: float, out, d_out,
+                      shape: L.IpaShape):
+    """Gradient of `ipa_attention_fwd` (exact mode): returns (d_proj [B*L, stride], P [B,H,L,L], dS [B,H,L,L], d_hw_rows [B*L,H])."""
+    proj, rot, trans = _dev(proj, name="proj"), _dev(rot, name="rot"), _dev(trans, name="trans")
+    pair_bias, pair_value = _dev(pair_bias, name="pair_bias"), _dev(pair_value, name="pair_value")
+    key_bias = None if key_bias is None else _dev(key_bias, name="key_bias")
+    head_weight, out, d_out = _dev(head_weight, name="head_weight"), _dev(out, name="out"), _dev(d_out, name="d_out")
+    B, n, H = shape.batch, shape.len, shape.heads
+    d_proj = torch.empty_like(proj)
+    p_ws = torch.empty(B, H, n, n, dtype=torch.float32, device=proj.device)
+    ds_ws = torch.empty_like(p_ws)
+    d_hw_rows = torch.empty(B * n, H, dtype=torch.float32, device=proj.device)
+    with _guard(proj):
+        L.check(L.lib().se3_ipa_attention_bwd(_p(proj), _p(rot), _p(trans), _p(pair_bias), _p(pair_value), _p(key_bias),
+                                              _p(head_weight), float(scalar_weight), _p(out), _p(d_out), _p(d_proj), _p(p_ws),
+                                              _p(ds_ws), _p(d_hw_rows), C.byref(shape), _stream(proj)), "se3_ipa_attention_bwd")
+    return d_proj, p_ws, ds_ws, d_hw_rows
+
+
+class IpaAttention(torch.autograd.Function):
+    """`ipa_attention_fwd` (exact fp32) as a differentiable operator: gradients for the projection, the pair bias, the pair
+    values and the head weights from `se3_ipa_attention_bwd`; the frames are constants (stored rollout states)."""
+
+    @staticmethod
+    def forward(ctx, proj, rot, trans, pair_bias, pair_value, key_bias, head_weight, scalar_weight, shape):
+        if rot.requires_grad or trans.requires_grad:
+            raise L.Se3LibraryError("IpaAttention: frames with requires_grad are not supported (no gradient is produced for them)")
+        proj, pair_bias, pair_value = proj.contiguous(), pair_bias.contiguous(), pair_value.contiguous()
+        out = ipa_attention_fwd(proj, rot, trans, pair_bias, pair_value, key_bias, head_weight, scalar_weight, shape, IPA_EXACT)
+        ctx.save_for_backward(proj, rot, trans, pair_bias, pair_value, key_bias, head_weight, out)
+        ctx.scalar_weight, ctx.shape = float(scalar_weight), shape
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        proj, rot, trans, pair_bias, pair_value, key_bias, head_weight, out = ctx.saved_tensors
+        sh = ctx.shape
+        B, n, H, dk = sh.batch, sh.len, sh.heads, sh.dk
+        d_out = d_out.contiguous()
+        d_proj, P, dS, d_hw_rows = ipa_attention_bwd(proj, rot, trans, pair_bias, pair_value, key_bias, head_weight,
+                                                      ctx.scalar_weight, out, d_out, sh)
+        hd, c_z = H * dk, H * dk + 3 * H * sh.pv
+        d_bias = d_pv = None
+        if ctx.needs_input_grad[3]:
+            d_bias = dS.sum(0, keepdim=True) if sh.pair_batch == 1 else dS
+        if ctx.needs_input_grad[4]:
+            gz = d_out[:, c_z:c_z + hd].reshape(B, n, H, dk)
+            if sh.pair_batch == 1:                                      # GEMM over the samples, per (head, query)
+                d_pv = torch.einsum("bhij,bihc->ijhc", P, gz).reshape(1, n, n, hd)
+            else:
+                d_pv = (P.permute(0, 2, 3, 1).unsqueeze(-1) * gz.unsqueeze(2)).reshape(B, n, n, hd)
+        d_hw = d_hw_rows.sum(0) if ctx.needs_input_grad[6] else None
+        return d_proj, None, None, d_bias, d_pv, None, d_hw, None, None
+
+
 def debug_umma_gemm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """tcgen05 self-test: a [128,K] bf16, b [N,K] bf16 -> a @ b.T in fp32 via UMMA/TMEM."""
     a, b = _dev(a, torch.bfloat16, "a"), _dev(b, torch.bfloat16, "b")

@@ -1080,3 +1080,58 @@ def test_backbone_atoms_and_physicality_filter():
     xyz, keep = bb.backbone_trajectory(pos_b.to(DEV) * 0.1, rot_b, seq, filter_samples=False)
     assert xyz.shape == (B, 5 * L - seq.count("G"), 3) and keep.tolist() == list(range(B))
     assert xyz.mean(dim=1).abs().max() < 0.5                    # centred on the CA centroid, in nm
+
+
+@pytest.mark.parametrize("B,L,H,dk,shared,masked,scale", [
+    (5, 84, 4, 16, True, False, 1.0),       # the control model of config.yaml:12-22 on PDZ3
+    (3, 57, 4, 16, False, True, 3.0),       # per-sample pair tensors, odd length, padded keys
+    (2, 128, 2, 8, True, False, 1.0),       # longest supported sequence
+    (2, 33, 32, 16, True, False, 10.0),     # bioemu-v1.0 head count
+])
+def test_ipa_backward_kernel_vs_torch_autograd(B, L, H, dk, shared, masked, scale, monkeypatch):
+    """se3_ipa_attention_bwd (behind ops.IpaAttention, used by the differentiable forward) against torch autograd of the
+    same operator written as einsums (structure_module.py:131-216): fp64 autograd is the truth, the fp32 einsum graph sets
+    the scale of acceptable error.  Gradients w.r.t. the layer input, the pair representation and every parameter."""
+    import copy
+
+    from se3diff_b200 import ops
+    from se3diff_b200.models import DistributionalGraphormer, SAAttention
+
+    torch.manual_seed(L * 1000 + H)
+    D, dp = H * dk, 32
+    a = SAAttention(D, dp, H, dropout=0.0).to(DEV)
+    x1d = torch.randn(B, L, D, device=DEV)
+    x2d = torch.randn(1 if shared else B, L, L, dp, device=DEV)
+    Tr = torch.randn(B, L, 3, device=DEV) * scale
+    R = oso3.rotvec_to_rotmat(rand_rotvecs(B * L, 5, adversarial=False)).view(B, L, 3, 3).to(DEV)
+    bias = None
+    if masked:
+        kb = torch.zeros(B, L, device=DEV)
+        kb[1, L - 9:] = float("-inf")
+        kb[2, L - 1:] = float("-inf")
+        bias = kb[:, None, None, :]
+    w_out = torch.randn(B, L, D, device=DEV)
+
+    def run(mod, dtype, fused):
+        monkeypatch.setenv("SE3DIFF_B200_IPA_BWD", "1" if fused else "0")
+        xs = [x1d.to(dtype).requires_grad_(True), x2d.to(dtype).requires_grad_(True)]
+        with torch.enable_grad():
+            y = DistributionalGraphormer._ipa_torch(mod, xs[0], xs[1], Tr.to(dtype), R.to(dtype), None if bias is None else bias.to(dtype))
+            loss = (y * w_out.to(dtype)).sum()
+            params = [p for _, p in sorted(mod.named_parameters())]
+            grads = torch.autograd.grad(loss, xs + params)
+        return y.detach(), grads
+
+    y64, g64 = run(copy.deepcopy(a).double(), torch.float64, False)
+    y32, g32 = run(a, torch.float32, False)
+    calls, bwd = [], ops.ipa_attention_bwd                              # (the library's launch counter is per thread and
+    monkeypatch.setattr(ops, "ipa_attention_bwd", lambda *x, **k: (calls.append(1), bwd(*x, **k))[1])   # autograd has its own)
+    launches0 = ops.launch_count()
+    yk, gk = run(a, torch.float32, True)
+    assert ops.launch_count() >= launches0 + 1 and len(calls) == 1      # the forward and the backward kernel ran
+    assert rel_err(yk, y64, floor=float(y64.abs().max())) <= 1e-5
+    names = ["x1d", "x2d"] + [n for n, _ in sorted(a.named_parameters())]
+    for n, r, t, k in zip(names, g64, g32, gk):
+        fl = float(r.abs().max()) + 1e-30
+        e_t, e_k = rel_err(t, r, floor=fl), rel_err(k, r, floor=fl)
+        assert e_k <= max(4 * e_t, 2e-5), (n, e_k, e_t)
