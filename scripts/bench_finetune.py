@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--length", type=int, default=84)
     ap.add_argument("--em-steps", type=int, default=200)
     ap.add_argument("--micro", type=int, default=20, help="stored states per backward chunk (finetune.py micro_batch_size)")
+    ap.add_argument("--profile", default=None, help="write a torch-profiler kernel table of one extra step to this file (rank 0)")
     a = ap.parse_args()
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"
@@ -101,6 +102,14 @@ def main():
             "data": "synthetic", "trainable_parameters": n_train, "loss": float(loss), "grad_norm": gn, "finite": bool(torch.isfinite(loss)),
             "config": {"workload": f"PDZ3 fine-tune step L={L} B={B}/GPU, {T} EM steps with control, micro_batch_size={a.micro}, "
                                    f"allreduce of {n_train} gradient floats" + (" over NCCL" if world > 1 else " (single rank: none)")}}), flush=True)
+    if a.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            step(77_000)
+            torch.cuda.synchronize(dev)
+        with open(a.profile, "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=90))
     if world > 1:
         dist.destroy_process_group()
 
