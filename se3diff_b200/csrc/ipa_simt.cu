@@ -32,8 +32,10 @@ k_ipa_rows(const float* __restrict__ proj, const float* __restrict__ rot, const 
     constexpr int KW = 2 * DK + 3 * PQ + 3 * PV;  // floats per staged key: k_s | k_pt | v_s | v_pt
     constexpr int O_KS = 0, O_KP = DK, O_VS = DK + 3 * PQ, O_VP = 2 * DK + 3 * PQ;
     extern __shared__ __align__(16) float smem[];
+    constexpr int ZS = 8 * DK + 4;            // floats per thread: two chunks of 4 keys x DK pair values, +4: conflict-free LDS.128
     float* keys = smem;                       // [tile_keys][KW]
     float* kbias = smem + tile_keys * KW;     // [tile_keys]
+    float* zslot = kbias + tile_keys + threadIdx.x * ZS;   // this thread's pair-value ring (cp.async, one chunk ahead)
 
     const int L = sh.len, H = sh.heads;
     const int b = blockIdx.z, h = blockIdx.y;
@@ -70,6 +72,23 @@ k_ipa_rows(const float* __restrict__ proj, const float* __restrict__ rot, const 
 
     const float* bias_row = pair_bias + (((int64_t)pb * H + h) * L + (active ? i : 0)) * L;
     const float* pv_row = pair_value + (((int64_t)pb * L + (active ? i : 0)) * L) * ((int64_t)H * DK) + h * DK;
+    // pair_value[i, j, h, :] is this thread's own 4*DK-byte slice per key, 4*H*DK bytes apart: fetched with ordinary loads
+    // inside the accumulation it exposed one L2 round trip per chunk (ncu at B = 64: long-scoreboard 7.2 of 10.6 stall
+    // cycles per issue).  The slices of the NEXT 4-key chunk are copied into a thread-private shared-memory ring by cp.async
+    // while the current chunk is computed; the arithmetic is unchanged.
+    auto prefetch = [&](int jg) {
+        float* dst = zslot + ((jg >> 2) & 1) * 4 * DK;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (jg + u < L) {
+                const float* src = pv_row + (int64_t)(jg + u) * H * DK;
+#pragma unroll
+                for (int c4 = 0; c4 < DK / 4; ++c4)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst + u * DK + c4 * 4)), "l"(src + c4 * 4) : "memory");
+            }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (active) prefetch(0);
 
     for (int j0 = 0; j0 < L; j0 += tile_keys) {
         const int nk = min(tile_keys, L - j0);
@@ -98,6 +117,9 @@ k_ipa_rows(const float* __restrict__ proj, const float* __restrict__ rot, const 
 
         // ---- stream the tile in chunks of 4 keys -----------------------------------------------
         for (int jj = 0; jj < nk; jj += 4) {
+            prefetch(j0 + jj + 4);                                     // (an empty group past the last key)
+            asm volatile("cp.async.wait_group 1;" ::: "memory");      // this chunk's slices have landed
+            const float* zc = zslot + (((j0 + jj) >> 2) & 1) * 4 * DK;
             float s[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -154,10 +176,10 @@ k_ipa_rows(const float* __restrict__ proj, const float* __restrict__ rot, const 
                         const float4 v = vr[DK / 4 + c4];
                         acc_p[c4 * 4] += p * v.x; acc_p[c4 * 4 + 1] += p * v.y; acc_p[c4 * 4 + 2] += p * v.z; acc_p[c4 * 4 + 3] += p * v.w;
                     }
-                    const float4* zr = reinterpret_cast<const float4*>(pv_row + (int64_t)(j0 + j) * H * DK);
+                    const float4* zr = reinterpret_cast<const float4*>(zc + u * DK);
 #pragma unroll
                     for (int c4 = 0; c4 < DK / 4; ++c4) {
-                        const float4 v = __ldg(zr + c4);
+                        const float4 v = zr[c4];
                         acc_z[c4 * 4] += p * v.x; acc_z[c4 * 4 + 1] += p * v.y; acc_z[c4 * 4 + 2] += p * v.z; acc_z[c4 * 4 + 3] += p * v.w;
                     }
                 }
@@ -195,7 +217,7 @@ int launch(const float* proj, const float* rot, const float* trans, const float*
     const int L = sh.len;
     const int threads = L >= 128 ? 128 : ((L + 31) / 32) * 32;
     const int tile_keys = L < 128 ? ((L + 3) / 4) * 4 : 128;
-    const size_t smem = (size_t)tile_keys * (KW + 1) * sizeof(float);
+    const size_t smem = ((size_t)tile_keys * (KW + 1) + (size_t)threads * (8 * DK + 4)) * sizeof(float);
     dim3 grid((L + threads - 1) / threads, sh.heads, sh.batch);
     auto kern = fast ? k_ipa_rows<DK, true> : k_ipa_rows<DK, false>;
     if (smem > 48 * 1024) {
