@@ -99,6 +99,16 @@ def cpu_reference_run(L: int, sample_B: int, sample_steps: int, state_dict, tabl
     return times, cores
 
 
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  NCCL prints its version banner on file descriptor 1 from native code (at any
+    NCCL_DEBUG level from VERSION up), so the descriptor itself is pointed at stderr for the whole run and the result line
+    is written to a private duplicate of the original stdout."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
+
+
 def reference_arm(args):
     """`--impl reference`: rank 0 only, CPU, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -152,8 +162,7 @@ def main():
     from se3diff_b200.chemgraph import Batch, ChemGraph, complete_graph_edge_index
     from se3diff_b200.distributed import gather_ensemble, init_from_env
 
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line (NCCL prints its version banner there)
+    result_out = claim_stdout()
     rank, world, local_rank = init_from_env(args.gpus)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -267,7 +276,7 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": t_e2e / args.steps * 1e3},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_other_kernels": roof_extra, "cpu_baseline": cpu,
-        }), flush=True)
+        }), file=result_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -30,8 +30,7 @@ def main():
     ap.add_argument("--micro", type=int, default=20, help="stored states per backward chunk (finetune.py micro_batch_size)")
     ap.add_argument("--profile", default=None, help="write a torch-profiler kernel table of one extra step to this file (rank 0)")
     a = ap.parse_args()
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    result_out = Bn.claim_stdout()                          # stdout = the one JSON line (NCCL's banner goes to stderr)
     rank, world, local = init_from_env(a.gpus)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -101,7 +100,7 @@ def main():
             "ms_exchange_optimizer": float(t[2]) / a.steps * 1e3, "scaling": "weak", "dtype": "bf16 score model, fp32 control model and SDE algebra",
             "data": "synthetic", "trainable_parameters": n_train, "loss": float(loss), "grad_norm": gn, "finite": bool(torch.isfinite(loss)),
             "config": {"workload": f"PDZ3 fine-tune step L={L} B={B}/GPU, {T} EM steps with control, micro_batch_size={a.micro}, "
-                                   f"allreduce of {n_train} gradient floats" + (" over NCCL" if world > 1 else " (single rank: none)")}}), flush=True)
+                                   f"allreduce of {n_train} gradient floats" + (" over NCCL" if world > 1 else " (single rank: none)")}}), file=result_out, flush=True)
     if a.profile and rank == 0:
         from torch.profiler import ProfilerActivity, profile
 
