@@ -10,9 +10,11 @@
 //   dq_i = sw sum_j dS_ij k_j        dk_j = sum_i dS_ij (sw q_i)      dv_j = sum_i P_ij dO_s,i
 //   dQp_i = hw sum_j dS_ij sum_p (Qp_i - Kp_j)/|.|   (dKp_j: minus the same, summed over i)   dVp_j = sum_i P_ij g_pg,i
 //   d hw  = sum_ij dS_ij sum_p |Qp_i - Kp_j|        point gradients return to the local frame through R^T.
-// One CTA per (sample, head), all L <= 128 keys resident.  Phase 1: one thread per QUERY row recomputes the logits and
-// the softmax (rows of P and dS stay in shared memory) and accumulates the query-side gradients; phase 2: one thread per
-// KEY column walks the same two matrices down the rows for the key-side gradients -- no atomics, deterministic.  P and
+// One CTA per (sample, head), all L <= 128 keys resident.  Phase 1: TWO lanes per QUERY row (even / odd keys; row maximum,
+// row sum and the partial gradients joined by one shuffle) recompute the logits and the softmax (rows of P and dS stay in
+// shared memory) and accumulate the query-side gradients; phase 2: two lanes per KEY column (even / odd rows) walk the
+// same two matrices down the rows for the key-side gradients -- no atomics, deterministic.  Value points are staged
+// relative to the sample's first residue, so that dO.(Vp_j - o_pg) is formed from nm-sized numbers.  P and
 // dS also go to global memory (coalesced): the caller reduces them over the samples into the gradients of the shared
 // pair tensors (d pair_bias = sum_b dS; d pair_value[i,j,h,:] = sum_b P_hij dO_pair_i -- a GEMM with K = samples).
 #include <math_constants.h>
@@ -25,8 +27,10 @@ namespace {
 
 constexpr int PQ = 4, PV = 8;
 
-template <int DK>
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ float pair_sum(float v) { return v + __shfl_xor_sync(0xffffffffu, v, 1); }
+
+template <int DK, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT <= 192 ? 2 : 1)
 k_ipa_bwd(const float* __restrict__ proj, const float* __restrict__ rot, const float* __restrict__ trans,
           const float* __restrict__ pair_bias, const float* __restrict__ pair_value, const float* __restrict__ key_bias,
           const float* __restrict__ head_weight, float scalar_weight, const float* __restrict__ out,
@@ -44,8 +48,10 @@ k_ipa_bwd(const float* __restrict__ proj, const float* __restrict__ rot, const f
     float* kbias = Sm + L * LS;       // [L]
 
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-    const bool active = tid < L;
-    const int i = active ? tid : 0;
+    const int lane2 = tid & 1;                                                    // which half of the keys (phase 1) / rows (phase 2)
+    const bool active = (tid >> 1) < L;
+    const int i = active ? (tid >> 1) : 0;
+    const int n_act = active ? L : 0;                                             // idle lanes run empty loops, join the shuffles
     const int pb = sh.pair_batch == 1 ? 0 : b;
     const int64_t row_i = (int64_t)b * L + i;
     const float hw = head_weight[h];
@@ -67,15 +73,17 @@ k_ipa_bwd(const float* __restrict__ proj, const float* __restrict__ rot, const f
         const float x = pr[0], y = pr[1], z = pr[2];
         const float* R = rot + rj * 9;
         const float* T = trans + rj * 3;
+        const float* C0 = trans + (int64_t)b * L * 3;                 // centre of the value points: the sample's first residue
         float* dst = keys + j * KW + (p < PQ ? O_KP + p * 3 : O_VP + (p - PQ) * 3);
 #pragma unroll
-        for (int r = 0; r < 3; ++r) dst[r] = ((R[r * 3] * x + R[r * 3 + 1] * y) + R[r * 3 + 2] * z) + T[r];
+        for (int r = 0; r < 3; ++r)
+            dst[r] = ((R[r * 3] * x + R[r * 3 + 1] * y) + R[r * 3 + 2] * z) + (p < PQ ? T[r] : T[r] - C0[r]);
     }
     for (int idx = tid; idx < L; idx += blockDim.x) kbias[idx] = key_bias ? key_bias[(int64_t)b * L + idx] : 0.f;
 
     // ---- the thread's query row: operands, incoming gradients, D_i ---------------------------------------------
-    float q[DK], qp[3 * PQ], gs[DK], gp[3 * PV], gzp[DK], opg[3 * PV], Ri[9];
-    float Ds = 0.f;                                                    // dO_s.o_s + dO_pair.o_pair
+    float q[DK], qp[3 * PQ], gs[DK], gp[3 * PV], gzp[DK], Ri[9];
+    float Ds = 0.f;                                                    // D_i = dO_s.o_s + dO_pair.o_pair + g_pg.(o_pg - c0)
     if (active) {
         const float* pr = proj + row_i * sh.proj_stride;
         const float* o = out + row_i * (int64_t)W;
@@ -110,27 +118,30 @@ k_ipa_bwd(const float* __restrict__ proj, const float* __restrict__ rot, const f
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 gp[p * 3 + r] = (Ri[r * 3] * gx + Ri[r * 3 + 1] * gy) + Ri[r * 3 + 2] * gz;
-                opg[p * 3 + r] = ((Ri[r * 3] * lx + Ri[r * 3 + 1] * ly) + Ri[r * 3 + 2] * lz) + Ti[r];
+                const float opg = ((Ri[r * 3] * lx + Ri[r * 3 + 1] * ly) + Ri[r * 3 + 2] * lz) + (Ti[r] - trans[(int64_t)b * L * 3 + r]);
+                Ds += gp[p * 3 + r] * opg;
             }
         }
-        float* qr = qrec + i * KW;
+        if (lane2 == 0) {
+            float* qr = qrec + i * KW;
 #pragma unroll
-        for (int c = 0; c < DK; ++c) { qr[O_Q + c] = q[c]; qr[O_GS + c] = gs[c]; }
+            for (int c = 0; c < DK; ++c) { qr[O_Q + c] = q[c]; qr[O_GS + c] = gs[c]; }
 #pragma unroll
-        for (int c = 0; c < 3 * PQ; ++c) qr[O_QP + c] = qp[c];
+            for (int c = 0; c < 3 * PQ; ++c) qr[O_QP + c] = qp[c];
 #pragma unroll
-        for (int c = 0; c < 3 * PV; ++c) qr[O_GP + c] = gp[c];
+            for (int c = 0; c < 3 * PV; ++c) qr[O_GP + c] = gp[c];
+        }
     }
     __syncthreads();
 
     // ---- phase 1: query rows ----------------------------------------------------------------------------------------
-    if (active) {
+    {
         const float* bias_row = pair_bias + (((int64_t)pb * H + h) * L + i) * L;
         const float* pv_row = pair_value + (((int64_t)pb * L + i) * L) * (int64_t)HD + h * DK;
         float* Prow = Pm + i * LS;
         float* Srow = Sm + i * LS;
         float m = -CUDART_INF_F;
-        for (int j = 0; j < L; ++j) {                                 // logits (ipa_simt.cu evaluates the same expression)
+        for (int j = lane2; j < n_act; j += 2) {                      // logits (ipa_simt.cu evaluates the same expression)
             const float4* kr = reinterpret_cast<const float4*>(keys + j * KW);
             float dot = 0.f;
 #pragma unroll
@@ -154,19 +165,21 @@ k_ipa_bwd(const float* __restrict__ proj, const float* __restrict__ rot, const f
             Srow[j] = s;
             m = fmaxf(m, s);
         }
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
         float l = 0.f;
-        for (int j = 0; j < L; ++j) {
+        for (int j = lane2; j < n_act; j += 2) {
             const float e = m == -CUDART_INF_F ? 0.f : expf(Srow[j] - m);
             Prow[j] = e;
             l += e;
         }
+        l = pair_sum(l);
         const float inv = l > 0.f ? 1.0f / l : 0.f;
         float dq[DK], dQp[3 * PQ], dhw = 0.f;
 #pragma unroll
         for (int c = 0; c < DK; ++c) dq[c] = 0.f;
 #pragma unroll
         for (int c = 0; c < 3 * PQ; ++c) dQp[c] = 0.f;
-        for (int j = 0; j < L; ++j) {
+        for (int j = lane2; j < n_act; j += 2) {
             const float p = Prow[j] * inv;
             const float4* kr = reinterpret_cast<const float4*>(keys + j * KW);
             float dP = -Ds;
@@ -178,8 +191,7 @@ k_ipa_bwd(const float* __restrict__ proj, const float* __restrict__ rot, const f
 #pragma unroll
             for (int c4 = 0; c4 < 3 * PV / 4; ++c4) {
                 const float4 v = kr[O_VP / 4 + c4];
-                dP += gp[c4 * 4] * (v.x - opg[c4 * 4]); dP += gp[c4 * 4 + 1] * (v.y - opg[c4 * 4 + 1]);
-                dP += gp[c4 * 4 + 2] * (v.z - opg[c4 * 4 + 2]); dP += gp[c4 * 4 + 3] * (v.w - opg[c4 * 4 + 3]);
+                dP += gp[c4 * 4] * v.x; dP += gp[c4 * 4 + 1] * v.y; dP += gp[c4 * 4 + 2] * v.z; dP += gp[c4 * 4 + 3] * v.w;
             }
             const float4* zr = reinterpret_cast<const float4*>(pv_row + (int64_t)j * HD);
 #pragma unroll
@@ -213,15 +225,24 @@ k_ipa_bwd(const float* __restrict__ proj, const float* __restrict__ rot, const f
             }
             dhw += ds * dsum;
         }
+#pragma unroll
+        for (int c = 0; c < DK; ++c) dq[c] = pair_sum(dq[c]);
+#pragma unroll
+        for (int c = 0; c < 3 * PQ; ++c) dQp[c] = pair_sum(dQp[c]);
+        dhw = pair_sum(dhw);
         float* gr = d_proj + row_i * sh.proj_stride;
+        if (active && lane2 == 0) {
 #pragma unroll
-        for (int c = 0; c < DK; ++c) gr[sh.off_q + h * sh.hs_scalar + c] = dq[c] * scalar_weight;
+            for (int c = 0; c < DK; ++c) gr[sh.off_q + h * sh.hs_scalar + c] = dq[c] * scalar_weight;
+            d_hw_rows[row_i * H + h] = dhw;
+        }
+        if (active && lane2 == 1) {
 #pragma unroll
-        for (int pt = 0; pt < PQ; ++pt)
+            for (int pt = 0; pt < PQ; ++pt)
 #pragma unroll
-            for (int c = 0; c < 3; ++c)                                 // local = R^T global
-                gr[sh.off_qp + h * sh.hs_point + pt * 3 + c] = (Ri[c] * dQp[pt * 3] + Ri[3 + c] * dQp[pt * 3 + 1]) + Ri[6 + c] * dQp[pt * 3 + 2];
-        d_hw_rows[row_i * H + h] = dhw;
+                for (int c = 0; c < 3; ++c)                             // local = R^T global
+                    gr[sh.off_qp + h * sh.hs_point + pt * 3 + c] = (Ri[c] * dQp[pt * 3] + Ri[3 + c] * dQp[pt * 3 + 1]) + Ri[6 + c] * dQp[pt * 3 + 2];
+        }
     }
     __syncthreads();
 
@@ -237,8 +258,8 @@ k_ipa_bwd(const float* __restrict__ proj, const float* __restrict__ rot, const f
     }
 
     // ---- phase 2: key columns -----------------------------------------------------------------------------------------
-    if (active) {
-        const int j = tid;
+    {
+        const int j = i;
         float kp[3 * PQ], dk[DK], dv[DK], dVp[3 * PV], dKp[3 * PQ];
 #pragma unroll
         for (int c = 0; c < 3 * PQ; ++c) { kp[c] = keys[j * KW + O_KP + c]; dKp[c] = 0.f; }
@@ -246,7 +267,7 @@ k_ipa_bwd(const float* __restrict__ proj, const float* __restrict__ rot, const f
         for (int c = 0; c < DK; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
 #pragma unroll
         for (int c = 0; c < 3 * PV; ++c) dVp[c] = 0.f;
-        for (int r = 0; r < L; ++r) {
+        for (int r = lane2; r < n_act; r += 2) {
             const float p = Pm[r * LS + j], ds = Sm[r * LS + j];
             const float4* qr = reinterpret_cast<const float4*>(qrec + r * KW);
 #pragma unroll
@@ -279,23 +300,33 @@ k_ipa_bwd(const float* __restrict__ proj, const float* __restrict__ rot, const f
                 dKp[pt * 3] -= coef * dx; dKp[pt * 3 + 1] -= coef * dy; dKp[pt * 3 + 2] -= coef * dz;
             }
         }
+#pragma unroll
+        for (int c = 0; c < DK; ++c) { dk[c] = pair_sum(dk[c]); dv[c] = pair_sum(dv[c]); }
+#pragma unroll
+        for (int c = 0; c < 3 * PQ; ++c) dKp[c] = pair_sum(dKp[c]);
+#pragma unroll
+        for (int c = 0; c < 3 * PV; ++c) dVp[c] = pair_sum(dVp[c]);
         // Ri is this thread's own residue (i == j): gradients of the local points are R^T (global gradient)
         float* gr = d_proj + row_i * sh.proj_stride;
+        if (active && lane2 == 0) {
 #pragma unroll
-        for (int c = 0; c < DK; ++c) {
-            gr[sh.off_k + h * sh.hs_scalar + c] = dk[c];
-            gr[sh.off_v + h * sh.hs_scalar + c] = dv[c];
+            for (int c = 0; c < DK; ++c) {
+                gr[sh.off_k + h * sh.hs_scalar + c] = dk[c];
+                gr[sh.off_v + h * sh.hs_scalar + c] = dv[c];
+            }
+#pragma unroll
+            for (int pt = 0; pt < PQ; ++pt)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    gr[sh.off_kp + h * sh.hs_point + pt * 3 + c] = (Ri[c] * dKp[pt * 3] + Ri[3 + c] * dKp[pt * 3 + 1]) + Ri[6 + c] * dKp[pt * 3 + 2];
         }
+        if (active && lane2 == 1) {
 #pragma unroll
-        for (int pt = 0; pt < PQ; ++pt)
+            for (int pt = 0; pt < PV; ++pt)
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-                gr[sh.off_kp + h * sh.hs_point + pt * 3 + c] = (Ri[c] * dKp[pt * 3] + Ri[3 + c] * dKp[pt * 3 + 1]) + Ri[6 + c] * dKp[pt * 3 + 2];
-#pragma unroll
-        for (int pt = 0; pt < PV; ++pt)
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                gr[sh.off_vp + h * sh.hs_vpoint + pt * 3 + c] = (Ri[c] * dVp[pt * 3] + Ri[3 + c] * dVp[pt * 3 + 1]) + Ri[6 + c] * dVp[pt * 3 + 2];
+                for (int c = 0; c < 3; ++c)
+                    gr[sh.off_vp + h * sh.hs_vpoint + pt * 3 + c] = (Ri[c] * dVp[pt * 3] + Ri[3 + c] * dVp[pt * 3 + 1]) + Ri[6 + c] * dVp[pt * 3 + 2];
+        }
     }
 }
 
@@ -305,9 +336,9 @@ int launch(const float* proj, const float* rot, const float* trans, const float*
            float* d_proj, float* p_ws, float* ds_ws, float* d_hw_rows, const se3_ipa_shape& sh, cudaStream_t st) {
     constexpr int KW = 2 * DK + 3 * PQ + 3 * PV;
     const int L = sh.len, LS = L | 1;
-    const int threads = ((L + 31) / 32) * 32;
+    const int threads = ((2 * L + 31) / 32) * 32;                     // two lanes per row / column
     const size_t smem = ((size_t)2 * L * KW + (size_t)2 * L * LS + L) * sizeof(float);
-    auto kern = k_ipa_bwd<DK>;
+    auto kern = threads <= 192 ? k_ipa_bwd<DK, 192> : k_ipa_bwd<DK, 256>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("ipa bwd smem attribute (%zu bytes): %s", smem, cudaGetErrorString(e)); return SE3_ECUDA; }
