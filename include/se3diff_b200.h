@@ -169,6 +169,30 @@ int se3_frame_traceback(const float* rot, const float* pos, const float* rot_nex
                         se3_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Translation (R^3) updates alone -- the position half of the steps above on bare [n, 3] positions, for callers that step
+ * the two fields separately (EulerMaruyamaPredictor with a CosineVPSDE corruption, denoiser.py:72-97; the position lines
+ * of dpm_solver :699-701, 733-735 and of heun_denoiser :413-459).  Same expressions, same rounding: results are
+ * bit-identical to the pos outputs of the fused kernels.  pos_out may alias pos.  Scalar structs as above (the rotation
+ * members are ignored).
+ * ------------------------------------------------------------------------------------------ */
+/* pos_out = (pos + drift*dt) + sqrt(beta)*dW, drift = -0.5*beta*pos - beta*(m_pos/std)*w [+ sqrt(beta)*u_pos*w],
+ * dW = noise_weight*sqrt|dt|*z_pos; u_pos, dw_pos optional (NULL). */
+int se3_r3_update_em(const float* pos, const float* m_pos, const float* u_pos, const float* z_pos, float* pos_out,
+                     float* dw_pos, int64_t n, const se3_em_scalars* h_scalars, se3_stream_t stream);
+/* DPM-Solver-2 position update: final_half = 0: c_x_mid*pos + c_s_mid*(m_pos/std_t) (denoiser.py:699-701);
+ * final_half = 1: c_x_fin*pos + c_s_fin*(m_pos/std_lambda) with m_pos the model output at t_lambda (:733-735). */
+int se3_r3_update_dpm(const float* pos, const float* m_pos, float* pos_out, int64_t n, const se3_dpm_scalars* h_scalars,
+                      int final_half, se3_stream_t stream);
+/* Heun: churn t -> t_hat (forward SDE step, noise weight 1, denoiser.py:413-418); first-order step from pos_hat
+ * (pos_pred = m_pos_next = NULL, :423-437) or the corrected step averaging the drifts at t_hat and at
+ * (t_next, pos_pred) (:440-459). */
+int se3_r3_heun_churn(const float* pos, const float* z_pos, float* pos_hat, int64_t n, const se3_heun_scalars* h_scalars,
+                      se3_stream_t stream);
+int se3_r3_heun_step(const float* pos_hat, const float* m_pos_hat, const float* pos_pred, const float* m_pos_next,
+                     float* pos_out, int64_t n, const se3_heun_scalars* h_scalars, se3_stream_t stream);
+
+
+/* ------------------------------------------------------------------------------------------
  * K1 -- IGSO(3): truncated series, lookup tables, inverse-CDF sampling       so3_sde.py:993-2042
  * ------------------------------------------------------------------------------------------ */
 /* igso3_expansion / digso3_expansion / dlog_igso3_expansion (so3_sde.py:1731-1940) for n

@@ -59,6 +59,10 @@ SIGNATURES = {
     "se3_frame_heun_predict": [f32p] * 6 + [i64, C.POINTER(HeunScalars), vp],
     "se3_frame_heun_correct": [f32p] * 9 + [i64, C.POINTER(HeunScalars), vp],
     "se3_frame_traceback": [f32p] * 10 + [i64, C.POINTER(EmScalars), vp],
+    "se3_r3_update_em": [f32p] * 6 + [i64, C.POINTER(EmScalars), vp],
+    "se3_r3_update_dpm": [f32p] * 3 + [i64, C.POINTER(DpmScalars), i32, vp],
+    "se3_r3_heun_churn": [f32p] * 3 + [i64, C.POINTER(HeunScalars), vp],
+    "se3_r3_heun_step": [f32p] * 5 + [i64, C.POINTER(HeunScalars), vp],
     "se3_igso3_series_f32": [f32p] * 5 + [i64, i32, f32, vp],
     "se3_igso3_series_f64": [f64p] * 5 + [i64, i32, f64, vp],
     "se3_igso3_score": [f32p, f32p, f32p, i64, i32, f32, vp],

@@ -19,6 +19,7 @@ SOURCES = {
     "api.cu": [],
     "so3_kernels.cu": ["-fmad=false"],
     "frame_kernels.cu": ["-fmad=false"],
+    "r3_kernels.cu": ["-fmad=false"],
     "igso3_kernels.cu": ["-fmad=false"],
     "ipa_simt.cu": [],
     "ipa_bwd.cu": [],

@@ -204,6 +204,58 @@ def so3_update_em(rot, m_rot, z_rot, scalars: L.EmScalars, u_rot=None, want_dw=F
     return rot_out, dw
 
 
+def _pos(x, name="pos"):
+    x = _dev(x, name=name)
+    if x.shape[-1] != 3:
+        raise ValueError(f"{name}: expected [..., 3], got {tuple(x.shape)}")
+    return x, x.numel() // 3
+
+
+def r3_update_em(pos, m_pos, z_pos, scalars: L.EmScalars, u_pos=None, want_dw=False, pos_out=None):
+    """The translation half of the Euler-Maruyama step alone (EulerMaruyamaPredictor with a CosineVPSDE corruption,
+    denoiser.py:54-97): returns (pos_out, dW or None).  Bit-identical to the pos outputs of `frame_update_em`."""
+    pos, n = _pos(pos)
+    m_pos, z_pos, u_pos = _vec(m_pos, n, "m_pos"), _vec(z_pos, n, "z_pos"), _vec(u_pos, n, "u_pos")
+    pos_out = torch.empty_like(pos) if pos_out is None else pos_out
+    dw = torch.empty_like(pos) if want_dw else None
+    with _guard(pos):
+        L.check(L.lib().se3_r3_update_em(_p(pos), _p(m_pos), _p(u_pos), _p(z_pos), _p(pos_out), _p(dw), n, C.byref(scalars),
+                                         _stream(pos)), "se3_r3_update_em")
+    return pos_out, dw
+
+
+def r3_update_dpm(pos, m_pos, scalars: L.DpmScalars, final_half: bool, pos_out=None):
+    """Position line of a DPM-Solver-2 half step (denoiser.py:699-701 / 733-735)."""
+    pos, n = _pos(pos)
+    m_pos = _vec(m_pos, n, "m_pos")
+    pos_out = torch.empty_like(pos) if pos_out is None else pos_out
+    with _guard(pos):
+        L.check(L.lib().se3_r3_update_dpm(_p(pos), _p(m_pos), _p(pos_out), n, C.byref(scalars), int(bool(final_half)), _stream(pos)),
+                "se3_r3_update_dpm")
+    return pos_out
+
+
+def r3_heun_churn(pos, z_pos, scalars: L.HeunScalars, pos_out=None):
+    pos, n = _pos(pos)
+    z_pos = _vec(z_pos, n, "z_pos")
+    pos_out = torch.empty_like(pos) if pos_out is None else pos_out
+    with _guard(pos):
+        L.check(L.lib().se3_r3_heun_churn(_p(pos), _p(z_pos), _p(pos_out), n, C.byref(scalars), _stream(pos)), "se3_r3_heun_churn")
+    return pos_out
+
+
+def r3_heun_step(pos_hat, m_pos_hat, scalars: L.HeunScalars, pos_pred=None, m_pos_next=None, pos_out=None):
+    """Heun position step from pos_hat: first order, or corrected when (pos_pred, m_pos_next) are given (denoiser.py:423-459)."""
+    pos_hat, n = _pos(pos_hat, "pos_hat")
+    m_pos_hat = _vec(m_pos_hat, n, "m_pos_hat")
+    pos_pred, m_pos_next = _vec(pos_pred, n, "pos_pred"), _vec(m_pos_next, n, "m_pos_next")
+    pos_out = torch.empty_like(pos_hat) if pos_out is None else pos_out
+    with _guard(pos_hat):
+        L.check(L.lib().se3_r3_heun_step(_p(pos_hat), _p(m_pos_hat), _p(pos_pred), _p(m_pos_next), _p(pos_out), n, C.byref(scalars),
+                                         _stream(pos_hat)), "se3_r3_heun_step")
+    return pos_out
+
+
 def frame_update_dpm_mid(rot, pos, m_rot, m_pos, scalars: L.DpmScalars, rot_out=None, pos_out=None):
     rot, pos, n = _chk_frames(rot, pos)
     m_rot, m_pos = _vec(m_rot, n, "m_rot"), _vec(m_pos, n, "m_pos")

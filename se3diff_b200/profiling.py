@@ -83,6 +83,9 @@ def elementwise_rooflines(n: int = 10_000_000, device="cuda"):
         ("se3_frame_update_em", 144, lambda: ops.frame_update_em(r, pos, w, v, z1, z2, em, rot_out=out_r, pos_out=out_p)),
         ("se3_frame_update_dpm_mid", 120, lambda: ops.frame_update_dpm_mid(r, pos, w, v, dp, rot_out=out_r, pos_out=out_p)),
         ("se3_frame_update_dpm_final", 132, lambda: ops.frame_update_dpm_final(r, pos, w, z1, v, dp, rot_out=out_r, pos_out=out_p)),
+        # translation updates alone: pos + score + noise in, pos out = 48 B/residue; DPM: pos + score in, pos out = 36
+        ("se3_r3_update_em", 48, lambda: ops.r3_update_em(pos, v, z2, em, pos_out=out_p)),
+        ("se3_r3_update_dpm", 36, lambda: ops.r3_update_dpm(pos, v, dp, final_half=False, pos_out=out_p)),
     ]
     # IGSO3 noising (sample_marginal, so3_sde.py:249-288) with the full-size table (8 MB, L2-resident): 36 B in + 36 B out
     # + 16 B of passed-in noise = 88 B/rotation; 72 B with in-kernel Philox

@@ -1135,3 +1135,53 @@ def test_ipa_backward_kernel_vs_torch_autograd(B, L, H, dk, shared, masked, scal
         fl = float(r.abs().max()) + 1e-30
         e_t, e_k = rel_err(t, r, floor=fl), rel_err(k, r, floor=fl)
         assert e_k <= max(4 * e_t, 2e-5), (n, e_k, e_t)
+
+
+@pytest.mark.parametrize("n,offset", [(1037, 0), (4096, 0), (1000, 1), (2_000_003, 0), (0, 0)])
+def test_r3_translation_kernels_equal_the_fused_frame_kernels(n, offset):
+    """se3_r3_update_{em,dpm}, se3_r3_heun_{churn,step}: the position half of each sampler step on bare positions.  The fused
+    frame kernels are pinned bit-exactly to the CPU oracle above (same seeds, same schedules); the stand-alone translation
+    kernels must reproduce their position outputs bit for bit -- vector path, scalar tail, unaligned views (offset rows)
+    and the grid-stride path at 2 M residues."""
+    from se3diff_b200 import ops, schedule
+    from se3diff_b200.sdes import CosineVPSDE
+
+    r3, tab = _sdes_small()
+    rot, pos, (m_rot, m_pos, z_rot, z_pos, u_rot, u_pos) = _state(n + offset, 21, 3.0)
+    d = lambda x: x.to(DEV)[offset:]                                    # offset rows: 12-byte-shifted, unaligned views
+    rot, pos, m_rot, m_pos, z_rot, z_pos, u_rot, u_pos = (d(x) for x in (rot, pos, m_rot, m_pos, z_rot, z_pos, u_rot, u_pos))
+    if n == 0:
+        sc = schedule.em_scalars(CosineVPSDE(0.008), _So3Shim(tab), torch.full((1,), 0.4), torch.tensor([-0.02]))[0]
+        p, dw = ops.r3_update_em(pos, m_pos, z_pos, sc, want_dw=True)
+        assert p.shape == (0, 3) and dw.shape == (0, 3)
+        return
+    # Euler-Maruyama, with and without control / dW
+    for tval, dtval in ((0.99, -0.00494), (0.0208, -0.0198)):
+        sc = schedule.em_scalars(CosineVPSDE(0.008), _So3Shim(tab), torch.full((1,), tval), torch.tensor([dtval]))[0]
+        for with_u in (False, True):
+            _, p_f, _, dw_f = ops.frame_update_em(rot, pos, m_rot, m_pos, z_rot, z_pos, sc, u_rot=u_rot if with_u else None,
+                                                  u_pos=u_pos if with_u else None, want_dw=True)
+            p, dw = ops.r3_update_em(pos, m_pos, z_pos, sc, u_pos=u_pos if with_u else None, want_dw=True)
+            assert torch.equal(p, p_f) and torch.equal(dw, dw_f)
+            p2, none = ops.r3_update_em(pos, m_pos, z_pos, sc, u_pos=u_pos if with_u else None)
+            assert none is None and torch.equal(p2, p_f)
+    # DPM-Solver-2 halves
+    for st in schedule.dpm_schedule(CosineVPSDE(0.008), _So3Shim(tab), 12, 0.99, 0.001)[::5]:
+        _, p_mid = ops.frame_update_dpm_mid(rot, pos, m_rot, m_pos, st.scalars)
+        assert torch.equal(ops.r3_update_dpm(pos, m_pos, st.scalars, final_half=False), p_mid)
+        _, p_fin = ops.frame_update_dpm_final(rot, pos, m_rot, u_rot, u_pos, st.scalars)
+        assert torch.equal(ops.r3_update_dpm(pos, u_pos, st.scalars, final_half=True), p_fin)
+    # Heun: churn, first-order step, corrected step
+    for st in schedule.heun_schedule(CosineVPSDE(0.008), _So3Shim(tab), 20, 0.99, 0.001, 0.5)[::9]:
+        _, p_h = ops.frame_heun_churn(rot, pos, z_rot, z_pos, st.scalars)
+        assert torch.equal(ops.r3_heun_churn(pos, z_pos, st.scalars), p_h)
+        _, p_1 = ops.frame_heun_predict(rot, p_h, m_rot, m_pos, st.scalars)
+        assert torch.equal(ops.r3_heun_step(p_h, m_pos, st.scalars), p_1)
+        _, p_c = ops.frame_heun_correct(rot, p_h, m_rot, m_pos, p_1, u_rot, u_pos, st.scalars)
+        assert torch.equal(ops.r3_heun_step(p_h, m_pos, st.scalars, pos_pred=p_1, m_pos_next=u_pos), p_c)
+    # in place
+    sc = schedule.em_scalars(CosineVPSDE(0.008), _So3Shim(tab), torch.full((1,), 0.4), torch.tensor([-0.02]))[0]
+    want, _ = ops.r3_update_em(pos, m_pos, z_pos, sc)
+    buf = pos.clone()
+    ops.r3_update_em(buf, m_pos, z_pos, sc, pos_out=buf)
+    assert torch.equal(buf, want)
