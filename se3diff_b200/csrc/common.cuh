@@ -80,6 +80,45 @@ __device__ __forceinline__ void tile_store(T* __restrict__ g, const T* __restric
     }
 }
 
+// Per-warp edition of the same movement: warp w of the CTA moves its own 32 elements [first + 32w, first + 32w + 32)
+// to / from the SAME shared-memory layout (offset 32*w*W), so a kernel whose threads only ever touch their own element of
+// arrays with one fixed W needs __syncwarp() instead of __syncthreads(): the warps of a CTA run their load / compute /
+// store phases independently instead of meeting at two CTA barriers per tile (ncu on k_dpm_mid: 5.4 warps stalled at
+// the barrier per issued instruction, DRAM at 53 %).
+template <int W, typename T>
+__device__ __forceinline__ void warp_tile_load(const T* __restrict__ g, T* __restrict__ s, int64_t first, int count) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wcount = min(32, count - 32 * w);
+    if (wcount <= 0) return;
+    const T* src = g + (first + 32 * w) * W;
+    T* dst = s + 32 * w * W;
+    constexpr int kPerVec = 16 / sizeof(T);
+    if (wcount == 32 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (32 * W) % kPerVec == 0) {
+        constexpr int nvec = 32 * W / kPerVec;
+#pragma unroll
+        for (int i = lane; i < nvec; i += 32) reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+    } else {
+        for (int i = lane; i < wcount * W; i += 32) dst[i] = src[i];
+    }
+}
+
+template <int W, typename T>
+__device__ __forceinline__ void warp_tile_store(T* __restrict__ g, const T* __restrict__ s, int64_t first, int count) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wcount = min(32, count - 32 * w);
+    if (wcount <= 0) return;
+    T* dst = g + (first + 32 * w) * W;
+    const T* src = s + 32 * w * W;
+    constexpr int kPerVec = 16 / sizeof(T);
+    if (wcount == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (32 * W) % kPerVec == 0) {
+        constexpr int nvec = 32 * W / kPerVec;
+#pragma unroll
+        for (int i = lane; i < nvec; i += 32) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+    } else {
+        for (int i = lane; i < wcount * W; i += 32) dst[i] = src[i];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // SO(3) maps on register-resident 3-vectors / row-major 3x3 matrices.
 // Operation order follows the reference expression by expression (so3_sde.py) so that, with FMA

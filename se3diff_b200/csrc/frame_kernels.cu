@@ -1,8 +1,9 @@
 // K3 + frame update -- fused per-step SDE algebra of the three samplers (denoiser.py:30-166,
 // 245-262, 401-459, 668-762) including the score conversion of _get_score (denoiser.py:169-203).
 //
-// One thread per residue, one CTA per 256 residues.  Every operand array ([n,9] rotations,
-// [n,3] vectors) is moved with 128-bit coalesced accesses through shared memory (common.cuh).
+// One thread per residue, one CTA per 256 residues, one WARP per 32: every operand array ([n,9] rotations, [n,3]
+// vectors) is moved with 128-bit coalesced accesses through shared memory by the warp that owns the residues
+// (common.cuh: warp_tile_load / warp_tile_store), so only __syncwarp() separates load, compute and store.
 // HBM-bound: 120-168 algorithmic bytes per residue against ~150 flop + 2 sincos.
 // Compiled with -fmad=false: each expression is evaluated in the reference's order, so the R3
 // half is bit-identical to the fp32 torch path and the SO(3) half differs only in sin/cos.
@@ -61,17 +62,17 @@ k_em(const float* __restrict__ rot, const float* __restrict__ pos, const float* 
     __shared__ __align__(16) float s_v[HAS_U ? 7 : 5][kTile * 3];  // pos, m_rot, m_pos, z_rot, z_pos, [u_rot, u_pos]
     const int64_t first = (int64_t)blockIdx.x * kTile;
     const int count = (int)min((int64_t)kTile, n - first);
-    tile_load<9>(rot, s_rot, first, count);
-    tile_load<3>(pos, s_v[0], first, count);
-    tile_load<3>(m_rot, s_v[1], first, count);
-    tile_load<3>(m_pos, s_v[2], first, count);
-    tile_load<3>(z_rot, s_v[3], first, count);
-    tile_load<3>(z_pos, s_v[4], first, count);
+    warp_tile_load<9>(rot, s_rot, first, count);
+    warp_tile_load<3>(pos, s_v[0], first, count);
+    warp_tile_load<3>(m_rot, s_v[1], first, count);
+    warp_tile_load<3>(m_pos, s_v[2], first, count);
+    warp_tile_load<3>(z_rot, s_v[3], first, count);
+    warp_tile_load<3>(z_pos, s_v[4], first, count);
     if (HAS_U) {
-        tile_load<3>(u_rot, s_v[5], first, count);
-        tile_load<3>(u_pos, s_v[6], first, count);
+        warp_tile_load<3>(u_rot, s_v[5], first, count);
+        warp_tile_load<3>(u_pos, s_v[6], first, count);
     }
-    __syncthreads();
+    __syncwarp();
     const int t = threadIdx.x;
     if (t < count) {
         float r[9], mean[9], out[9];
@@ -96,12 +97,12 @@ k_em(const float* __restrict__ rot, const float* __restrict__ pos, const float* 
         st3(s_v[0], t, {(x.x + dp.x * c.dt) + q * dwp.x, (x.y + dp.y * c.dt) + q * dwp.y, (x.z + dp.z * c.dt) + q * dwp.z});
         if (OUT_DW) { st3(s_v[3], t, dwr); st3(s_v[4], t, dwp); }
     }
-    __syncthreads();
-    tile_store<9>(rot_out, s_rot, first, count);
-    tile_store<3>(pos_out, s_v[0], first, count);
+    __syncwarp();
+    warp_tile_store<9>(rot_out, s_rot, first, count);
+    warp_tile_store<3>(pos_out, s_v[0], first, count);
     if (OUT_DW) {
-        if (dw_rot) tile_store<3>(dw_rot, s_v[3], first, count);
-        if (dw_pos) tile_store<3>(dw_pos, s_v[4], first, count);
+        if (dw_rot) warp_tile_store<3>(dw_rot, s_v[3], first, count);
+        if (dw_pos) warp_tile_store<3>(dw_pos, s_v[4], first, count);
     }
 }
 
@@ -115,11 +116,11 @@ k_em_so3(const float* __restrict__ rot, const float* __restrict__ m_rot, const f
     __shared__ __align__(16) float s_v[HAS_U ? 3 : 2][kTile * 3];  // m_rot, z_rot, [u_rot]
     const int64_t first = (int64_t)blockIdx.x * kTile;
     const int count = (int)min((int64_t)kTile, n - first);
-    tile_load<9>(rot, s_rot, first, count);
-    tile_load<3>(m_rot, s_v[0], first, count);
-    tile_load<3>(z_rot, s_v[1], first, count);
-    if (HAS_U) tile_load<3>(u_rot, s_v[2], first, count);
-    __syncthreads();
+    warp_tile_load<9>(rot, s_rot, first, count);
+    warp_tile_load<3>(m_rot, s_v[0], first, count);
+    warp_tile_load<3>(z_rot, s_v[1], first, count);
+    if (HAS_U) warp_tile_load<3>(u_rot, s_v[2], first, count);
+    __syncwarp();
     const int t = threadIdx.x;
     if (t < count) {
         float r[9], mean[9], out[9];
@@ -136,9 +137,9 @@ k_em_so3(const float* __restrict__ rot, const float* __restrict__ m_rot, const f
         st9(s_rot, t, out);
         if (OUT_DW) st3(s_v[1], t, dwr);
     }
-    __syncthreads();
-    tile_store<9>(rot_out, s_rot, first, count);
-    if (OUT_DW) tile_store<3>(dw_rot, s_v[1], first, count);
+    __syncwarp();
+    warp_tile_store<9>(rot_out, s_rot, first, count);
+    if (OUT_DW) warp_tile_store<3>(dw_rot, s_v[1], first, count);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -152,11 +153,11 @@ k_dpm_mid(const float* __restrict__ rot, const float* __restrict__ pos, const fl
     __shared__ __align__(16) float s_v[3][kTile * 3];
     const int64_t first = (int64_t)blockIdx.x * kTile;
     const int count = (int)min((int64_t)kTile, n - first);
-    tile_load<9>(rot, s_rot, first, count);
-    tile_load<3>(pos, s_v[0], first, count);
-    tile_load<3>(m_rot, s_v[1], first, count);
-    tile_load<3>(m_pos, s_v[2], first, count);
-    __syncthreads();
+    warp_tile_load<9>(rot, s_rot, first, count);
+    warp_tile_load<3>(pos, s_v[0], first, count);
+    warp_tile_load<3>(m_rot, s_v[1], first, count);
+    warp_tile_load<3>(m_pos, s_v[2], first, count);
+    __syncwarp();
     const int t = threadIdx.x;
     if (t < count) {
         float r[9], out[9];
@@ -171,9 +172,9 @@ k_dpm_mid(const float* __restrict__ rot, const float* __restrict__ pos, const fl
                         c.pos_c_x_mid * x.y + c.pos_c_s_mid * (mp.y / c.pos_std_t),
                         c.pos_c_x_mid * x.z + c.pos_c_s_mid * (mp.z / c.pos_std_t)});
     }
-    __syncthreads();
-    tile_store<9>(rot_u, s_rot, first, count);
-    tile_store<3>(pos_u, s_v[0], first, count);
+    __syncwarp();
+    warp_tile_store<9>(rot_u, s_rot, first, count);
+    warp_tile_store<3>(pos_u, s_v[0], first, count);
 }
 
 __global__ void __launch_bounds__(kTile)
@@ -184,12 +185,12 @@ k_dpm_final(const float* __restrict__ rot, const float* __restrict__ pos, const 
     __shared__ __align__(16) float s_v[4][kTile * 3];
     const int64_t first = (int64_t)blockIdx.x * kTile;
     const int count = (int)min((int64_t)kTile, n - first);
-    tile_load<9>(rot, s_rot, first, count);
-    tile_load<3>(pos, s_v[0], first, count);
-    tile_load<3>(m_rot_t, s_v[1], first, count);
-    tile_load<3>(m_rot_l, s_v[2], first, count);
-    tile_load<3>(m_pos_l, s_v[3], first, count);
-    __syncthreads();
+    warp_tile_load<9>(rot, s_rot, first, count);
+    warp_tile_load<3>(pos, s_v[0], first, count);
+    warp_tile_load<3>(m_rot_t, s_v[1], first, count);
+    warp_tile_load<3>(m_rot_l, s_v[2], first, count);
+    warp_tile_load<3>(m_pos_l, s_v[3], first, count);
+    __syncwarp();
     const int t = threadIdx.x;
     if (t < count) {
         float r[9], out[9];
@@ -211,9 +212,9 @@ k_dpm_final(const float* __restrict__ rot, const float* __restrict__ pos, const 
                         c.pos_c_x_fin * x.y + c.pos_c_s_fin * (mp.y / c.pos_std_lam),
                         c.pos_c_x_fin * x.z + c.pos_c_s_fin * (mp.z / c.pos_std_lam)});
     }
-    __syncthreads();
-    tile_store<9>(rot_out, s_rot, first, count);
-    tile_store<3>(pos_out, s_v[0], first, count);
+    __syncwarp();
+    warp_tile_store<9>(rot_out, s_rot, first, count);
+    warp_tile_store<3>(pos_out, s_v[0], first, count);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -227,11 +228,11 @@ k_heun_churn(const float* __restrict__ rot, const float* __restrict__ pos, const
     __shared__ __align__(16) float s_v[3][kTile * 3];
     const int64_t first = (int64_t)blockIdx.x * kTile;
     const int count = (int)min((int64_t)kTile, n - first);
-    tile_load<9>(rot, s_rot, first, count);
-    tile_load<3>(pos, s_v[0], first, count);
-    tile_load<3>(z_rot, s_v[1], first, count);
-    tile_load<3>(z_pos, s_v[2], first, count);
-    __syncthreads();
+    warp_tile_load<9>(rot, s_rot, first, count);
+    warp_tile_load<3>(pos, s_v[0], first, count);
+    warp_tile_load<3>(z_rot, s_v[1], first, count);
+    warp_tile_load<3>(z_pos, s_v[2], first, count);
+    __syncwarp();
     const int t = threadIdx.x;
     if (t < count) {
         float r[9], mean[9], out[9];
@@ -246,9 +247,9 @@ k_heun_churn(const float* __restrict__ rot, const float* __restrict__ pos, const
         st3(s_v[0], t, {(x.x + (hb * x.x) * c.churn_dt) + q * (nsd * zp.x), (x.y + (hb * x.y) * c.churn_dt) + q * (nsd * zp.y),
                         (x.z + (hb * x.z) * c.churn_dt) + q * (nsd * zp.z)});
     }
-    __syncthreads();
-    tile_store<9>(rot_hat, s_rot, first, count);
-    tile_store<3>(pos_hat, s_v[0], first, count);
+    __syncwarp();
+    warp_tile_store<9>(rot_hat, s_rot, first, count);
+    warp_tile_store<3>(pos_hat, s_v[0], first, count);
 }
 
 // CORRECT=false: first-order step from (rot_hat,pos_hat) with the drift at t_hat.
@@ -263,16 +264,16 @@ k_heun_step(const float* __restrict__ rot_hat, const float* __restrict__ pos_hat
     __shared__ __align__(16) float s_v[CORRECT ? 6 : 3][kTile * 3];
     const int64_t first = (int64_t)blockIdx.x * kTile;
     const int count = (int)min((int64_t)kTile, n - first);
-    tile_load<9>(rot_hat, s_rot, first, count);
-    tile_load<3>(pos_hat, s_v[0], first, count);
-    tile_load<3>(m_rot_hat, s_v[1], first, count);
-    tile_load<3>(m_pos_hat, s_v[2], first, count);
+    warp_tile_load<9>(rot_hat, s_rot, first, count);
+    warp_tile_load<3>(pos_hat, s_v[0], first, count);
+    warp_tile_load<3>(m_rot_hat, s_v[1], first, count);
+    warp_tile_load<3>(m_pos_hat, s_v[2], first, count);
     if (CORRECT) {
-        tile_load<3>(pos_pred, s_v[3], first, count);
-        tile_load<3>(m_rot_next, s_v[4], first, count);
-        tile_load<3>(m_pos_next, s_v[5], first, count);
+        warp_tile_load<3>(pos_pred, s_v[3], first, count);
+        warp_tile_load<3>(m_rot_next, s_v[4], first, count);
+        warp_tile_load<3>(m_pos_next, s_v[5], first, count);
     }
-    __syncthreads();
+    __syncwarp();
     const int t = threadIdx.x;
     if (t < count) {
         float r[9], out[9];
@@ -302,9 +303,9 @@ k_heun_step(const float* __restrict__ rot_hat, const float* __restrict__ pos_hat
         st9(s_rot, t, out);
         st3(s_v[0], t, {xo[0], xo[1], xo[2]});
     }
-    __syncthreads();
-    tile_store<9>(rot_out, s_rot, first, count);
-    tile_store<3>(pos_out, s_v[0], first, count);
+    __syncwarp();
+    warp_tile_store<9>(rot_out, s_rot, first, count);
+    warp_tile_store<3>(pos_out, s_v[0], first, count);
 }
 
 // traceback_brownian_motion (denoiser.py:133-166)
@@ -318,14 +319,14 @@ k_traceback(const float* __restrict__ rot, const float* __restrict__ pos, const 
     __shared__ __align__(16) float s_v[HAS_U ? 6 : 4][kTile * 3];
     const int64_t first = (int64_t)blockIdx.x * kTile;
     const int count = (int)min((int64_t)kTile, n - first);
-    tile_load<9>(rot, s_rot[0], first, count);
-    tile_load<9>(rot_next, s_rot[1], first, count);
-    tile_load<3>(pos, s_v[0], first, count);
-    tile_load<3>(pos_next, s_v[1], first, count);
-    tile_load<3>(m_rot, s_v[2], first, count);
-    tile_load<3>(m_pos, s_v[3], first, count);
-    if (HAS_U) { tile_load<3>(u_rot, s_v[4], first, count); tile_load<3>(u_pos, s_v[5], first, count); }
-    __syncthreads();
+    warp_tile_load<9>(rot, s_rot[0], first, count);
+    warp_tile_load<9>(rot_next, s_rot[1], first, count);
+    warp_tile_load<3>(pos, s_v[0], first, count);
+    warp_tile_load<3>(pos_next, s_v[1], first, count);
+    warp_tile_load<3>(m_rot, s_v[2], first, count);
+    warp_tile_load<3>(m_pos, s_v[3], first, count);
+    if (HAS_U) { warp_tile_load<3>(u_rot, s_v[4], first, count); warp_tile_load<3>(u_pos, s_v[5], first, count); }
+    __syncwarp();
     const int t = threadIdx.x;
     if (t < count) {
         float r[9], rn[9], mean[9], rel[9], lg[3];
@@ -345,9 +346,9 @@ k_traceback(const float* __restrict__ rot, const float* __restrict__ pos, const 
                          pos_drift(b, q, x.z, mp.z / c.pos_std, w, HAS_U, up.z)};
         st3(s_v[3], t, {(xn.x - (x.x + dp.x * c.dt)) / q, (xn.y - (x.y + dp.y * c.dt)) / q, (xn.z - (x.z + dp.z * c.dt)) / q});
     }
-    __syncthreads();
-    tile_store<3>(dw_rot, s_v[2], first, count);
-    tile_store<3>(dw_pos, s_v[3], first, count);
+    __syncwarp();
+    warp_tile_store<3>(dw_rot, s_v[2], first, count);
+    warp_tile_store<3>(dw_pos, s_v[3], first, count);
 }
 
 }  // namespace
