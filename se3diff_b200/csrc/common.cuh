@@ -85,13 +85,15 @@ __device__ __forceinline__ void tile_store(T* __restrict__ g, const T* __restric
 // arrays with one fixed W needs __syncwarp() instead of __syncthreads(): the warps of a CTA run their load / compute /
 // store phases independently instead of meeting at two CTA barriers per tile (ncu on k_dpm_mid: 5.4 warps stalled at
 // the barrier per issued instruction, DRAM at 53 %).
-template <int W, typename T>
+// SLOT: elements of shared memory each thread owns (>= W): a kernel that reads W_in and writes W_out values per element
+// through one buffer gives every warp a private 32*SLOT slice, SLOT = max(W_in, W_out).
+template <int W, int SLOT = W, typename T>
 __device__ __forceinline__ void warp_tile_load(const T* __restrict__ g, T* __restrict__ s, int64_t first, int count) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wcount = min(32, count - 32 * w);
     if (wcount <= 0) return;
     const T* src = g + (first + 32 * w) * W;
-    T* dst = s + 32 * w * W;
+    T* dst = s + 32 * w * SLOT;
     constexpr int kPerVec = 16 / sizeof(T);
     if (wcount == 32 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (32 * W) % kPerVec == 0) {
         constexpr int nvec = 32 * W / kPerVec;
@@ -102,13 +104,13 @@ __device__ __forceinline__ void warp_tile_load(const T* __restrict__ g, T* __res
     }
 }
 
-template <int W, typename T>
+template <int W, int SLOT = W, typename T>
 __device__ __forceinline__ void warp_tile_store(T* __restrict__ g, const T* __restrict__ s, int64_t first, int count) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wcount = min(32, count - 32 * w);
     if (wcount <= 0) return;
     T* dst = g + (first + 32 * w) * W;
-    const T* src = s + 32 * w * W;
+    const T* src = s + 32 * w * SLOT;
     constexpr int kPerVec = 16 / sizeof(T);
     if (wcount == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (32 * W) % kPerVec == 0) {
         constexpr int nvec = 32 * W / kPerVec;

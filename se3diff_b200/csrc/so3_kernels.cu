@@ -10,26 +10,29 @@ namespace {
 
 inline dim3 grid_for(int64_t n) { return dim3((unsigned)((n + kTile - 1) / kTile)); }
 
+// k_exp / k_log / k_compose: every warp owns a private 32 x 9 slice of the buffer (common.cuh: warp_tile_load / _store with
+// SLOT = 9), so only __syncwarp() separates its load, compute and store phases.
 template <typename T>
 __global__ void __launch_bounds__(kTile) k_exp(const T* __restrict__ v, T* __restrict__ out, int64_t n, T tol) {
     __shared__ __align__(16) T s[kTile * 9];
     const int64_t first = (int64_t)blockIdx.x * kTile;
     const int count = (int)min((int64_t)kTile, n - first);
-    tile_load<3>(v, s, first, count);
-    __syncthreads();
+    const int t = threadIdx.x, lane = t & 31;
+    T* sw = s + (t >> 5) * 32 * 9;
+    warp_tile_load<3, 9>(v, s, first, count);
+    __syncwarp();
     T a[3], r[9];
-    const int t = threadIdx.x;
     if (t < count) {
-        a[0] = s[t * 3]; a[1] = s[t * 3 + 1]; a[2] = s[t * 3 + 2];
+        a[0] = sw[lane * 3]; a[1] = sw[lane * 3 + 1]; a[2] = sw[lane * 3 + 2];
         so3_exp(a, tol, r);
     }
-    __syncthreads();
+    __syncwarp();
     if (t < count) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) s[t * 9 + k] = r[k];
+        for (int k = 0; k < 9; ++k) sw[lane * 9 + k] = r[k];
     }
-    __syncthreads();
-    tile_store<9>(out, s, first, count);
+    __syncwarp();
+    warp_tile_store<9, 9>(out, s, first, count);
 }
 
 template <typename T>
@@ -37,19 +40,20 @@ __global__ void __launch_bounds__(kTile) k_log(const T* __restrict__ rm, T* __re
     __shared__ __align__(16) T s[kTile * 9];
     const int64_t first = (int64_t)blockIdx.x * kTile;
     const int count = (int)min((int64_t)kTile, n - first);
-    tile_load<9>(rm, s, first, count);
-    __syncthreads();
+    const int t = threadIdx.x, lane = t & 31;
+    T* sw = s + (t >> 5) * 32 * 9;
+    warp_tile_load<9, 9>(rm, s, first, count);
+    __syncwarp();
     T r[9], v[3];
-    const int t = threadIdx.x;
     if (t < count) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) r[k] = s[t * 9 + k];
+        for (int k = 0; k < 9; ++k) r[k] = sw[lane * 9 + k];
         so3_log(r, v);
     }
-    __syncthreads();
-    if (t < count) { s[t * 3] = v[0]; s[t * 3 + 1] = v[1]; s[t * 3 + 2] = v[2]; }
-    __syncthreads();
-    tile_store<3>(out, s, first, count);
+    __syncwarp();
+    if (t < count) { sw[lane * 3] = v[0]; sw[lane * 3 + 1] = v[1]; sw[lane * 3 + 2] = v[2]; }
+    __syncwarp();
+    warp_tile_store<3, 9>(out, s, first, count);
 }
 
 __global__ void __launch_bounds__(kTile) k_angle(const float* __restrict__ rm, float* __restrict__ ang,
@@ -81,21 +85,23 @@ __global__ void __launch_bounds__(kTile) k_compose(const float* __restrict__ a, 
     __shared__ __align__(16) float sb[kTile * 9];
     const int64_t first = (int64_t)blockIdx.x * kTile;
     const int count = (int)min((int64_t)kTile, n - first);
-    tile_load<9>(a, sa, first, count);
-    if (MODE == 0) tile_load<3>(b, sb, first, count); else tile_load<9>(b, sb, first, count);
-    __syncthreads();
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31;
+    float* swa = sa + (t >> 5) * 32 * 9;
+    float* swb = sb + (t >> 5) * 32 * 9;
+    warp_tile_load<9, 9>(a, sa, first, count);
+    if (MODE == 0) warp_tile_load<3, 9>(b, sb, first, count); else warp_tile_load<9, 9>(b, sb, first, count);
+    __syncwarp();
     float ra[9], rb[9], rc[9], v[3];
     if (t < count) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) ra[k] = sa[t * 9 + k];
+        for (int k = 0; k < 9; ++k) ra[k] = swa[lane * 9 + k];
         if (MODE == 0) {
-            v[0] = sb[t * 3]; v[1] = sb[t * 3 + 1]; v[2] = sb[t * 3 + 2];
+            v[0] = swb[lane * 3]; v[1] = swb[lane * 3 + 1]; v[2] = swb[lane * 3 + 2];
             so3_exp(v, tol, rb);
             so3_mul<float, false>(ra, rb, rc);
         } else {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) rb[k] = sb[t * 9 + k];
+            for (int k = 0; k < 9; ++k) rb[k] = swb[lane * 9 + k];
             if (MODE == 1) {
                 if (transpose_a) so3_mul<float, true>(ra, rb, rc); else so3_mul<float, false>(ra, rb, rc);
             } else {
@@ -109,18 +115,18 @@ __global__ void __launch_bounds__(kTile) k_compose(const float* __restrict__ a, 
             }
         }
     }
-    __syncthreads();
+    __syncwarp();
     if (MODE == 2) {
-        if (t < count) { sa[t * 3] = v[0]; sa[t * 3 + 1] = v[1]; sa[t * 3 + 2] = v[2]; }
-        __syncthreads();
-        tile_store<3>(out, sa, first, count);
+        if (t < count) { swa[lane * 3] = v[0]; swa[lane * 3 + 1] = v[1]; swa[lane * 3 + 2] = v[2]; }
+        __syncwarp();
+        warp_tile_store<3, 9>(out, sa, first, count);
     } else {
         if (t < count) {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) sa[t * 9 + k] = rc[k];
+            for (int k = 0; k < 9; ++k) swa[lane * 9 + k] = rc[k];
         }
-        __syncthreads();
-        tile_store<9>(out, sa, first, count);
+        __syncwarp();
+        warp_tile_store<9, 9>(out, sa, first, count);
     }
 }
 
