@@ -266,3 +266,23 @@ def test_batch_of_one_repeated_graph_tracks_replication():
     distinct = Batch.from_data_list([g, g.replace(pos=torch.randn(L, 3)), g])
     assert distinct.h2d_nbytes() == full(distinct)
     assert torch.equal(b.to("cpu")["pair_embeds"], b["pair_embeds"])
+
+
+def test_ipa_backward_shape_gate_and_cpu_refusal():
+    """ops.ipa_bwd_supported mirrors the shared-memory bound of se3_ipa_attention_bwd (include/se3diff_b200.h), and the
+    differentiable operator has no CPU path."""
+    from se3diff_b200 import _lib, ops
+
+    ok = lambda B, n, H, dk: ops.ipa_bwd_supported(ops.ipa_shape(B, n, H, dk, 1, head_major=False))
+    assert ok(1280, 84, 4, 16) and ok(64, 56, 4, 16) and ok(2, 128, 2, 8) and ok(2, 128, 32, 16)
+    assert not ok(2, 129, 4, 16)                      # keys of a (sample, head) no longer fit one CTA
+    assert not ok(2, 128, 4, 32)                      # 235 KB of shared memory
+    assert ok(2, 96, 4, 32)
+    assert not ok(0, 84, 4, 16) and not ok(70000, 84, 4, 16) and not ok(2, 84, 4, 12)
+    sh = ops.ipa_shape(1, 8, 2, 4, 1, head_major=False)
+    x = torch.zeros(8, sh.proj_stride)
+    with pytest.raises(_lib.Se3LibraryError):
+        ops.IpaAttention.apply(x, torch.zeros(8, 9), torch.zeros(8, 3), torch.zeros(1, 2, 8, 8), torch.zeros(1, 8, 8, 8), None,
+                               torch.zeros(2), 0.5, sh)
+    with pytest.raises(_lib.Se3LibraryError):
+        ops.r3_update_dpm(torch.zeros(4, 3), torch.zeros(4, 3), _lib.DpmScalars(), final_half=False)
