@@ -60,12 +60,14 @@ k_ipa_bwd(const float* __restrict__ proj, const float* __restrict__ rot, const f
     const int C_S = h * DK, C_P = HD + h * PV * 3, C_Z = HD + 3 * H * PV + h * DK, C_N = 2 * HD + 3 * H * PV + h * PV;
 
     // ---- phase 0: stage the keys of this (sample, head) in the global frame --------------------------------
+#pragma unroll 4
     for (int idx = tid; idx < L * DK; idx += blockDim.x) {
         const int j = idx / DK, c = idx - j * DK;
         const float* pr = proj + ((int64_t)b * L + j) * sh.proj_stride;
         keys[j * KW + O_KS + c] = pr[sh.off_k + h * sh.hs_scalar + c];
         keys[j * KW + O_VS + c] = pr[sh.off_v + h * sh.hs_scalar + c];
     }
+#pragma unroll 4
     for (int idx = tid; idx < L * (PQ + PV); idx += blockDim.x) {
         const int j = idx / (PQ + PV), p = idx - j * (PQ + PV);
         const int64_t rj = (int64_t)b * L + j;
@@ -250,6 +252,7 @@ k_ipa_bwd(const float* __restrict__ proj, const float* __restrict__ rot, const f
     {
         float* pg = p_ws + ((int64_t)b * H + h) * L * L;
         float* sg = ds_ws + ((int64_t)b * H + h) * L * L;
+#pragma unroll 4
         for (int idx = tid; idx < L * L; idx += blockDim.x) {
             const int r = idx / L, c = idx - r * L;
             pg[idx] = Pm[r * LS + c];

@@ -94,12 +94,14 @@ k_ipa_rows(const float* __restrict__ proj, const float* __restrict__ rot, const 
         const int nk = min(tile_keys, L - j0);
         __syncthreads();
         // ---- stage this key tile (all threads) -------------------------------------------------
+#pragma unroll 4
         for (int idx = threadIdx.x; idx < nk * DK; idx += blockDim.x) {
             const int j = idx / DK, c = idx - j * DK;
             const float* pr = proj + ((int64_t)b * L + j0 + j) * sh.proj_stride;
             keys[j * KW + O_KS + c] = pr[sh.off_k + h * sh.hs_scalar + c];
             keys[j * KW + O_VS + c] = pr[sh.off_v + h * sh.hs_scalar + c];
         }
+#pragma unroll 4
         for (int idx = threadIdx.x; idx < nk * (PQ + PV); idx += blockDim.x) {
             const int j = idx / (PQ + PV), p = idx - j * (PQ + PV);
             const int64_t rj = (int64_t)b * L + j0 + j;
