@@ -104,6 +104,26 @@ __device__ __forceinline__ void warp_tile_load(const T* __restrict__ g, T* __res
     }
 }
 
+// cp.async edition of warp_tile_load (tile_load_wait(), then __syncwarp(), publishes the warp's slice)
+template <int W, int SLOT = W, typename T>
+__device__ __forceinline__ void warp_tile_load_async(const T* __restrict__ g, T* __restrict__ s, int64_t first, int count) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wcount = min(32, count - 32 * w);
+    if (wcount <= 0) return;
+    const T* src = g + (first + 32 * w) * W;
+    T* dst = s + 32 * w * SLOT;
+    constexpr int kPerVec = 16 / sizeof(T);
+    if (wcount == 32 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (32 * W) % kPerVec == 0) {
+        constexpr int nvec = 32 * W / kPerVec;
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+#pragma unroll
+        for (int i = lane; i < nvec; i += 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d + (uint32_t)i * 16u), "l"(reinterpret_cast<const float4*>(src) + i) : "memory");
+    } else {
+        for (int i = lane; i < wcount * W; i += 32) dst[i] = src[i];
+    }
+}
+
 template <int W, int SLOT = W, typename T>
 __device__ __forceinline__ void warp_tile_store(T* __restrict__ g, const T* __restrict__ s, int64_t first, int count) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;

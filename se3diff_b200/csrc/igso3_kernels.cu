@@ -362,8 +362,9 @@ k_sample(const float* __restrict__ sigma, const float* __restrict__ sigma_grid, 
     const int count = (int)min((int64_t)kTile, n - first);
     // three independent fetches per rotation -- the operand tiles, (sigma, u), and the guide record that depends on (sigma, u)
     // -- are put in flight together: the tiles by cp.async, so the table lookup proceeds under them
-    if (x) tile_load_async<9>(x, s_rot, first, count);
-    if (normals) tile_load_async<3>(normals, s_nrm, first, count);
+    // (per warp: each warp moves, computes and stores its own 32 rotations; only __syncwarp() between the phases)
+    if (x) warp_tile_load_async<9>(x, s_rot, first, count);
+    if (normals) warp_tile_load_async<3>(normals, s_nrm, first, count);
     const int t = threadIdx.x;
     const int64_t e = first + t;
     int stop = 0;
@@ -402,7 +403,7 @@ k_sample(const float* __restrict__ sigma, const float* __restrict__ sigma_grid, 
         }
     }
     tile_load_wait();
-    __syncthreads();
+    __syncwarp();
     if (t < count) {
         if (normals) { nx = s_nrm[t * 3]; ny = s_nrm[t * 3 + 1]; nz = s_nrm[t * 3 + 2]; }
         const int start = stop > 0 ? stop - 1 : 0;
@@ -433,8 +434,8 @@ k_sample(const float* __restrict__ sigma, const float* __restrict__ sigma_grid, 
         }
         if (angle_out) angle_out[e] = ang;
     }
-    __syncthreads();
-    tile_store<9>(out, s_rot, first, count);
+    __syncwarp();
+    warp_tile_store<9>(out, s_rot, first, count);
 }
 
 inline int series_grid(int64_t n) {
