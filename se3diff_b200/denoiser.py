@@ -85,16 +85,16 @@ def _fields(sdes):
 
 
 # ------------------------------------------------------------------------------------------------
-# CUDA-graph replay of the deterministic dpm loop.  All per-step quantities are kernel arguments fixed at capture
-# time and the loop has no host synchronisation, so the whole 2*num_steps network evaluations + frame updates of one
-# call are a single graph launch.  Used when the same device-resident batch (same embedding tensors), model and SDEs
+# CUDA-graph replay of a whole sampler loop (dpm_solver; since r1l also the plain Euler-Maruyama and Heun loops).  All
+# per-step quantities are kernel arguments fixed at capture time and the loops have no host synchronisation, so the
+# network evaluations + frame updates (+ noise draws) of one call are a single graph launch.  Used when the same device-resident batch (same embedding tensors), model and SDEs
 # come back: first call eager, second call captures, later calls replay.  SE3DIFF_B200_CUDA_GRAPH=0 disables it.
 _GRAPHS: "collections.OrderedDict" = None  # type: ignore[assignment]
 _GRAPH_SEEN: set = set()
 _MAX_GRAPHS = 4
 
 
-def _graph_key(batch, sdes, so3, score_model, num_steps, max_t, min_t, device):
+def _graph_key(batch, sdes, so3, score_model, num_steps, max_t, min_t, device, tag=("dpm",)):
     import os
 
     from .models import DiGConditionalScoreModel
@@ -110,7 +110,7 @@ def _graph_key(batch, sdes, so3, score_model, num_steps, max_t, min_t, device):
     ctx = nn_._context(batch)       # by identity, else by exact value: a fresh Batch of the same sequence maps to the same context
     key = (id(score_model), id(ctx), nn_.precision, nn_._weights_version(), nn_.x1d_proj[1].weight.data_ptr(), tuple(batch["pos"].shape),
            id(so3), sc.data_ptr(), sc._version, so3.sigma_min, so3.sigma_max, getattr(sdes["pos"], "s", None), num_steps, max_t, min_t,
-           str(device))
+           str(device), tag)
     return key, (score_model, ctx, nn_._layer_weights(torch.bfloat16 if nn_.precision == "bf16" else torch.float32), so3, sc)
 
 
@@ -128,7 +128,14 @@ def _dpm_loop(batch, score_model, steps, device):
 
 
 def _dpm_graphed(key, keep_alive, batch, score_model, steps, device):
+    return _loop_graphed(key, keep_alive, batch, lambda static: _dpm_loop(static, score_model, steps, device), device)
+
+
+def _loop_graphed(key, keep_alive, batch, loop_fn, device):
     """Returns the denoised batch through capture/replay, or None when this key has only been seen once.
+    `loop_fn(batch) -> batch` is the whole sampler loop after the prior draw.  Loops that draw noise (Euler-Maruyama, Heun)
+    are captured too: torch's CUDA generator hands a captured graph its seed and offset at every replay, so a replay
+    consumes the generator exactly like the eager loop (same seed => same trajectory; `test_em_heun_loop_graphs_match_eager`).
     `keep_alive` are the objects whose device pointers the graph bakes in (context, cached weights, SDE tables); the
     entry owns them so that a replay can never read recycled memory."""
     import collections
@@ -151,7 +158,7 @@ def _dpm_graphed(key, keep_alive, batch, score_model, steps, device):
         before = ops.launch_count()
         torch.cuda.synchronize(device)
         with torch.cuda.graph(graph):
-            out = _dpm_loop(static, score_model, steps, device)
+            out = loop_fn(static)
         entry.update(graph=graph, pos_out=out["pos"], rot_out=out["node_orientations"], launches=ops.launch_count() - before)
         ops.count_replayed_launches(-entry["launches"])     # recorded, not executed: the replay below is what runs
         _GRAPHS[key] = entry
@@ -205,6 +212,22 @@ def _em_loop(batch, sdes, score_model, finetune_model, num_steps, max_t, min_t, 
     fields = _fields(sdes)
     record = finetune_model is not None
     lengths = batch_lengths(batch) if record else None
+    if not record and not S._HOST_NOISE:
+        def plain(b):
+            for st in steps:
+                out = score_model(b, _t(st.t, B, device))
+                z = {f: S.noise_randn((b["pos"].shape[0], 3), device) for f in fields}  # per-field draw order = sdes key order
+                rot, pos, _, _ = ops.frame_update_em(b["node_orientations"], b["pos"], out["node_orientations"], out["pos"],
+                                                     z["node_orientations"], z["pos"], st.scalars)
+                b = b.replace(pos=pos, node_orientations=rot)
+            return b
+
+        keyed = _graph_key(batch, sdes, so3, score_model, num_steps, max_t, min_t, device, tag=("em", tuple(fields)))
+        if keyed is not None:
+            done = _loop_graphed(keyed[0], keyed[1], batch, plain, device)
+            if done is not None:
+                return done
+        return plain(batch)
     batches, us, dWs = [batch], defaultdict(list), defaultdict(list)
     for st in steps:
         t = _t(st.t, B, device)
@@ -309,22 +332,30 @@ def _heun_loop(batch, sdes, score_model, finetune_model, num_steps, max_t, min_t
             for _ in fields:
                 torch.randn(n, 3)
 
-    for st in steps:
-        pos, rot = batch["pos"], batch["node_orientations"]
-        z = {f: S.noise_randn((n, 3), device) for f in fields}
-        rot_h, pos_h = ops.frame_heun_churn(rot, pos, z["node_orientations"], z["pos"], st.scalars)
-        batch_hat = batch.replace(pos=pos_h, node_orientations=rot_h)
-        out_h = score_model(batch_hat, _t(st.t_hat, B, device))
-        draws()
-        rot1, pos1 = ops.frame_heun_predict(rot_h, pos_h, out_h["node_orientations"], out_h["pos"], st.scalars)
-        batch = batch.replace(pos=pos1, node_orientations=rot1)
-        if st.correct:
-            out_n = score_model(batch, _t(st.t_next, B, device))
+    def loop(batch):
+        for st in steps:
+            pos, rot = batch["pos"], batch["node_orientations"]
+            z = {f: S.noise_randn((n, 3), device) for f in fields}
+            rot_h, pos_h = ops.frame_heun_churn(rot, pos, z["node_orientations"], z["pos"], st.scalars)
+            batch_hat = batch.replace(pos=pos_h, node_orientations=rot_h)
+            out_h = score_model(batch_hat, _t(st.t_hat, B, device))
             draws()
-            rot2, pos2 = ops.frame_heun_correct(rot_h, pos_h, out_h["node_orientations"], out_h["pos"], pos1,
-                                                out_n["node_orientations"], out_n["pos"], st.scalars)
-            batch = batch.replace(pos=pos2, node_orientations=rot2)
-    return batch
+            rot1, pos1 = ops.frame_heun_predict(rot_h, pos_h, out_h["node_orientations"], out_h["pos"], st.scalars)
+            batch = batch.replace(pos=pos1, node_orientations=rot1)
+            if st.correct:
+                out_n = score_model(batch, _t(st.t_next, B, device))
+                draws()
+                rot2, pos2 = ops.frame_heun_correct(rot_h, pos_h, out_h["node_orientations"], out_h["pos"], pos1,
+                                                    out_n["node_orientations"], out_n["pos"], st.scalars)
+                batch = batch.replace(pos=pos2, node_orientations=rot2)
+        return batch
+
+    keyed = _graph_key(batch, sdes, so3, score_model, num_steps, max_t, min_t, device, tag=("heun", float(noise), tuple(fields)))
+    if keyed is not None:                                   # (None under host noise, with a foreign score model, ...)
+        done = _loop_graphed(keyed[0], keyed[1], batch, loop, device)
+        if done is not None:
+            return done
+    return loop(batch)
 
 
 @torch.no_grad()

@@ -1185,3 +1185,33 @@ def test_r3_translation_kernels_equal_the_fused_frame_kernels(n, offset):
     buf = pos.clone()
     ops.r3_update_em(buf, m_pos, z_pos, sc, pos_out=buf)
     assert torch.equal(buf, want)
+
+
+@pytest.mark.parametrize("sampler,extra", [("euler_maruyama_predictor", {}), ("heun_denoiser", {"noise": 0.5})])
+def test_em_heun_loop_graphs_match_eager(sampler, extra, monkeypatch):
+    """The stochastic samplers replay a captured CUDA graph of their whole loop from the second call with the same context.
+    A replay takes its Philox seed and offset from torch's CUDA generator like the eager loop does: with the same seed it
+    must reproduce the eager trajectory bit for bit, and a different seed must give a different one."""
+    from se3diff_b200 import denoiser, shortcuts
+
+    g, m, fm, sdes, batch, S = _traj_setup()
+    m = m.to(DEV)
+    sdes["node_orientations"] = sdes["node_orientations"].to(DEV)
+    kw = dict(batch=batch.to(DEV), sdes=sdes, score_model=m, num_steps=5, max_t=0.99, min_t=0.001, device=DEV, **extra)
+    fn = getattr(shortcuts, sampler)
+    monkeypatch.setenv("SE3DIFF_B200_CUDA_GRAPH", "0")
+    torch.manual_seed(5)
+    ref = fn(**kw)
+    torch.manual_seed(6)
+    other = fn(**kw)
+    monkeypatch.setenv("SE3DIFF_B200_CUDA_GRAPH", "1")
+    tag = "em" if sampler.startswith("euler") else "heun"
+    outs = []
+    for i in range(4):
+        torch.manual_seed(6 if i == 2 else 5)
+        outs.append(fn(**kw))
+    assert any(k[-1][0] == tag for k in denoiser._GRAPHS), "second call must have captured a graph of this loop"   # (LRU of 4)
+    for i, o in enumerate(outs):
+        want = other if i == 2 else ref
+        assert torch.equal(o["pos"], want["pos"]) and torch.equal(o["node_orientations"], want["node_orientations"]), i
+    assert not torch.equal(ref["pos"], other["pos"])
