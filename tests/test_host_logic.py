@@ -286,3 +286,19 @@ def test_ipa_backward_shape_gate_and_cpu_refusal():
                                torch.zeros(2), 0.5, sh)
     with pytest.raises(_lib.Se3LibraryError):
         ops.r3_update_dpm(torch.zeros(4, 3), torch.zeros(4, 3), _lib.DpmScalars(), final_half=False)
+
+
+def test_bench_stdout_carries_only_the_result_line():
+    """bench.claim_stdout(): whatever native code prints on file descriptor 1 during the run (NCCL's version banner under
+    torchrun) goes to stderr; the one JSON line goes to the real stdout."""
+    import subprocess
+    import sys
+
+    code = ("import os, sys, json; sys.path.insert(0, %r); import bench; out = bench.claim_stdout(); "
+            "os.write(1, b'NCCL version 2.28.9+cuda12.9\\n'); print('python-level chatter'); "
+            "print(json.dumps({'metric': 'm', 'value': 1.0}), file=out, flush=True)") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert lines == ['{"metric": "m", "value": 1.0}'], r.stdout
+    assert "NCCL version" in r.stderr and "python-level chatter" in r.stderr
