@@ -302,3 +302,43 @@ def test_bench_stdout_carries_only_the_result_line():
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert lines == ['{"metric": "m", "value": 1.0}'], r.stdout
     assert "NCCL version" in r.stderr and "python-level chatter" in r.stderr
+
+
+def test_einsum_attention_formulation_equals_the_oracle_on_cpu():
+    """`DistributionalGraphormer._ipa_torch` (the autograd formulation the backward kernel is tested against, fp64, on the
+    GPU) evaluated on CPU tensors against `ScoreModelOracle._ipa`, the restatement pinned bit-exactly to the reference's
+    SAAttention.forward (structure_module.py:109-220): values in fp32 and fp64, and fp64 gradients of a linear functional."""
+    from oracle.score_model import ScoreModelOracle
+    from se3diff_b200.models import DistributionalGraphormer, SAAttention
+
+    torch.manual_seed(3)
+    B, n, H, dk, dp = 2, 19, 4, 16, 32
+    D = H * dk
+    a = SAAttention(D, dp, H, dropout=0.0)
+    x1d, x2d = torch.randn(B, n, D), torch.randn(B, n, n, dp)
+    T = torch.randn(B, n, 3) * 2.0
+    R = torch.linalg.qr(torch.randn(B, n, 3, 3))[0]
+    R = R * torch.sign(torch.linalg.det(R))[..., None, None]
+    bias = torch.zeros(B, 1, 1, n)
+    bias[1, ..., n - 3:] = float("-inf")
+    pre = "st_module.encoder.layers.0.attn."
+    sd = {"model_nn." + pre + k: v for k, v in a.state_dict().items()}
+    sd["model_nn.x1d_proj.1.weight"] = torch.zeros(D, 4)
+    with torch.no_grad():
+        want = ScoreModelOracle(sd, num_heads=H)._ipa(x1d, x2d, T, R, bias, pre)
+        got = DistributionalGraphormer._ipa_torch(a, x1d, x2d, T, R, bias)
+    assert (got - want).abs().max() <= 2e-6 * want.abs().max()
+    # fp64: values and gradients (autograd through both formulations)
+    a64 = SAAttention(D, dp, H, dropout=0.0).double()
+    a64.load_state_dict({k: v.double() for k, v in a.state_dict().items()})
+    orc = ScoreModelOracle(sd, num_heads=H)
+    orc.p = {k: v.double().requires_grad_(True) for k, v in orc.p.items()}
+    x1, x2 = x1d.double().requires_grad_(True), x2d.double().requires_grad_(True)
+    w = torch.randn(B, n, D, dtype=torch.float64)
+    (orc._ipa(x1, x2, T.double(), R.double(), bias.double(), pre) * w).sum().backward()
+    g_want = (x1.grad.clone(), x2.grad.clone(), orc.p[pre + "trained_point_weight"].grad.clone(), orc.p[pre + "pair_value.weight"].grad.clone())
+    x1.grad = x2.grad = None
+    (DistributionalGraphormer._ipa_torch(a64, x1, x2, T.double(), R.double(), bias.double()) * w).sum().backward()
+    g_got = (x1.grad, x2.grad, a64.trained_point_weight.grad, a64.pair_value.weight.grad)
+    for u, v in zip(g_got, g_want):
+        assert (u - v).abs().max() <= 1e-6 * v.abs().max()      # the reference aggregates the points in fp32 (:193-196) even in an fp64 run
