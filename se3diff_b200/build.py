@@ -25,6 +25,7 @@ SOURCES = {
     "ipa_bwd.cu": [],
     "tc_selftest.cu": [],
     "ipa_tc.cu": [],
+    "ipa_tc_pp.cu": [],
     "fused_rows.cu": [],
     "observables.cu": [],
     "backbone.cu": [],

@@ -31,20 +31,12 @@
 
 #include <type_traits>
 
-#include "common.cuh"
-#include "tc_common.cuh"
+#include "ipa_tc_shared.cuh"
 
 using namespace se3;
+using namespace se3::ipa_tc;
 
 namespace {
-
-constexpr int DK = 16, PQ = 4, PV = 8;
-constexpr int NV = 80;   // accumulator columns of the second product: v 16 | v_pt hi 24 | v_pt lo 24 | ones 1 | 15 x zero
-constexpr int NVP = 64;  // ... of which the point operand (hi | lo | ones | zero) is a separate N = 64 MMA
-constexpr float kLog2e = 1.4426950408889634f;
-
-__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // thread-block cluster primitives (split edition)
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -63,18 +55,6 @@ __device__ __forceinline__ float ld_peer_f32(const float* own_smem_ptr, uint32_t
     float v;
     asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
     return v;
-}
-
-// N contiguous outputs (N % 8 == 0, destination 16-byte aligned) as 128-bit stores
-template <int N> __device__ __forceinline__ void store_vec(float* dst, const float (&v)[N]) {
-#pragma unroll
-    for (int c = 0; c < N / 4; ++c) reinterpret_cast<float4*>(dst)[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-}
-template <int N> __device__ __forceinline__ void store_vec(__nv_bfloat16* dst, const float (&v)[N]) {
-#pragma unroll
-    for (int c = 0; c < N / 8; ++c)
-        reinterpret_cast<uint4*>(dst)[c] = make_uint4(tc::pack_bf16(v[8 * c], v[8 * c + 1]), tc::pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                                                      tc::pack_bf16(v[8 * c + 4], v[8 * c + 5]), tc::pack_bf16(v[8 * c + 6], v[8 * c + 7]));
 }
 
 struct Pass1Smem {
@@ -121,35 +101,6 @@ __device__ __forceinline__ Pass1Smem carve1(uint8_t* base, int L, int LK, int Lp
     s.raw = wide ? reinterpret_cast<float*>(after) : reinterpret_cast<float*>(s.p);
     s.xo = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s.raw) + (size_t)LK * 192);   // split edition only
     return s;
-}
-
-// N consecutive coordinates (N % 4 == 0) of a point record starting at element `first` (a multiple of 4): fp32 records are read
-// as float4, bf16 records (4 values per 8-byte load) are widened
-template <bool kBf16, int N>
-__device__ __forceinline__ void load_coords(const void* row, int first, float (&l)[N]) {
-    if constexpr (kBf16) {
-        const uint2* p = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(row) + first * 2);
-#pragma unroll
-        for (int c = 0; c < N / 4; ++c) {
-            const uint2 v = p[c];
-            l[4 * c] = __uint_as_float(v.x << 16); l[4 * c + 1] = __uint_as_float(v.x & 0xffff0000u);
-            l[4 * c + 2] = __uint_as_float(v.y << 16); l[4 * c + 3] = __uint_as_float(v.y & 0xffff0000u);
-        }
-    } else {
-        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(row) + first);
-#pragma unroll
-        for (int c = 0; c < N / 4; ++c) {
-            const float4 v = p[c];
-            l[4 * c] = v.x; l[4 * c + 1] = v.y; l[4 * c + 2] = v.z; l[4 * c + 3] = v.w;
-        }
-    }
-}
-
-// global = R.local + T for one point
-__device__ __forceinline__ void to_global(const float (&R)[9], const float (&T)[3], float x, float y, float z, float& gx, float& gy, float& gz) {
-    gx = R[0] * x + R[1] * y + R[2] * z + T[0];
-    gy = R[3] * x + R[4] * y + R[5] * z + T[1];
-    gz = R[6] * x + R[7] * y + R[8] * z + T[2];
 }
 
 // kSplit = false: one CTA per (sample, head, query tile), all keys (L <= 256).   LpB = LpT = L rounded up to 16.
@@ -658,29 +609,9 @@ k_ipa_tc_pass2(const __grid_constant__ CUtensorMap map_p, const float* __restric
 
 long long* g_phase_dbg = nullptr;  // set by se3_debug_set_phase_buffer
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
-        return (EncodeTiledFn)p;
-    }();
-    return fn;
-}
-// row-major [rows][cols] matrix with a row pitch; box = box_cols x box_rows elements, dense in shared memory
-int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems,
-                uint32_t box_cols, uint32_t box_rows, const char* what, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_NONE) {
-    EncodeTiledFn fn = encode_tiled_fn();
-    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SE3_ECUDA; }
-    const cuuint64_t dims[2] = {cols, rows}, strides[1] = {pitch_elems * (uint64_t)elem_bytes};
-    const cuuint32_t box[2] = {box_cols, box_rows}, estr[2] = {1, 1};
-    const CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
-                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("tensor map for %s: cuTensorMapEncodeTiled failed with %d", what, (int)r); return SE3_ECUDA; }
-    return SE3_OK;
+bool pingpong_disabled() {   // work in progress: opt-in with SE3DIFF_B200_IPA_PP=1 until it beats the one-item-per-CTA edition
+    const char* v = getenv("SE3DIFF_B200_IPA_PP");
+    return !(v && v[0] == '1');
 }
 
 template <typename OutT, bool kPtsBf16>
@@ -723,7 +654,21 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const void* pts, int p
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
     const int n_items = ntile * sh.heads * sh.batch;
-    if (!split) {
+    // L <= 128: the warp-specialised ping-pong edition (ipa_tc_pp.cu) when its shared-memory plan fits; SE3DIFF_B200_IPA_PP=0 keeps
+    // the one-item-per-CTA edition below (A/B timing)
+    bool pass1_done = false;
+    if (L <= 128 && !pingpong_disabled()) {
+        Pass1Args a;
+        a.scal = scal; a.scal_stride = scal_stride; a.pts = pts; a.pts_stride = pts_stride; a.pts_bf16 = kPtsBf16;
+        a.rot = rot; a.trans = trans; a.pair_bias = pair_bias; a.key_bias = key_bias; a.head_weight = head_weight;
+        a.out = out; a.out_bf16 = std::is_same<OutT, __nv_bfloat16>::value; a.pbuf = pbuf; a.inv_sum = inv_sum;
+        a.sh = sh; a.Lp = Lp; a.Bpad = Bpad; a.stream = st;
+        const int rc = launch_pass1_pingpong(a);
+        if (rc == SE3_OK) pass1_done = true;
+        else if (rc != SE3_EUNSUPPORTED) return rc;
+    }
+    if (pass1_done) {
+    } else if (!split) {
         auto k1 = wide ? k_ipa_tc_pass1<OutT, false, true, kPtsBf16> : k_ipa_tc_pass1<OutT, false, false, kPtsBf16>;
         e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e != cudaSuccess) { set_error("ipa_tc pass1 smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
@@ -755,9 +700,10 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const void* pts, int p
                                pts, pts_stride, g_phase_dbg);
         if (e != cudaSuccess) { set_error("ipa_tc pass1 (split) launch: %s", cudaGetErrorString(e)); return SE3_ECUDA; }
     }
-    count_launch();
-    int rc = check_launch("se3_ipa_attention_tc_fwd(pass 1)");
-    if (rc) return rc;
+    if (!pass1_done) {
+        count_launch();
+        if (int rc = check_launch("se3_ipa_attention_tc_fwd(pass 1)")) return rc;
+    }
     const size_t smem2 = (size_t)((Lp + 63) / 64) * 16384 + (size_t)Lp * 32 + 1024;   // + slack for the 1024-byte alignment of the swizzled tiles
     auto k2 = k_ipa_tc_pass2<OutT>;
     e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
