@@ -36,3 +36,5 @@ print("item", k, "consumer chunk-ready stamps (rel. to item start):", [round(v) 
 print("item", k, "issuer: ops_ready seen", round(rel[k, 24].item()), " chunk issue times", [round(v) for v in rel[k, 16:24].tolist()], " p_ready seen", round(rel[k, 25].item()), " P.V committed", round(rel[k, 26].item()))
 print("mean over items: ops_ready seen", round(rel[:, 24].mean().item()), "chunk-ready", [round(v) for v in rel[:, 8:14].mean(0).tolist()], "issue", [round(v) for v in rel[:, 18:22].mean(0).tolist()],
       "p_ready seen", round(rel[:, 25].mean().item()), "P.V committed", round(rel[:, 26].mean().item()), "consumer stamps", [round(v) for v in rel[:, :8].mean(0).tolist()])
+print("mean: group 0 chunk 0: ready", round(rel[:, 8].mean().item()), "loaded", round(rel[:, 27].mean().item()), "math+store done", round(rel[:, 28].mean().item()),
+      "| issuer chunk 2: issue start", round(rel[:, 18].mean().item()), "committed", round(rel[:, 30].mean().item()), "| group 0 sees chunk 2", round(rel[:, 10].mean().item()))

@@ -1,4 +1,4 @@
-// K4, pass 1 of the tensor-core IPA operator for L <= 128: the warp-specialised "ping-pong" edition.
+// K4, pass 1 of the tensor-core IPA operator for L <= 96: the warp-specialised "ping-pong" edition.
 //
 // What is different from the one-item-per-CTA edition in ipa_tc.cu (structure_module.py:168-186):
 //
@@ -9,27 +9,24 @@
 //        b(j) = [  kh(3) |   kl(3) |   kh(3) |   kl(3) | 256 256   | nk_h nk_l]      a.b = |q|^2 + |k|^2 - 2 q.k
 //    with x = xh + xl (fp16 pair: 22 significant bits, coordinates re-centred on the sample's first residue) and
 //    n = |x|^2 / 256 split the same way (products with the exact constant 256 restore the scale; |x - x_0| < 4000 nm).
-//    The logit pass then costs 4 MUFU.SQRT + ~8 other instructions per key instead of ~29 (no subtractions, no squares, no
-//    key points in shared memory), which moves it from the issue / FMA / XU triple point onto the XU roof alone.
-//  * One persistent CTA per SM runs TWO consumer warpgroups (256 threads each: two threads per query row -- "groups" 0 and 1 --
-//    taking the even / odd 16-key chunks) and two issuer warps (one lane each: TMA loads and every tcgen05.mma of its
-//    warpgroup's items).  The warpgroups work on different items and hand the XU-bound phase (logits + exponentials) to
-//    each other through a pair of named barriers, so one warpgroup's staging / frame transforms / P.V product / epilogue run
-//    under the other's square roots.  The distance accumulators are produced in 16-key chunks into one 64-column TMEM
-//    stage per group: a chunk is pulled into registers, the stage is handed back to the issuer, and the group's next
-//    chunk's MMAs run under the square roots of this one; the two groups of a row share an SM sub-partition and fall into
-//    complementary phases (one waits / loads while the other feeds the XU pipe).
-//    Registers: 640 threads are launched with 96 registers each (61,440: the CTA's pool); the consumers raise their budget to
-//    104 with setmaxnreg, which the issuer warpgroup (two working warps, two idle) pays for by dropping to 64.
+//    The logit pass then costs 4 MUFU.SQRT + ~9 other instructions per key instead of ~29 (no subtractions, no squares, no
+//    key points in shared memory).
+//  * One persistent CTA (512 threads, 128 registers each) per SM runs TWO warpgroups on different items.  In a warpgroup the six
+//    warps that own TMEM lanes 0..95 are the consumers: two threads per query row -- "groups" 0 and 1 -- taking the even / odd
+//    16-key chunks.  The warp of lane quadrant 3 (rows 96..127 do not exist for L <= 96) is the ISSUER: one lane issues
+//    every TMA load and every tcgen05.mma of the warpgroup's items and never touches data.  The distance accumulators
+//    are produced chunk by chunk into one 64-column TMEM stage per group: a chunk is pulled into registers (80 of them),
+//    the stage is handed back to the issuer, and the group's next chunk is contracted under the square roots of this one.
+//    The warpgroups can hand the XU-bound phase (logits + exponentials) to each other through a pair of named barriers,
+//    so that one warpgroup's staging / frame transforms / P.V product / epilogue run under the other's square roots.
 //
 // Per item (sample b, head h) and warpgroup:
 //   issuer   TMA: bf16 q | k | v records as UMMA K-chunks, the head's point records, the sample's frames (prefetched one item
-//            ahead: issued as soon as the previous S = Q.K^T has consumed q / k), the head's pair-bias slab
-//   group 0  key side of the frame transform: 4 key points -> global, re-centred, hi/lo fp16 rows of the B operands;
-//            8 value points -> hi/lo bf16 MN-major operand with the ones column (as in ipa_tc.cu)
-//   group 1  query side: 4 query points -> rows of the A operands
-//   issuer   S = Q.K^T (N = Lq), D_p chunks 0 and 1 (4 MMAs N = 16 each) -> one commit per stage
-//   XU phase (owning the ping-pong token)
+//            ahead), the head's pair-bias slab; S = Q.K^T as soon as q / k have landed
+//   group 0  4 key points -> global frame, re-centred, hi/lo fp16 rows of the B operands     } then the issuer contracts
+//   group 1  4 query points -> rows of the A operands                                        } D_p chunks 0 and 1
+//   both     value points 4g .. 4g+3 -> hi/lo bf16 channels of the MN-major value operand (off the critical path)
+//   XU phase
 //     pass A per 16-key chunk: tcgen05.ld S and the four D_p, release the stage, logits =
 //            S + hw * sum_p sqrt|D_p| + pair_bias + key_bias (log2 domain) parked back into the S columns, row maximum
 //     pass B: P = exp2(l - max) -> bf16 -> shared memory (A operand of P.V; overlays the dead point operands) and the row
@@ -48,16 +45,18 @@ using namespace se3::ipa_tc;
 
 namespace {
 
-constexpr int kThreadsPP = 640;          // 2 consumer warpgroups x 256 + one warpgroup holding the 2 issuer warps (setmaxnreg works per 4 warps)
+constexpr int kThreadsPP = 512;          // 2 warpgroups x 8 warps: 6 consumers, 1 issuer, 1 helper
+constexpr int kConsumers = 192;          // consumer threads per warpgroup
+constexpr int kMaxLenPP = 96;
 constexpr int kTurn0 = 1, kTurn1 = 2;    // named barriers: permission to enter the XU phase
-constexpr int kWgBar0 = 3;               // + wg: barrier over the 256 threads of one warpgroup
+constexpr int kWgBar0 = 3;               // + wg: barrier over the consumers of one warpgroup
 constexpr float kNormScale = 1.0f / 256.0f;
 
 struct PpPlan {
     uint32_t raw, q, k, vs, vs_step, frm, frm_step, vp, ops, bias, kb, hmax, total;   // vs / frm: two buffers `step` bytes apart
     int Lq, Lpi, nck;                                                                 // keys padded to 16, bias row pitch, 16-key chunks
 };
-// Shared memory of ONE warpgroup.  Lq = keys padded to 16 (chunk size of the distance MMAs).
+// Shared memory of ONE warpgroup.
 __host__ __device__ inline PpPlan pp_plan(int L, bool pts_bf16) {
     const uint32_t Lq = (uint32_t)(L + 15) & ~15u, Lpi = (uint32_t)(L + 7) & ~7u;
     auto up = [](uint32_t x) { return (x + 127u) & ~127u; };
@@ -80,15 +79,25 @@ __host__ __device__ inline PpPlan pp_plan(int L, bool pts_bf16) {
 }
 
 struct PpBars {   // per warpgroup
-    uint64_t in_full, bias_full, ops_ready, st_full[2], st_free[2], p_ready, o_full;
+    uint64_t in_full, bias_full, ops_ready, raw_free, st_full[2], st_free[2], p_ready, o_full;
 };
 
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) { return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16); }
-__device__ __forceinline__ void split_h(float x, __half& h, __half& l) {
-    h = __float2half_rn(x);
-    l = __float2half_rn(x - __half2float(h));
+__device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+// (a, b) -> fp16 pair of the leading halves and fp16 pair of the remainders (F2FP packs; the scalar cvt runs on the XU pipe)
+__device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    hi = h2_bits(h);
+    lo = h2_bits(__floats2half2_rn(a - f.x, b - f.y));
+}
+// bf16 at a shared-window address -> float (32-bit address arithmetic; a generic pointer costs 64-bit adds and LD instead of LDS)
+__device__ __forceinline__ float lds_bf16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return __uint_as_float((uint32_t)v << 16);
 }
 __device__ __forceinline__ float sqrt_abs(float x) { return fast_sqrt(fabsf(x)); }
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // ---- issuer-side helpers (one thread) ---------------------------------------------------------------------------------
 // every input of item (b, h) except the pair-bias slab: point records, q / k / v K-chunks, frames -> `in_full`
@@ -140,8 +149,8 @@ k_ipa_tc_pass1_pp(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const int Lq = pl.Lq, Lpi = pl.Lpi, LpT = pl.Lq;
     const int nck = pl.nck;                                  // 16-key chunks; chunk c belongs to group c & 1
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool issuer = warp >= 16;
-    const int wg = issuer ? (warp - 16) & 1 : warp >> 3;     // warpgroup this thread belongs to / serves
+    const int wg = warp >> 3, wi = warp & 7;                 // warpgroup, warp within it
+    const int quad = wi & 3;                                 // TMEM lane quadrant this warp may touch (= warp % 4)
     uint8_t* base = smem_raw + (size_t)wg * pl.total;
     PpBars& bar = bars[wg];
     const bool bulk_frames = ((L & 3) == 0) && ((reinterpret_cast<uintptr_t>(rot) | reinterpret_cast<uintptr_t>(trans)) & 15) == 0;
@@ -160,15 +169,29 @@ k_ipa_tc_pass1_pp(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int w = 0; w < 2; ++w) {
             tc::mbar_init(&bars[w].in_full, 1);
             tc::mbar_init(&bars[w].bias_full, 1);
-            tc::mbar_init(&bars[w].ops_ready, 8);
+            tc::mbar_init(&bars[w].ops_ready, 6);
+            tc::mbar_init(&bars[w].raw_free, 6);
             tc::mbar_init(&bars[w].st_full[0], 1);
             tc::mbar_init(&bars[w].st_full[1], 1);
-            tc::mbar_init(&bars[w].st_free[0], 4);
-            tc::mbar_init(&bars[w].st_free[1], 4);
-            tc::mbar_init(&bars[w].p_ready, 8);
+            tc::mbar_init(&bars[w].st_free[0], 3);
+            tc::mbar_init(&bars[w].st_free[1], 3);
+            tc::mbar_init(&bars[w].p_ready, 6);
             tc::mbar_init(&bars[w].o_full, 1);
         }
         tc::mbar_fence_init();
+    }
+    if (wi == 7) {
+        // helper warp, once per kernel: the value operand's padding keys must be exactly zero (0 * garbage could be NaN) and keep
+        // logits of -inf; nothing else ever writes those rows.  (Padding rows of the distance operands only feed accumulator
+        // entries that are never read.)
+        float* s_kb = reinterpret_cast<float*>(base + pl.kb);
+        for (int j = lane; j < Lq; j += 32) s_kb[j] = j < L ? 0.f : -CUDART_INF_F;
+        for (int j = L + lane; j < Lq; j += 32) {
+            uint8_t* vcol = base + pl.vp + (size_t)(j >> 3) * (NVP * 16) + (size_t)(j & 7) * 16;
+#pragma unroll
+            for (int c = 0; c < NVP / 8; ++c) *reinterpret_cast<uint4*>(vcol + c * 128) = make_uint4(0, 0, 0, 0);
+        }
+        tc::fence_async_smem();
     }
     tc::fence_before();
     __syncthreads();
@@ -176,10 +199,9 @@ k_ipa_tc_pass1_pp(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const uint32_t tmem_s = tmem_slot + (uint32_t)wg * 256u;   // S / logits: Lq columns
     const uint32_t tmem_st = tmem_s + 128u;                    // two stages of 4 x 16 distance columns (one per group), later the O accumulator (80)
 
-    if (issuer) {
+    if (wi == 3) {
         // ================================ issuer warp: TMA + tcgen05.mma of warpgroup `wg` ================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        if (warp < 18 && lane == 0 && n_mine > 0) {
+        if (lane == 0 && n_mine > 0) {
             pp_issue_loads<kPtsBf16>(first, 0, L, Lq, H, base, pl, &map_q, &map_kv, &map_pts, rot, trans, bulk_frames, &bar.in_full);
             pp_issue_bias(first, L, Lpi, H, base + pl.bias, pair_bias_t, &bar.bias_full);
             const uint32_t a_ops = tc::smem_u32(base + pl.ops), b_ops = a_ops + 16384u;
@@ -188,14 +210,17 @@ k_ipa_tc_pass1_pp(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             uint32_t n_full0 = 0, n_free0 = 0, n_free1 = 0;   // completed phases of st_full[0] / phases of st_free[g] already waited for
             for (int it = 0; it < n_mine; ++it) {
                 const int item = first + it * stride, buf = it & 1;
+                tc::mbar_wait(&bar.in_full, (uint32_t)(it & 1));
+                tc::fence_after();                             // (the previous item's logits left the S columns before its p_ready)
+                tc::mma_bf16(tmem_s, tc::make_desc(tc::smem_u32(base + pl.q), 128), tc::make_desc(tc::smem_u32(base + pl.k), (uint32_t)Lq), idesc_s, false);
                 tc::mbar_wait(&bar.ops_ready, (uint32_t)(it & 1));
                 tc::fence_after();
                 if (dbg) dbg[(int64_t)item * 32 + 24] = clock64();
-                tc::mma_bf16(tmem_s, tc::make_desc(tc::smem_u32(base + pl.q), 128), tc::make_desc(tc::smem_u32(base + pl.k), (uint32_t)Lq), idesc_s, false);
                 pp_issue_dist(0, tmem_st, a_ops, b_ops, Lq, idesc_d, &bar.st_full[0]);
                 if (nck > 1) pp_issue_dist(1, tmem_st, a_ops, b_ops, Lq, idesc_d, &bar.st_full[1]);
-                if (it + 1 < n_mine) {         // q / k / raw points are dead once S exists: prefetch the next item's inputs
+                if (it + 1 < n_mine) {         // q / k are dead once S exists, the point records once the value points are transformed
                     tc::mbar_wait(&bar.st_full[0], n_full0 & 1u);
+                    tc::mbar_wait(&bar.raw_free, (uint32_t)(it & 1));
                     pp_issue_loads<kPtsBf16>(item + stride, buf ^ 1, L, Lq, H, base, pl, &map_q, &map_kv, &map_pts, rot, trans, bulk_frames, &bar.in_full);
                 }
                 n_full0 += (uint32_t)((nck + 1) >> 1);
@@ -205,6 +230,7 @@ k_ipa_tc_pass1_pp(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     tc::fence_after();
                     if (dbg) dbg[(int64_t)item * 32 + 16 + c] = clock64();
                     pp_issue_dist(c, tmem_st, a_ops, b_ops, Lq, idesc_d, &bar.st_full[c & 1]);
+                    if (dbg && c == 2) dbg[(int64_t)item * 32 + 30] = clock64();
                 }
                 tc::mbar_wait(&bar.p_ready, (uint32_t)(it & 1));
                 tc::fence_after();
@@ -221,15 +247,14 @@ k_ipa_tc_pass1_pp(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             }
         }
         __syncwarp();
-    } else {
-        // ================================ consumer warpgroup ================================================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-        const int t = tid & 255;                             // thread within the warpgroup
-        const int g = t >> 7;                                // group: even / odd 16-key chunks; which side of the transform
-        const int row = t & 127;                             // query row = TMEM lane (also: residue of the transform)
-        const uint32_t lane_base = (uint32_t)((warp & 3) * 32);
+    } else if (wi != 7) {
+        // ================================ consumer warps (TMEM lane quadrants 0..2) =========================================
+        const int g = wi >> 2;                               // group: even / odd 16-key chunks; which side of the transform
+        const int row = quad * 32 + lane;                    // query row = TMEM lane (also: residue of the transform), 0..95
+        const int t = g * 96 + row;                          // consumer index within the warpgroup
+        const uint32_t lane_base = (uint32_t)(quad * 32);
         const bool row_ok = row < L;
-        const bool warp_ok = (warp & 3) * 32 < L;
+        const bool warp_ok = quad * 32 < L;
         const int wgbar = kWgBar0 + wg;
         const int my_turn = wg ? kTurn1 : kTurn0, other_turn = wg ? kTurn0 : kTurn1;
         float* s_kb = reinterpret_cast<float*>(base + pl.kb);
@@ -238,7 +263,7 @@ k_ipa_tc_pass1_pp(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         uint8_t* s_ops = base + pl.ops;
         uint32_t n_full = 0;
 #define SE3_STAMP(k) do { if (dbg && t == 0) dbg[((int64_t)(first + it * stride)) * 32 + (k)] = clock64(); } while (0)
-        if (use_turns && wg == 1 && n_other > 0) tc::bar_arrive(kTurn0, 512);   // warpgroup 0 goes first
+        if (use_turns && wg == 1 && n_other > 0) tc::bar_arrive(kTurn0, 2 * kConsumers);   // warpgroup 0 goes first
 
         for (int it = 0; it < n_mine; ++it) {
             const int item = first + it * stride, buf = it & 1;
@@ -247,168 +272,158 @@ k_ipa_tc_pass1_pp(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             tc::mbar_wait(&bar.in_full, (uint32_t)(it & 1));
             SE3_STAMP(1);
             const float* s_rot = reinterpret_cast<const float*>(base + pl.frm + buf * pl.frm_step);
-            const float* s_trn = s_rot + L * 9;
-            const float* g_rot = rot + (int64_t)b * L * 9;
-            const float* g_trn = trans + (int64_t)b * L * 3;
-            const float* f_rot = bulk_frames ? s_rot : g_rot;      // unaligned sample blocks: frames straight from global memory
-            const float* f_trn = bulk_frames ? s_trn : g_trn;
+            const float* f_rot = bulk_frames ? s_rot : rot + (int64_t)b * L * 9;        // unaligned sample blocks: frames straight from global memory
+            const float* f_trn = bulk_frames ? s_rot + L * 9 : trans + (int64_t)b * L * 3;
             const float cx = f_trn[0], cy = f_trn[1], cz = f_trn[2];   // re-centring: the sample's first residue
 
-            // ---- frame transform, one thread per (residue, group): group 0 = the key points (rows of the B operands), group 1 = the
-            //      query points (rows of the A operands); value points 4g .. 4g+3 (hi / lo bf16 channels of the MN-major operand)
+            // ---- frame transform, one thread per (residue, group) ------------------------------------------------------------
+            float R[9], T[3];
+            const uint8_t* rawrow = base + pl.raw + (size_t)(row_ok ? row : 0) * kRawRow;
             {
-                // rows of the distance operands: chunk 0 at +0, chunk 1 at +k1 (16 bytes per row), point p at +p * pstep
-                const uint32_t pstep = g ? 4096u : (uint32_t)Lq * 32u, k1 = g ? 2048u : (uint32_t)Lq * 16u;
-                uint8_t* drow = s_ops + (g ? 0 : 16384) + (size_t)row * 16;
-                uint8_t* vcol = base + pl.vp + (size_t)(row >> 3) * (NVP * 16) + (size_t)(row & 7) * 16;   // 16-byte channel chunk c of this key at + c * 128
-                const int nrows = g ? 128 : Lq;
-                if (row < L) {
-                    float R[9], T[3];
+                const int r = row_ok ? row : 0;
 #pragma unroll
-                    for (int c = 0; c < 9; ++c) R[c] = f_rot[row * 9 + c];
-                    T[0] = f_trn[row * 3] - cx; T[1] = f_trn[row * 3 + 1] - cy; T[2] = f_trn[row * 3 + 2] - cz;
-                    const uint8_t* rawrow = base + pl.raw + (size_t)row * kRawRow;
-                    {
-                        float l[12];
-                        load_coords<kPtsBf16, 12>(rawrow, g ? 0 : 12, l);
-                        const __half c256 = __float2half_rn(256.f);
-                        const float sc = g ? -2.f : 1.f;           // the query side carries the factor of -2 q.k (exact, commutes with the split)
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) {
-                            float gx, gy, gz;
-                            to_global(R, T, l[3 * p], l[3 * p + 1], l[3 * p + 2], gx, gy, gz);
-                            __half hx, lx, hy, ly, hz, lz, nh, nl;
-                            split_h(sc * gx, hx, lx); split_h(sc * gy, hy, ly); split_h(sc * gz, hz, lz);
-                            split_h((gx * gx + gy * gy + gz * gz) * kNormScale, nh, nl);
-                            uint8_t* dst = drow + (size_t)p * pstep;
-                            if (g) {   // a = [h h l | l n n 256 256]
-                                *reinterpret_cast<uint4*>(dst) = make_uint4(pack_h2(hx, hy), pack_h2(hz, hx), pack_h2(hy, hz), pack_h2(lx, ly));
-                                *reinterpret_cast<uint4*>(dst + k1) = make_uint4(pack_h2(lz, lx), pack_h2(ly, lz), pack_h2(nh, nl), pack_h2(c256, c256));
-                            } else {   // b = [h l h | l 256 256 n n]
-                                *reinterpret_cast<uint4*>(dst) = make_uint4(pack_h2(hx, hy), pack_h2(hz, lx), pack_h2(ly, lz), pack_h2(hx, hy));
-                                *reinterpret_cast<uint4*>(dst + k1) = make_uint4(pack_h2(hz, lx), pack_h2(ly, lz), pack_h2(c256, c256), pack_h2(nh, nl));
-                            }
-                        }
-                    }
-                    {
-                        // value points 4g .. 4g+3 = channels 12g .. 12g+11 of the 24 hi (and of the 24 lo) channels:
-                        // group 0: chunk 0 and the first half of chunk 1; group 1: the second half of chunk 1 and chunk 2
-                        float l[12], gv[12];
-                        load_coords<kPtsBf16, 12>(rawrow, 24 + 12 * g, l);
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) to_global(R, T, l[3 * p], l[3 * p + 1], l[3 * p + 2], gv[3 * p], gv[3 * p + 1], gv[3 * p + 2]);
-                        uint32_t hi[6], lo[6];
-#pragma unroll
-                        for (int c = 0; c < 6; ++c) {
-                            const __nv_bfloat162 hh = __floats2bfloat162_rn(gv[2 * c], gv[2 * c + 1]);
-                            hi[c] = *reinterpret_cast<const uint32_t*>(&hh);
-                            lo[c] = tc::pack_bf16(gv[2 * c] - __bfloat162float(hh.x), gv[2 * c + 1] - __bfloat162float(hh.y));
-                        }
-                        if (g == 0) {
-                            *reinterpret_cast<uint4*>(vcol) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                            *reinterpret_cast<uint2*>(vcol + 128) = make_uint2(hi[4], hi[5]);
-                            *reinterpret_cast<uint4*>(vcol + 3 * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                            *reinterpret_cast<uint2*>(vcol + 4 * 128) = make_uint2(lo[4], lo[5]);
-                            *reinterpret_cast<uint4*>(vcol + 6 * 128) = make_uint4(0x00003F80u, 0, 0, 0);     // bf16 1.0 in channel 48: row sum of the rounded probabilities
-                            *reinterpret_cast<uint4*>(vcol + 7 * 128) = make_uint4(0, 0, 0, 0);
-                            s_kb[row] = key_bias ? key_bias[(int64_t)b * L + row] * kLog2e : 0.f;
-                        } else {
-                            *reinterpret_cast<uint2*>(vcol + 128 + 8) = make_uint2(hi[0], hi[1]);
-                            *reinterpret_cast<uint4*>(vcol + 2 * 128) = make_uint4(hi[2], hi[3], hi[4], hi[5]);
-                            *reinterpret_cast<uint2*>(vcol + 4 * 128 + 8) = make_uint2(lo[0], lo[1]);
-                            *reinterpret_cast<uint4*>(vcol + 5 * 128) = make_uint4(lo[2], lo[3], lo[4], lo[5]);
-                        }
-                    }
-                } else if (row < nrows) {                      // padding rows: operands exactly zero (padding keys get logits of -inf)
+                for (int c = 0; c < 9; ++c) R[c] = f_rot[r * 9 + c];
+                T[0] = f_trn[r * 3] - cx; T[1] = f_trn[r * 3 + 1] - cy; T[2] = f_trn[r * 3 + 2] - cz;
+            }
+            if (row_ok) {
+                {
+                    // group 0: the key points = rows of the B operands; group 1: the query points = rows of the A operands.
+                    // chunk 0 at +0, chunk 1 at +k1 (16 bytes per row), point p at +p * pstep
+                    const uint32_t pstep = g ? 4096u : (uint32_t)Lq * 32u, k1 = g ? 2048u : (uint32_t)Lq * 16u;
+                    uint8_t* drow = s_ops + (g ? 0 : 16384) + (size_t)row * 16;
+                    float l[12];
+                    load_coords<kPtsBf16, 12>(rawrow, g ? 0 : 12, l);
+                    const float sc = g ? -2.f : 1.f;           // the query side carries the factor of -2 q.k (exact, commutes with the split)
+                    constexpr uint32_t c256 = 0x5C005C00u;     // fp16 (256, 256)
 #pragma unroll
                     for (int p = 0; p < 4; ++p) {
-                        *reinterpret_cast<uint4*>(drow + (size_t)p * pstep) = make_uint4(0, 0, 0, 0);
-                        *reinterpret_cast<uint4*>(drow + (size_t)p * pstep + k1) = make_uint4(0, 0, 0, 0);
-                    }
-                    if (g == 0) {
-#pragma unroll
-                        for (int c = 0; c < NVP / 8; ++c) *reinterpret_cast<uint4*>(vcol + c * 128) = make_uint4(0, 0, 0, 0);
-                        s_kb[row] = -CUDART_INF_F;
+                        float gx, gy, gz;
+                        to_global(R, T, l[3 * p], l[3 * p + 1], l[3 * p + 2], gx, gy, gz);
+                        uint32_t hxy, lxy, hzn, lzn;           // (x, y) and (z, |.|^2 / 256): leading halves, remainders
+                        split_h2(sc * gx, sc * gy, hxy, lxy);
+                        split_h2(sc * gz, (gx * gx + gy * gy + gz * gz) * kNormScale, hzn, lzn);
+                        const uint32_t nn = __byte_perm(hzn, lzn, 0x7632);    // (n_h, n_l)
+                        const uint32_t lyz = __byte_perm(lxy, lzn, 0x5432);   // (l_y, l_z)
+                        uint8_t* dst = drow + (size_t)p * pstep;
+                        if (g) {   // a = [hx hy hz hx hy hz lx ly | lz lx ly lz n_h n_l 256 256]
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(hxy, __byte_perm(hzn, hxy, 0x5410), __byte_perm(hxy, hzn, 0x5432), lxy);
+                            *reinterpret_cast<uint4*>(dst + k1) = make_uint4(__byte_perm(lzn, lxy, 0x5410), lyz, nn, c256);
+                        } else {   // b = [hx hy hz lx ly lz hx hy | hz lx ly lz 256 256 n_h n_l]
+                            const uint32_t hzlx = __byte_perm(hzn, lxy, 0x5410);
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(hxy, hzlx, lyz, hxy);
+                            *reinterpret_cast<uint4*>(dst + k1) = make_uint4(hzlx, lyz, c256, nn);
+                        }
                     }
                 }
             }
             tc::fence_async_smem();
-            tc::fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&bar.ops_ready);
+            if (row_ok) {
+                {
+                    // value points 4g .. 4g+3 = channels 12g .. 12g+11 of the 24 hi (and of the 24 lo) channels:
+                    // group 0: chunk 0 and the first half of chunk 1; group 1: the second half of chunk 1 and chunk 2
+                    uint8_t* vcol = base + pl.vp + (size_t)(row >> 3) * (NVP * 16) + (size_t)(row & 7) * 16;   // 16-byte channel chunk c of this key at + c * 128
+                    float l[12], gv[12];
+                    load_coords<kPtsBf16, 12>(rawrow, 24 + 12 * g, l);
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) to_global(R, T, l[3 * p], l[3 * p + 1], l[3 * p + 2], gv[3 * p], gv[3 * p + 1], gv[3 * p + 2]);
+                    uint32_t hi[6], lo[6];
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) {
+                        const __nv_bfloat162 hh = __floats2bfloat162_rn(gv[2 * c], gv[2 * c + 1]);
+                        hi[c] = *reinterpret_cast<const uint32_t*>(&hh);
+                        lo[c] = tc::pack_bf16(gv[2 * c] - __bfloat162float(hh.x), gv[2 * c + 1] - __bfloat162float(hh.y));
+                    }
+                    if (g == 0) {
+                        *reinterpret_cast<uint4*>(vcol) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint2*>(vcol + 128) = make_uint2(hi[4], hi[5]);
+                        *reinterpret_cast<uint4*>(vcol + 3 * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<uint2*>(vcol + 4 * 128) = make_uint2(lo[4], lo[5]);
+                        *reinterpret_cast<uint4*>(vcol + 6 * 128) = make_uint4(0x00003F80u, 0, 0, 0);     // bf16 1.0 in channel 48: row sum of the rounded probabilities
+                        *reinterpret_cast<uint4*>(vcol + 7 * 128) = make_uint4(0, 0, 0, 0);
+                        if (key_bias) s_kb[row] = key_bias[(int64_t)b * L + row] * kLog2e;
+                    } else {
+                        *reinterpret_cast<uint2*>(vcol + 128 + 8) = make_uint2(hi[0], hi[1]);
+                        *reinterpret_cast<uint4*>(vcol + 2 * 128) = make_uint4(hi[2], hi[3], hi[4], hi[5]);
+                        *reinterpret_cast<uint2*>(vcol + 4 * 128 + 8) = make_uint2(lo[0], lo[1]);
+                        *reinterpret_cast<uint4*>(vcol + 5 * 128) = make_uint4(lo[2], lo[3], lo[4], lo[5]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bar.raw_free);        // the point records are consumed
             SE3_STAMP(2);
 
             // ---- XU phase ------------------------------------------------------------------------------------------------
-            if (use_turns) tc::bar_sync(my_turn, 512);
-            SE3_STAMP(3);
+            if (use_turns) tc::bar_sync(my_turn, 2 * kConsumers);
             tc::mbar_wait(&bar.bias_full, (uint32_t)(it & 1));
+            SE3_STAMP(3);
             float m = -CUDART_INF_F;
             const float hw = head_weight[h] * kLog2e;
-            const __nv_bfloat16* bias_col = s_bias + min(row, Lpi - 1);   // [j][query]: conflict-free 2-byte LDS
+            const uint32_t bias_col = tc::smem_u32(s_bias + min(row, Lpi - 1));   // [j][query]: conflict-free 2-byte LDS
             for (int c = g; c < nck; c += 2) {
-                const int j0 = c * 16;                         // this group's chunk, walked in two rounds of 8 keys (40 live registers each)
+                const int j0 = c * 16;                         // this group's chunk: 16 keys, S and four D_p = 80 registers
                 tc::mbar_wait(&bar.st_full[g], n_full & 1u);
                 ++n_full;
                 tc::fence_after();
-                if (dbg && (t & 127) == 0) dbg[((int64_t)(first + it * stride)) * 32 + 8 + c] = clock64();
+                if (dbg && (t == 0 || t == 96)) dbg[((int64_t)(first + it * stride)) * 32 + 8 + c] = clock64();
                 const bool active = warp_ok && j0 < L;         // warp-uniform
+                uint32_t d[4][16];
+                if (active) {
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int jh = j0 + 8 * half;
-                    uint32_t s[8], d[4][8];
-                    if (active) {
-                        tc::tmem_ld8(tc::tmem_addr(tmem_s, lane_base, (uint32_t)jh), s);
+                    for (int p = 0; p < 4; ++p) tc::tmem_ld16(tc::tmem_addr(tmem_st, lane_base, (uint32_t)(g * 64 + p * 16)), d[p]);
+                    tc::tmem_wait_ld();
+                }
+                if (dbg && t == 0 && c == 0) dbg[((int64_t)(first + it * stride)) * 32 + 27] = clock64();
+                if (c + 2 < nck) {                             // the stage may be overwritten by this group's next chunk
+                    tc::fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&bar.st_free[g]);
+                }
+                if (active) {
+                    // sum of the four distances per key; the S chunk is fetched under the second half of the square roots
+                    // (64 + 16 live registers would not fit beside the loop's own state)
+                    const int nk = min(16, L - j0);            // real keys in this chunk (warp-uniform)
+                    float ds[16];
+                    uint32_t s[16];
 #pragma unroll
-                        for (int p = 0; p < 4; ++p) tc::tmem_ld8(tc::tmem_addr(tmem_st, lane_base, (uint32_t)(g * 64 + p * 16 + 8 * half)), d[p]);
-                        tc::tmem_wait_ld();
+                    for (int u = 0; u < 16; ++u) {
+                        if (u == 8) tc::tmem_ld16(tc::tmem_addr(tmem_s, lane_base, (uint32_t)j0), s);
+                        ds[u] = (u < nk) ? (sqrt_abs(__uint_as_float(d[0][u])) + sqrt_abs(__uint_as_float(d[1][u]))) +
+                                               (sqrt_abs(__uint_as_float(d[2][u])) + sqrt_abs(__uint_as_float(d[3][u])))
+                                         : 0.f;
                     }
-                    if (half == 1 && c + 2 < nck) {            // the stage may be overwritten by this group's next chunk
-                        tc::fence_before();
-                        __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(&bar.st_free[g]);
-                    }
-                    if (active) {
-                        const __nv_bfloat16* bj = bias_col + jh * Lpi;
-                        if (jh + 8 <= L) {                     // warp-uniform: a full round
-                            const float4 kb0 = *reinterpret_cast<const float4*>(s_kb + jh), kb1 = *reinterpret_cast<const float4*>(s_kb + jh + 4);
-                            const float kbv[8] = {kb0.x, kb0.y, kb0.z, kb0.w, kb1.x, kb1.y, kb1.z, kb1.w};
+                    tc::tmem_wait_ld();
+                    uint32_t bj = bias_col + (uint32_t)(j0 * Lpi * 2);   // walked key by key (precomputed offsets would cost 15 registers)
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                const float ds = (sqrt_abs(__uint_as_float(d[0][u])) + sqrt_abs(__uint_as_float(d[1][u]))) +
-                                                 (sqrt_abs(__uint_as_float(d[2][u])) + sqrt_abs(__uint_as_float(d[3][u])));
-                                float lg = fmaf(hw, ds, __uint_as_float(s[u]) + kbv[u]);
-                                lg = fmaf(__bfloat162float(bj[u * Lpi]), kLog2e, lg);
-                                m = fmaxf(m, lg);
-                                s[u] = __float_as_uint(lg);
-                            }
-                        } else {
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const float4 kb4 = *reinterpret_cast<const float4*>(s_kb + j0 + 4 * q4);   // -inf on padding keys
+                        const float kbv[4] = {kb4.x, kb4.y, kb4.z, kb4.w};
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                if (jh + u < L) {              // warp-uniform
-                                    const float ds = (sqrt_abs(__uint_as_float(d[0][u])) + sqrt_abs(__uint_as_float(d[1][u]))) +
-                                                     (sqrt_abs(__uint_as_float(d[2][u])) + sqrt_abs(__uint_as_float(d[3][u])));
-                                    float lg = fmaf(hw, ds, __uint_as_float(s[u]) + s_kb[jh + u]);
-                                    lg = fmaf(__bfloat162float(bj[u * Lpi]), kLog2e, lg);
-                                    m = fmaxf(m, lg);
-                                    s[u] = __float_as_uint(lg);
-                                } else {
-                                    s[u] = __float_as_uint(-CUDART_INF_F);
-                                }
-                            }
+                        for (int e = 0; e < 4; ++e) {
+                            const int u = 4 * q4 + e;
+                            float lg = fmaf(hw, ds[u], __uint_as_float(s[u]) + kbv[e]);
+                            if (u < nk) lg = fmaf(lds_bf16(bj), kLog2e, lg);
+                            asm volatile("" : "+r"(bj));       // keep the address a loop-carried register
+                            bj += (uint32_t)(Lpi * 2);
+                            m = fmaxf(m, lg);
+                            s[u] = __float_as_uint(lg);
                         }
-                        tc::tmem_st8(tc::tmem_addr(tmem_s, lane_base, (uint32_t)jh), s);
-                    } else if (warp_ok) {                      // a whole chunk of padding keys
-                        uint32_t ninf[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) ninf[u] = __float_as_uint(-CUDART_INF_F);
-                        tc::tmem_st8(tc::tmem_addr(tmem_s, lane_base, (uint32_t)jh), ninf);
                     }
+                    tc::tmem_st16(tc::tmem_addr(tmem_s, lane_base, (uint32_t)j0), s);
+                    if (dbg && t == 0 && c == 0) dbg[((int64_t)(first + it * stride)) * 32 + 28] = clock64();
+                } else if (warp_ok) {                          // a whole chunk of padding keys
+                    uint32_t s[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) s[u] = __float_as_uint(-CUDART_INF_F);
+                    tc::tmem_st16(tc::tmem_addr(tmem_s, lane_base, (uint32_t)j0), s);
                 }
             }
             tc::tmem_wait_st();
             s_hmax[t] = m;
-            tc::bar_sync(wgbar, 256);                          // both key halves of every row have their maximum; every D chunk is consumed
-            m = fmaxf(s_hmax[row], s_hmax[128 + row]);
+            tc::bar_sync(wgbar, kConsumers);                   // both key halves of every row have their maximum; every D chunk is consumed
+            m = fmaxf(s_hmax[row], s_hmax[96 + row]);
             if (m == -CUDART_INF_F) m = 0.f;
             SE3_STAMP(4);
             if (warp_ok) {
@@ -433,7 +448,7 @@ k_ipa_tc_pass1_pp(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&bar.p_ready);
             SE3_STAMP(5);
-            if (use_turns && it < n_other - (wg ? 1 : 0)) tc::bar_arrive(other_turn, 512);   // the other warpgroup still has an item waiting for the XU phase
+            if (use_turns && it < n_other - (wg ? 1 : 0)) tc::bar_arrive(other_turn, 2 * kConsumers);   // the other warpgroup still has an item waiting for the XU phase
 
             // ---- epilogue: group 0 scalars + points 0..3, group 1 points 4..7 ---------------------------------------------------
             tc::mbar_wait(&bar.o_full, (uint32_t)(it & 1));
@@ -452,7 +467,7 @@ k_ipa_tc_pass1_pp(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #pragma unroll
                     for (int c = 0; c < 9; ++c) Ri[c] = f_rot[row * 9 + c];
                     Ti[0] = cx - f_trn[row * 3]; Ti[1] = cy - f_trn[row * 3 + 1]; Ti[2] = cz - f_trn[row * 3 + 2];
-                    const float inv = 1.0f / __uint_as_float(rs[0]);
+                    const float inv = fast_rcp(__uint_as_float(rs[0]));
                     const int HD = H * DK;
                     OutT* orow = out + ((int64_t)b * L + row) * (int64_t)(2 * HD + 4 * H * PV);
                     float pl4[12], nr[4];
@@ -464,7 +479,7 @@ k_ipa_tc_pass1_pp(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         pl4[p * 3] = Ri[0] * gx + Ri[3] * gy + Ri[6] * gz;
                         pl4[p * 3 + 1] = Ri[1] * gx + Ri[4] * gy + Ri[7] * gz;
                         pl4[p * 3 + 2] = Ri[2] * gx + Ri[5] * gy + Ri[8] * gz;
-                        nr[p] = sqrtf(pl4[p * 3] * pl4[p * 3] + pl4[p * 3 + 1] * pl4[p * 3 + 1] + pl4[p * 3 + 2] * pl4[p * 3 + 2]);
+                        nr[p] = fast_sqrt(pl4[p * 3] * pl4[p * 3] + pl4[p * 3 + 1] * pl4[p * 3 + 1] + pl4[p * 3 + 2] * pl4[p * 3 + 2]);
                     }
                     OutT* pdst = orow + HD + h * PV * 3 + g * 12;
                     OutT* ndst = orow + 2 * HD + 3 * H * PV + h * PV + g * 4;
@@ -487,6 +502,7 @@ k_ipa_tc_pass1_pp(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     }
                 }
             }
+            tc::fence_before();                                // the accumulator reads are ordered before the next item's ops_ready arrive
             SE3_STAMP(7);
         }
 #undef SE3_STAMP
@@ -534,7 +550,7 @@ namespace se3 {
 namespace ipa_tc {
 
 int launch_pass1_pingpong(const Pass1Args& a) {
-    if (a.sh.len > 128) return SE3_EUNSUPPORTED;
+    if (a.sh.len > kMaxLenPP) return SE3_EUNSUPPORTED;       // rows 96..127 belong to the issuer / helper warps
     if (a.out_bf16) return a.pts_bf16 ? launch_pp<__nv_bfloat16, true>(a) : launch_pp<__nv_bfloat16, false>(a);
     return a.pts_bf16 ? launch_pp<float, true>(a) : launch_pp<float, false>(a);
 }
@@ -543,6 +559,6 @@ int launch_pass1_pingpong(const Pass1Args& a) {
 }  // namespace se3
 
 extern "C" {
-/* developer hook (not in the public header): 32 clock64 slots per item of the ping-pong pass 1 (scripts/ipa_pp_phase_times.py) are written to `buf` when non-null */
+/* developer hook (not in the public header): 32 clock64 slots per item of the ping-pong pass 1 (scripts/ipa_pp_phase_times.py) */
 void se3_debug_set_pp_phase_buffer(long long* buf) { g_pp_dbg = buf; }
 }
