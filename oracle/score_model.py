@@ -57,8 +57,12 @@ class ScoreModelOracle:
     list of sample.py:165-171 is row-major (i, j), so to_dense_adj == reshape); lengths list[int].
     """
 
-    def __init__(self, state_dict: dict, num_heads: int, num_buckets: int = 64, max_distance: int = 128):
-        self.p = {k.removeprefix("model_nn."): v.detach().to(torch.float32) for k, v in state_dict.items()}
+    def __init__(self, state_dict: dict, num_heads: int, num_buckets: int = 64, max_distance: int = 128, dtype=torch.float32):
+        # dtype: float32 restates the reference bit for bit; float64 evaluates the SAME expressions in double precision
+        # (inputs are widened, outputs returned in float32) -- used by the tests to measure the fp32 noise floor of the
+        # reference itself, i.e. how far two correct fp32 evaluations may differ.
+        self.dtype = dtype
+        self.p = {k.removeprefix("model_nn."): v.detach().to(dtype) for k, v in state_dict.items()}
         self.h = num_heads
         self.num_buckets, self.max_distance = num_buckets, max_distance
         self.n_layer = 1 + max(int(k.split(".")[3]) for k in self.p if k.startswith("st_module.encoder.layers."))
@@ -68,7 +72,7 @@ class ScoreModelOracle:
     def set_context(self, single_embeds, pair_embeds, lengths, pos_is_known=None):
         self.single, self.lengths = single_embeds, list(lengths)
         lmax = max(lengths)
-        pr = torch.zeros(len(lengths), lmax, lmax, pair_embeds[0].shape[-1])
+        pr = torch.zeros(len(lengths), lmax, lmax, pair_embeds[0].shape[-1], dtype=self.dtype)
         for g, n in enumerate(lengths):
             pr[g, :n, :n] = pair_embeds[g]
         self.pair = pr
@@ -104,7 +108,7 @@ class ScoreModelOracle:
         attn = torch.softmax(s_attn + p_attn + pair_attn + bias, dim=-1)
 
         o_s = torch.einsum("bhij,bjhc->bihc", attn, v).reshape(*lead, -1)
-        o_pg = torch.einsum("bhij,bjhcp->bihcp", attn.float(), vp.float())
+        o_pg = torch.einsum("bhij,bjhcp->bihcp", attn.to(self.dtype), vp.to(self.dtype))   # explicit fp32 in the reference (:193-196)
         o_pl = torch.matmul(R.transpose(-1, -2)[:, :, None, None],
                             (o_pg - T[:, :, None, None]).unsqueeze(-1)).squeeze(-1)
         o_n = torch.norm(o_pl, dim=-1).reshape(*lead, -1)
@@ -117,24 +121,25 @@ class ScoreModelOracle:
     def __call__(self, pos, rot, t):
         """-> (pos_out [N,3], rot_out [N,3]); t [B] in [0,1] (scaled by 1000 as models.py:365)."""
         p, lengths = self.p, self.lengths
-        T, mask = to_dense(pos, lengths)
-        R, _ = to_dense(rot, lengths)  # rotation; the wrapper transposes and IPA transposes back
+        dt = self.dtype
+        T, mask = to_dense(pos.to(dt), lengths)
+        R, _ = to_dense(rot.to(dt), lengths)  # rotation; the wrapper transposes and IPA transposes back
         single, _ = to_dense(self.single, lengths)
         if self.pos_is_known is not None:
             known = to_dense(self.pos_is_known, lengths)[0].bool()
             attn_mask = ~(mask & known)
         else:
             attn_mask = ~mask
-        te = t * 1000
-        x1d = F.linear(self._ln(single.float(), "x1d_proj.0"), p["x1d_proj.1.weight"]) + sinusoid(te, self.d_model)[:, None]
-        x2d = F.linear(self._ln(self.pair.float(), "x2d_proj.0"), p["x2d_proj.1.weight"])
+        te = t.to(dt) * 1000
+        x1d = F.linear(self._ln(single.to(dt), "x1d_proj.0"), p["x1d_proj.1.weight"]) + sinusoid(te, self.d_model).to(dt)[:, None]
+        x2d = F.linear(self._ln(self.pair.to(dt), "x2d_proj.0"), p["x2d_proj.1.weight"])
         seq = torch.arange(T.shape[1])
         rel = seq.unsqueeze(1) - seq.unsqueeze(0)
         bucket = relative_position_bucket(rel, self.num_buckets, self.max_distance)
         x2d = x2d + F.embedding(bucket, p["rp_proj.relative_attention_bias.weight"])[None]
         z = (~attn_mask).long().sum(-1, keepdims=True)
         filled = attn_mask.masked_fill(z == 0, False)
-        bias = filled.float().masked_fill(filled, float("-inf"))[:, None, :, None].permute(0, 3, 1, 2)
+        bias = filled.to(dt).masked_fill(filled, float("-inf"))[:, None, :, None].permute(0, 3, 1, 2)
         for n in range(self.n_layer):
             pre = f"st_module.encoder.layers.{n}."
             x1d = x1d + self._ipa(self._ln(x1d, pre + "norm1"), x2d, T, R, bias, pre + "attn.")
@@ -152,7 +157,7 @@ class ScoreModelOracle:
         T_eps, IR_eps = head("fc_t"), head("fc_eps")
         # models.py:305 -- IR_perturbed^T = R
         T_out = torch.matmul(R, T_eps.unsqueeze(-1)).squeeze(-1)
-        return T_out[mask], IR_eps[mask]
+        return T_out[mask].float(), IR_eps[mask].float()
 
 
 def make_edge_index(seq_len: int) -> torch.Tensor:

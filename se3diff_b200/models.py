@@ -282,7 +282,9 @@ class DistributionalGraphormer(nn.Module):
         x2d = self.x2d_proj(pair_d) + self.rp_proj.relative_attention_bias(bucket)[None]   # [Bp, L, L, d_pair]
         attn0 = self.st_module.encoder.layers[0].attn
         probe = ops.ipa_shape(B, lmax, attn0.n_head, attn0.d_k, 1 if c.shared else B, head_major=False)
-        c.tc = self.precision == "bf16" and ops.ipa_tc_supported(probe)      # tcgen05 attention path
+        # tcgen05 attention path: decided with the SAME predicate as the fused bf16 forward that is its only caller
+        # (`_forward_kernels`): a bf16 model of another width takes `_forward_plain`, which feeds the SIMT kernel the fp32 layouts
+        c.tc = self._fused_bf16() and ops.ipa_tc_supported(probe)
         c.pair_bias, c.pair_value, c.pair_value_packed = [], [], []
         for lyr in self.st_module.encoder.layers:
             a = lyr.attn
@@ -331,6 +333,10 @@ class DistributionalGraphormer(nn.Module):
         return out.view(c.batch, c.lmax, *x.shape[1:])
 
     # -- forward ------------------------------------------------------------------------------------------
+    def _fused_bf16(self) -> bool:
+        """bf16 throughput path (`_forward_fused`): widths the fused residual + LayerNorm kernel takes."""
+        return self.precision == "bf16" and self.d_model % 128 == 0 and self.d_model <= 1024
+
     def _linear(self, x, w, bias=None, out_fp32=True):
         if w.dtype == torch.float32:
             return F.linear(x, w, bias)
@@ -577,8 +583,7 @@ class DistributionalGraphormer(nn.Module):
         H, dk = attn0.n_head, attn0.d_k
         shape = ops.ipa_shape(B, Lm, H, dk, 1 if c.shared else B, head_major=self.precision != "fp32" and dk == 16)
         flags = ops.IPA_EXACT if self.precision == "fp32" else ops.IPA_FAST_MATH
-        fused = self.precision == "bf16" and D % 128 == 0 and D <= 1024
-        if fused:
+        if self._fused_bf16():
             T_out, IR_eps = self._forward_fused(x1d.contiguous(), R, T, c, w, shape, flags)   # the head kernel applies R (models.py:305)
         else:
             T_eps, IR_eps = self._forward_plain(x1d, R, T, c, w, shape, flags)

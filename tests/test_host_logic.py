@@ -342,3 +342,39 @@ def test_einsum_attention_formulation_equals_the_oracle_on_cpu():
     g_got = (x1.grad, x2.grad, a64.trained_point_weight.grad, a64.pair_value.weight.grad)
     for u, v in zip(g_got, g_want):
         assert (u - v).abs().max() <= 1e-6 * v.abs().max()      # the reference aggregates the points in fp32 (:193-196) even in an fp64 run
+
+
+def test_tc_operator_truth_function_equals_the_oracle_on_cpu():
+    """`tests/ipa_tc_reference.ref` -- the fp64 einsum the tensor-core attention kernels are tested against on the GPU -- evaluated on
+    CPU tensors against `ScoreModelOracle._ipa`, the restatement pinned bit-exactly to the reference's SAAttention.forward
+    (structure_module.py:109-220), with per-sample pair tensors, a key mask and 10-nm translations."""
+    import math
+
+    import torch.nn.functional as F
+    from ipa_tc_reference import ref
+    from oracle.score_model import ScoreModelOracle
+    from se3diff_b200.models import SAAttention
+
+    torch.manual_seed(5)
+    for B, n, H, dk, dp, shared in ((2, 19, 4, 16, 32, False), (3, 33, 8, 16, 24, True)):
+        D = H * dk
+        a = SAAttention(D, dp, H, dropout=0.0)
+        x1d = torch.randn(B, n, D)
+        x2d = torch.randn(1 if shared else B, n, n, dp)
+        T = torch.randn(B, n, 3) * 10.0
+        R = torch.linalg.qr(torch.randn(B, n, 3, 3))[0]
+        R = R * torch.sign(torch.linalg.det(R))[..., None, None]
+        key_bias = torch.zeros(B, n)
+        key_bias[1, n - 3:] = float("-inf")
+        pre = "st_module.encoder.layers.0.attn."
+        sd = {"model_nn." + pre + k: v for k, v in a.state_dict().items()}
+        sd["model_nn.x1d_proj.1.weight"] = torch.zeros(D, 4)
+        with torch.no_grad():
+            want = ScoreModelOracle(sd, num_heads=H)._ipa(x1d, x2d.expand(B, -1, -1, -1), T, R, key_bias[:, None, None, :], pre)
+            proj = F.linear(x1d, a.fused_projection_weight()).reshape(B * n, -1)
+            pair_bias = (a.pair_weight * a.pair_bias(x2d)).permute(0, 3, 1, 2)
+            hw = -0.5 * a.point_weight * F.softplus(a.trained_point_weight)
+            feat = ref(proj, R.reshape(B * n, 9), T.reshape(B * n, 3), pair_bias, a.pair_value(x2d), hw, B, n, heads=H, d_k=dk, key_bias=key_bias)
+            got = F.linear(feat.float().view(B, n, -1), a.fc_out.weight, a.fc_out.bias)
+        assert a.point_weight == 1.0 / math.sqrt(54)
+        assert (got - want).abs().max() <= 3e-6 * want.abs().max(), (got - want).abs().max() / want.abs().max()
