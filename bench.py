@@ -2,7 +2,11 @@
 """Benchmark of the batched SE(3) reverse-diffusion sampling path (BASELINE.json metric:
 residue-steps/s = B * L * num_steps / time of the denoiser call).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c4|c5]
+
+--config selects the BASELINE.json configuration: c2 (default, the one the metric is quoted on: PDZ3 L = 84, B = 256 per GPU),
+c5 (synthetic 512-residue ensemble, 1024 samples over 8 GPUs = 128 per GPU) -- both this file's dpm_solver step -- and c4 (PDZ3
+fine-tune step, B = 64 per GPU with the gradient all-reduce: scripts/bench_finetune.py under the same launch contract).
 
 One bench "step" = ONE complete `dpm_solver` call (config/denoiser/dpm.yaml: 50 diffusion steps,
 0.99 -> 0.001, i.e. 100 score-model evaluations + prior sampling) over one batch of synthetic input:
@@ -25,6 +29,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(name="PSD95-PDZ3 dpm_solver", L=84, B=256, num_steps=50, max_t=0.99, min_t=0.001)
+CONFIGS = {"c2": dict(L=84, B=256, name="PSD95-PDZ3 dpm_solver"),                       # BASELINE.json configs[1]
+           "c5": dict(L=512, B=128, name="synthetic 512-residue ensemble dpm_solver")}  # configs[4]: 1024 samples / 8 GPUs
+HBM_NOMINAL_GBS = 8000.0   # north_star's "~8 TB/s" (DGX figure; HGX B200: 7.7 TB/s); reported next to the measured copy bandwidth
 FULL_SDE = dict(eps_t=0.001, num_sigma=1000, num_omega=2000, omega_exponent=3, l_max=2000, sigma_min=0.02, sigma_max=2.33,
                 tol=1e-7)
 METRIC, UNIT = "SE(3) reverse-diffusion residue-steps/sec", "residue-steps/s"
@@ -145,16 +152,30 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=WORKLOAD["B"], help="samples per GPU")
-    ap.add_argument("--length", type=int, default=WORKLOAD["L"])
+    ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"], help="BASELINE.json configuration (default: the headline one)")
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default: the configuration's)")
+    ap.add_argument("--length", type=int, default=None)
     ap.add_argument("--diffusion-steps", type=int, default=WORKLOAD["num_steps"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true", help="skip the instrumented per-kernel pass (used for ncu launch lists)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fp32-mode and replicated-host-batch passes after the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
         return reference_arm(args)
+    if args.config == "c4":                                   # the fine-tune step has its own driver under the same launch contract
+        import runpy
+
+        sys.argv = [os.path.join(ROOT, "scripts", "bench_finetune.py"), "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        if args.batch is not None:
+            sys.argv += ["--batch", str(args.batch)]
+        if args.length is not None:
+            sys.argv += ["--length", str(args.length)]
+        return runpy.run_path(sys.argv[0], run_name="__main__")
+    cfg = CONFIGS[args.config]
+    args.batch = cfg["B"] if args.batch is None else args.batch
+    args.length = cfg["L"] if args.length is None else args.length
 
     import torch.distributed as dist
 
@@ -239,13 +260,56 @@ def main():
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     t_dev, t_e2e = times.tolist()
 
+    # ---- after the timed region: the parity-precision figure and the PyG-shaped host batch -------------------------------
+    extras = {}
+    if not args.no_extras:
+        def timed(fn, warm, reps):
+            for w in range(warm):
+                fn(w)
+            barrier()
+            ev = []
+            for k in range(reps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn(100 + k)
+                e1.record()
+                ev.append((e0, e1))
+            barrier()
+            tt = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / 1e3], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return tt.item()
+
+        # (1) the same step in the OTHER precision mode (fp32 = the parity mode: SIMT fp32 attention, fp32 GEMMs)
+        other = "fp32" if args.precision == "bf16" else "bf16"
+        model.set_precision(other)
+        t_o = timed(lambda k: one_step(4000 + rank * B + k, dev_batch, True), args.warmup, args.steps)
+        model.set_precision(args.precision)
+        extras[other] = {"value": world * B * L * S * args.steps / t_o, "unit": UNIT, "ms_per_step": t_o / args.steps * 1e3,
+                         "note": "same workload, W warm-up + K timed steps, device-resident batch"}
+        # (2) end to end with the batch an unchanged sample.py builds through PyG: every field materialised B times on the host
+        # (pinned), i.e. the whole replicated pair embedding crosses PCIe every step
+        if args.config == "c2" or B * L * L * 128 * 4 <= (2 << 30):
+            rep = Batch.from_data_list([ChemGraph(**dict(graph.items())) for _ in range(B)])     # distinct graph objects: no replica shortcut
+            for k, v in rep.items():
+                if torch.is_tensor(v):
+                    rep[k] = v.pin_memory()
+            h2d_rep = rep.h2d_nbytes()
+            t_p = timed(lambda k: one_step(5000 + rank * B + k, rep, False).to("cpu"), min(args.warmup, 2), args.steps)
+            extras["e2e_pyg"] = {"value": world * B * L * S * args.steps / t_p, "unit": UNIT, "h2d_bytes_per_step": h2d_rep, "d2h_bytes_per_step": d2h,
+                                 "ms_per_step": t_p / args.steps * 1e3,
+                                 "note": "host batch with the pair embedding replicated B times (what PyG's Batch.from_data_list holds at sample.py:223), pinned"}
+            del rep
+
     # ---- per-kernel roofline pass (same workload, instrumented, after the timed region) -------------------
     roof, roof_extra = None, []
     if rank == 0 and not args.no_roofline:
         try:
             from se3diff_b200.profiling import kernel_rooflines
 
-            roof, roof_extra = kernel_rooflines(lambda: one_step(3000, dev_batch, False), L=L, B=B)
+            roof, roof_extra = kernel_rooflines(lambda: one_step(3000, dev_batch, False), L=L, B=B, sm_mhz=(clk or {}).get("sm_mhz"),
+                                                with_elementwise=args.config == "c2")
         except Exception as e:  # noqa: BLE001
             roof = {"error": repr(e)}
 
@@ -258,7 +322,7 @@ def main():
                 sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
                 tables = dict(omega_grid=so3.igso3.omega_grid.cpu(), cdf_igso3=so3.igso3.cdf_igso3.cpu(),
                               cdf_uso3=so3.uso3.cdf_igso3.cpu(), score_scaling=so3.score_function.score_scaling.cpu())
-                sB, sS = 8, 20                                             # ~10-20 s of CPU work on the box's host cores
+                sB, sS = (8, 20) if L <= 128 else (1, 2)                   # ~10-20 s of CPU work on the box's host cores
                 (t_cpu,), cores = cpu_reference_run(L, sB, sS, sd, tables)
                 cpu = {"value": sB * L * sS / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
                        "sample": f"oracle dpm_solver, B={sB} of {B} samples, {sS} of {S} diffusion steps, L={L}, fp32, "
@@ -269,13 +333,14 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD['name'] if L == WORKLOAD['L'] else 'synthetic-sequence dpm_solver'} L={L} B={B}/GPU {S} diffusion steps (2 score evals each), "
+            "config": {"workload": f"{cfg['name'] if L == cfg['L'] else 'synthetic-sequence dpm_solver'} L={L} B={B}/GPU {S} diffusion steps (2 score evals each), "
                                    f"bioemu-v1.0 architecture random-init, synthetic embeddings",
                        "step": "one dpm_solver call incl. prior sampling" + (" + NCCL ensemble all_gather" if world > 1 else ""),
                        "l2": "512 MiB buffer written between timed iterations", "parallelism": f"dp{world} (independent samples)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": t_e2e / args.steps * 1e3},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_other_kernels": roof_extra, "cpu_baseline": cpu,
+            **extras,
         }), file=result_out, flush=True)
     if world > 1:
         dist.destroy_process_group()

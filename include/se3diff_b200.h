@@ -32,6 +32,8 @@ extern "C" {
 typedef void* se3_stream_t; /* cudaStream_t */
 
 const char* se3_last_error(void);
+/* bumped whenever a signature or a by-value struct of this header changes; the loader compares it with the header it was written against */
+#define SE3_ABI_VERSION 2
 int se3_abi_version(void);
 /* number of kernels launched by this library in the calling thread since the last reset
  * (bench.py's `gpu_launches`). */
@@ -301,9 +303,10 @@ int se3_ipa_attention_bwd(const float* proj, const float* rot, const float* tran
                           float* ds_ws, float* d_hw_rows, const se3_ipa_shape* h_shape, se3_stream_t stream);
 
 /* Tensor-core edition of the same operator (tcgen05.mma + TMEM, bf16 operands, fp32 accumulation): two passes, see
- * se3diff_b200/csrc/ipa_tc.cu.  Requirements: dk = 16, 4 / 8 points, shared pair tensors (pair_batch = 1), L <= 256.
- * The projection (structure_module.py:131-135) is delivered as TWO head-major matrices, which the bf16 score network
- * produces with two GEMMs over row-permuted slices of the fused projection weight:
+ * se3diff_b200/csrc/ipa_tc.cu.  Requirements: dk = 16, 4 / 8 points, shared pair tensors (pair_batch = 1), L <= 512 (257..512: the
+ * keys of a query tile are split over a 2-CTA cluster).
+ * The projection (structure_module.py:131-135) is delivered as two head-major record sets -- column slices of ONE bf16 GEMM
+ * over row-permuted slices of the fused projection weight (se3_ipa_split_perm), or two separate matrices:
  *   scalars_bf16 : bf16 [B*L][scalar_stride], head h owns elements [h*48, h*48+48) = q 16 | k 16 | v 16; the q block
  *                  must already carry the factor scalar_weight * log2(e) (folded into the weight rows by the caller).
  *                  Each 16-byte piece is one chunk of a UMMA operand and is copied verbatim (cp.async), no conversion.
@@ -327,6 +330,22 @@ int se3_ipa_attention_tc_fwd(const void* scalars_bf16, int64_t scalar_stride, co
                              const void* pair_value_packed, const float* key_bias, const float* head_weight, void* out,
                              int out_is_bf16, void* p_workspace, float* inv_workspace, const se3_ipa_shape* h_shape,
                              se3_stream_t stream);
+
+/* The two operand packs above, from the tensors the per-sequence pair precompute produces (models.py:243-293 feeding
+ * structure_module.py:179, 209; SURVEY.md 8b `pair_precompute`), so that a caller holding only device pointers can feed
+ * se3_ipa_attention_tc_fwd:
+ *   pair_bias  [len(i)][len(j)][heads] fp32 = pair_weight * Linear(x2d)   -> bias_packed  (se3_ipa_tc_packed_pair_bytes: bias_bytes)
+ *   pair_value [len(i)][len(j)][heads*16] fp32 = Linear(x2d)              -> value_packed (value_bytes), 16-byte aligned
+ * Either pair (input, output) may be NULL to run only the other pack.  Pure byte movement plus one round-to-nearest-even. */
+int64_t se3_ipa_tc_packed_pair_bytes(int len, int heads, int64_t* bias_bytes, int64_t* value_bytes);
+int se3_ipa_tc_pack_pair(const float* pair_bias, const float* pair_value, void* bias_packed, void* value_packed, int len,
+                         int heads, se3_stream_t stream);
+/* HOST function (no device work): row index sets of the reference's fused projection weight
+ * [scalar_query | scalar_key | scalar_value | point_query | point_key | point_value] (structure_module.py:56-107, rows in the
+ * reference's parameter order) for the head-major records of se3_ipa_attention_tc_fwd:
+ *   h_scalar_rows [heads*3*dk] : head h -> q dk | k dk | v dk;   h_point_rows [heads*48] : head h -> q_pts 12 | k_pts 12 | v_pts 24;
+ *   h_q_positions [heads*dk] (optional): positions of the q rows inside h_scalar_rows -- the rows that carry scalar_weight * log2(e). */
+int se3_ipa_split_perm(int heads, int dk, int32_t* h_scalar_rows, int32_t* h_point_rows, int32_t* h_q_positions);
 
 /* Fused residual update + pre-LayerNorm of the next block (bf16 throughput mode of the score network):
  *   x[rows,dim] += y[rows,dim] + bias[dim]      (y fp32 or bf16, bias optional: NULL skips the update; structure_module.py:247-248)

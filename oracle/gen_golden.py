@@ -476,19 +476,33 @@ def backbone(ns):
                                                                        mask=mask, aatype=aatype)))
 
 
+CACHE_SDE = dict(eps_t=0.001, num_sigma=8, num_omega=64, omega_exponent=3, l_max=64, sigma_min=0.02, sigma_max=2.33, tol=1e-7)
+
+
+def so3_cache(ns):
+    """The reference's own npz lookup-table cache (so3_sde.py:914-990 `SO3LookupCache.save_cache`, file names at :1098, 1354,
+    1607) for a tiny table set: three files written by the unmodified `DiGSO3SDE.__init__` into tests/golden/so3_cache/."""
+    import shutil
+
+    d = os.path.join(OUT, "so3_cache")
+    shutil.rmtree(d, ignore_errors=True)
+    ns.so3_sde.DiGSO3SDE(**CACHE_SDE, cache_dir=d, overwrite_cache=False)
+    print("  cache files:", sorted(os.listdir(d)))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_harness.load()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     every = (so3_maps, igso3_series, so3_tables, schedules, score_model_tiny, score_model_small, trajectories,
-             analytic_denoise, toy, finetune_step, backbone)
+             analytic_denoise, toy, finetune_step, backbone, so3_cache)
     only = set(sys.argv[1:])                      # e.g. `python -m oracle.gen_golden toy` regenerates one file
     for fn in every:
         if only and fn.__name__ not in only:
             continue
         print("golden:", fn.__name__, flush=True)
         fn(ns)
-    print({f: os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT))})
+    print({f: os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT)) if os.path.isfile(os.path.join(OUT, f))})
 
 
 if __name__ == "__main__":

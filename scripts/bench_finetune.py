@@ -76,9 +76,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    from se3diff_b200 import ops as _ops
+
+    h2d = sum(v.numel() * v.element_size() for _, v in graph.items() if torch.is_tensor(v))
     for w in range(a.warmup):
         step(rank * 1000 + w)
     barrier()
+    _ops.launch_count_reset()
     parts = torch.zeros(3, dtype=torch.float64)
     for k in range(a.steps):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -86,6 +90,7 @@ def main():
         torch.cuda.synchronize(dev)
         parts += torch.tensor([ev[i].elapsed_time(ev[i + 1]) for i in range(3)], dtype=torch.float64)
     barrier()
+    Bn_launches = _ops.launch_count()
     t = parts.to(dev) / 1e3
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -98,6 +103,9 @@ def main():
             "value": world * B * L * T * a.steps / total, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": total / a.steps * 1e3, "ms_rollout": float(t[0]) / a.steps * 1e3, "ms_loss_backward": float(t[1]) / a.steps * 1e3,
             "ms_exchange_optimizer": float(t[2]) / a.steps * 1e3, "scaling": "weak", "dtype": "bf16 score model, fp32 control model and SDE algebra",
+            "higher_is_better": True, "vs_baseline": None, "gpu_launches": int(Bn_launches),
+            "e2e": {"value": world * B * L * T * a.steps / total, "unit": "residue-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                    "note": "the step itself starts from the host-resident graph (generate_finetune_batch moves it) and ends with the loss scalar on the host"},
             "data": "synthetic", "trainable_parameters": n_train, "loss": float(loss), "grad_norm": gn, "finite": bool(torch.isfinite(loss)),
             "config": {"workload": f"PDZ3 fine-tune step L={L} B={B}/GPU, {T} EM steps with control, micro_batch_size={a.micro}, "
                                    f"allreduce of {n_train} gradient floats" + (" over NCCL" if world > 1 else " (single rank: none)")}}), file=result_out, flush=True)

@@ -39,6 +39,8 @@ class IpaShape(C.Structure):
         "off_vp", "hs_scalar", "hs_point", "hs_vpoint", "pair_batch")]
 
 
+ABI_VERSION = 2   # SE3_ABI_VERSION of include/se3diff_b200.h this module's signature table was written against
+
 # name -> argtypes (all return int unless listed in _RESTYPES).  Must list every symbol of the header.
 SIGNATURES = {
     "se3_so3_exp": [f32p, f32p, i64, f32, vp],
@@ -76,6 +78,9 @@ SIGNATURES = {
     "se3_ipa_attention_bwd": [f32p] * 7 + [f32] + [f32p] * 6 + [C.POINTER(IpaShape), vp],
     "se3_ipa_tc_workspace_bytes": [C.POINTER(IpaShape), C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
     "se3_ipa_attention_tc_fwd": [vp, i64, vp, i32, i64, f32p, f32p, vp, vp, f32p, f32p, vp, i32, vp, f32p, C.POINTER(IpaShape), vp],
+    "se3_ipa_tc_packed_pair_bytes": [i32, i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
+    "se3_ipa_tc_pack_pair": [f32p, f32p, vp, vp, i32, i32, vp],
+    "se3_ipa_split_perm": [i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
     "se3_folded_proportion": [f32p, f32p, f32p, f32p, i64, i32, f32, f32, f32, vp],
     "se3_backbone_atoms": [f32p, f32p, vp, vp, f32p, i64, i32, vp],
     "se3_physicality": [f32p, vp, f32p, i64, i32, vp],
@@ -88,7 +93,7 @@ SIGNATURES = {
     "se3_launch_count": [],
     "se3_launch_count_reset": [],
 }
-_RESTYPES = {"se3_ipa_tc_workspace_bytes": C.c_int64, "se3_igso3_cdf_index_floats": C.c_int64, "se3_last_error": C.c_char_p, "se3_launch_count": C.c_int64, "se3_launch_count_reset": None}
+_RESTYPES = {"se3_ipa_tc_workspace_bytes": C.c_int64, "se3_ipa_tc_packed_pair_bytes": C.c_int64, "se3_igso3_cdf_index_floats": C.c_int64, "se3_last_error": C.c_char_p, "se3_launch_count": C.c_int64, "se3_launch_count_reset": None}
 
 
 class Se3LibraryError(RuntimeError):
@@ -104,14 +109,17 @@ def lib():
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
-            try:
-                from .build import build
+        # A library that does not match the sources / header on disk would be called with mismatched pointers and structs:
+        # rebuild when the digest differs (a no-op when it matches), and refuse a stale binary that cannot be rebuilt.
+        from .build import build, stale
 
+        if stale():
+            try:
                 build()
             except Exception as e:  # noqa: BLE001
+                what = "is missing" if not os.path.exists(LIB_PATH) else "was built from other sources than the ones on disk"
                 raise Se3LibraryError(
-                    f"libse3diff_b200.so is missing at {LIB_PATH} and could not be built ({e}); "
+                    f"libse3diff_b200.so {what} at {LIB_PATH} and could not be rebuilt ({e}); "
                     "run `python -m se3diff_b200.build` (needs nvcc)") from e
         try:
             h = C.CDLL(LIB_PATH)
@@ -124,6 +132,8 @@ def lib():
                 raise Se3LibraryError(f"{LIB_PATH} does not export {name}; rebuild it") from e
             fn.argtypes = args
             fn.restype = _RESTYPES.get(name, C.c_int)
+        if h.se3_abi_version() != ABI_VERSION:
+            raise Se3LibraryError(f"{LIB_PATH} reports ABI version {h.se3_abi_version()}, this package was written against {ABI_VERSION}; rebuild it")
         _lib = h
     return _lib
 

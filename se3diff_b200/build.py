@@ -26,6 +26,7 @@ SOURCES = {
     "tc_selftest.cu": [],
     "ipa_tc.cu": [],
     "ipa_tc_pp.cu": [],
+    "pair_pack.cu": [],
     "fused_rows.cu": [],
     "observables.cu": [],
     "backbone.cu": [],
@@ -48,6 +49,12 @@ def _digest() -> str:
                 h.update(open(os.path.join(root, f), "rb").read())
     h.update(repr(sorted(SOURCES.items())).encode())
     return h.hexdigest()
+
+
+def stale() -> bool:
+    """True when the library on disk was not built from the sources on disk (or there is no record of what it was built from)."""
+    stamp = os.path.join(OUT_DIR, "build.sha256")
+    return not (os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == _digest())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -32,7 +32,7 @@ void count_launch(int n) { g_launches += n; }
 
 extern "C" {
 const char* se3_last_error(void) { return se3::g_err; }
-int se3_abi_version(void) { return 1; }
+int se3_abi_version(void) { return SE3_ABI_VERSION; }
 int64_t se3_launch_count(void) { return se3::g_launches; }
 void se3_launch_count_reset(void) { se3::g_launches = 0; }
 }

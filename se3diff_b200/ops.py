@@ -536,26 +536,40 @@ def ipa_tc_supported(shape: L.IpaShape) -> bool:
     return shape.dk == 16 and shape.pq == 4 and shape.pv == 8 and shape.pair_batch == 1 and shape.len <= 512
 
 
+def _packed_pair_sizes(length: int, heads: int):
+    bb, vb = C.c_int64(0), C.c_int64(0)
+    if L.lib().se3_ipa_tc_packed_pair_bytes(int(length), int(heads), C.byref(bb), C.byref(vb)) < 0:
+        raise ValueError(f"ipa_tc pack: bad shape L={length} H={heads}")
+    return bb.value, vb.value
+
+
 def ipa_tc_pack_pair_value(pair_value: torch.Tensor, heads: int) -> torch.Tensor:
     """[1, L, L, H*16] (pair_value(x2d), structure_module.py:209) -> bf16 [L][H][Lp/8][16][8], the UMMA K-major
-    operand layout read by pass 2 of the tensor-core attention."""
+    operand layout read by pass 2 of the tensor-core attention (se3_ipa_tc_pack_pair)."""
     Lq = pair_value.shape[1]
+    if pair_value.numel() != Lq * Lq * heads * 16:
+        raise ValueError(f"pair_value must be [1, L, L, H*16], got {tuple(pair_value.shape)} for H={heads}")
+    pv = _dev(pair_value, name="pair_value")
     Lp = (Lq + 15) // 16 * 16
-    pv = pair_value.reshape(Lq, Lq, heads, 16)
-    if Lp != Lq:
-        pv = torch.nn.functional.pad(pv, (0, 0, 0, 0, 0, Lp - Lq))
-    return pv.view(Lq, Lp // 8, 8, heads, 16).permute(0, 3, 1, 4, 2).contiguous().to(torch.bfloat16)
+    out = torch.empty(Lq, heads, Lp // 8, 16, 8, dtype=torch.bfloat16, device=pv.device)
+    assert out.numel() * 2 == _packed_pair_sizes(Lq, heads)[1]
+    with _guard(pv):
+        L.check(L.lib().se3_ipa_tc_pack_pair(None, _p(pv), None, _p(out), Lq, heads, _stream(pv)), "se3_ipa_tc_pack_pair")
+    return out
 
 
 def ipa_tc_pack_pair_bias(pair_bias: torch.Tensor) -> torch.Tensor:
     """[1, L(i), L(j), H] (= pair_weight * pair_bias(x2d), structure_module.py:179) -> bf16 [H][L(j)][round_up(L,8)(i)],
-    the transposed slab layout the tensor-core attention fetches with TMA."""
-    Lq = pair_bias.shape[1]
-    t = pair_bias[0].permute(2, 1, 0)                                  # [H, j, i]
-    pad = (-Lq) % 8
-    if pad:
-        t = torch.nn.functional.pad(t, (0, pad))
-    return t.contiguous().to(torch.bfloat16)
+    the transposed slab layout the tensor-core attention fetches with TMA (se3_ipa_tc_pack_pair)."""
+    Lq, heads = pair_bias.shape[1], pair_bias.shape[-1]
+    if pair_bias.numel() != Lq * Lq * heads:
+        raise ValueError(f"pair_bias must be [1, L, L, H], got {tuple(pair_bias.shape)}")
+    pb = _dev(pair_bias, name="pair_bias")
+    out = torch.empty(heads, Lq, (Lq + 7) // 8 * 8, dtype=torch.bfloat16, device=pb.device)
+    assert out.numel() * 2 == _packed_pair_sizes(Lq, heads)[0]
+    with _guard(pb):
+        L.check(L.lib().se3_ipa_tc_pack_pair(_p(pb), None, _p(out), None, Lq, heads, _stream(pb)), "se3_ipa_tc_pack_pair")
+    return out
 
 
 def ipa_tc_workspace(shape: L.IpaShape, device) -> tuple[torch.Tensor, torch.Tensor]:
@@ -566,15 +580,11 @@ def ipa_tc_workspace(shape: L.IpaShape, device) -> tuple[torch.Tensor, torch.Ten
 
 def ipa_split_perms(heads: int, dk: int = 16):
     """Row index sets of the fused projection weight [q | k | v | q_pt | k_pt | v_pt] (structure_module.py:131-135) for the
-    split layout of se3_ipa_attention_tc_fwd: (scalar rows, point rows, positions of the q rows inside the first)."""
-    hd = heads * dk
-    ar = torch.arange
-    sc, pt, qpos = [], [], []
-    for h in range(heads):
-        qpos.append(h * 3 * dk + ar(dk))
-        sc += [h * dk + ar(dk), hd + h * dk + ar(dk), 2 * hd + h * dk + ar(dk)]
-        pt += [3 * hd + h * 12 + ar(12), 3 * hd + 12 * heads + h * 12 + ar(12), 3 * hd + 24 * heads + h * 24 + ar(24)]
-    return torch.cat(sc), torch.cat(pt), torch.cat(qpos)
+    split layout of se3_ipa_attention_tc_fwd: (scalar rows, point rows, positions of the q rows inside the first), from the
+    library's host function se3_ipa_split_perm."""
+    sc, pt, qpos = (C.c_int32 * (heads * 3 * dk))(), (C.c_int32 * (heads * 48))(), (C.c_int32 * (heads * dk))()
+    L.check(L.lib().se3_ipa_split_perm(int(heads), int(dk), sc, pt, qpos), "se3_ipa_split_perm")
+    return (torch.tensor(list(sc), dtype=torch.int64), torch.tensor(list(pt), dtype=torch.int64), torch.tensor(list(qpos), dtype=torch.int64))
 
 
 def _rows_view(t, dtype, name):

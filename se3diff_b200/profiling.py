@@ -61,6 +61,70 @@ def _time_alone(fn, iters=10, warmup=3):
     return e0.elapsed_time(e1) / iters
 
 
+HBM_NOMINAL_GBS = 8000.0      # north_star's "~8 TB/s" (DGX B200 figure; HGX: 7.7 TB/s) -- reported next to the measured copy bandwidth
+SMS, XU_LANES_PER_CLK_SM = 148, 16      # MUFU: 4 lanes / clock / SM sub-partition (measured: 8 cycles per warp instruction, scripts/microbench)
+FP64_LANES_PER_CLK_SM = 2     # B200 DFMA rate per SM (64 : 1 against FP32)
+
+
+def _hbm_line(name, n, bytes_per, ms, pk, **extra):
+    gbs = bytes_per * n / ms / 1e6
+    return {"kernel": name, "bound": "hbm", "n": n, "bytes_per_unit": bytes_per, "ms": ms, "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+            "frac": gbs / pk["hbm"], "peak_source": pk["source"], "peak_nominal": HBM_NOMINAL_GBS, "frac_nominal": gbs / HBM_NOMINAL_GBS,
+            "traffic": None, **extra}
+
+
+def series_rooflines(device="cuda", sm_mhz=None):
+    """K1a / K1b (so3_sde.py:1731-1940, 1131-1187, 1637-1696): the truncated IGSO(3) series and the table builds.  They are
+    arithmetic-bound (sin / exp per term), not HBM-bound: reported as series TERMS per second against the unit that evaluates
+    a term -- the XU (MUFU) pipe for fp32 (one sin + one exp per term and lane: 2 MUFU ops), the FP64 pipe for the tables
+    (a term is ~40 DFMA: range-reduced sin and exp polynomials).  The term count is the number actually evaluated: terms whose
+    exponential underflows to exactly zero are skipped (sum unchanged bit for bit), so it depends on sigma."""
+    import math
+
+    clk = (sm_mhz or 1965) * 1e6
+    g = torch.Generator(device=device).manual_seed(1)
+    n, l_max = 1_000_000, 2000
+    om = torch.rand(n, generator=g, device=device) * math.pi
+    sg = 0.02 * (2.33 / 0.02) ** torch.rand(n, generator=g, device=device)
+    # terms evaluated per element: l runs while exp(-l(l+1) sigma^2 / 2) > 0 in the working precision
+    def terms(sigma, tiny):
+        lcut = torch.sqrt(2.0 * (-math.log(tiny)) / sigma.double() ** 2)
+        return torch.clamp(lcut.ceil(), max=l_max + 1)
+    t32 = terms(sg, 1.4e-45).sum().item()
+    res = []
+    xu_peak = SMS * XU_LANES_PER_CLK_SM * clk / 2          # terms / s if every term costs one sin + one exp on the XU pipe
+    ms = _time_alone(lambda: ops.igso3_series(om, sg, l_max, want=("f", "df", "dlog")))
+    res.append({"kernel": "se3_igso3_series_f32 (f, df, dlog)", "bound": "xu", "n": n, "l_max": l_max, "terms_evaluated": t32, "ms": ms,
+                "achieved": t32 / ms / 1e6, "peak": xu_peak / 1e9, "unit": "Gterm/s", "frac": t32 / ms / 1e6 / (xu_peak / 1e9),
+                "peak_source": f"148 SMs x 16 MUFU lanes x {clk / 1e6:.0f} MHz / 2 MUFU ops per term"})
+    rv = torch.randn(n, 3, generator=g, device=device)
+    ms = _time_alone(lambda: ops.igso3_score(rv, sg, l_max))
+    res.append({"kernel": "se3_igso3_score", "bound": "xu", "n": n, "l_max": l_max, "terms_evaluated": t32, "ms": ms,
+                "achieved": t32 / ms / 1e6, "peak": xu_peak / 1e9, "unit": "Gterm/s", "frac": t32 / ms / 1e6 / (xu_peak / 1e9),
+                "peak_source": f"148 SMs x 16 MUFU lanes x {clk / 1e6:.0f} MHz / 2 MUFU ops per term"})
+    n64 = 200_000
+    om64, sg64 = om[:n64].double(), sg[:n64].double()
+    t64 = terms(sg64, 4.9e-324).sum().item()
+    f64_peak = SMS * FP64_LANES_PER_CLK_SM * clk / 40
+    ms = _time_alone(lambda: ops.igso3_series(om64, sg64, l_max, want=("f", "df", "dlog")), iters=5)
+    res.append({"kernel": "se3_igso3_series_f64 (f, df, dlog)", "bound": "fp64", "n": n64, "l_max": l_max, "terms_evaluated": t64, "ms": ms,
+                "achieved": t64 / ms / 1e6, "peak": f64_peak / 1e9, "unit": "Gterm/s", "frac": t64 / ms / 1e6 / (f64_peak / 1e9),
+                "peak_source": f"148 SMs x 2 DFMA lanes x {clk / 1e6:.0f} MHz / ~40 DFMA per term (sin + exp in fp64)"})
+    # table builds of the shipped configuration (config.yaml:23-35): 1000 sigma rows x 2001 omega points x <= 2001 terms, fp64
+    sig_grid = 0.02 * (2.33 / 0.02) ** torch.linspace(0.001, 1.0, 1000, device=device)
+    om_pts = (torch.linspace(0.0, 1, 2001, device=device, dtype=torch.float64) ** 3 * math.pi)
+    tt = (terms(sig_grid, 4.9e-324) * 2001).sum().item()
+    ms = _time_alone(lambda: ops.igso3_build_cdf(sig_grid, om_pts, 2000), iters=3, warmup=1)
+    res.append({"kernel": "se3_igso3_build_cdf (1000 x 2000 table)", "bound": "fp64", "terms_evaluated": tt, "ms": ms, "achieved": tt / ms / 1e6,
+                "peak": f64_peak / 1e9, "unit": "Gterm/s", "frac": tt / ms / 1e6 / (f64_peak / 1e9),
+                "peak_source": f"148 SMs x 2 DFMA lanes x {clk / 1e6:.0f} MHz / ~40 DFMA per term", "note": "once per process (or read from the npz cache)"})
+    ms = _time_alone(lambda: ops.igso3_build_score_scaling(sig_grid, om_pts, 2000), iters=3, warmup=1)
+    res.append({"kernel": "se3_igso3_build_score_scaling (1000 rows)", "bound": "fp64", "terms_evaluated": 2 * tt, "ms": ms, "achieved": 2 * tt / ms / 1e6,
+                "peak": f64_peak / 1e9, "unit": "Gterm/s", "frac": 2 * tt / ms / 1e6 / (f64_peak / 1e9),
+                "peak_source": f"148 SMs x 2 DFMA lanes x {clk / 1e6:.0f} MHz / ~40 DFMA per term", "note": "f and df series per (sigma, omega)"})
+    return res
+
+
 def elementwise_rooflines(n: int = 10_000_000, device="cuda"):
     """BASELINE config 3: SO(3) exp/log/compose, IGSO3 noising and the fused frame updates at n = 1e7
     (inputs 120-1200 MB, i.e. larger than L2).  Algorithmic bytes per unit from SURVEY.md 8(d)."""
@@ -100,16 +164,10 @@ def elementwise_rooflines(n: int = 10_000_000, device="cuda"):
         ("se3_igso3_sample(noise passed in)", 88, lambda: ops.igso3_sample(cdf, omg, n, sigma=sig, sigma_grid=sig_grid, normals=z1, u=uu, x=r, cdf_index=cidx)),
         ("se3_igso3_sample(philox)", 72, lambda: ops.igso3_sample(cdf, omg, n, sigma=sig, sigma_grid=sig_grid, seed=1, x=r, cdf_index=cidx)),
     ]
-    res = []
-    for name, bytes_per, fn in cases:
-        ms = _time_alone(fn)
-        gbs = bytes_per * n / ms / 1e6
-        res.append({"kernel": name, "bound": "hbm", "n": n, "bytes_per_unit": bytes_per, "ms": ms, "achieved": gbs,
-                    "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "peak_source": pk["source"], "traffic": None})
-    return res
+    return [_hbm_line(name, n, bytes_per, _time_alone(fn), pk) for name, bytes_per, fn in cases]
 
 
-def kernel_rooflines(step_fn, L: int, B: int, heads: int = 32):
+def kernel_rooflines(step_fn, L: int, B: int, heads: int = 32, sm_mhz=None, with_elementwise: bool = True):
     """(dominant-kernel roofline, other kernels).  The dominant kernel of this library inside the sampling step is the
     IPA attention operator (both passes of the tensor-core edition are timed together: one C-ABI call).
 
@@ -148,7 +206,13 @@ def kernel_rooflines(step_fn, L: int, B: int, heads: int = 32):
     nbytes = proj_bytes + rows * 48 + out_bytes + heads * L * L * pair_el + L * L * heads * 16 * pair_el
     flops = 4608.0 * L * L * B
     gbs, tf = nbytes / ms / 1e6, flops / ms / 1e9
+    # the unit that actually binds the operator: 4 sqrt per (i, j, head) for the un-squared point distances + 1 exp, on the XU pipe
+    xu_ops = 5.0 * L * L * heads * B
+    xu_peak = SMS * XU_LANES_PER_CLK_SM * (sm_mhz or 1965) * 1e6
     roof = {"kernel": "se3_" + name, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+            "peak_nominal": HBM_NOMINAL_GBS, "frac_nominal": gbs / HBM_NOMINAL_GBS,
+            "xu": {"ops_per_launch": xu_ops, "achieved_gops": xu_ops / ms / 1e6, "peak_gops": xu_peak / 1e9, "frac": xu_ops / ms / 1e6 / (xu_peak / 1e9),
+                   "peak_source": f"148 SMs x 16 MUFU lanes x {sm_mhz or 1965} MHz (SM clock {'sampled under load' if sm_mhz else 'maximum'})"},
             "traffic": _ncu_traffic(name, L, B), "launches_timed": n, "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes,
             "peak_source": pk["source"], "edition": edition,
             "tensor": {"algorithmic_flops_per_launch": flops, "achieved_tflops": tf, "peak_tflops": pk["tensor_sustained"],
@@ -156,7 +220,7 @@ def kernel_rooflines(step_fn, L: int, B: int, heads: int = 32):
             "note": "HBM is the binding roof of the two (bytes/peak >> flops/peak); the kernel itself is issue/MUFU-bound: 128 sqrt + "
                     "32 exp per (i,j) pair per layer are not a contraction (structure_module.py:170).  `traffic` is the ncu "
                     "dram read+write of both passes per call, including the un-normalised probability tiles pass 1 hands to pass 2."}
-    return roof, elementwise_rooflines()
+    return roof, (elementwise_rooflines() + series_rooflines(sm_mhz=sm_mhz) if with_elementwise else [])
 
 
 def _ncu_traffic(name: str, L: int, B: int):

@@ -715,6 +715,24 @@ def test_ipa_tensor_core_operator_vs_fp64(B, L, scale):
             assert err <= 1.5e-2 * ref_max * (2.0 if odt == torch.bfloat16 else 1.0), (name, odt, err, ref_max)
 
 
+@pytest.mark.parametrize("L,H", [(84, 32), (11, 4), (57, 32), (130, 8), (16, 1)])
+def test_tc_operand_packs_are_bit_exact(L, H):
+    """se3_ipa_tc_pack_pair (the C-ABI entry that turns the per-sequence pair tensors of models.py:243-293 / structure_module.py:179,209
+    into the TMA slab and UMMA operand layouts of se3_ipa_attention_tc_fwd) against permute / pad / round-to-bf16 in torch: byte
+    movement plus one rounding, so the comparison is exact."""
+    from se3diff_b200 import ops
+
+    g = torch.Generator().manual_seed(L * 100 + H)
+    pb = torch.randn(1, L, L, H, generator=g).to(DEV)                  # [1, i, j, h]
+    pv = torch.randn(1, L, L, H * 16, generator=g).to(DEV)
+    got_b, got_v = ops.ipa_tc_pack_pair_bias(pb), ops.ipa_tc_pack_pair_value(pv, H)
+    want_b = torch.nn.functional.pad(pb[0].permute(2, 1, 0), (0, (-L) % 8)).contiguous().to(torch.bfloat16)          # [H, j, i_pad]
+    Lp = (L + 15) // 16 * 16
+    want_v = torch.nn.functional.pad(pv.reshape(L, L, H, 16), (0, 0, 0, 0, 0, Lp - L)).view(L, Lp // 8, 8, H, 16).permute(0, 3, 1, 4, 2).contiguous().to(torch.bfloat16)
+    assert got_b.shape == want_b.shape and torch.equal(got_b.view(torch.int16), want_b.view(torch.int16))
+    assert got_v.shape == want_v.shape and torch.equal(got_v.view(torch.int16), want_v.view(torch.int16))
+
+
 def test_bf16_forward_long_sequence_uses_split_attention():
     """L = 300 (> 256): bf16 mode must stay on the tensor-core attention (cluster-split keys) and agree with the fp32 parity
     path of the same model to the bf16 level (2 layers, B = 2, physical-scale frames)."""
@@ -905,8 +923,8 @@ def test_bf16_mode_at_the_benched_config_vs_the_oracle():
     """north_star: "bf16 attention within a stated tolerance on final C-alpha RMSD" -- at the BENCHED configuration and against the
     ORACLE (not against this library's own fp32 mode): bioemu-v1.0 widths, 8 layers, L = 84, 50 dpm steps (dpm.yaml), B = 4,
     identical prior draw.  Stated tolerance: RMSD (no superposition) of every sample's final C-alpha positions against the fp32
-    oracle's <= 1e-2 of the ensemble's radius of gyration, rotation matrices within 0.2; the fp32 parity mode of this library is
-    held to 1e-4 * Rg on the same run (it accumulates 100 network evaluations of last-ulp differences)."""
+    oracle's <= 2.5e-3 of the ensemble's radius of gyration (measured: 8e-4), rotation matrices within 5e-2 (measured: 4e-3); the fp32
+    parity mode of this library is held to 2e-5 * Rg and 1e-4 on the same run (measured: 1.6e-6, 1.2e-5; it accumulates 100 network evaluations of last-ulp differences)."""
     from se3diff_b200 import shortcuts
 
     L, B, nsteps = 84, 4, 50
@@ -929,14 +947,15 @@ def test_bf16_mode_at_the_benched_config_vs_the_oracle():
     assert md.model_nn._ctx.tc, "bf16 mode must run the tensor-core attention path here"
     print("8 layers, L = 84, 50 steps vs the fp32 oracle: RMSD / Rg per sample fp32 mode", res["fp32"][0].tolist(), "bf16 mode", res["bf16"][0].tolist(),
           "| max rotation-matrix difference fp32 %.2e bf16 %.2e | Rg %.1f" % (res["fp32"][1], res["bf16"][1], rg.mean().item()))
-    assert (res["fp32"][0] <= 1e-4).all() and res["fp32"][1] <= 1e-3, res["fp32"]
-    assert (res["bf16"][0] <= 1e-2).all() and res["bf16"][1] <= 0.2, res["bf16"]
+    assert (res["fp32"][0] <= 2e-5).all() and res["fp32"][1] <= 1e-4, res["fp32"]
+    assert (res["bf16"][0] <= 2.5e-3).all() and res["bf16"][1] <= 5e-2, res["bf16"]
 
 
 def test_bf16_mode_physical_scale_steps_vs_the_oracle():
     """The same comparison where random-init weights do not inflate the coordinates: 4 consecutive dpm steps
     late in the schedule (t: 0.30 -> 0.22) from ~1 nm frames, the GPU carrying its OWN state from step to step.  Stated tolerance:
-    C-alpha RMSD against the fp32 oracle <= 5e-3 nm per sample in bf16 mode (1e-5 nm in fp32 mode), rotations within 2e-2 (1e-5)."""
+    C-alpha RMSD against the fp32 oracle <= 1e-3 nm per sample in bf16 mode (measured 1.5e-4; 1e-5 nm in fp32 mode, measured 1.3e-7),
+    rotations within 1e-3 (1e-5)."""
     from se3diff_b200 import schedule
 
     L, B, nsteps = 84, 2, 4
@@ -947,7 +966,7 @@ def test_bf16_mode_physical_scale_steps_vs_the_oracle():
     p_ref, r_ref = osamp.dpm_solver(o32, ctx[2], r3, tab, nsteps, 0.30, 0.22, init=init)
     steps = schedule.dpm_schedule(sdes["pos"], sdes["node_orientations"], nsteps, 0.30, 0.22)
     md, bd = m.to(DEV), batch.to(DEV)
-    tol = {"fp32": (1e-5, 1e-5), "bf16": (5e-3, 2e-2)}
+    tol = {"fp32": (1e-5, 1e-5), "bf16": (1e-3, 1e-3)}
     for prec in ("fp32", "bf16"):
         md.set_precision(prec)
         pos, rot = init[0].to(DEV), init[1].to(DEV)
@@ -981,6 +1000,99 @@ def test_bf16_mode_with_a_narrow_model_takes_the_simt_attention():
     scale = max(o32["pos"].abs().max().item(), o32["node_orientations"].abs().max().item())
     assert torch.isfinite(o16["pos"]).all()
     assert (o16["pos"] - o32["pos"]).abs().max().item() <= 3e-2 * scale and (o16["node_orientations"] - o32["node_orientations"]).abs().max().item() <= 3e-2 * scale
+
+
+def _foreign_batch_classes():
+    """The batch type an unchanged sample.py hands over (sample.py:223): PyG's `Batch.from_data_list` of the reference's
+    `ChemGraph(Data)`.  torch_geometric is absent here, oracle/_pyg_shim restates its Data / Batch (2.6.1 semantics: attribute store
+    with `_parent`, dynamic `ChemGraphBatch` subclass, `ptr`, `to_data_list`); ChemGraph is the reference's own class where
+    /root/reference exists (build container), else its body restated (chemgraph.py:12-31)."""
+    import copy
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim = os.path.join(root, "oracle", "_pyg_shim")
+    if shim not in sys.path:
+        sys.path.insert(0, shim)
+    from torch_geometric.data import Batch as PygBatch
+    from torch_geometric.data import Data
+
+    ref_src = "/root/reference/bioemu/src"
+    if os.path.isdir(os.path.join(ref_src, "bioemu")):
+        if ref_src not in sys.path:
+            sys.path.insert(0, ref_src)
+        from bioemu.chemgraph import ChemGraph as RefChemGraph
+    else:
+        class RefChemGraph(Data):
+            def replace(self, **kwargs):
+                out = self.__class__.__new__(self.__class__)
+                for key, value in self.__dict__.items():
+                    out.__dict__[key] = value
+                out.__dict__["_store"] = copy.copy(self._store)
+                for key, value in kwargs.items():
+                    out._store[key] = value
+                out._store._parent = out
+                return out
+    return RefChemGraph, PygBatch
+
+
+def test_samplers_take_a_pyg_batch_of_reference_chemgraphs():
+    """Drop-in boundary (sample.py:223-236): `shortcuts.dpm_solver` and `shortcuts.euler_maruyama_predictor` driven with a
+    PyG-style `Batch` of the reference's `ChemGraph`s -- not this package's container -- return that same foreign type, its
+    `.to_data_list()` yields per-sample graphs with `pos [L, 3]` / `node_orientations [L, 3, 3]`, and the frames equal the run on
+    this package's own `Batch` bit for bit (same prior draw, same kernels)."""
+    from se3diff_b200 import shortcuts
+    from se3diff_b200.chemgraph import Batch, ChemGraph, complete_graph_edge_index
+
+    RefChemGraph, PygBatch = _foreign_batch_classes()
+    g, m, fm, sdes, _, S = _traj_setup()
+    L, B = int(g["L"]), int(g["B"])
+    nan = float("nan")
+    fields = dict(pos=torch.full((L, 3), nan), node_orientations=torch.full((L, 3, 3), nan), edge_index=complete_graph_edge_index(L),
+                  single_embeds=T(g["single"]), pair_embeds=T(g["pair"]).reshape(L * L, -1))
+    foreign = PygBatch.from_data_list([RefChemGraph(sequence="A" * L, **fields)] * B)      # sample.py:223 replicates one graph object
+    own = Batch.from_data_list([ChemGraph(**fields)] * B)
+    assert not isinstance(foreign, ChemGraph) and isinstance(foreign, RefChemGraph)
+    for solver, kw in ((shortcuts.dpm_solver, dict(num_steps=6)), (shortcuts.euler_maruyama_predictor, dict(num_steps=5))):
+        outs = []
+        for batch in (foreign, own):
+            with S.host_noise():
+                torch.manual_seed(123)
+                outs.append(solver(batch=batch, sdes=sdes, score_model=m, max_t=0.99, min_t=0.001, device=DEV, **kw))
+        f, o = outs
+        assert type(f) is type(foreign)
+        assert torch.equal(f["pos"], o["pos"]) and torch.equal(f["node_orientations"], o["node_orientations"])
+        parts = f.to_data_list()
+        assert len(parts) == B and all(isinstance(p, RefChemGraph) for p in parts)
+        assert [tuple(p.pos.shape) for p in parts] == [(L, 3)] * B and [tuple(p.node_orientations.shape) for p in parts] == [(L, 3, 3)] * B
+        assert torch.equal(torch.cat([p.pos for p in parts]), f["pos"]) and parts[0].sequence == "A" * L
+        assert torch.isfinite(f["pos"]).all()
+
+
+def test_so3_table_cache_is_written_in_the_reference_format(tmp_path):
+    """npz cache interop, writing side (so3_sde.py:951-990): tables built by the CUDA kernels are saved under the reference's file
+    names, with its keys, dtypes and shapes (tests/golden/so3_cache/ was written by the unmodified reference), values within the
+    table tolerance; a second construction reads the files back instead of rebuilding."""
+    import os
+
+    import numpy as np
+    from oracle.gen_golden import CACHE_SDE
+    from se3diff_b200 import sdes as S
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "so3_cache")
+    a = S.DiGSO3SDE(**CACHE_SDE, cache_dir=str(tmp_path), overwrite_cache=False)
+    assert sorted(os.listdir(tmp_path)) == sorted(os.listdir(gold))
+    for f in os.listdir(gold):
+        want, got = np.load(os.path.join(gold, f)), np.load(os.path.join(tmp_path, f))
+        assert sorted(want.files) == sorted(got.files)
+        for k in want.files:
+            assert want[k].dtype == got[k].dtype and want[k].shape == got[k].shape, (f, k)
+            assert np.abs(want[k] - got[k]).max() <= 2e-6 * max(1.0, np.abs(want[k]).max()), (f, k)
+    stamp = {f: os.path.getmtime(os.path.join(tmp_path, f)) for f in os.listdir(tmp_path)}
+    b = S.DiGSO3SDE(**CACHE_SDE, cache_dir=str(tmp_path), overwrite_cache=False)
+    assert stamp == {f: os.path.getmtime(os.path.join(tmp_path, f)) for f in os.listdir(tmp_path)}
+    assert torch.equal(a.igso3.cdf_igso3.cpu(), b.igso3.cdf_igso3.cpu()) and torch.equal(a.score_function.score_scaling.cpu(), b.score_function.score_scaling.cpu())
 
 
 def test_dpm_cuda_graph_replay_matches_eager():

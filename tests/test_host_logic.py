@@ -25,7 +25,7 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(h, name), f"{name} declared in include/se3diff_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
     lib = _lib.lib()
-    assert lib.se3_abi_version() == 1
+    assert lib.se3_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header():
@@ -378,3 +378,102 @@ def test_tc_operator_truth_function_equals_the_oracle_on_cpu():
             got = F.linear(feat.float().view(B, n, -1), a.fc_out.weight, a.fc_out.bias)
         assert a.point_weight == 1.0 / math.sqrt(54)
         assert (got - want).abs().max() <= 3e-6 * want.abs().max(), (got - want).abs().max() / want.abs().max()
+
+
+def test_split_perm_host_function_equals_its_restatement():
+    """se3_ipa_split_perm (a host function of the C ABI): the row index sets that turn the reference's fused projection weight
+    [q | k | v | q_pt | k_pt | v_pt] (structure_module.py:56-107, parameter order) into head-major records -- integer work, exact."""
+    from se3diff_b200 import ops
+
+    for heads, dk in ((32, 16), (4, 16), (3, 8)):
+        hd, ar = heads * dk, torch.arange
+        sc, pt, qpos = [], [], []
+        for h in range(heads):
+            qpos.append(h * 3 * dk + ar(dk))
+            sc += [h * dk + ar(dk), hd + h * dk + ar(dk), 2 * hd + h * dk + ar(dk)]
+            pt += [3 * hd + h * 12 + ar(12), 3 * hd + 12 * heads + h * 12 + ar(12), 3 * hd + 24 * heads + h * 24 + ar(24)]
+        got = ops.ipa_split_perms(heads, dk)
+        for g, w in zip(got, (torch.cat(sc), torch.cat(pt), torch.cat(qpos))):
+            assert torch.equal(g, w)
+        assert sorted(torch.cat(got[:2]).tolist()) == list(range(3 * hd + 48 * heads))       # a permutation of all rows
+
+
+def _instantiate(node):
+    """What hydra.utils.instantiate does with the two YAML idioms the reference uses (sample.py:120-138, finetune.py:150-188):
+    `_target_` = dotted name of a callable, remaining keys = keyword arguments (nested nodes first), `_partial_: true` = return
+    functools.partial instead of calling."""
+    import functools
+    import importlib
+
+    if isinstance(node, dict) and "_target_" in node:
+        kw = {k: _instantiate(v) for k, v in node.items() if k not in ("_target_", "_partial_")}
+        mod, name = node["_target_"].rsplit(".", 1)
+        fn = getattr(importlib.import_module(mod), name)
+        return functools.partial(fn, **kw) if node.get("_partial_") else fn(**kw)
+    if isinstance(node, dict):
+        return {k: _instantiate(v) for k, v in node.items()}
+    return node
+
+
+def test_plugin_yaml_targets_resolve():
+    """The drop-in mechanism itself: the YAMLs shipped under se3diff_b200/config/ are the reference's
+    config/denoiser/*.yaml and checkpoints/bioemu-v1.0/config.yaml with `_target_` pointed at se3diff_b200.shortcuts.  Resolved
+    the way sample.py:120-138 resolves them: every denoiser becomes a partial carrying the reference's own settings, the score
+    models are constructed with the reference's parameter count, the SDE nodes bind to classes that accept the reference's keywords."""
+    import inspect
+
+    import yaml
+    from se3diff_b200 import shortcuts
+
+    cfg_dir = os.path.join(ROOT, "se3diff_b200", "config")
+    want = {"dpm": ("dpm_solver", 50, None), "euler_maruyama": ("euler_maruyama_predictor", 200, None),
+            "euler_maruyama_finetune": ("euler_maruyama_predictor_finetune", 200, None), "heun": ("heun_denoiser", 100, 0.5),
+            "heun_finetune": ("heun_denoiser_finetune", 100, 0.5), "sde_dpm_finetune": ("sde_dpm_solver_finetune", 50, None)}
+    for name, (fn, steps, noise) in want.items():
+        node = yaml.safe_load(open(os.path.join(cfg_dir, "denoiser", name + ".yaml")))
+        d = _instantiate(node)
+        assert d.func is getattr(shortcuts, fn)
+        assert d.keywords["num_steps"] == steps and d.keywords["max_t"] == 0.99 and d.keywords["min_t"] == 0.001
+        assert d.keywords.get("noise") == noise
+        # the call site binds exactly these four more (sample.py:227-232; finetune.py adds finetune_model)
+        params = inspect.signature(d.func).parameters
+        assert {"batch", "sdes", "score_model", "device"} <= set(params) and all(p.kind is p.KEYWORD_ONLY for p in params.values())
+    node = yaml.safe_load(open(os.path.join(cfg_dir, "bioemu-v1.0", "config.yaml")))
+    model = _instantiate(node["score_model"])
+    assert isinstance(model, shortcuts.DiGConditionalScoreModel)
+    assert sum(p.numel() for p in model.parameters()) == 31_284_486                      # SURVEY a18
+    control = _instantiate(node["finetune_model"])
+    assert sum(p.numel() for p in control.parameters()) == 193_806                       # SURVEY a21
+    pos_sde = _instantiate(node["sdes"]["pos"])
+    assert isinstance(pos_sde, shortcuts.CosineVPSDE) and pos_sde.s == 0.008
+    so3 = node["sdes"]["node_orientations"]
+    assert list(node["sdes"]) == ["node_orientations", "pos"]                             # key order fixes the RNG order (denoiser.py:233)
+    assert so3["_target_"] == "se3diff_b200.shortcuts.DiGSO3SDE"
+    inspect.signature(shortcuts.DiGSO3SDE.__init__).bind(None, **{k: v for k, v in so3.items() if k != "_target_"})
+    # shadowing bioemu.shortcuts (INTEGRATION.md section 1) exposes every name the reference's alias module does
+    for name in ("CosineVPSDE", "DiGConditionalScoreModel", "DiGSO3SDE", "dpm_solver", "heun_denoiser", "euler_maruyama_predictor",
+                 "euler_maruyama_predictor_finetune", "heun_denoiser_finetune", "sde_dpm_solver_finetune"):
+        assert hasattr(shortcuts, name), name
+
+
+def test_so3_table_cache_written_by_the_reference_is_read_back():
+    """npz cache interop (so3_sde.py:914-990; file names :1098, 1354, 1607).  tests/golden/so3_cache/ holds the three files the
+    UNMODIFIED reference's `DiGSO3SDE.__init__` wrote through `SO3LookupCache.save_cache` for a tiny table set
+    (oracle/gen_golden.py::so3_cache).  This package must find them under the same names, load them without a GPU (no table
+    build), and hold exactly their contents in buffers of the reference's names."""
+    import numpy as np
+    from oracle.gen_golden import CACHE_SDE
+    from se3diff_b200 import sdes as S
+
+    d = os.path.join(ROOT, "tests", "golden", "so3_cache")
+    files = sorted(os.listdir(d))
+    assert files == ["cache_igso3_s0.020-2.330-8_l64_o64-3.npz", "cache_score-scaling_s0.020-2.330-8_l65_o64-3.npz",
+                     "cache_uso3_s0.020-2.330-8_o64-3.npz"]
+    sde = S.DiGSO3SDE(**CACHE_SDE, cache_dir=d, overwrite_cache=False)         # would raise on this CPU-only box if it had to build
+    ig, us, sc = (np.load(os.path.join(d, f)) for f in files[:1] + files[2:] + files[1:2])
+    assert sde.igso3._get_cache_name() == files[0] and sde.uso3._get_cache_name() == files[2]
+    assert torch.equal(sde.igso3.cdf_igso3, torch.from_numpy(ig["cdf_igso3"])) and torch.equal(sde.igso3.omega_grid, torch.from_numpy(ig["omega_grid"]))
+    assert torch.equal(sde.uso3.cdf_igso3, torch.from_numpy(us["cdf_igso3"])) and torch.equal(sde.uso3.omega_grid, torch.from_numpy(us["omega_grid"]))
+    assert torch.equal(sde.score_function.score_scaling, torch.from_numpy(sc["score_scaling"]))
+    assert sde.igso3.cdf_igso3.dtype == torch.float32 and tuple(sde.igso3.cdf_igso3.shape) == (8, 64) and tuple(sde.uso3.cdf_igso3.shape) == (1, 64)
+    assert sorted(os.listdir(d)) == files                                         # nothing rewritten
