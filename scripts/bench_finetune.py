@@ -76,6 +76,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    from se3diff_b200 import denoiser as _den
     from se3diff_b200 import ops as _ops
 
     h2d = sum(v.numel() * v.element_size() for _, v in graph.items() if torch.is_tensor(v))
@@ -92,8 +93,11 @@ def main():
     barrier()
     Bn_launches = _ops.launch_count()
     t = parts.to(dev) / 1e3
+    per_rank = [t.clone() for _ in range(world)]
     if world > 1:
+        dist.all_gather(per_rank, t)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    per_rank = [[round(float(v) / a.steps * 1e3, 1) for v in r.cpu()] for r in per_rank]
     t = t.cpu()
     gn = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in ctrl.parameters() if p.grad is not None)).item()
     if rank == 0:
@@ -103,7 +107,7 @@ def main():
             "value": world * B * L * T * a.steps / total, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": total / a.steps * 1e3, "ms_rollout": float(t[0]) / a.steps * 1e3, "ms_loss_backward": float(t[1]) / a.steps * 1e3,
             "ms_exchange_optimizer": float(t[2]) / a.steps * 1e3, "scaling": "weak", "dtype": "bf16 score model, fp32 control model and SDE algebra",
-            "higher_is_better": True, "vs_baseline": None, "gpu_launches": int(Bn_launches),
+            "higher_is_better": True, "vs_baseline": None, "gpu_launches": int(Bn_launches), "loop_graphs": dict(_den.GRAPH_STATS), "ms_per_rank_rollout_loss_exchange": per_rank,
             "e2e": {"value": world * B * L * T * a.steps / total, "unit": "residue-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "note": "the step itself starts from the host-resident graph (generate_finetune_batch moves it) and ends with the loss scalar on the host"},
             "data": "synthetic", "trainable_parameters": n_train, "loss": float(loss), "grad_norm": gn, "finite": bool(torch.isfinite(loss)),

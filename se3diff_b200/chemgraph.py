@@ -73,9 +73,55 @@ class ChemGraph:
         return 0
 
 
+class _Replicated:
+    """Placeholder for a concatenated field of a batch that holds B references to ONE graph: the concatenation is only built
+    when somebody reads the field on the host.  sample.py:223 and finetune.py:325 build such a batch per call and hand it
+    straight to the denoiser, which moves it to the device -- there the graph is shipped once and replicated on the GPU, so the
+    B-fold host copy (231 MB per fine-tune step at L = 84, B = 64) is never needed."""
+
+    __slots__ = ("src", "copies", "is_edge_index", "nodes")
+
+    def __init__(self, src, copies, is_edge_index, nodes):
+        self.src, self.copies, self.is_edge_index, self.nodes = src, copies, is_edge_index, nodes
+
+    def build(self):
+        if self.is_edge_index:
+            e = self.src.shape[1]
+            return self.src.repeat(1, self.copies) + (torch.arange(self.copies, device=self.src.device) * self.nodes).repeat_interleave(e)
+        return self.src.repeat(self.copies, *([1] * (self.src.dim() - 1)))
+
+
 class Batch(ChemGraph):
     """Concatenated graphs with PyG's `batch`/`ptr` bookkeeping (Batch.from_data_list as used at
     sample.py:223 and finetune.py:325)."""
+
+    # -- lazily concatenated fields of a replicated batch -------------------------------------------------------------------
+    def _materialise(self, key, value):
+        if not isinstance(value, _Replicated):
+            return value
+        t = value.build()
+        self._fields[key] = t
+        rep = self.__dict__.get("_replica")
+        if rep is not None:
+            rep[1][key] = (t, t._version, value.src)      # `.to(cuda)` still ships the single graph while this copy is unmodified
+        return t
+
+    def __getattr__(self, key):
+        f = object.__getattribute__(self, "_fields")
+        if key in f:
+            return self._materialise(key, f[key])
+        raise AttributeError(key)
+
+    def __getitem__(self, key):
+        return self._materialise(key, self._fields[key])
+
+    def items(self):
+        return [(k, self._materialise(k, v)) for k, v in list(self._fields.items())]
+
+    @property
+    def num_nodes(self) -> int:
+        own = self.__dict__.get("_lengths")
+        return sum(own) if own is not None else super().num_nodes
 
     @classmethod
     def from_data_list(cls, graphs):
@@ -84,10 +130,16 @@ class Batch(ChemGraph):
         for n in lengths:
             offsets.append(offsets[-1] + n)
         fields = {}
+        # B references to ONE graph (sample.py:223 and finetune.py:325 build their batch exactly so): the concatenated tensors are
+        # plain replications of the single-graph tensors, so they are not built here (see _Replicated) and `.to(cuda)` ships the
+        # graph once (3.9 MB instead of 988 MB at L = 84, B = 256) and replicates on the device
+        replicated = len(graphs) > 1 and all(g is graphs[0] for g in graphs)
         for k in graphs[0].keys():
             vals = [g[k] for g in graphs]
             if not torch.is_tensor(vals[0]):
                 fields[k] = vals
+            elif replicated:
+                fields[k] = _Replicated(vals[0], len(graphs), k == "edge_index", lengths[0])
             elif k == "edge_index":
                 fields[k] = torch.cat([v + o for v, o in zip(vals, offsets[:-1])], dim=1)
             else:
@@ -97,16 +149,14 @@ class Batch(ChemGraph):
         out = cls(**fields)
         object.__setattr__(out, "_lengths", lengths)
         object.__setattr__(out, "_edges", [int(g["edge_index"].shape[1]) if "edge_index" in g else 0 for g in graphs])
-        if len(graphs) > 1 and all(g is graphs[0] for g in graphs):
-            # B references to ONE graph (sample.py:223 builds its batch exactly so): remember which concatenated tensors are
-            # plain replications of which single-graph tensor, so that `.to(cuda)` ships the graph once (3.9 MB instead of
-            # 988 MB at L = 84, B = 256) and replicates on the device.  Entries: field -> (built tensor, its version, source).
-            rep = {k: (fields[k], fields[k]._version, graphs[0][k]) for k in graphs[0].keys() if torch.is_tensor(graphs[0][k])}
-            object.__setattr__(out, "_replica", (len(graphs), rep))
+        if replicated:      # field -> (built tensor, its version, source), filled in as fields are materialised on the host
+            object.__setattr__(out, "_replica", (len(graphs), {}))
         return out
 
     def _replica_source(self, key, value):
         """The single-graph tensor `value` (field `key`) is B copies of, or None (field replaced / modified / not a replica)."""
+        if isinstance(value, _Replicated):
+            return value.src if value.src.device.type == "cpu" else None
         rep = self.__dict__.get("_replica")
         if rep is None or not torch.is_tensor(value):
             return None
@@ -119,7 +169,9 @@ class Batch(ChemGraph):
         """Bytes `.to(cuda)` copies from the host for this batch."""
         n = 0
         for k, v in self._fields.items():
-            if torch.is_tensor(v) and v.device.type == "cpu":
+            if isinstance(v, _Replicated):
+                n += v.src.numel() * v.src.element_size() if v.src.device.type == "cpu" else 0
+            elif torch.is_tensor(v) and v.device.type == "cpu":
                 src = self._replica_source(k, v)
                 n += (src if src is not None else v).numel() * v.element_size()
         return n
@@ -127,14 +179,16 @@ class Batch(ChemGraph):
     def to(self, device, non_blocking: bool = False):
         dev = torch.device(device)
         if dev.type != "cuda" or self.__dict__.get("_replica") is None:
-            return super().to(device, non_blocking=non_blocking)
+            return self._clone_meta({k: (v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else
+                                         (_Replicated(v.src.to(device, non_blocking=non_blocking), v.copies, v.is_edge_index, v.nodes) if isinstance(v, _Replicated) else v))
+                                     for k, v in self._fields.items()})
         B = self.__dict__["_replica"][0]
         n, e = self.__dict__["_lengths"][0], self.__dict__["_edges"][0]
         out = {}
         for k, v in self._fields.items():
             src = self._replica_source(k, v)
             if src is None:
-                out[k] = v.to(dev, non_blocking=non_blocking) if torch.is_tensor(v) else v
+                out[k] = v.to(dev, non_blocking=non_blocking) if torch.is_tensor(v) else (v.build().to(dev) if isinstance(v, _Replicated) else v)
                 continue
             one = src.to(dev, non_blocking=non_blocking)
             if k == "edge_index":
@@ -160,7 +214,9 @@ class Batch(ChemGraph):
             for k, v in self._fields.items():
                 if k in ("batch", "ptr"):
                     continue
-                if not torch.is_tensor(v):
+                if isinstance(v, _Replicated):
+                    f[k] = v.src
+                elif not torch.is_tensor(v):
                     f[k] = v[g] if isinstance(v, list) and len(v) == len(lengths) else v
                 elif k == "edge_index":
                     f[k] = v[:, eo:eo + e] - o

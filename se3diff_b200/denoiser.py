@@ -92,9 +92,10 @@ def _fields(sdes):
 _GRAPHS: "collections.OrderedDict" = None  # type: ignore[assignment]
 _GRAPH_SEEN: set = set()
 _MAX_GRAPHS = 4
+GRAPH_STATS = {"eager_first_sighting": 0, "captures": 0, "replays": 0}     # whole-loop graphs: what the calls of this process did
 
 
-def _graph_key(batch, sdes, so3, score_model, num_steps, max_t, min_t, device, tag=("dpm",)):
+def _graph_key(batch, sdes, so3, score_model, num_steps, max_t, min_t, device, tag=("dpm",), control=None):
     import os
 
     from .models import DiGConditionalScoreModel
@@ -103,15 +104,25 @@ def _graph_key(batch, sdes, so3, score_model, num_steps, max_t, min_t, device, t
         return None
     if not isinstance(score_model, DiGConditionalScoreModel) or not isinstance(so3, S.DiGSO3SDE):
         return None
+    if control is not None and not isinstance(control, DiGConditionalScoreModel):
+        return None
     if "single_embeds" not in batch or "pair_embeds" not in batch:
         return None
     sc = so3.score_function.score_scaling
-    nn_ = score_model.model_nn
-    ctx = nn_._context(batch)       # by identity, else by exact value: a fresh Batch of the same sequence maps to the same context
-    key = (id(score_model), id(ctx), nn_.precision, nn_._weights_version(), nn_.x1d_proj[1].weight.data_ptr(), tuple(batch["pos"].shape),
-           id(so3), sc.data_ptr(), sc._version, so3.sigma_min, so3.sigma_max, getattr(sdes["pos"], "s", None), num_steps, max_t, min_t,
-           str(device), tag)
-    return key, (score_model, ctx, nn_._layer_weights(torch.bfloat16 if nn_.precision == "bf16" else torch.float32), so3, sc)
+    parts, keep = [], []
+    for m in (score_model,) if control is None else (score_model, control):
+        nn_ = m.model_nn
+        if m.training and nn_.dropout_p > 0:
+            return None             # the dropout path is torch autograd code with fresh masks per call: never replayed
+        ctx = nn_._context(batch)   # by identity, else by exact value: a fresh Batch of the same sequence maps to the same context
+        weights = nn_._layer_weights(torch.bfloat16 if nn_.precision == "bf16" else torch.float32)
+        # `_struct_gen` moves when the model's cached tensors were REPLACED; in-place weight updates (optimizer steps on the
+        # control model) refresh them inside their storage, so a captured loop stays valid across them
+        parts.append((id(m), id(ctx), nn_.precision, nn_._struct_gen, m.training, nn_.x1d_proj[1].weight.data_ptr()))
+        keep += [m, ctx, weights]
+    key = (tuple(parts), tuple(batch["pos"].shape), id(so3), sc.data_ptr(), sc._version, so3.sigma_min, so3.sigma_max, so3.tol,
+           type(sdes["pos"]).__name__, getattr(sdes["pos"], "s", None), num_steps, max_t, min_t, str(device), tag)
+    return key, (*keep, so3, sc)
 
 
 def _dpm_loop(batch, score_model, steps, device):
@@ -131,13 +142,25 @@ def _dpm_graphed(key, keep_alive, batch, score_model, steps, device):
     return _loop_graphed(key, keep_alive, batch, lambda static: _dpm_loop(static, score_model, steps, device), device)
 
 
-def _loop_graphed(key, keep_alive, batch, loop_fn, device):
-    """Returns the denoised batch through capture/replay, or None when this key has only been seen once.
-    `loop_fn(batch) -> batch` is the whole sampler loop after the prior draw.  Loops that draw noise (Euler-Maruyama, Heun)
-    are captured too: torch's CUDA generator hands a captured graph its seed and offset at every replay, so a replay
-    consumes the generator exactly like the eager loop (same seed => same trajectory; `test_em_heun_loop_graphs_match_eager`).
-    `keep_alive` are the objects whose device pointers the graph bakes in (context, cached weights, SDE tables); the
-    entry owns them so that a replay can never read recycled memory."""
+def _tree_map(fn, tree):
+    if torch.is_tensor(tree):
+        return fn(tree)
+    if isinstance(tree, dict):
+        return {k: _tree_map(fn, v) for k, v in tree.items()}
+    if isinstance(tree, (list, tuple)):
+        return type(tree)(_tree_map(fn, v) for v in tree)
+    return tree
+
+
+def _loop_graphed(key, keep_alive, batch, loop_fn, device, returns_batch: bool = True):
+    """Returns the loop's result through capture/replay, or None when this key has only been seen once.
+    `loop_fn(batch)` is the whole sampler loop after the prior draw; it returns the denoised batch (`returns_batch`) or any tree
+    (dict / list / tuple) of tensors -- the recording fine-tune rollouts return their stacked states, controls and Brownian
+    increments.  Loops that draw noise (Euler-Maruyama, Heun) are captured too: torch's CUDA generator hands a captured graph
+    its seed and offset at every replay, so a replay consumes the generator exactly like the eager loop (same seed => same
+    trajectory; `test_em_heun_loop_graphs_match_eager`).  `keep_alive` are the objects whose device pointers the graph bakes in
+    (context, cached weights, SDE tables); the entry owns them so that a replay can never read recycled memory.  Results are
+    handed out as clones: the graph's own output buffers are overwritten by the next replay."""
     import collections
 
     global _GRAPHS
@@ -149,7 +172,9 @@ def _loop_graphed(key, keep_alive, batch, loop_fn, device):
             if len(_GRAPH_SEEN) > 256:
                 _GRAPH_SEEN.clear()
             _GRAPH_SEEN.add(key)
+            GRAPH_STATS["eager_first_sighting"] += 1
             return None
+        GRAPH_STATS["captures"] += 1
         entry = dict(pos_in=torch.empty_like(batch["pos"]), rot_in=torch.empty_like(batch["node_orientations"]), keep_alive=keep_alive)
         static = batch.replace(pos=entry["pos_in"], node_orientations=entry["rot_in"])
         entry["pos_in"].copy_(batch["pos"])
@@ -159,7 +184,9 @@ def _loop_graphed(key, keep_alive, batch, loop_fn, device):
         torch.cuda.synchronize(device)
         with torch.cuda.graph(graph):
             out = loop_fn(static)
-        entry.update(graph=graph, pos_out=out["pos"], rot_out=out["node_orientations"], launches=ops.launch_count() - before)
+        if returns_batch:
+            out = (out["pos"], out["node_orientations"])
+        entry.update(graph=graph, out=out, launches=ops.launch_count() - before)
         ops.count_replayed_launches(-entry["launches"])     # recorded, not executed: the replay below is what runs
         _GRAPHS[key] = entry
         while len(_GRAPHS) > _MAX_GRAPHS:
@@ -169,8 +196,10 @@ def _loop_graphed(key, keep_alive, batch, loop_fn, device):
     entry["pos_in"].copy_(batch["pos"])
     entry["rot_in"].copy_(batch["node_orientations"])
     entry["graph"].replay()
+    GRAPH_STATS["replays"] += 1
     ops.count_replayed_launches(entry["launches"])
-    return batch.replace(pos=entry["pos_out"].clone(), node_orientations=entry["rot_out"].clone())
+    out = _tree_map(torch.clone, entry["out"])
+    return batch.replace(pos=out[0], node_orientations=out[1]) if returns_batch else out
 
 
 @torch.no_grad()
@@ -228,28 +257,45 @@ def _em_loop(batch, sdes, score_model, finetune_model, num_steps, max_t, min_t, 
             if done is not None:
                 return done
         return plain(batch)
-    batches, us, dWs = [batch], defaultdict(list), defaultdict(list)
-    for st in steps:
-        t = _t(st.t, B, device)
-        pos, rot = batch["pos"], batch["node_orientations"]
-        out = score_model(batch, t)
-        u = finetune_model(batch, t) if record else None
-        z = {f: S.noise_randn((pos.shape[0], 3), device) for f in fields}  # per-field draw order = sdes key order
-        rot, pos, dw_rot, dw_pos = ops.frame_update_em(
-            rot, pos, out["node_orientations"], out["pos"], z["node_orientations"], z["pos"], st.scalars,
-            u_rot=None if u is None else u["node_orientations"], u_pos=None if u is None else u["pos"], want_dw=record)
-        batch = batch.replace(pos=pos, node_orientations=rot)
-        if record:
-            dw = {"pos": dw_pos, "node_orientations": dw_rot}
-            for f in fields:
-                us[f].append(_dense(u[f], batch, lengths))
-                dWs[f].append(_dense(dw[f], batch, lengths))
-            batches.append(batch)
+    def recorded(b):
+        """The recording loop on stacked outputs: states [T+1, N, .], controls and Brownian increments [T, B, L, 3] per field."""
+        pos_all, rot_all, us, dWs = [b["pos"]], [b["node_orientations"]], defaultdict(list), defaultdict(list)
+        for st in steps:
+            t = _t(st.t, B, device)
+            pos, rot = b["pos"], b["node_orientations"]
+            out = score_model(b, t)
+            u = finetune_model(b, t) if record else None
+            z = {f: S.noise_randn((pos.shape[0], 3), device) for f in fields}  # per-field draw order = sdes key order
+            rot, pos, dw_rot, dw_pos = ops.frame_update_em(
+                rot, pos, out["node_orientations"], out["pos"], z["node_orientations"], z["pos"], st.scalars,
+                u_rot=None if u is None else u["node_orientations"], u_pos=None if u is None else u["pos"], want_dw=record)
+            b = b.replace(pos=pos, node_orientations=rot)
+            if record:
+                dw = {"pos": dw_pos, "node_orientations": dw_rot}
+                for f in fields:
+                    us[f].append(_dense(u[f], b, lengths))
+                    dWs[f].append(_dense(dw[f], b, lengths))
+                pos_all.append(pos)
+                rot_all.append(rot)
+        if not record:
+            return dict(pos=b["pos"][None], rot=b["node_orientations"][None])
+        return dict(pos=torch.stack(pos_all), rot=torch.stack(rot_all), us={f: torch.stack(us[f], dim=0) for f in fields},
+                    dWs={f: torch.stack(dWs[f], dim=0) for f in fields})
+
+    res = None
+    if record and not S._HOST_NOISE:
+        # the whole recording rollout (200 score + 200 control evaluations, noise draws, frame updates) as ONE graph launch: the
+        # per-step host work (two model calls, bookkeeping) is what a rank waits for when several ranks share a host
+        keyed = _graph_key(batch, sdes, so3, score_model, num_steps, max_t, min_t, device, tag=("em-record", tuple(fields)), control=finetune_model)
+        if keyed is not None:
+            res = _loop_graphed(keyed[0], keyed[1], batch, recorded, device, returns_batch=False)
+    if res is None:
+        res = recorded(batch)
     if not record:
-        return batch
+        return batch.replace(pos=res["pos"][-1], node_orientations=res["rot"][-1])
     ts, _ = schedule.timesteps(max_t, min_t, num_steps)
-    return DenoisedSDEPath(batches=batches, timesteps=ts.to(device), us_batch={f: torch.stack(us[f], dim=0) for f in fields},
-                           dWs_batch={f: torch.stack(dWs[f], dim=0) for f in fields})
+    batches = [batch.replace(pos=res["pos"][i], node_orientations=res["rot"][i]) for i in range(res["pos"].shape[0])]
+    return DenoisedSDEPath(batches=batches, timesteps=ts.to(device), us_batch=res["us"], dWs_batch=res["dWs"])
 
 
 @torch.no_grad()

@@ -180,13 +180,32 @@ class DistributionalGraphormer(nn.Module):
         self.precision = "fp32"
         self._ctx: _Context | None = None
         self._wcache: dict = {}
+        self._struct_gen = 0          # bumped whenever a cache was REPLACED (new device pointers); graph keys carry it
 
     # -- caches ---------------------------------------------------------------------------------------
     def _weights_version(self) -> int:
         return sum(p._version for p in self.parameters())
 
+    @staticmethod
+    def _adopt(old, new) -> bool:
+        """Writes the tensors of `new` into the storage of the same-shaped tensors of `old` (nested dicts / lists / tuples), so that
+        CUDA graphs which baked the old pointers in see the new values.  False when the two do not have the same structure."""
+        if torch.is_tensor(old) and torch.is_tensor(new):
+            if old.shape != new.shape or old.dtype != new.dtype or old.device != new.device:
+                return False
+            if old.data_ptr() != new.data_ptr():
+                old.copy_(new)
+            return True
+        if isinstance(old, dict) and isinstance(new, dict):
+            return old.keys() == new.keys() and all(DistributionalGraphormer._adopt(old[k], new[k]) for k in old if k != "key")
+        if isinstance(old, (list, tuple)) and isinstance(new, (list, tuple)):
+            return len(old) == len(new) and all(DistributionalGraphormer._adopt(a, b) for a, b in zip(old, new))
+        return old is None and new is None
+
     def _layer_weights(self, dtype: torch.dtype):
-        """Fused / cast weights, rebuilt when a parameter was updated in place or moved."""
+        """Fused / cast weights, rebuilt when a parameter was updated in place or moved.  After an in-place update (an optimizer
+        step on the fine-tune control model) the new values are written into the EXISTING cache tensors, so captured graphs of
+        this model stay valid; `_struct_gen` counts the rebuilds that did change pointers."""
         dev = self.x1d_proj[1].weight.device
         key = (dtype, dev, self._weights_version())
         if self._wcache.get("key") != key:
@@ -215,7 +234,13 @@ class DistributionalGraphormer(nn.Module):
             for name in ("fc_t", "fc_eps"):
                 seq = getattr(self.st_module.diff_head, name)
                 heads[name] = (seq[1].weight.detach().to(dtype).contiguous(), seq[3].weight.detach().float().contiguous())
-            self._wcache = dict(key=key, layers=layers, heads=heads)
+            fresh = dict(key=key, layers=layers, heads=heads)
+            old = self._wcache
+            if old.get("key") is not None and old["key"][:2] == key[:2] and not torch.cuda.is_current_stream_capturing() and self._adopt(old, fresh):
+                old["key"] = key
+            else:
+                self._wcache = fresh
+                self._struct_gen += 1
         return self._wcache
 
     @torch.no_grad()
@@ -229,19 +254,37 @@ class DistributionalGraphormer(nn.Module):
         versions = tuple(None if a is None else a._version for a in src)
         key = (self._weights_version(), self.precision, self.x1d_proj[1].weight.data_ptr())
         c = self._ctx
-        if c is not None and c.key == key:
+        if c is not None and c.key[1:] == key[1:]:
             # The cache owns references to the tensors it was built from, so neither an address nor an id can be
             # recycled under it.  Fast path: the very same tensor objects, unmodified.  Otherwise (a fresh Batch of the
             # same sequence, sample.py:223 builds one per call) compare by VALUE, exactly, once.
-            if versions == c.src_versions and all(a is b for a, b in zip(src, c.src)):
+            same = versions == c.src_versions and all(a is b for a, b in zip(src, c.src))
+            if not same:
+                held_intact = c.src_versions == tuple(None if a is None else a._version for a in c.src)
+                same = (held_intact and not torch.cuda.is_current_stream_capturing()
+                        and all((a is None) == (b is None) for a, b in zip(src, c.src))
+                        and all(a is None or (a.shape == b.shape and a.dtype == b.dtype and a.device == b.device and torch.equal(a, b))
+                                for a, b in zip(src, c.src)))
+                if same:
+                    c.src, c.src_versions = src, versions
+            if same and c.key == key:
                 return c
-            held_intact = c.src_versions == tuple(None if a is None else a._version for a in c.src)
-            if (held_intact and not torch.cuda.is_current_stream_capturing()
-                    and all((a is None) == (b is None) for a, b in zip(src, c.src))
-                    and all(a is None or (a.shape == b.shape and a.dtype == b.dtype and a.device == b.device and torch.equal(a, b))
-                            for a, b in zip(src, c.src))):
-                c.src, c.src_versions = src, versions
-                return c
+            if same and not torch.cuda.is_current_stream_capturing():
+                # same sequence, weights updated in place (optimizer step on the control model): recompute the weight-dependent
+                # tensors and write them into the existing buffers -- the context object and its device pointers survive, and
+                # with them every CUDA graph captured over it
+                fresh = self._build_context(ctx_graph, src, versions, key)
+                if fresh.shared == c.shared and fresh.tc == c.tc and self._adopt(
+                        [c.x1d_base, c.pair_bias, c.pair_value, c.pair_value_packed], [fresh.x1d_base, fresh.pair_bias, fresh.pair_value, fresh.pair_value_packed]):
+                    c.key = key
+                    return c
+        c = self._build_context(ctx_graph, src, versions, key)
+        self._ctx = c
+        self._struct_gen += 1
+        return c
+
+    def _build_context(self, ctx_graph, src, versions, key) -> _Context:
+        single, pair, bidx, known, edges = src
         dev = single.device
         lengths = batch_lengths(ctx_graph)
         B, lmax = len(lengths), max(lengths)
@@ -297,7 +340,6 @@ class DistributionalGraphormer(nn.Module):
             else:
                 c.pair_value.append(pv.contiguous())
         c.workspace = ops.ipa_tc_workspace(probe, dev) if c.tc else None
-        self._ctx = c
         return c
 
     @staticmethod
@@ -429,28 +471,19 @@ class DistributionalGraphormer(nn.Module):
         Heun, the fine-tune rollouts: 200 evaluations per call) are launch-bound at small batches -- 2.3 ms of CPU enqueue per
         evaluation of the 8-layer model against 1.2 ms of kernels at L = 84, B = 64.  A (context, weights, shape) triple is
         evaluated eagerly twice, captured on its third sighting and replayed from then on; the entry owns the context and the
-        cached weights whose device pointers the graph baked in.  A model whose weights keep changing (the control model
-        between optimizer steps) stops being captured after its graphs were invalidated twice.  Returns None when this call
-        has to run eagerly."""
+        cached weights whose device pointers the graph baked in.  In-place weight updates (the control model between optimizer
+        steps) do not invalidate a graph: the derived tensors are refreshed inside their existing storage (`_adopt`).  Returns
+        None when this call has to run eagerly."""
         import os
 
         if os.environ.get("SE3DIFF_B200_MODEL_GRAPH", "1") == "0" or torch.cuda.is_current_stream_capturing():
             return None
         c = self._context(context)
         dtype = torch.float32 if self.precision == "fp32" else torch.bfloat16
-        wv = self._weights_version()
-        key = (id(c), self.precision, wv, self.x1d_proj[1].weight.data_ptr(), tuple(x.shape), tuple(t.shape), str(x.device))
+        self._layer_weights(dtype)                             # refreshes the cached weights in place after an optimizer step
+        key = (id(c), self.precision, self._struct_gen, self.x1d_proj[1].weight.data_ptr(), tuple(x.shape), tuple(t.shape), str(x.device))
         graphs = self.__dict__.setdefault("_fgraphs", {})
         seen = self.__dict__.setdefault("_fgraph_seen", {})
-        st = self.__dict__.setdefault("_fgraph_state", {"wv": wv, "invalidated": 0})
-        if st["wv"] != wv:                                      # the weights were written to: every graph of this model is stale
-            st["wv"] = wv
-            if graphs:
-                st["invalidated"] += 1
-                graphs.clear()
-            seen.clear()
-        if st["invalidated"] >= 2:
-            return None
         ent = graphs.get(key)
         if ent is None:
             n = seen.get(key, 0) + 1

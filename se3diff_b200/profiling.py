@@ -63,7 +63,7 @@ def _time_alone(fn, iters=10, warmup=3):
 
 HBM_NOMINAL_GBS = 8000.0      # north_star's "~8 TB/s" (DGX B200 figure; HGX: 7.7 TB/s) -- reported next to the measured copy bandwidth
 SMS, XU_LANES_PER_CLK_SM = 148, 16      # MUFU: 4 lanes / clock / SM sub-partition (measured: 8 cycles per warp instruction, scripts/microbench)
-FP64_LANES_PER_CLK_SM = 2     # B200 DFMA rate per SM (64 : 1 against FP32)
+FP32_LANES_PER_CLK_SM, FP64_LANES_PER_CLK_SM = 128, 64     # B200: 128 FFMA and 64 DFMA lanes per SM and clock (~37 TFLOP/s FP64 chip-wide)
 
 
 def _hbm_line(name, n, bytes_per, ms, pk, **extra):
@@ -75,10 +75,13 @@ def _hbm_line(name, n, bytes_per, ms, pk, **extra):
 
 def series_rooflines(device="cuda", sm_mhz=None):
     """K1a / K1b (so3_sde.py:1731-1940, 1131-1187, 1637-1696): the truncated IGSO(3) series and the table builds.  They are
-    arithmetic-bound (sin / exp per term), not HBM-bound: reported as series TERMS per second against the unit that evaluates
-    a term -- the XU (MUFU) pipe for fp32 (one sin + one exp per term and lane: 2 MUFU ops), the FP64 pipe for the tables
-    (a term is ~40 DFMA: range-reduced sin and exp polynomials).  The term count is the number actually evaluated: terms whose
-    exponential underflows to exactly zero are skipped (sum unchanged bit for bit), so it depends on sigma."""
+    arithmetic-bound, not HBM-bound (one element = up to 2001 terms from 8 bytes of input): reported as series TERMS per second
+    against the instruction rate of the pipe that evaluates a term.  A term of the (f, df) pair is one exp and three sin in the
+    working precision -- libm-accurate, because the tables and scores must round like torch's (the fast MUFU forms are 2 ulp
+    off) -- plus ~12 multiply-adds: ~100 FP32-pipe instructions in fp32, ~200 FP64-pipe instructions in fp64; a table row shares
+    its exponential factors across the omega grid (~50 per term for the density, ~150 with the derivative).  The term count is
+    the number actually evaluated: terms whose exponential underflows to exactly zero are skipped (the sum is unchanged bit
+    for bit), so it depends on sigma."""
     import math
 
     clk = (sm_mhz or 1965) * 1e6
@@ -86,42 +89,35 @@ def series_rooflines(device="cuda", sm_mhz=None):
     n, l_max = 1_000_000, 2000
     om = torch.rand(n, generator=g, device=device) * math.pi
     sg = 0.02 * (2.33 / 0.02) ** torch.rand(n, generator=g, device=device)
-    # terms evaluated per element: l runs while exp(-l(l+1) sigma^2 / 2) > 0 in the working precision
-    def terms(sigma, tiny):
+
+    def terms(sigma, tiny):      # l runs while exp(-l(l+1) sigma^2 / 2) > 0 in the working precision
         lcut = torch.sqrt(2.0 * (-math.log(tiny)) / sigma.double() ** 2)
         return torch.clamp(lcut.ceil(), max=l_max + 1)
+
+    def line(name, n_terms, ms, lanes, per_term, what, **extra):
+        peak = SMS * lanes * clk / per_term
+        return {"kernel": name, "bound": what, "terms_evaluated": n_terms, "ms": ms, "achieved": n_terms / ms / 1e6, "peak": peak / 1e9,
+                "unit": "Gterm/s", "frac": n_terms / ms / 1e6 / (peak / 1e9),
+                "peak_source": f"148 SMs x {lanes} {what} lanes x {clk / 1e6:.0f} MHz / ~{per_term} instructions per term (estimate, see profiling.py)", **extra}
+
     t32 = terms(sg, 1.4e-45).sum().item()
-    res = []
-    xu_peak = SMS * XU_LANES_PER_CLK_SM * clk / 2          # terms / s if every term costs one sin + one exp on the XU pipe
-    ms = _time_alone(lambda: ops.igso3_series(om, sg, l_max, want=("f", "df", "dlog")))
-    res.append({"kernel": "se3_igso3_series_f32 (f, df, dlog)", "bound": "xu", "n": n, "l_max": l_max, "terms_evaluated": t32, "ms": ms,
-                "achieved": t32 / ms / 1e6, "peak": xu_peak / 1e9, "unit": "Gterm/s", "frac": t32 / ms / 1e6 / (xu_peak / 1e9),
-                "peak_source": f"148 SMs x 16 MUFU lanes x {clk / 1e6:.0f} MHz / 2 MUFU ops per term"})
+    res = [line("se3_igso3_series_f32 (f, df, dlog)", t32, _time_alone(lambda: ops.igso3_series(om, sg, l_max, want=("f", "df", "dlog"))),
+                FP32_LANES_PER_CLK_SM, 100, "fp32", n=n, l_max=l_max)]
     rv = torch.randn(n, 3, generator=g, device=device)
-    ms = _time_alone(lambda: ops.igso3_score(rv, sg, l_max))
-    res.append({"kernel": "se3_igso3_score", "bound": "xu", "n": n, "l_max": l_max, "terms_evaluated": t32, "ms": ms,
-                "achieved": t32 / ms / 1e6, "peak": xu_peak / 1e9, "unit": "Gterm/s", "frac": t32 / ms / 1e6 / (xu_peak / 1e9),
-                "peak_source": f"148 SMs x 16 MUFU lanes x {clk / 1e6:.0f} MHz / 2 MUFU ops per term"})
+    res.append(line("se3_igso3_score", t32, _time_alone(lambda: ops.igso3_score(rv, sg, l_max)), FP32_LANES_PER_CLK_SM, 100, "fp32", n=n, l_max=l_max))
     n64 = 200_000
     om64, sg64 = om[:n64].double(), sg[:n64].double()
     t64 = terms(sg64, 4.9e-324).sum().item()
-    f64_peak = SMS * FP64_LANES_PER_CLK_SM * clk / 40
-    ms = _time_alone(lambda: ops.igso3_series(om64, sg64, l_max, want=("f", "df", "dlog")), iters=5)
-    res.append({"kernel": "se3_igso3_series_f64 (f, df, dlog)", "bound": "fp64", "n": n64, "l_max": l_max, "terms_evaluated": t64, "ms": ms,
-                "achieved": t64 / ms / 1e6, "peak": f64_peak / 1e9, "unit": "Gterm/s", "frac": t64 / ms / 1e6 / (f64_peak / 1e9),
-                "peak_source": f"148 SMs x 2 DFMA lanes x {clk / 1e6:.0f} MHz / ~40 DFMA per term (sin + exp in fp64)"})
+    res.append(line("se3_igso3_series_f64 (f, df, dlog)", t64, _time_alone(lambda: ops.igso3_series(om64, sg64, l_max, want=("f", "df", "dlog")), iters=5),
+                    FP64_LANES_PER_CLK_SM, 200, "fp64", n=n64, l_max=l_max))
     # table builds of the shipped configuration (config.yaml:23-35): 1000 sigma rows x 2001 omega points x <= 2001 terms, fp64
     sig_grid = 0.02 * (2.33 / 0.02) ** torch.linspace(0.001, 1.0, 1000, device=device)
     om_pts = (torch.linspace(0.0, 1, 2001, device=device, dtype=torch.float64) ** 3 * math.pi)
     tt = (terms(sig_grid, 4.9e-324) * 2001).sum().item()
-    ms = _time_alone(lambda: ops.igso3_build_cdf(sig_grid, om_pts, 2000), iters=3, warmup=1)
-    res.append({"kernel": "se3_igso3_build_cdf (1000 x 2000 table)", "bound": "fp64", "terms_evaluated": tt, "ms": ms, "achieved": tt / ms / 1e6,
-                "peak": f64_peak / 1e9, "unit": "Gterm/s", "frac": tt / ms / 1e6 / (f64_peak / 1e9),
-                "peak_source": f"148 SMs x 2 DFMA lanes x {clk / 1e6:.0f} MHz / ~40 DFMA per term", "note": "once per process (or read from the npz cache)"})
-    ms = _time_alone(lambda: ops.igso3_build_score_scaling(sig_grid, om_pts, 2000), iters=3, warmup=1)
-    res.append({"kernel": "se3_igso3_build_score_scaling (1000 rows)", "bound": "fp64", "terms_evaluated": 2 * tt, "ms": ms, "achieved": 2 * tt / ms / 1e6,
-                "peak": f64_peak / 1e9, "unit": "Gterm/s", "frac": 2 * tt / ms / 1e6 / (f64_peak / 1e9),
-                "peak_source": f"148 SMs x 2 DFMA lanes x {clk / 1e6:.0f} MHz / ~40 DFMA per term", "note": "f and df series per (sigma, omega)"})
+    res.append(line("se3_igso3_build_cdf (1000 x 2000 table)", tt, _time_alone(lambda: ops.igso3_build_cdf(sig_grid, om_pts, 2000), iters=3, warmup=1),
+                    FP64_LANES_PER_CLK_SM, 50, "fp64", note="once per process (or read from the npz cache)"))
+    res.append(line("se3_igso3_build_score_scaling (1000 rows)", tt, _time_alone(lambda: ops.igso3_build_score_scaling(sig_grid, om_pts, 2000), iters=3, warmup=1),
+                    FP64_LANES_PER_CLK_SM, 150, "fp64", note="density and derivative series per (sigma, omega)"))
     return res
 
 

@@ -243,6 +243,8 @@ class BaseSampleSO3(nn.Module):
         `randn(n, m, 3)` then uniforms `rand(n, m)` (so3_sde.py:1204-1205, 1240, 1262)."""
         dev = self.cdf_igso3.device
         n, m = sigma.shape[0], num_samples
+        if (normals is None) != (u is None):
+            raise ValueError("BaseSampleSO3.sample: pass both `normals` [n, m, 3] and `u` [n, m], or neither")
         if normals is None:
             normals = noise_randn((n, m, 3), dev)
             u = noise_rand((n, m), dev)
@@ -381,9 +383,16 @@ class SO3SDE(SDE, nn.Module):
         """x(t) | x(0) = x . r, r ~ IGSO3(sigma(t)) (so3_sde.py:249-288); fused into one kernel."""
         _, std = self.marginal_prob(x=x, t=t, batch_idx=batch_idx)
         lead = x.shape[:-2]
-        std = std.expand(lead) if std.shape != lead else std
-        out = self.igso3.sample(std.reshape(-1), 1, left=x.reshape(-1, 3, 3).to(self.igso3.cdf_igso3.device))
-        return out.view(*lead, 3, 3)
+        dev = self.igso3.cdf_igso3.device
+        if tuple(std.shape) == tuple(lead):            # one rotation per matrix (the sparse [N, 3, 3] layout): sample and compose in one kernel
+            out = self.igso3.sample(std.reshape(-1), 1, left=x.reshape(-1, 3, 3).to(dev))
+            return out.view(*lead, 3, 3)
+        if std.dim() == 1 and len(lead) > 1 and std.shape[0] == lead[0]:
+            # dense [B, L, 3, 3] with per-graph t: the reference draws ONE rotation per graph and applies it to every frame of
+            # that graph (einsum "b...j,b...sjk->b...sk" with r [B, 1, 3, 3], so3_sde.py:274-283)
+            r = self.igso3.sample(std, 1)[:, 0]                                   # [B, 3, 3]
+            return torch.matmul(x.to(dev), r.view(lead[0], *([1] * (len(lead) - 1)), 3, 3))
+        raise ValueError(f"sample_marginal: std of shape {tuple(std.shape)} does not match x of shape {tuple(x.shape)}")
 
 
 class DiGSO3SDE(SO3SDE):

@@ -1095,6 +1095,35 @@ def test_so3_table_cache_is_written_in_the_reference_format(tmp_path):
     assert torch.equal(a.igso3.cdf_igso3.cpu(), b.igso3.cdf_igso3.cpu()) and torch.equal(a.score_function.score_scaling.cpu(), b.score_function.score_scaling.cpu())
 
 
+def test_sample_marginal_dense_layout_draws_one_rotation_per_graph():
+    """so3_sde.py:249-288 on a dense [B, L, 3, 3] input with per-graph t and no batch_idx: ONE IGSO(3) rotation per graph, applied to
+    all of its frames (the einsum broadcasts r [B, 1, 3, 3] over L) -- also when B == L, where a per-frame draw would have the
+    same shapes.  Checked against the oracle's sampler on the same host noise stream."""
+    from oracle.gen_golden import SMALL_SDE
+    from se3diff_b200 import sdes as S
+
+    tab = oso3.SO3Tables(**SMALL_SDE)
+    so3 = S.DiGSO3SDE(**SMALL_SDE).to(DEV)
+    so3.igso3.cdf_igso3.copy_(tab.cdf_igso3)
+    for B, L in ((3, 5), (4, 4)):
+        g = torch.Generator().manual_seed(B)
+        x = oso3.rotvec_to_rotmat(torch.randn(B * L, 3, generator=g)).view(B, L, 3, 3)
+        t = torch.rand(B, generator=g) * 0.9 + 0.05
+        with S.host_noise():
+            torch.manual_seed(5)
+            got = so3.sample_marginal(x.to(DEV), t.to(DEV)).cpu()
+        rel = torch.matmul(x.transpose(-1, -2), got)                       # x^T (x r) = r, per frame
+        assert (rel - rel[:, :1]).abs().max() < 1e-5                       # the same rotation for every frame of a graph
+        assert (rel[0, 0] - rel[1, 0]).abs().max() > 1e-3                  # different graphs, different draws
+        torch.manual_seed(5)
+        want = tab.sample_marginal(x, t)                                  # the oracle's einsum "b...j,b...sjk->b...sk" (so3_sde.py:283)
+        assert tuple(want.shape) == (B, L, 3, 3) and (got - want).abs().max() < 1e-5
+    with pytest.raises(ValueError):
+        so3.sample_marginal(torch.eye(3).expand(2, 5, 3, 3).to(DEV), torch.rand(3).to(DEV))
+    with pytest.raises(ValueError):
+        so3.igso3.sample(torch.full((4,), 0.5, device=DEV), 1, normals=torch.randn(4, 1, 3, device=DEV))
+
+
 def test_dpm_cuda_graph_replay_matches_eager():
     """Third call with the same device-resident batch replays a captured CUDA graph of the whole dpm loop; with the
     same seed it must reproduce the eager result bit for bit (same kernels, same arguments)."""
