@@ -211,6 +211,55 @@ __device__ __forceinline__ void so3_mul(const T a[9], const T b[9], T c[9]) {
         }
 }
 
+// ---- fused editions for the frame-update kernels ---------------------------------------------------------------------
+// The rotation half of a frame update is never bit-identical to the CPU reference (its sin / cos come from another libm), so
+// nothing is lost by spelling it with explicit fused multiply-adds (these translation units are compiled with -fmad=false,
+// which only stops CONTRACTION of a*b+c; fmaf() is always fused) and a short sincos: two-constant Cody-Waite reduction by
+// pi/2 and the degree-7 / degree-8 minimax polynomials of Cephes' sinf / cosf on [-pi/4, pi/4] (approximation error 3e-9 /
+// 1e-10, i.e. 1 ulp-class results for the |theta| << 1e4 a step's rotation vector has).  ~3x fewer instructions than the
+// reference-order so3_exp + so3_mul: ncu showed k_em issue-bound at 0.6 of the HBM roof, not latency-bound.
+__device__ __forceinline__ void sincos_fused(float x, float* s, float* c) {
+    const float k = rintf(x * 0.636619772367581343f);
+    float r = fmaf(-k, 1.5707963705062866f, x);
+    r = fmaf(-k, -4.371138828673793e-08f, r);
+    const float r2 = r * r;
+    const float sp = fmaf(fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f), r2 * r, r);
+    const float cp = fmaf(fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f), r2 * r2, fmaf(-0.5f, r2, 1.0f));
+    const int q = (int)k;
+    const float ss = (q & 1) ? cp : sp, cc = (q & 1) ? sp : cp;
+    *s = (q & 2) ? -ss : ss;
+    *c = ((q + 1) & 2) ? -cc : cc;
+}
+// out = R . Exp(v)  (apply_rotvec_to_rotmat, so3_sde.py:782-802; Rodrigues with the Taylor branch below `tol`, :533-554)
+__device__ __forceinline__ void so3_apply_rotvec_fused(const float r[9], float x, float y, float z, float tol, float out[9]) {
+    const float th2 = fmaf(x, x, fmaf(y, y, z * z));
+    const float th = __fsqrt_rn(th2);
+    float a, b;
+    if (th < tol) {
+        a = fmaf(th2, -1.0f / 6.0f, 1.0f);
+        b = fmaf(th2, -1.0f / 24.0f, 0.5f);
+    } else {
+        float s, c;
+        sincos_fused(th, &s, &c);
+        a = __fdividef(s, th);
+        b = __fdividef(1.0f - c, th2);
+    }
+    // E = I + a K + b K^2,  K = [[0,-z,y],[z,0,-x],[-y,x,0]],  K^2 = v v^T - |v|^2 I
+    const float bx = b * x, by = b * y, bz = b * z;
+    const float e00 = fmaf(-b, fmaf(y, y, z * z), 1.0f), e11 = fmaf(-b, fmaf(x, x, z * z), 1.0f), e22 = fmaf(-b, fmaf(x, x, y * y), 1.0f);
+    const float e01 = fmaf(bx, y, -a * z), e10 = fmaf(bx, y, a * z);
+    const float e02 = fmaf(bx, z, a * y), e20 = fmaf(bx, z, -a * y);
+    const float e12 = fmaf(by, z, -a * x), e21 = fmaf(by, z, a * x);
+    (void)bz;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float r0 = r[i * 3], r1 = r[i * 3 + 1], r2 = r[i * 3 + 2];
+        out[i * 3] = fmaf(r2, e20, fmaf(r1, e10, r0 * e00));
+        out[i * 3 + 1] = fmaf(r2, e21, fmaf(r1, e11, r0 * e01));
+        out[i * 3 + 2] = fmaf(r2, e22, fmaf(r1, e12, r0 * e02));
+    }
+}
+
 // angle_from_rotmat (so3_sde.py:651-676)
 template <typename T>
 __device__ __forceinline__ T so3_angle(const T r[9], T w[3], T* sin_out, T* cos_out) {

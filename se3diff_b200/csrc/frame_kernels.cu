@@ -5,8 +5,9 @@
 // vectors) is moved with 128-bit coalesced accesses through shared memory by the warp that owns the residues
 // (common.cuh: warp_tile_load / warp_tile_store), so only __syncwarp() separates load, compute and store.
 // HBM-bound: 120-168 algorithmic bytes per residue against ~150 flop + 2 sincos.
-// Compiled with -fmad=false: each expression is evaluated in the reference's order, so the R3
-// half is bit-identical to the fp32 torch path and the SO(3) half differs only in sin/cos.
+// Compiled with -fmad=false: each R3 expression is evaluated in the reference's order, so the R3
+// half is bit-identical to the fp32 torch path.  The SO(3) half (which could never be bit-identical: other libm) uses
+// explicit FMAs and a short sincos (common.cuh: so3_apply_rotvec_fused) and agrees to ~1e-6.
 #include "common.cuh"
 
 using namespace se3;
@@ -28,11 +29,9 @@ __device__ __forceinline__ void st9(float* s, int t, const float r[9]) {
     for (int k = 0; k < 9; ++k) s[t * 9 + k] = r[k];
 }
 
-// R . Exp(v)   (apply_rotvec_to_rotmat, so3_sde.py:782-802)
+// R . Exp(v)   (apply_rotvec_to_rotmat, so3_sde.py:782-802), fused edition (common.cuh)
 __device__ __forceinline__ void apply_rotvec(const float r[9], Vec3 v, float tol, float out[9]) {
-    float a[3] = {v.x, v.y, v.z}, e[9];
-    so3_exp(a, tol, e);
-    so3_mul<float, false>(r, e, out);
+    so3_apply_rotvec_fused(r, v.x, v.y, v.z, tol, out);
 }
 
 // SO(3) reverse drift (denoiser.py:64-68 with so3_sde.py:173-194): 0 - g^2*score*w [+ g*u*w]
@@ -51,6 +50,33 @@ __device__ __forceinline__ float pos_drift(float beta, float sqb, float x, float
 // ---------------------------------------------------------------------------------------------
 // Euler-Maruyama step (denoiser.py:54-116)
 // ---------------------------------------------------------------------------------------------
+// One residue of the Euler-Maruyama step, in place in shared memory: s_rot [.][9], sv[0..4(6)] = pos, m_rot, m_pos, z_rot, z_pos
+// [, u_rot, u_pos] as [.][3]; results overwrite rot / pos (and z_rot / z_pos with the Brownian increments when OUT_DW)
+template <bool HAS_U, bool OUT_DW>
+__device__ __forceinline__ void em_element(float* s_rot, float* const* s_v, int t, const se3_em_scalars& c) {
+    float r[9], mean[9], out[9];
+    ld9(s_rot, t, r);
+    const Vec3 x = ld3(s_v[0], t), mr = ld3(s_v[1], t), mp = ld3(s_v[2], t), zr = ld3(s_v[3], t), zp = ld3(s_v[4], t);
+    Vec3 ur = {0, 0, 0}, up = {0, 0, 0};
+    if (HAS_U) { ur = ld3(s_v[5], t); up = ld3(s_v[6], t); }
+    const float w = c.score_weight, g = c.rot_g, nsd = c.noise_weight * c.sqrt_abs_dt;
+    // rotations: mean = R.Exp(drift*dt); sample = mean.Exp(g*dW)
+    const Vec3 sr = {mr.x * c.rot_scale, mr.y * c.rot_scale, mr.z * c.rot_scale};
+    const Vec3 dr = {rot_drift(g, sr.x, w, HAS_U, ur.x), rot_drift(g, sr.y, w, HAS_U, ur.y), rot_drift(g, sr.z, w, HAS_U, ur.z)};
+    const Vec3 dwr = {nsd * zr.x, nsd * zr.y, nsd * zr.z};
+    apply_rotvec(r, {dr.x * c.dt, dr.y * c.dt, dr.z * c.dt}, c.tol, mean);
+    apply_rotvec(mean, {g * dwr.x, g * dwr.y, g * dwr.z}, c.tol, out);
+    st9(s_rot, t, out);
+    // positions: mean = x + drift*dt; sample = mean + sqrt(beta)*dW
+    const Vec3 sp = {mp.x / c.pos_std, mp.y / c.pos_std, mp.z / c.pos_std};
+    const float b = c.pos_beta, q = c.pos_sqrt_beta;
+    const Vec3 dp = {pos_drift(b, q, x.x, sp.x, w, HAS_U, up.x), pos_drift(b, q, x.y, sp.y, w, HAS_U, up.y),
+                     pos_drift(b, q, x.z, sp.z, w, HAS_U, up.z)};
+    const Vec3 dwp = {nsd * zp.x, nsd * zp.y, nsd * zp.z};
+    st3(s_v[0], t, {(x.x + dp.x * c.dt) + q * dwp.x, (x.y + dp.y * c.dt) + q * dwp.y, (x.z + dp.z * c.dt) + q * dwp.z});
+    if (OUT_DW) { st3(s_v[3], t, dwr); st3(s_v[4], t, dwp); }
+}
+
 template <bool HAS_U, bool OUT_DW>
 __global__ void __launch_bounds__(kTile)
 k_em(const float* __restrict__ rot, const float* __restrict__ pos, const float* __restrict__ m_rot,
@@ -75,27 +101,8 @@ k_em(const float* __restrict__ rot, const float* __restrict__ pos, const float* 
     __syncwarp();
     const int t = threadIdx.x;
     if (t < count) {
-        float r[9], mean[9], out[9];
-        ld9(s_rot, t, r);
-        const Vec3 x = ld3(s_v[0], t), mr = ld3(s_v[1], t), mp = ld3(s_v[2], t), zr = ld3(s_v[3], t), zp = ld3(s_v[4], t);
-        Vec3 ur = {0, 0, 0}, up = {0, 0, 0};
-        if (HAS_U) { ur = ld3(s_v[5], t); up = ld3(s_v[6], t); }
-        const float w = c.score_weight, g = c.rot_g, nsd = c.noise_weight * c.sqrt_abs_dt;
-        // rotations: mean = R.Exp(drift*dt); sample = mean.Exp(g*dW)
-        const Vec3 sr = {mr.x * c.rot_scale, mr.y * c.rot_scale, mr.z * c.rot_scale};
-        const Vec3 dr = {rot_drift(g, sr.x, w, HAS_U, ur.x), rot_drift(g, sr.y, w, HAS_U, ur.y), rot_drift(g, sr.z, w, HAS_U, ur.z)};
-        const Vec3 dwr = {nsd * zr.x, nsd * zr.y, nsd * zr.z};
-        apply_rotvec(r, {dr.x * c.dt, dr.y * c.dt, dr.z * c.dt}, c.tol, mean);
-        apply_rotvec(mean, {g * dwr.x, g * dwr.y, g * dwr.z}, c.tol, out);
-        st9(s_rot, t, out);
-        // positions: mean = x + drift*dt; sample = mean + sqrt(beta)*dW
-        const Vec3 sp = {mp.x / c.pos_std, mp.y / c.pos_std, mp.z / c.pos_std};
-        const float b = c.pos_beta, q = c.pos_sqrt_beta;
-        const Vec3 dp = {pos_drift(b, q, x.x, sp.x, w, HAS_U, up.x), pos_drift(b, q, x.y, sp.y, w, HAS_U, up.y),
-                         pos_drift(b, q, x.z, sp.z, w, HAS_U, up.z)};
-        const Vec3 dwp = {nsd * zp.x, nsd * zp.y, nsd * zp.z};
-        st3(s_v[0], t, {(x.x + dp.x * c.dt) + q * dwp.x, (x.y + dp.y * c.dt) + q * dwp.y, (x.z + dp.z * c.dt) + q * dwp.z});
-        if (OUT_DW) { st3(s_v[3], t, dwr); st3(s_v[4], t, dwp); }
+        float* sv[7] = {s_v[0], s_v[1], s_v[2], s_v[3], s_v[4], HAS_U ? s_v[5] : nullptr, HAS_U ? s_v[6] : nullptr};
+        em_element<HAS_U, OUT_DW>(s_rot, sv, t, c);
     }
     __syncwarp();
     warp_tile_store<9>(rot_out, s_rot, first, count);
@@ -103,6 +110,68 @@ k_em(const float* __restrict__ rot, const float* __restrict__ pos, const float* 
     if (OUT_DW) {
         if (dw_rot) warp_tile_store<3>(dw_rot, s_v[3], first, count);
         if (dw_pos) warp_tile_store<3>(dw_pos, s_v[4], first, count);
+    }
+}
+
+
+// Pipelined edition of k_em for large n: every WARP walks 32-residue groups on its own, with the NEXT group's operand tiles in
+// flight (cp.async into the other half of a two-stage shared-memory ring) while it computes and stores the current one.
+// k_em alone keeps ~half of its resident warps in the compute phase, so the bytes in flight cover ~0.6 of the HBM roof
+// (profiles/r1l_elementwise_per_warp_ncu_summary.txt); here a warp always has a group's worth of loads outstanding.
+template <bool HAS_U, bool OUT_DW>
+__global__ void __launch_bounds__(kTile, 4)
+k_em_pipe(const float* __restrict__ rot, const float* __restrict__ pos, const float* __restrict__ m_rot,
+          const float* __restrict__ m_pos, const float* __restrict__ u_rot, const float* __restrict__ u_pos,
+          const float* __restrict__ z_rot, const float* __restrict__ z_pos, float* __restrict__ rot_out,
+          float* __restrict__ pos_out, float* __restrict__ dw_rot, float* __restrict__ dw_pos, int64_t n,
+          const se3_em_scalars c) {
+    constexpr int NV = HAS_U ? 7 : 5;
+    constexpr int kStage = 32 * 9 + NV * 32 * 3;             // floats per stage: one group of every operand
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* wbase = smem + (size_t)warp * 2 * kStage;
+    const float* srcs[7] = {pos, m_rot, m_pos, z_rot, z_pos, u_rot, u_pos};
+    const int64_t ngroups = (n + 31) >> 5, gstride = (int64_t)gridDim.x * (kTile / 32);
+    auto issue = [&](int64_t grp, float* st) {               // the whole warp; full groups only (the launcher sends ragged tails to k_em)
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(st);
+        const float4* r4 = reinterpret_cast<const float4*>(rot + grp * 32 * 9);
+#pragma unroll
+        for (int i = lane; i < 72; i += 32) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d + (uint32_t)i * 16u), "l"(r4 + i) : "memory");
+#pragma unroll
+        for (int a = 0; a < NV; ++a) {
+            const float4* v4 = reinterpret_cast<const float4*>(srcs[a] + grp * 32 * 3);
+            if (lane < 24) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d + (uint32_t)(288 + a * 96) * 4u + (uint32_t)lane * 16u), "l"(v4 + lane) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int64_t g = (int64_t)blockIdx.x * (kTile / 32) + warp;
+    if (g < ngroups) issue(g, wbase);
+    for (int k = 0; g < ngroups; g += gstride, k ^= 1) {
+        float* st = wbase + k * kStage;
+        const int64_t next = g + gstride;
+        if (next < ngroups) {
+            issue(next, wbase + (k ^ 1) * kStage);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+        float* sv[7];
+#pragma unroll
+        for (int a = 0; a < 7; ++a) sv[a] = a < NV ? st + 288 + a * 96 : nullptr;
+        em_element<HAS_U, OUT_DW>(st, sv, lane, c);
+        __syncwarp();
+        float4* ro = reinterpret_cast<float4*>(rot_out + g * 32 * 9);
+#pragma unroll
+        for (int i = lane; i < 72; i += 32) ro[i] = reinterpret_cast<const float4*>(st)[i];
+        if (lane < 24) {
+            reinterpret_cast<float4*>(pos_out + g * 32 * 3)[lane] = reinterpret_cast<const float4*>(sv[0])[lane];
+            if (OUT_DW) {
+                if (dw_rot) reinterpret_cast<float4*>(dw_rot + g * 32 * 3)[lane] = reinterpret_cast<const float4*>(sv[3])[lane];
+                if (dw_pos) reinterpret_cast<float4*>(dw_pos + g * 32 * 3)[lane] = reinterpret_cast<const float4*>(sv[4])[lane];
+            }
+        }
+        __syncwarp();                                          // the stage is refilled by the copies issued at the top of the next round
     }
 }
 
@@ -369,11 +438,44 @@ int se3_frame_update_em(const float* rot, const float* pos, const float* m_rot, 
     SE3_REQUIRE((u_rot == nullptr) == (u_pos == nullptr), "u_rot and u_pos must be given together");
     cudaStream_t st = (cudaStream_t)stream;
     const bool has_u = u_rot != nullptr, out_dw = dw_rot != nullptr || dw_pos != nullptr;
-#define EM_ARGS rot, pos, m_rot, m_pos, u_rot, u_pos, z_rot, z_pos, rot_out, pos_out, dw_rot, dw_pos, n, *h
-    if (has_u && out_dw) k_em<true, true><<<grid_for(n), kTile, 0, st>>>(EM_ARGS);
-    else if (has_u) k_em<true, false><<<grid_for(n), kTile, 0, st>>>(EM_ARGS);
-    else if (out_dw) k_em<false, true><<<grid_for(n), kTile, 0, st>>>(EM_ARGS);
-    else k_em<false, false><<<grid_for(n), kTile, 0, st>>>(EM_ARGS);
+    // Large inputs: the pipelined edition over the whole groups of 32 (every pointer 16-byte aligned), k_em for the rest.
+    int64_t n_pipe = 0;
+    {
+        uintptr_t bits = 0;
+        for (const void* p : {(const void*)rot, (const void*)pos, (const void*)m_rot, (const void*)m_pos, (const void*)u_rot, (const void*)u_pos, (const void*)z_rot,
+                              (const void*)z_pos, (const void*)rot_out, (const void*)pos_out, (const void*)dw_rot, (const void*)dw_pos})
+            bits |= reinterpret_cast<uintptr_t>(p);
+        if ((bits & 15) == 0 && n >= 148 * 4 * (int64_t)kTile * 4) n_pipe = n & ~(int64_t)31;
+    }
+    if (n_pipe) {
+        const size_t smem = (size_t)(kTile / 32) * 2 * (32 * 9 + (has_u ? 7 : 5) * 32 * 3) * sizeof(float);
+        const int64_t want = (n_pipe / 32 + kTile / 32 - 1) / (kTile / 32);
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+#define EM_PIPE(U, D)                                                                                                            \
+        do {                                                                                                                    \
+            int occ = 0;                                                                                                        \
+            cudaFuncSetAttribute(k_em_pipe<U, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                      \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_em_pipe<U, D>, kTile, smem) != cudaSuccess || occ < 1) occ = 1; \
+            const unsigned grid = (unsigned)(want < (int64_t)sms * occ ? want : (int64_t)sms * occ);   /* one resident wave of persistent CTAs */ \
+            k_em_pipe<U, D><<<grid, kTile, smem, st>>>(rot, pos, m_rot, m_pos, u_rot, u_pos, z_rot, z_pos, rot_out, pos_out, dw_rot, dw_pos, n_pipe, *h); \
+        } while (0)
+        if (has_u && out_dw) EM_PIPE(true, true);
+        else if (has_u) EM_PIPE(true, false);
+        else if (out_dw) EM_PIPE(false, true);
+        else EM_PIPE(false, false);
+#undef EM_PIPE
+        count_launch();
+        if (int rc = check_launch("se3_frame_update_em(pipelined)")) return rc;
+        if (n_pipe == n) return SE3_OK;
+    }
+    const int64_t o = n_pipe, m = n - n_pipe;                     // the remainder (everything for small or unaligned inputs)
+#define EM_ARGS rot + o * 9, pos + o * 3, m_rot + o * 3, m_pos + o * 3, u_rot ? u_rot + o * 3 : nullptr, u_pos ? u_pos + o * 3 : nullptr, z_rot + o * 3, \
+                z_pos + o * 3, rot_out + o * 9, pos_out + o * 3, dw_rot ? dw_rot + o * 3 : nullptr, dw_pos ? dw_pos + o * 3 : nullptr, m, *h
+    if (has_u && out_dw) k_em<true, true><<<grid_for(m), kTile, 0, st>>>(EM_ARGS);
+    else if (has_u) k_em<true, false><<<grid_for(m), kTile, 0, st>>>(EM_ARGS);
+    else if (out_dw) k_em<false, true><<<grid_for(m), kTile, 0, st>>>(EM_ARGS);
+    else k_em<false, false><<<grid_for(m), kTile, 0, st>>>(EM_ARGS);
 #undef EM_ARGS
     SE3_LAUNCH_CHECK("se3_frame_update_em");
 }

@@ -417,21 +417,20 @@ k_sample(const float* __restrict__ sigma, const float* __restrict__ sigma_grid, 
         // translation unit is built with -fmad=false, so the FMAs are spelled out
         float ang = w < 0.5f ? fmaf(w, diff, o0) : fmaf(-diff, 1.0f - w, o1);
         if (sigma && sg < tol) ang = 0.0f;  // SampleIGSO3._process_angles
-        const float nn = sqrtf(nx * nx + ny * ny + nz * nz);
-        float v[3] = {(nx / nn) * ang, (ny / nn) * ang, (nz / nn) * ang};
-        float r[9];
-        so3_exp(v, tol, r);
+        // axis-angle -> rotation and x . r with explicit FMAs (common.cuh: so3_apply_rotvec_fused): the angle above is the
+        // bit-exact part of this kernel; the matrix entries depend on sin / cos and agree with the reference to ~1e-6 either way
+        const float scale = __fdividef(ang, __fsqrt_rn(fmaf(nx, nx, fmaf(ny, ny, nz * nz))));
+        float xr[9], o[9];
         if (x) {
-            float xr[9], o[9];
 #pragma unroll
             for (int k = 0; k < 9; ++k) xr[k] = s_rot[t * 9 + k];
-            so3_mul<float, false>(xr, r, o);
-#pragma unroll
-            for (int k = 0; k < 9; ++k) s_rot[t * 9 + k] = o[k];
         } else {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) s_rot[t * 9 + k] = r[k];
+            for (int k = 0; k < 9; ++k) xr[k] = (k % 4 == 0) ? 1.0f : 0.0f;
         }
+        so3_apply_rotvec_fused(xr, nx * scale, ny * scale, nz * scale, tol, o);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) s_rot[t * 9 + k] = o[k];
         if (angle_out) angle_out[e] = ang;
     }
     __syncwarp();

@@ -189,6 +189,28 @@ def test_frame_update_em_vs_oracle(with_u):
         assert rel_err(r_o, out["rot"][0]) <= 3e-6
 
 
+@pytest.mark.parametrize("with_u", [False, True])
+def test_frame_update_em_pipelined_edition_equals_the_tile_edition(with_u):
+    """Large inputs take the pipelined kernel (per-warp two-stage cp.async ring) for the whole groups of 32 and the tile kernel
+    for the ragged tail; both run the same per-residue function, so the result must equal, bit for bit, the same call made in
+    chunks small enough to stay on the tile kernel (which the oracle tests above pin)."""
+    from se3diff_b200 import _lib as L
+    from se3diff_b200 import ops
+
+    n = 148 * 4 * 256 * 4 + 32 * 7 + 13
+    g = torch.Generator(device=DEV).manual_seed(3)
+    rot = ops.so3_exp(torch.randn(n, 3, generator=g, device=DEV))
+    pos, m_rot, m_pos, z_rot, z_pos, u_rot, u_pos = (torch.randn(n, 3, generator=g, device=DEV) for _ in range(7))
+    em = L.EmScalars(-0.02, 0.1414, 1.0, 1.0, 0.67, 4.0, 3.1, 1.76, 0.7, 1e-7)
+    kw = dict(u_rot=u_rot, u_pos=u_pos) if with_u else {}
+    full = ops.frame_update_em(rot, pos, m_rot, m_pos, z_rot, z_pos, em, want_dw=True, **kw)
+    step = 100_000
+    parts = [ops.frame_update_em(rot[o:o + step], pos[o:o + step], m_rot[o:o + step], m_pos[o:o + step], z_rot[o:o + step], z_pos[o:o + step], em,
+                                 want_dw=True, **{k: v[o:o + step] for k, v in kw.items()}) for o in range(0, n, step)]
+    for i, name in enumerate(("rot", "pos", "dw_rot", "dw_pos")):
+        assert torch.equal(full[i], torch.cat([p[i] for p in parts])), name
+
+
 def test_frame_update_dpm_vs_oracle_trace():
     """One full oracle dpm_solver run with a cheap analytic score; every (u, rot_u, pos_next, rot_next)
     of its trace is reproduced by the two fused kernels from the oracle's own inputs."""
