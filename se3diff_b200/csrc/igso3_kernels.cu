@@ -351,11 +351,82 @@ __device__ __forceinline__ void philox(uint64_t seed, uint64_t idx, uint32_t str
 }
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }  // [0,1)
 
+// ---- per-rotation pieces of the sampler, shared by the tile edition and the pipelined edition ---------------------------------
+struct SampleDraw { int stop; float c0, c1, sg, uu, nx, ny, nz; };
+
+// everything that does not need the operand tiles: the uniform (passed in or Philox), the sigma row, the CDF lookup
+__device__ __forceinline__ SampleDraw sample_lookup(int64_t e, bool have_normals, float u_in, float sg_in, bool have_sigma, const float* __restrict__ sigma_grid,
+                                                    int num_sigma, const float* __restrict__ cdf, int num_omega, uint64_t seed,
+                                                    const float* __restrict__ cdf_index, int guide_bins_n) {
+    SampleDraw d = {0, 0.f, 0.f, sg_in, u_in, 0.f, 0.f, 0.f};
+    if (!have_normals) {
+        // One Philox4x32-10 block per rotation: a direction uniform on the sphere from two uniforms (z = 2a - 1, phi = 2 pi b) --
+        // the same law as the reference's normalised Gaussian triple (so3_sde.py:1229-1242), which would take four uniforms,
+        // two logarithms and a second block -- and the CDF uniform from the third.  (Bit parity with the reference's torch
+        // generator is the business of the noise-passed-in mode; this mode only has to draw from the same distribution.)
+        uint32_t r[4];
+        philox(seed, (uint64_t)e, 0u, r);
+        const float z = 2.0f * u01(r[0]) - 1.0f;
+        const float rho = sqrtf(fmaxf(1.0f - z * z, 0.0f));
+        float sp, cp;
+        sincospif(2.0f * u01(r[1]), &sp, &cp);
+        d.nx = rho * cp; d.ny = rho * sp; d.nz = z;
+        if (d.nx == 0.0f && d.ny == 0.0f && d.nz == 0.0f) d.nz = 1.0f;
+        d.uu = u01(r[2]);
+    }
+    int row = 0;
+    if (have_sigma) {
+        row = lower_bound_geometric(sigma_grid, num_sigma, d.sg);  // torch.bucketize(sigma, sigma_grid)
+        row = row < num_sigma ? row : num_sigma - 1;   // the reference would raise (so3_sde.py:1633)
+    }
+    const float* c = cdf + (int64_t)row * num_omega;
+    if (cdf_index) {
+        d.stop = lookup_guided(c, cdf_index + (int64_t)row * guide_bins_n * 8, num_omega, guide_bins_n, d.uu, d.c0, d.c1);
+    } else {
+        int stop = lower_bound(c, num_omega, d.uu);
+        stop = stop < num_omega ? stop : num_omega - 1;
+        d.c0 = __ldg(c + (stop > 0 ? stop - 1 : 0)); d.c1 = __ldg(c + stop);
+        d.stop = stop;
+    }
+    return d;
+}
+
+// angle by interpolation (bit-exact against torch.lerp), axis-angle -> rotation, [x .] r written over the rotation slot `s_rot9`
+__device__ __forceinline__ float sample_compose(const SampleDraw& d, bool have_sigma, bool have_x, const float* __restrict__ omega_grid, float tol,
+                                                float* s_rot9) {
+    const int start = d.stop > 0 ? d.stop - 1 : 0;
+    const float delta = fmaxf(d.c1 - d.c0, tol);
+    float w = (d.uu - d.c0) / delta;
+    w = fminf(fmaxf(w, 0.0f), 1.0f);
+    const float o0 = __ldg(omega_grid + start), o1 = __ldg(omega_grid + d.stop);
+    // torch.lerp (CPU/CUDA kernels): w < 0.5 ? a + w*(b-a) : b - (b-a)*(1-w)
+    const float diff = o1 - o0;
+    // ATen contracts both branches into one FMA (CPU: vec::fmadd in lerp_vec / -mfma scalar code; CUDA: nvcc -fmad), and this
+    // translation unit is built with -fmad=false, so the FMAs are spelled out
+    float ang = w < 0.5f ? fmaf(w, diff, o0) : fmaf(-diff, 1.0f - w, o1);
+    if (have_sigma && d.sg < tol) ang = 0.0f;  // SampleIGSO3._process_angles
+    // axis-angle -> rotation and x . r with explicit FMAs (common.cuh: so3_apply_rotvec_fused): the angle above is the
+    // bit-exact part of this kernel; the matrix entries depend on sin / cos and agree with the reference to ~1e-6 either way
+    const float scale = __fdividef(ang, __fsqrt_rn(fmaf(d.nx, d.nx, fmaf(d.ny, d.ny, d.nz * d.nz))));
+    float xr[9], o[9];
+    if (have_x) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) xr[k] = s_rot9[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) xr[k] = (k % 4 == 0) ? 1.0f : 0.0f;
+    }
+    so3_apply_rotvec_fused(xr, d.nx * scale, d.ny * scale, d.nz * scale, tol, o);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s_rot9[k] = o[k];
+    return ang;
+}
+
 __global__ void __launch_bounds__(kTile)
 k_sample(const float* __restrict__ sigma, const float* __restrict__ sigma_grid, int num_sigma, const float* __restrict__ cdf,
          const float* __restrict__ omega_grid, int num_omega, const float* __restrict__ normals, const float* __restrict__ u,
          uint64_t seed, const float* __restrict__ x, float* __restrict__ out, float* __restrict__ angle_out, int64_t n,
-         float tol, const float* __restrict__ cdf_index, int guide_bins_n) {
+         float tol, const float* __restrict__ cdf_index, int guide_bins_n, int64_t first_index) {
     __shared__ __align__(16) float s_rot[kTile * 9];
     __shared__ __align__(16) float s_nrm[kTile * 3];
     const int64_t first = (int64_t)blockIdx.x * kTile;
@@ -367,70 +438,15 @@ k_sample(const float* __restrict__ sigma, const float* __restrict__ sigma_grid, 
     if (normals) warp_tile_load_async<3>(normals, s_nrm, first, count);
     const int t = threadIdx.x;
     const int64_t e = first + t;
-    int stop = 0;
-    float c0 = 0.f, c1 = 0.f, sg = 0.f, uu = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
-    if (t < count) {
-        if (normals) {
-            uu = u[e];
-        } else {
-            // One Philox4x32-10 block per rotation: a direction uniform on the sphere from two uniforms (z = 2a - 1, phi = 2 pi b) --
-            // the same law as the reference's normalised Gaussian triple (so3_sde.py:1229-1242), which would take four uniforms,
-            // two logarithms and a second block -- and the CDF uniform from the third.  (Bit parity with the reference's torch
-            // generator is the business of the noise-passed-in mode; this mode only has to draw from the same distribution.)
-            uint32_t r[4];
-            philox(seed, (uint64_t)e, 0u, r);
-            const float z = 2.0f * u01(r[0]) - 1.0f;
-            const float rho = sqrtf(fmaxf(1.0f - z * z, 0.0f));
-            float sp, cp;
-            sincospif(2.0f * u01(r[1]), &sp, &cp);
-            nx = rho * cp; ny = rho * sp; nz = z;
-            if (nx == 0.0f && ny == 0.0f && nz == 0.0f) nz = 1.0f;
-            uu = u01(r[2]);
-        }
-        int row = 0;
-        if (sigma) {
-            sg = sigma[e];
-            row = lower_bound_geometric(sigma_grid, num_sigma, sg);  // torch.bucketize(sigma, sigma_grid)
-            row = row < num_sigma ? row : num_sigma - 1;   // the reference would raise (so3_sde.py:1633)
-        }
-        const float* c = cdf + (int64_t)row * num_omega;
-        if (cdf_index) {
-            stop = lookup_guided(c, cdf_index + (int64_t)row * guide_bins_n * 8, num_omega, guide_bins_n, uu, c0, c1);
-        } else {
-            stop = lower_bound(c, num_omega, uu);
-            stop = stop < num_omega ? stop : num_omega - 1;
-            c0 = __ldg(c + (stop > 0 ? stop - 1 : 0)); c1 = __ldg(c + stop);
-        }
-    }
+    SampleDraw d = {};
+    if (t < count)
+        d = sample_lookup(first_index + e, normals != nullptr, normals ? u[e] : 0.f, sigma ? sigma[e] : 0.f, sigma != nullptr, sigma_grid, num_sigma, cdf,
+                          num_omega, seed, cdf_index, guide_bins_n);      // (first_index: this launch's offset inside the caller's array = Philox counter)
     tile_load_wait();
     __syncwarp();
     if (t < count) {
-        if (normals) { nx = s_nrm[t * 3]; ny = s_nrm[t * 3 + 1]; nz = s_nrm[t * 3 + 2]; }
-        const int start = stop > 0 ? stop - 1 : 0;
-        const float delta = fmaxf(c1 - c0, tol);
-        float w = (uu - c0) / delta;
-        w = fminf(fmaxf(w, 0.0f), 1.0f);
-        const float o0 = __ldg(omega_grid + start), o1 = __ldg(omega_grid + stop);
-        // torch.lerp (CPU/CUDA kernels): w < 0.5 ? a + w*(b-a) : b - (b-a)*(1-w)
-        const float diff = o1 - o0;
-        // ATen contracts both branches into one FMA (CPU: vec::fmadd in lerp_vec / -mfma scalar code; CUDA: nvcc -fmad), and this
-        // translation unit is built with -fmad=false, so the FMAs are spelled out
-        float ang = w < 0.5f ? fmaf(w, diff, o0) : fmaf(-diff, 1.0f - w, o1);
-        if (sigma && sg < tol) ang = 0.0f;  // SampleIGSO3._process_angles
-        // axis-angle -> rotation and x . r with explicit FMAs (common.cuh: so3_apply_rotvec_fused): the angle above is the
-        // bit-exact part of this kernel; the matrix entries depend on sin / cos and agree with the reference to ~1e-6 either way
-        const float scale = __fdividef(ang, __fsqrt_rn(fmaf(nx, nx, fmaf(ny, ny, nz * nz))));
-        float xr[9], o[9];
-        if (x) {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) xr[k] = s_rot[t * 9 + k];
-        } else {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) xr[k] = (k % 4 == 0) ? 1.0f : 0.0f;
-        }
-        so3_apply_rotvec_fused(xr, nx * scale, ny * scale, nz * scale, tol, o);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) s_rot[t * 9 + k] = o[k];
+        if (normals) { d.nx = s_nrm[t * 3]; d.ny = s_nrm[t * 3 + 1]; d.nz = s_nrm[t * 3 + 2]; }
+        const float ang = sample_compose(d, sigma != nullptr, x != nullptr, omega_grid, tol, s_rot + t * 9);
         if (angle_out) angle_out[e] = ang;
     }
     __syncwarp();
@@ -537,9 +553,11 @@ int se3_igso3_sample(const float* sigma, const float* sigma_grid, int num_sigma,
     SE3_REQUIRE(cdf && omega_grid && out, "null pointer");
     SE3_REQUIRE(!sigma || (sigma_grid && num_sigma >= 1), "sigma given without sigma_grid");
     SE3_REQUIRE((normals == nullptr) == (u == nullptr), "normals and u must be given together");
-    k_sample<<<(unsigned)((n + kTile - 1) / kTile), kTile, 0, (cudaStream_t)stream>>>(sigma, sigma_grid, num_sigma, cdf, omega_grid,
-                                                                                    num_omega, normals, u, seed, x, out, angle_out, n, tol, num_omega <= 65535 ? cdf_index : nullptr,
-                                                                                    guide_bins(num_omega));
+    // (A pipelined per-warp edition like k_em_pipe was measured and dropped: 0.529 -> 0.536 of the HBM roof with the noise passed
+    // in, 0.478 -> 0.399 in Philox mode -- this kernel is bound by its ~250 instructions per rotation at 64 resident warps, and
+    // the ring costs occupancy.)
+    k_sample<<<(unsigned)((n + kTile - 1) / kTile), kTile, 0, (cudaStream_t)stream>>>(sigma, sigma_grid, num_sigma, cdf, omega_grid, num_omega, normals, u, seed, x, out,
+                                                                                    angle_out, n, tol, num_omega <= 65535 ? cdf_index : nullptr, guide_bins(num_omega), 0);
     SE3_LAUNCH_CHECK("se3_igso3_sample");
 }
 

@@ -115,7 +115,7 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                const __grid_constant__ CUtensorMap map_bias, const float* __restrict__ rot, const float* __restrict__ trans, const __nv_bfloat16* __restrict__ pair_bias_t,
                const float* __restrict__ key_bias, const float* __restrict__ head_weight, OutT* __restrict__ out,
                __nv_bfloat16* __restrict__ pbuf, float* __restrict__ inv_sum, const se3_ipa_shape sh, int LpB, int LpT, int Bpad, int tmem_cols,
-               const void* __restrict__ pts, int pts_stride, long long* __restrict__ dbg) {
+               const void* __restrict__ pts, int pts_stride, long long* __restrict__ dbg, int head0) {
     constexpr int kRawRow = kPtsBf16 ? 96 : 192;            // bytes of one staged point record [qp 12 | kp 12 | vp 24]
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t bar, bar_bias, bar_in;
@@ -170,7 +170,7 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             const int bh = it / ntile;
             b_ = bh / H; h_ = bh - b_ * H; q0_ = (it - bh * ntile) * 128;
         } else {
-            b_ = blockIdx.z; h_ = blockIdx.y; q0_ = blockIdx.x * 128;
+            b_ = blockIdx.z; h_ = blockIdx.y + head0; q0_ = blockIdx.x * 128;      // head0: first head of this launch's head group
         }
     };
     auto issue_loads = [&](const int it) {                 // thread 0 only
@@ -553,12 +553,12 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 template <typename OutT>
 __global__ void __launch_bounds__(128)
 k_ipa_tc_pass2(const __grid_constant__ CUtensorMap map_p, const float* __restrict__ inv_sum, const __nv_bfloat16* __restrict__ pvc,
-               OutT* __restrict__ out, const se3_ipa_shape sh, int Lp, int Bpad) {
+               OutT* __restrict__ out, const se3_ipa_shape sh, int Lp, int Bpad, int head0) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t bar_tma, bar_mma;
     __shared__ uint32_t tmem_slot;
     const int L = sh.len, H = sh.heads, B = sh.batch;
-    const int bt = blockIdx.x, i = blockIdx.y, h = blockIdx.z;
+    const int bt = blockIdx.x, i = blockIdx.y, h = blockIdx.z + head0;
     const int tid = threadIdx.x, warp = tid >> 5;
     // A = probabilities of (h, i): rows = 128 samples, K = keys, fetched from the row-major workspace as 64-key boxes in the
     // 128-byte-swizzle operand layout (16 KB each, keys past LpT zero-filled by the TMA unit); B = pre-packed pair values
@@ -667,14 +667,41 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const void* pts, int p
         if (rc == SE3_OK) pass1_done = true;
         else if (rc != SE3_EUNSUPPORTED) return rc;
     }
+    const size_t smem2 = (size_t)((Lp + 63) / 64) * 16384 + (size_t)Lp * 32 + 1024;   // + slack for the 1024-byte alignment of the swizzled tiles
+    auto k2 = k_ipa_tc_pass2<OutT>;
+    e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e != cudaSuccess) { set_error("ipa_tc pass2 smem attribute (%zu B): %s", smem2, cudaGetErrorString(e)); return SE3_ECUDA; }
+    auto pass2 = [&](int head0, int nheads) {
+        dim3 g2(Bpad / 128, L, nheads);
+        k2<<<g2, 128, smem2, st>>>(map_p, inv_sum, pvc, out, sh, Lp, Bpad, head0);
+        count_launch();
+        return check_launch("se3_ipa_attention_tc_fwd(pass 2)");
+    };
     if (pass1_done) {
+        return pass2(0, sh.heads);
     } else if (!split) {
         auto k1 = wide ? k_ipa_tc_pass1<OutT, false, true, kPtsBf16> : k_ipa_tc_pass1<OutT, false, false, kPtsBf16>;
         e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e != cudaSuccess) { set_error("ipa_tc pass1 smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
-        const dim3 g1 = wide ? dim3((unsigned)(n_items < sms ? n_items : sms), 1, 1) : dim3(ntile, sh.heads, sh.batch);
-        k1<<<g1, wide ? 256 : 128, smem1, st>>>(map_q, map_kv, map_pts, map_bias, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad,
-                                                cols, pts, pts_stride, g_phase_dbg);
+        // One-item-per-CTA edition: optionally run pass 1 / pass 2 per GROUP of heads, so that pass 2 finds the group's probability
+        // tiles (33 MB for 8 heads at L = 84, B = 256) still in the 126 MB L2 instead of reading them back from DRAM.
+        // SE3DIFF_B200_IPA_HEAD_GROUP = heads per group (0 or unset: one group = all heads).
+        int group = sh.heads;
+        if (!wide) {
+            const char* v = getenv("SE3DIFF_B200_IPA_HEAD_GROUP");
+            const int gsz = v ? atoi(v) : 0;
+            if (gsz > 0 && gsz < sh.heads) group = gsz;
+        }
+        for (int h0 = 0; h0 < sh.heads; h0 += group) {
+            const int nh = sh.heads - h0 < group ? sh.heads - h0 : group;
+            const dim3 g1 = wide ? dim3((unsigned)(n_items < sms ? n_items : sms), 1, 1) : dim3(ntile, nh, sh.batch);
+            k1<<<g1, wide ? 256 : 128, smem1, st>>>(map_q, map_kv, map_pts, map_bias, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad,
+                                                    cols, pts, pts_stride, g_phase_dbg, h0);
+            count_launch();
+            if (int rc = check_launch("se3_ipa_attention_tc_fwd(pass 1)")) return rc;
+            if (int rc = pass2(h0, nh)) return rc;
+        }
+        return SE3_OK;
     } else {
         auto k1 = k_ipa_tc_pass1<OutT, true, true, kPtsBf16>;
         e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
@@ -697,21 +724,12 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const void* pts, int p
         if (ncl > n_items) ncl = n_items;
         cfg.gridDim = dim3(2 * ncl, 1, 1);
         e = cudaLaunchKernelEx(&cfg, k1, map_q, map_kv, map_pts, map_bias, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad, cols,
-                               pts, pts_stride, g_phase_dbg);
+                               pts, pts_stride, g_phase_dbg, 0);
         if (e != cudaSuccess) { set_error("ipa_tc pass1 (split) launch: %s", cudaGetErrorString(e)); return SE3_ECUDA; }
-    }
-    if (!pass1_done) {
         count_launch();
         if (int rc = check_launch("se3_ipa_attention_tc_fwd(pass 1)")) return rc;
+        return pass2(0, sh.heads);
     }
-    const size_t smem2 = (size_t)((Lp + 63) / 64) * 16384 + (size_t)Lp * 32 + 1024;   // + slack for the 1024-byte alignment of the swizzled tiles
-    auto k2 = k_ipa_tc_pass2<OutT>;
-    e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    if (e != cudaSuccess) { set_error("ipa_tc pass2 smem attribute (%zu B): %s", smem2, cudaGetErrorString(e)); return SE3_ECUDA; }
-    dim3 g2(Bpad / 128, L, sh.heads);
-    k2<<<g2, 128, smem2, st>>>(map_p, inv_sum, pvc, out, sh, Lp, Bpad);
-    count_launch();
-    return check_launch("se3_ipa_attention_tc_fwd(pass 2)");
 }
 
 }  // namespace
