@@ -20,11 +20,13 @@
 // unchanged), and rank 1 hands its partial O = P.[V | 1] to rank 0 the same way for the common epilogue.
 // Pass 2, one CTA per (128-sample tile, query i, head h):
 //   out_pair[b, i, h, :] = sum_j P[h,i,b,j] * pair_value[i,j,h,:]   (structure_module.py:209-213)
-//   as a tensor-core GEMM with the SAMPLE index as M.  Pass 1 writes P directly in the UMMA operand layout
-//   ([h][i][b/128][j/8][b%128][j%8]), so the A tile (128 x Lp bf16) and the pre-packed pair_value tile
-//   (16 x Lp bf16) are two contiguous blocks fetched with TMA bulk copies (cp.async.bulk -> UBLKCP) that
-//   signal an mbarrier; D[128 x 16] accumulates in TMEM.  pair_value is therefore read once per 128 samples
-//   instead of once per sample (3.7 GB -> 30 MB per layer at B=256, L=84).
+//   as a tensor-core GEMM with the SAMPLE index as M.  Pass 1 writes P row-major, bf16 [h][i][round_up(B,128)][Lp]: per (head,
+//   query) a [samples][keys] matrix whose rows are written as whole 32-byte sectors.  Pass 2 fetches 128-sample x 64-key boxes of
+//   it through a tensor map with CU_TENSOR_MAP_SWIZZLE_128B (UTMALDG) and consumes them through a SWIZZLE_128B K-major UMMA
+//   descriptor; the pre-packed pair_value tile (16 x Lp bf16, se3_ipa_tc_pack_pair) is one bulk copy (UBLKCP); D[128 x 16]
+//   accumulates in TMEM.  pair_value is therefore read once per 128 samples instead of once per sample (3.7 GB -> 30 MB per
+//   layer at B=256, L=84).
+// L <= 96 can also run pass 1 as the warp-specialised "ping-pong" edition of ipa_tc_pp.cu (SE3DIFF_B200_IPA_PP=1, experimental).
 #include <cuda.h>
 #include <math_constants.h>
 #include <stdlib.h>
