@@ -186,7 +186,9 @@ def _loop_graphed(key, keep_alive, batch, loop_fn, device, returns_batch: bool =
             out = loop_fn(static)
         if returns_batch:
             out = (out["pos"], out["node_orientations"])
-        entry.update(graph=graph, out=out, launches=ops.launch_count() - before)
+        # the captured kernels may read ANY field of the batch they were recorded on (graph index, pointers) and whatever device
+        # tensors the loop closed over: the entry keeps both alive for as long as the graph can be replayed
+        entry.update(graph=graph, out=out, launches=ops.launch_count() - before, static=static, loop_fn=loop_fn)
         ops.count_replayed_launches(-entry["launches"])     # recorded, not executed: the replay below is what runs
         _GRAPHS[key] = entry
         while len(_GRAPHS) > _MAX_GRAPHS:
@@ -332,35 +334,51 @@ def _heun_finetune_loop(batch, sdes, score_model, finetune_model, num_steps, max
     nois = {f: EulerMaruyamaPredictor(corruption=sdes[f], noise_weight=1.0) for f in fields}
     bi, B = batch["batch"], batch.num_graphs
     lengths = batch_lengths(batch)
-    batches, us, dWs = [batch], defaultdict(list), defaultdict(list)
-    for i in range(num_steps):
-        t = _t(float(ts[i]), B, device)
-        t_next = t + dts_dev[i]
-        churn = i > 0 and 0.0 < float(ts[i]) < 1.0
-        t_hat = t - noise * dts_dev[i] if churn else t
-        hat = batch.replace(**{f: nois[f].forward_sde_step(x=batch[f], t=t, dt=(t_hat - t)[0], batch_idx=bi)[0] for f in fields})
-        sc_h, u_h = _get_score(hat, sdes, score_model, t_hat), finetune_model(hat, t_hat)
-        if churn:
-            sc, u = _get_score(batch, sdes, score_model, t), finetune_model(batch, t)
-        else:
-            sc, u = sc_h, u_h
-        dh = {f: pred[f].reverse_drift_and_diffusion(x=hat[f], t=t_hat, score=sc_h[f], finetune_score=u_h[f], batch_idx=bi)[0] for f in fields}
-        step = (t_next - t_hat)[0]
-        new = batch.replace(**{f: pred[f].update_given_drift_and_diffusion(x=hat[f], dt=step, drift=dh[f], diffusion=0.0)[1] for f in fields})
-        if float(t_next[0]) > 0.0:
-            sc_n, u_n = _get_score(new, sdes, score_model, t_next), finetune_model(new, t_next)
-            avg = {f: (pred[f].reverse_drift_and_diffusion(x=new[f], t=t_next, score=sc_n[f], finetune_score=u_n[f], batch_idx=bi)[0]
-                       + dh[f]) / 2 for f in fields}
-            new = batch.replace(**{f: pred[f].update_given_drift_and_diffusion(x=hat[f], dt=step, drift=avg[f], diffusion=0.0)[1] for f in fields})
-        for f in fields:
-            dW = nois[f].traceback_brownian_motion(x_next=new[f], x=batch[f], t=t, dt=dts_dev[i], score=sc[f], finetune_score=u[f],
-                                                   batch_idx=bi)
-            us[f].append(_dense(u[f], batch, lengths))
-            dWs[f].append(_dense(dW, batch, lengths))
-        batch = new
-        batches.append(batch)
-    return DenoisedSDEPath(batches=batches, timesteps=ts_dev, us_batch={f: torch.stack(us[f], dim=0) for f in fields},
-                           dWs_batch={f: torch.stack(dWs[f], dim=0) for f in fields})
+
+    def recorded(batch):
+        """The whole rollout on stacked outputs.  Control flow uses the HOST copies of the time grid only (no device reads), so the
+        loop can be captured as one CUDA graph."""
+        pos_all, rot_all, us, dWs = [batch["pos"]], [batch["node_orientations"]], defaultdict(list), defaultdict(list)
+        for i in range(num_steps):
+            t = _t(float(ts[i]), B, device)
+            t_next = t + dts_dev[i]
+            churn = i > 0 and 0.0 < float(ts[i]) < 1.0
+            t_hat = t - noise * dts_dev[i] if churn else t
+            hat = batch.replace(**{f: nois[f].forward_sde_step(x=batch[f], t=t, dt=(t_hat - t)[0], batch_idx=bi)[0] for f in fields})
+            sc_h, u_h = _get_score(hat, sdes, score_model, t_hat), finetune_model(hat, t_hat)
+            if churn:
+                sc, u = _get_score(batch, sdes, score_model, t), finetune_model(batch, t)
+            else:
+                sc, u = sc_h, u_h
+            dh = {f: pred[f].reverse_drift_and_diffusion(x=hat[f], t=t_hat, score=sc_h[f], finetune_score=u_h[f], batch_idx=bi)[0] for f in fields}
+            step = (t_next - t_hat)[0]
+            new = batch.replace(**{f: pred[f].update_given_drift_and_diffusion(x=hat[f], dt=step, drift=dh[f], diffusion=0.0)[1] for f in fields})
+            if float(ts[i] + dts[i]) > 0.0:                    # = t_next, evaluated on the host in the same fp32 arithmetic
+                sc_n, u_n = _get_score(new, sdes, score_model, t_next), finetune_model(new, t_next)
+                avg = {f: (pred[f].reverse_drift_and_diffusion(x=new[f], t=t_next, score=sc_n[f], finetune_score=u_n[f], batch_idx=bi)[0]
+                           + dh[f]) / 2 for f in fields}
+                new = batch.replace(**{f: pred[f].update_given_drift_and_diffusion(x=hat[f], dt=step, drift=avg[f], diffusion=0.0)[1] for f in fields})
+            for f in fields:
+                dW = nois[f].traceback_brownian_motion(x_next=new[f], x=batch[f], t=t, dt=dts_dev[i], score=sc[f], finetune_score=u[f],
+                                                       batch_idx=bi)
+                us[f].append(_dense(u[f], batch, lengths))
+                dWs[f].append(_dense(dW, batch, lengths))
+            batch = new
+            pos_all.append(batch["pos"])
+            rot_all.append(batch["node_orientations"])
+        return dict(pos=torch.stack(pos_all), rot=torch.stack(rot_all), us={f: torch.stack(us[f], dim=0) for f in fields},
+                    dWs={f: torch.stack(dWs[f], dim=0) for f in fields})
+
+    res = None
+    if not S._HOST_NOISE:
+        keyed = _graph_key(batch, sdes, sdes["node_orientations"], score_model, num_steps, max_t, min_t, device,
+                           tag=("heun-record", float(noise), tuple(fields)), control=finetune_model)
+        if keyed is not None:
+            res = _loop_graphed(keyed[0], keyed[1], batch, recorded, device, returns_batch=False)
+    if res is None:
+        res = recorded(batch)
+    batches = [batch.replace(pos=res["pos"][i], node_orientations=res["rot"][i]) for i in range(res["pos"].shape[0])]
+    return DenoisedSDEPath(batches=batches, timesteps=ts_dev, us_batch=res["us"], dWs_batch=res["dWs"])
 
 
 def _heun_loop(batch, sdes, score_model, finetune_model, num_steps, max_t, min_t, noise, device):

@@ -159,7 +159,7 @@ class _Context:
     """Per-sequence tensors that do not depend on the sample, on t or on the frames."""
 
     __slots__ = ("src", "src_versions", "key", "lengths", "lmax", "batch", "shared", "mask", "dense_index", "x1d_base", "pair_bias",
-                 "pair_value", "key_bias", "uniform", "tc", "pair_value_packed", "workspace")
+                 "pair_value", "key_bias", "uniform", "tc", "pair_value_packed", "workspace", "x2d")
 
 
 class DistributionalGraphormer(nn.Module):
@@ -275,7 +275,8 @@ class DistributionalGraphormer(nn.Module):
                 # with them every CUDA graph captured over it
                 fresh = self._build_context(ctx_graph, src, versions, key)
                 if fresh.shared == c.shared and fresh.tc == c.tc and self._adopt(
-                        [c.x1d_base, c.pair_bias, c.pair_value, c.pair_value_packed], [fresh.x1d_base, fresh.pair_bias, fresh.pair_value, fresh.pair_value_packed]):
+                        [c.x1d_base, c.pair_bias, c.pair_value, c.pair_value_packed, c.x2d],
+                        [fresh.x1d_base, fresh.pair_bias, fresh.pair_value, fresh.pair_value_packed, fresh.x2d]):
                     c.key = key
                     return c
         c = self._build_context(ctx_graph, src, versions, key)
@@ -328,19 +329,31 @@ class DistributionalGraphormer(nn.Module):
         # tcgen05 attention path: decided with the SAME predicate as the fused bf16 forward that is its only caller
         # (`_forward_kernels`): a bf16 model of another width takes `_forward_plain`, which feeds the SIMT kernel the fp32 layouts
         c.tc = self._fused_bf16() and ops.ipa_tc_supported(probe)
-        c.pair_bias, c.pair_value, c.pair_value_packed = [], [], []
-        for lyr in self.st_module.encoder.layers:
-            a = lyr.attn
-            pb = a.pair_weight * a.pair_bias(x2d)                                                      # [Bp, L(i), L(j), H]
-            # SIMT kernel: fp32 [Bp, H, i, j]; tensor-core kernel: transposed bf16 slabs [H, j, i] fetched by TMA
-            c.pair_bias.append(ops.ipa_tc_pack_pair_bias(pb) if c.tc else pb.permute(0, 3, 1, 2).contiguous())
-            pv = a.pair_value(x2d)                                                                     # [Bp, L, L, H*dk]
-            if c.tc:
-                c.pair_value_packed.append(ops.ipa_tc_pack_pair_value(pv, a.n_head))
-            else:
-                c.pair_value.append(pv.contiguous())
+        c.pair_bias, c.pair_value, c.pair_value_packed, c.x2d = [], [], [], None
+        # Per-sample pair tensors (heterogeneous or ragged batches) cost layers * B * L^2 * (H + H*dk) floats when kept for every
+        # layer -- 30 GB at B = 256, L = 84 -- where the reference holds one layer at a time (structure_module.py:179, 209).  Above a
+        # byte budget (SE3DIFF_B200_PAIR_CACHE_GB, default 8) only x2d is cached and `_attention` projects it layer by layer.
+        n_layers = len(self.st_module.encoder.layers)
+        per_layer = x2d.shape[0] * lmax * lmax * attn0.n_head * (1 + attn0.d_k) * 4
+        if not c.shared and not c.tc and n_layers * per_layer > float(os.environ.get("SE3DIFF_B200_PAIR_CACHE_GB", "8")) * 2**30:
+            c.x2d = x2d
+            c.pair_bias = c.pair_value = None
+        else:
+            for lyr in self.st_module.encoder.layers:
+                pb_l, pv_l = self._pair_tensors(lyr.attn, x2d, c.tc)
+                c.pair_bias.append(pb_l)
+                (c.pair_value_packed if c.tc else c.pair_value).append(pv_l)
         c.workspace = ops.ipa_tc_workspace(probe, dev) if c.tc else None
         return c
+
+    @staticmethod
+    def _pair_tensors(a: SAAttention, x2d, tc: bool):
+        """(pair bias, pair values) of one layer in the layout its attention kernel reads (structure_module.py:179, 209)."""
+        pb = a.pair_weight * a.pair_bias(x2d)                                                      # [Bp, L(i), L(j), H]
+        pv = a.pair_value(x2d)                                                                     # [Bp, L, L, H*dk]
+        if tc:      # tensor-core kernel: transposed bf16 slabs [H, j, i] fetched by TMA; values in the UMMA K-major operand layout
+            return ops.ipa_tc_pack_pair_bias(pb), ops.ipa_tc_pack_pair_value(pv, a.n_head)
+        return pb.permute(0, 3, 1, 2).contiguous(), pv.contiguous()                                # SIMT kernel: fp32 [Bp, H, i, j]
 
     @staticmethod
     def _dense_pairs(ctx_graph, pair, c: _Context, dev):
@@ -386,8 +399,8 @@ class DistributionalGraphormer(nn.Module):
         return y if bias is None else y + bias
 
     def _attention(self, proj, R, T, c, lw, lyr, n, shape, flags):
-        return ops.ipa_attention_fwd(proj, R, T, c.pair_bias[n], c.pair_value[n], c.key_bias, lw["head_w"],
-                                     lyr.attn.scalar_weight, shape, flags)
+        pb, pv = (c.pair_bias[n], c.pair_value[n]) if c.x2d is None else self._pair_tensors(lyr.attn, c.x2d, False)
+        return ops.ipa_attention_fwd(proj, R, T, pb, pv, c.key_bias, lw["head_w"], lyr.attn.scalar_weight, shape, flags)
 
     def _forward_plain(self, x1d, R, T, c, w, shape, flags):
         """torch LayerNorm / Linear around the attention kernel (fp32 parity mode; bf16 for odd widths)."""

@@ -1000,6 +1000,31 @@ def test_bf16_mode_physical_scale_steps_vs_the_oracle():
         assert (rmsd <= tol[prec][0]).all() and dr <= tol[prec][1], (prec, rmsd, dr)
 
 
+def test_per_sample_pair_tensors_above_the_cache_budget_are_projected_layer_by_layer(monkeypatch):
+    """Heterogeneous batches keep per-sample pair tensors; cached for every layer they cost layers * B * L^2 * (H + H*dk) floats.
+    Above SE3DIFF_B200_PAIR_CACHE_GB only x2d is kept and each layer projects it on the fly (what the reference does,
+    structure_module.py:179, 209): same result, bit for bit."""
+    from se3diff_b200.models import DiGConditionalScoreModel
+
+    torch.manual_seed(0)
+    m = DiGConditionalScoreModel(dim_model=64, dim_pair=32, num_layers=2, num_heads=4, dim_hidden=128).eval().to(DEV)
+    L, B = 21, 3
+    g = torch.Generator().manual_seed(2)
+    single = torch.randn(B * L, 384, generator=g)
+    pairs = [torch.randn(L, L, 128, generator=g) for _ in range(B)]                       # three different sequences
+    pos = torch.randn(B * L, 3, generator=g)
+    rot = oso3.rotvec_to_rotmat(torch.randn(B * L, 3, generator=g))
+    t = torch.rand(B, generator=g).to(DEV)
+    batch = _make_batch(single, pairs, [L] * B, pos, rot).to(DEV)
+    a = m(batch, t)
+    assert not m.model_nn._ctx.shared and m.model_nn._ctx.x2d is None
+    monkeypatch.setenv("SE3DIFF_B200_PAIR_CACHE_GB", "0")
+    m.model_nn._ctx = None
+    b = m(_make_batch(single, pairs, [L] * B, pos, rot).to(DEV), t)
+    assert m.model_nn._ctx.x2d is not None and m.model_nn._ctx.pair_bias is None
+    assert torch.equal(a["pos"], b["pos"]) and torch.equal(a["node_orientations"], b["node_orientations"])
+
+
 def test_bf16_mode_with_a_narrow_model_takes_the_simt_attention():
     """bf16 precision on a model the fused bf16 forward does not take (dim_model 64, 4 heads: the fine-tune control model of
     bioemu-v1.0/config.yaml): `_forward_plain` with bf16 GEMM operands around the fp32 SIMT attention, fed the fp32 pair layouts
@@ -1531,3 +1556,50 @@ def test_em_heun_loop_graphs_match_eager(sampler, extra, monkeypatch):
         want = other if i == 2 else ref
         assert torch.equal(o["pos"], want["pos"]) and torch.equal(o["node_orientations"], want["node_orientations"]), i
     assert not torch.equal(ref["pos"], other["pos"])
+
+
+@pytest.mark.parametrize("sampler,extra,tag", [("euler_maruyama_predictor_finetune", {}, "em-record"),
+                                               ("heun_denoiser_finetune", {"noise": 0.5}, "heun-record")])
+def test_recording_rollout_graphs_match_eager_across_weight_updates(sampler, extra, tag, monkeypatch):
+    """The fine-tune rollouts (denoiser.py:267-348, 464-620) replay ONE captured graph of the whole recording loop -- states,
+    controls and Brownian increments of every step.  With the same seed a replay must equal the eager rollout bit for bit, and it
+    must stay valid after the control model's weights were updated in place (an optimizer step between rollouts): the derived
+    weight / pair tensors the graph reads are refreshed inside their storage."""
+    from se3diff_b200 import denoiser, shortcuts
+
+    g, m, fm, sdes, batch, S = _traj_setup()
+    m, fm = m.to(DEV), fm.to(DEV)
+    sdes["node_orientations"] = sdes["node_orientations"].to(DEV)
+    kw = dict(batch=batch.to(DEV), sdes=sdes, score_model=m, finetune_model=fm, num_steps=4, max_t=0.99, min_t=0.001, device=DEV, **extra)
+    fn = getattr(shortcuts, sampler)
+
+    def flat(path):
+        return torch.cat([torch.stack([b["pos"] for b in path.batches]).flatten(), torch.stack([b["node_orientations"] for b in path.batches]).flatten()]
+                         + [path.us_batch[f].flatten() for f in sorted(path.us_batch)] + [path.dWs_batch[f].flatten() for f in sorted(path.dWs_batch)])
+
+    def bump():                                                   # an "optimizer step": every parameter of the control model, in place
+        with torch.no_grad():
+            for p in fm.parameters():
+                p.add_(0.01 * torch.sign(p) + 0.003)
+
+    monkeypatch.setenv("SE3DIFF_B200_CUDA_GRAPH", "0")
+    monkeypatch.setenv("SE3DIFF_B200_MODEL_GRAPH", "0")
+    state = {k: v.clone() for k, v in fm.state_dict().items()}
+    torch.manual_seed(5)
+    ref_a = flat(fn(**kw))
+    bump()
+    torch.manual_seed(5)
+    ref_b = flat(fn(**kw))
+    assert not torch.equal(ref_a, ref_b), "the control must matter"
+    fm.load_state_dict(state)
+    monkeypatch.setenv("SE3DIFF_B200_CUDA_GRAPH", "1")
+    monkeypatch.setenv("SE3DIFF_B200_MODEL_GRAPH", "1")
+    before = dict(denoiser.GRAPH_STATS)
+    for i in range(3):                                            # eager, capture + replay, replay
+        torch.manual_seed(5)
+        assert torch.equal(flat(fn(**kw)), ref_a), i
+    bump()
+    torch.manual_seed(5)
+    assert torch.equal(flat(fn(**kw)), ref_b), "replay after an in-place weight update"
+    assert denoiser.GRAPH_STATS["captures"] == before["captures"] + 1 and denoiser.GRAPH_STATS["replays"] >= before["replays"] + 3
+    assert any(k[-1][0] == tag for k in denoiser._GRAPHS)
