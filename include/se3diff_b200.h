@@ -340,6 +340,22 @@ int se3_ipa_attention_tc_fwd(const void* scalars_bf16, int64_t scalar_stride, co
 int64_t se3_ipa_tc_packed_pair_bytes(int len, int heads, int64_t* bias_bytes, int64_t* value_bytes);
 int se3_ipa_tc_pack_pair(const float* pair_bias, const float* pair_value, void* bias_packed, void* value_packed, int len,
                          int heads, se3_stream_t stream);
+/* The per-sequence pair precompute itself (SURVEY.md 8b `pair_precompute`), fp32, once per sequence:
+ *   se3_pair_embed:   x2d[r, :] = LayerNorm(pair_embeds[r, :]; ln_gamma, ln_beta, ln_eps) . w_x2d^T + relpos_table[bucket[r % len^2], :]
+ *                     (models.py:243-293: `x2d_proj` on the dense pair embedding [pair_batch*len*len, dim_embed] plus the T5-style
+ *                     relative-position bias; `bucket` [len*len] int32 is the integer-exact bucket table the host evaluates,
+ *                     relpos_table [num_buckets, dim_pair], w_x2d [dim_pair, dim_embed]); x2d [pair_batch*len*len, dim_pair];
+ *                     stats_workspace: pair_batch*len*len*2 floats
+ *   se3_pair_project: one layer's pair tensors from x2d: bias = pair_weight * x2d . W_bias^T (structure_module.py:179) and value =
+ *                     x2d . W_value^T (:209); w_bias_value [heads + heads*dk, dim_pair] = the two weights stacked (bias rows first).
+ *                     packed = 0: fp32 bias_out [pair_batch, heads, len, len], value_out [pair_batch, len, len, heads*dk]  (se3_ipa_attention_fwd)
+ *                     packed = 1: the bf16 operands of se3_ipa_attention_tc_fwd (sizes: se3_ipa_tc_packed_pair_bytes; pair_batch = 1, dk = 16)
+ * Plain fp32 tile GEMMs (k ascending): results agree with a BLAS evaluation to fp32 summation-order differences. */
+int se3_pair_embed(const float* pair_embeds, const float* ln_gamma, const float* ln_beta, float ln_eps, const float* w_x2d,
+                   const float* relpos_table, const int32_t* bucket, float* x2d, float* stats_workspace, int64_t pair_batch,
+                   int len, int dim_embed, int dim_pair, se3_stream_t stream);
+int se3_pair_project(const float* x2d, const float* w_bias_value, float pair_weight, void* bias_out, void* value_out, int packed,
+                     int64_t pair_batch, int len, int heads, int dk, int dim_pair, se3_stream_t stream);
 /* HOST function (no device work): row index sets of the reference's fused projection weight
  * [scalar_query | scalar_key | scalar_value | point_query | point_key | point_value] (structure_module.py:56-107, rows in the
  * reference's parameter order) for the head-major records of se3_ipa_attention_tc_fwd:

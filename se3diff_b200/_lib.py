@@ -81,6 +81,8 @@ SIGNATURES = {
     "se3_ipa_tc_packed_pair_bytes": [i32, i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
     "se3_ipa_tc_pack_pair": [f32p, f32p, vp, vp, i32, i32, vp],
     "se3_ipa_split_perm": [i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
+    "se3_pair_embed": [f32p, f32p, f32p, f32, f32p, f32p, vp, f32p, f32p, i64, i32, i32, i32, vp],
+    "se3_pair_project": [f32p, f32p, f32, vp, vp, i32, i64, i32, i32, i32, i32, vp],
     "se3_folded_proportion": [f32p, f32p, f32p, f32p, i64, i32, f32, f32, f32, vp],
     "se3_backbone_atoms": [f32p, f32p, vp, vp, f32p, i64, i32, vp],
     "se3_physicality": [f32p, vp, f32p, i64, i32, vp],

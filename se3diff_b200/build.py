@@ -27,6 +27,7 @@ SOURCES = {
     "ipa_tc.cu": [],
     "ipa_tc_pp.cu": [],
     "pair_pack.cu": [],
+    "pair_precompute.cu": [],
     "fused_rows.cu": [],
     "observables.cu": [],
     "backbone.cu": [],

@@ -323,7 +323,11 @@ class DistributionalGraphormer(nn.Module):
             single_d, pair_d = single_d[:1], pair_d[:1]
         c.x1d_base = self.x1d_proj(single_d)                                        # [Bp, L, d_model]
         bucket = self.rp_proj.bucket_table(lmax).to(dev)
-        x2d = self.x2d_proj(pair_d) + self.rp_proj.relative_attention_bias(bucket)[None]   # [Bp, L, L, d_pair]
+        if ops.pair_precompute_supported(pair_d.shape[-1], self.x2d_proj[1].weight.shape[0]) and pair_d.dtype == torch.float32:
+            ln = self.x2d_proj[0]       # the library's own fp32 kernels (se3_pair_embed; se3_pair_project below): once per sequence
+            x2d = ops.pair_embed(pair_d.contiguous(), ln.weight, ln.bias, ln.eps, self.x2d_proj[1].weight, self.rp_proj.relative_attention_bias.weight, bucket)
+        else:
+            x2d = self.x2d_proj(pair_d) + self.rp_proj.relative_attention_bias(bucket)[None]   # [Bp, L, L, d_pair]
         attn0 = self.st_module.encoder.layers[0].attn
         probe = ops.ipa_shape(B, lmax, attn0.n_head, attn0.d_k, 1 if c.shared else B, head_major=False)
         # tcgen05 attention path: decided with the SAME predicate as the fused bf16 forward that is its only caller
@@ -349,6 +353,8 @@ class DistributionalGraphormer(nn.Module):
     @staticmethod
     def _pair_tensors(a: SAAttention, x2d, tc: bool):
         """(pair bias, pair values) of one layer in the layout its attention kernel reads (structure_module.py:179, 209)."""
+        if x2d.is_cuda and x2d.dtype == torch.float32 and ops.pair_precompute_supported(32, x2d.shape[-1]) and (not tc or a.d_k == 16):
+            return ops.pair_project(x2d, a.pair_bias.weight, a.pair_value.weight, a.pair_weight, a.n_head, a.d_k, packed=tc)
         pb = a.pair_weight * a.pair_bias(x2d)                                                      # [Bp, L(i), L(j), H]
         pv = a.pair_value(x2d)                                                                     # [Bp, L, L, H*dk]
         if tc:      # tensor-core kernel: transposed bf16 slabs [H, j, i] fetched by TMA; values in the UMMA K-major operand layout

@@ -572,6 +572,44 @@ def ipa_tc_pack_pair_bias(pair_bias: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def pair_precompute_supported(dim_embed: int, dim_pair: int) -> bool:
+    return dim_embed % 32 == 0 and dim_pair % 32 == 0
+
+
+def pair_embed(pair_dense, ln_weight, ln_bias, ln_eps: float, w_x2d, relpos_table, bucket) -> torch.Tensor:
+    """x2d = x2d_proj(pair) + relative-position bias (models.py:243-293): pair_dense [Bp, L, L, de] -> [Bp, L, L, dp] (se3_pair_embed)."""
+    pd = _dev(pair_dense, name="pair_dense")
+    Bp, Lq, de = pd.shape[0], pd.shape[1], pd.shape[-1]
+    w, rp = _dev(w_x2d, name="w_x2d"), _dev(relpos_table, name="relpos_table")
+    bk = _dev(bucket.reshape(-1), torch.int32, "bucket")
+    g, b = _dev(ln_weight, name="ln_weight"), _dev(ln_bias, name="ln_bias")
+    dp = w.shape[0]
+    out = torch.empty(Bp, Lq, Lq, dp, dtype=torch.float32, device=pd.device)
+    stats = torch.empty(Bp * Lq * Lq * 2, dtype=torch.float32, device=pd.device)
+    with _guard(pd):
+        L.check(L.lib().se3_pair_embed(_p(pd), _p(g), _p(b), float(ln_eps), _p(w), _p(rp), _p(bk), _p(out), _p(stats), Bp, Lq, de, dp, _stream(pd)),
+                "se3_pair_embed")
+    return out
+
+
+def pair_project(x2d, w_bias, w_value, pair_weight: float, heads: int, dk: int, packed: bool):
+    """One layer's pair tensors from x2d [Bp, L, L, dp] (structure_module.py:179, 209; se3_pair_project): fp32 ([Bp, H, L, L], [Bp, L, L, H*dk])
+    or, packed, the bf16 operands of the tensor-core attention ([H][L][round_up(L,8)], [L][H][Lp/8][16][8])."""
+    x = _dev(x2d, name="x2d")
+    Bp, Lq, dp = x.shape[0], x.shape[1], x.shape[-1]
+    w = torch.cat([_dev(w_bias, name="w_bias"), _dev(w_value, name="w_value")], dim=0).contiguous()
+    if packed:
+        bias = torch.empty(heads, Lq, (Lq + 7) // 8 * 8, dtype=torch.bfloat16, device=x.device)
+        value = torch.empty(Lq, heads, (Lq + 15) // 16 * 2, 16, 8, dtype=torch.bfloat16, device=x.device)
+    else:
+        bias = torch.empty(Bp, heads, Lq, Lq, dtype=torch.float32, device=x.device)
+        value = torch.empty(Bp, Lq, Lq, heads * dk, dtype=torch.float32, device=x.device)
+    with _guard(x):
+        L.check(L.lib().se3_pair_project(_p(x), _p(w), float(pair_weight), _p(bias), _p(value), int(packed), Bp, Lq, heads, dk, dp, _stream(x)),
+                "se3_pair_project")
+    return bias, value
+
+
 def ipa_tc_workspace(shape: L.IpaShape, device) -> tuple[torch.Tensor, torch.Tensor]:
     pb, ib = C.c_int64(0), C.c_int64(0)
     L.lib().se3_ipa_tc_workspace_bytes(C.byref(shape), C.byref(pb), C.byref(ib))

@@ -755,6 +755,40 @@ def test_tc_operand_packs_are_bit_exact(L, H):
     assert got_v.shape == want_v.shape and torch.equal(got_v.view(torch.int16), want_v.view(torch.int16))
 
 
+@pytest.mark.parametrize("L,Bp,H,dp", [(84, 1, 32, 256), (23, 3, 4, 32), (130, 1, 8, 64)])
+def test_pair_precompute_entries_vs_torch(L, Bp, H, dp):
+    """se3_pair_embed / se3_pair_project (SURVEY 8b `pair_precompute`: models.py:243-293 + structure_module.py:179, 209) against the same
+    expressions in torch fp64: x2d = x2d_proj(pair) + relative-position bias, then one layer's pair bias and pair values, in the fp32
+    layouts of the SIMT attention and in the packed bf16 operands of the tensor-core attention (equal to se3_ipa_tc_pack_pair of the
+    fp32 result up to a final-bit tie: the pack rounds the same numbers)."""
+    from se3diff_b200 import ops
+    from se3diff_b200.models import RelativePositionBias, SAAttention
+
+    torch.manual_seed(L)
+    de, dk = 128, 16
+    ln, lin = torch.nn.LayerNorm(de).to(DEV), torch.nn.Linear(de, dp, bias=False).to(DEV)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5); ln.bias.uniform_(-0.3, 0.3)
+    rp = RelativePositionBias(num_buckets=64, max_distance=128, out_dim=dp).to(DEV)
+    a = SAAttention(H * dk, dp, H, dropout=0.0).to(DEV)
+    pair = torch.randn(Bp, L, L, de, device=DEV) * 2.0 + 0.3
+    bucket = rp.bucket_table(L).to(DEV)
+    x2d = ops.pair_embed(pair, ln.weight, ln.bias, ln.eps, lin.weight, rp.relative_attention_bias.weight, bucket)
+    want = (torch.nn.functional.linear(torch.nn.functional.layer_norm(pair.double(), (de,), ln.weight.double(), ln.bias.double(), ln.eps), lin.weight.double())
+            + rp.relative_attention_bias.weight.double()[bucket][None])
+    assert (x2d.double() - want).abs().max() <= 2e-6 * want.abs().max()
+    pb, pv = ops.pair_project(x2d, a.pair_bias.weight, a.pair_value.weight, a.pair_weight, H, dk, packed=False)
+    want_b = (a.pair_weight * torch.nn.functional.linear(x2d.double(), a.pair_bias.weight.double())).permute(0, 3, 1, 2)
+    want_v = torch.nn.functional.linear(x2d.double(), a.pair_value.weight.double())
+    assert pb.shape == want_b.shape and (pb.double() - want_b).abs().max() <= 2e-6 * want_b.abs().max()
+    assert pv.shape == want_v.shape and (pv.double() - want_v).abs().max() <= 2e-6 * want_v.abs().max()
+    if Bp == 1:
+        kb, kv = ops.pair_project(x2d, a.pair_bias.weight, a.pair_value.weight, a.pair_weight, H, dk, packed=True)
+        rb, rv = ops.ipa_tc_pack_pair_bias(pb.permute(0, 2, 3, 1).contiguous()), ops.ipa_tc_pack_pair_value(pv, H)
+        assert kb.shape == rb.shape and kv.shape == rv.shape
+        assert torch.equal(kb.view(torch.int16), rb.view(torch.int16)) and torch.equal(kv.view(torch.int16), rv.view(torch.int16))
+
+
 def test_bf16_forward_long_sequence_uses_split_attention():
     """L = 300 (> 256): bf16 mode must stay on the tensor-core attention (cluster-split keys) and agree with the fp32 parity
     path of the same model to the bf16 level (2 layers, B = 2, physical-scale frames)."""
@@ -971,6 +1005,28 @@ def test_bf16_mode_at_the_benched_config_vs_the_oracle():
           "| max rotation-matrix difference fp32 %.2e bf16 %.2e | Rg %.1f" % (res["fp32"][1], res["bf16"][1], rg.mean().item()))
     assert (res["fp32"][0] <= 2e-5).all() and res["fp32"][1] <= 1e-4, res["fp32"]
     assert (res["bf16"][0] <= 2.5e-3).all() and res["bf16"][1] <= 5e-2, res["bf16"]
+
+
+def test_config1_sh3_shape_full_run_vs_the_oracle():
+    """BASELINE.json configs[0] -- the reference's own CPU-runnable case: SH3 length (L = 56), batch 10, the shipped dpm.yaml
+    (50 steps), bioemu-v1.0 architecture (8 layers) -- run end to end in the fp32 parity mode against the oracle's `dpm_solver`
+    on the same prior draw: C-alpha RMSD <= 2e-5 of the radius of gyration per sample, rotation matrices within 1e-4."""
+    from se3diff_b200 import shortcuts
+
+    L, B, nsteps = 56, 10, 50
+    m, ctx, tab, r3, sdes, batch, S = _bench_width_setup(L, B)
+    o32 = ScoreModelOracle(m.state_dict(), num_heads=32).set_context(*ctx)
+    torch.manual_seed(17)
+    p_ref, r_ref = osamp.dpm_solver(o32, ctx[2], r3, tab, nsteps, 0.99, 0.001)
+    p_ref = p_ref.view(B, L, 3).double()
+    rg = (p_ref - p_ref.mean(dim=1, keepdim=True)).pow(2).sum(-1).mean(-1).sqrt()
+    with S.host_noise():
+        torch.manual_seed(17)
+        o = shortcuts.dpm_solver(batch=batch, sdes=sdes, score_model=m.to(DEV), num_steps=nsteps, max_t=0.99, min_t=0.001, device=DEV)
+    rmsd = (o["pos"].view(B, L, 3).double().cpu() - p_ref).pow(2).sum(-1).mean(-1).sqrt()
+    dr = (o["node_orientations"].cpu() - r_ref).abs().max().item()
+    print("C1 shape (L = 56, B = 10, 50 steps), fp32 mode vs oracle: RMSD / Rg", (rmsd / rg).max().item(), "max |dR|", dr)
+    assert (rmsd <= 2e-5 * rg).all() and dr <= 1e-4, (rmsd / rg, dr)
 
 
 def test_bf16_mode_physical_scale_steps_vs_the_oracle():
