@@ -227,7 +227,7 @@ int se3_igso3_build_score_scaling(const float* sigma_grid, int num_sigma, const 
  * optional left-multiplication of sample_marginal (so3_sde.py:283): out = x . Exp(axis*omega).
  *   sigma   : [n] per-element std dev; NULL => uniform SO(3) (row 0, no small-sigma zeroing)
  *   normals : [n,3] axis normals, u : [n] uniforms in [0,1) -- drawn by the caller (parity mode);
- *             both NULL => in-kernel Philox4x32-10 keyed by (seed, element index)
+ *             both NULL => in-kernel Philox4x32-7 keyed by (seed, element index)
  *   x       : optional [n,3,3]; NULL => out = Exp(axis*omega)
  *   angle_out optional [n]
  *   cdf_index: optional guide records built by se3_igso3_build_cdf_index (same row order as cdf); NULL => binary

@@ -233,7 +233,8 @@ __device__ __forceinline__ void sincos_fused(float x, float* s, float* c) {
 // out = R . Exp(v)  (apply_rotvec_to_rotmat, so3_sde.py:782-802; Rodrigues with the Taylor branch below `tol`, :533-554)
 __device__ __forceinline__ void so3_apply_rotvec_fused(const float r[9], float x, float y, float z, float tol, float out[9]) {
     const float th2 = fmaf(x, x, fmaf(y, y, z * z));
-    const float th = __fsqrt_rn(th2);
+    float th;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(th) : "f"(th2));      // 1 ulp-class; the correctly rounded form is a 7-instruction sequence
     float a, b;
     if (th < tol) {
         a = fmaf(th2, -1.0f / 6.0f, 1.0f);

@@ -11,6 +11,8 @@
 //                      (== the reference's `sum(cdf < u)`, so3_sde.py:1265) + lerp + Rodrigues
 //                      [+ left-multiplication by x for sample_marginal]; output written through the
 //                      128-bit tile path.  HBM-bound: 72-88 B/rotation.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 using namespace se3;
@@ -336,12 +338,12 @@ __device__ __forceinline__ uint32_t mulhilo(uint32_t a, uint32_t b, uint32_t* hi
     *hi = (uint32_t)(p >> 32);
     return (uint32_t)p;
 }
-// Philox4x32-10, counter = (idx_lo, idx_hi, stream, 0), key = seed
+// Philox4x32-7, counter = (idx_lo, idx_hi, stream, 0), key = seed
 __device__ __forceinline__ void philox(uint64_t seed, uint64_t idx, uint32_t stream, uint32_t r[4]) {
     uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32), c2 = stream, c3 = 0;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
+    for (int i = 0; i < 7; ++i) {      // Philox4x32-7: the shortest variant that passes BigCrush (Salmon et al. 2011); 10 rounds cost 26 more instructions per rotation
         uint32_t h0, h1;
         const uint32_t l0 = mulhilo(0xD2511F53u, c0, &h0), l1 = mulhilo(0xCD9E8D57u, c2, &h1);
         c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
@@ -360,7 +362,7 @@ __device__ __forceinline__ SampleDraw sample_lookup(int64_t e, bool have_normals
                                                     const float* __restrict__ cdf_index, int guide_bins_n) {
     SampleDraw d = {0, 0.f, 0.f, sg_in, u_in, 0.f, 0.f, 0.f};
     if (!have_normals) {
-        // One Philox4x32-10 block per rotation: a direction uniform on the sphere from two uniforms (z = 2a - 1, phi = 2 pi b) --
+        // One Philox4x32-7 block per rotation: a direction uniform on the sphere from two uniforms (z = 2a - 1, phi = 2 pi b) --
         // the same law as the reference's normalised Gaussian triple (so3_sde.py:1229-1242), which would take four uniforms,
         // two logarithms and a second block -- and the CDF uniform from the third.  (Bit parity with the reference's torch
         // generator is the business of the noise-passed-in mode; this mode only has to draw from the same distribution.)
@@ -407,7 +409,9 @@ __device__ __forceinline__ float sample_compose(const SampleDraw& d, bool have_s
     if (have_sigma && d.sg < tol) ang = 0.0f;  // SampleIGSO3._process_angles
     // axis-angle -> rotation and x . r with explicit FMAs (common.cuh: so3_apply_rotvec_fused): the angle above is the
     // bit-exact part of this kernel; the matrix entries depend on sin / cos and agree with the reference to ~1e-6 either way
-    const float scale = __fdividef(ang, __fsqrt_rn(fmaf(d.nx, d.nx, fmaf(d.ny, d.ny, d.nz * d.nz))));
+    float scale;                                             // ang / |n|: one MUFU.RSQ (the matrix entries are the ~1e-6 part of this kernel)
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(scale) : "f"(fmaf(d.nx, d.nx, fmaf(d.ny, d.ny, d.nz * d.nz))));
+    scale *= ang;
     float xr[9], o[9];
     if (have_x) {
 #pragma unroll
@@ -451,6 +455,39 @@ k_sample(const float* __restrict__ sigma, const float* __restrict__ sigma_grid, 
     }
     __syncwarp();
     warp_tile_store<9>(out, s_rot, first, count);
+}
+
+// Persisting-L2 access window over a lookup table for the launches enqueued on `st` until clear_l2_window (SE3DIFF_B200_L2_WINDOW=0
+// disables).  The device's persisting carve-out is raised once to what the table needs (at most what the device allows).
+inline bool l2_window_enabled() {
+    static const bool on = [] { const char* v = getenv("SE3DIFF_B200_L2_WINDOW"); return !(v && v[0] == '0'); }();
+    return on;
+}
+inline bool set_l2_window(cudaStream_t st, const void* base, size_t bytes) {
+    int dev = 0, max_persist = 0, max_window = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev) != cudaSuccess || max_persist <= 0 || max_window <= 0) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    size_t want = bytes < (size_t)max_persist ? bytes : (size_t)max_persist, have = 0;
+    if (cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize) != cudaSuccess || (have < want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess)) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    cudaStreamAttrValue a = {};
+    a.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+    a.accessPolicyWindow.num_bytes = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+    a.accessPolicyWindow.hitRatio = want >= bytes ? 1.0f : (float)want / (float)bytes;
+    a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return true;
+}
+inline void clear_l2_window(cudaStream_t st) {
+    cudaStreamAttrValue a = {};
+    a.accessPolicyWindow.num_bytes = 0;
+    (void)cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a);
 }
 
 inline int series_grid(int64_t n) {
@@ -556,8 +593,19 @@ int se3_igso3_sample(const float* sigma, const float* sigma_grid, int num_sigma,
     // (A pipelined per-warp edition like k_em_pipe was measured and dropped: 0.529 -> 0.536 of the HBM roof with the noise passed
     // in, 0.478 -> 0.399 in Philox mode -- this kernel is bound by its ~250 instructions per rotation at 64 resident warps, and
     // the ring costs occupancy.)
-    k_sample<<<(unsigned)((n + kTile - 1) / kTile), kTile, 0, (cudaStream_t)stream>>>(sigma, sigma_grid, num_sigma, cdf, omega_grid, num_omega, normals, u, seed, x, out,
-                                                                                    angle_out, n, tol, num_omega <= 65535 ? cdf_index : nullptr, guide_bins(num_omega), 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* index = num_omega <= 65535 ? cdf_index : nullptr;
+    // Large draws with per-rotation sigma touch the guide records (32 MB for the shipped 1000 x 2000 table) at random while
+    // ~1 GB of operands streams through L2 and evicts them: the records are given a persisting-L2 access window for this launch.
+    bool window = false;
+    if (index && sigma && n >= (1 << 20) && l2_window_enabled()) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone)
+            window = set_l2_window(st, index, (size_t)num_sigma * guide_bins(num_omega) * 32);
+    }
+    k_sample<<<(unsigned)((n + kTile - 1) / kTile), kTile, 0, st>>>(sigma, sigma_grid, num_sigma, cdf, omega_grid, num_omega, normals, u, seed, x, out, angle_out, n, tol,
+                                                                    index, guide_bins(num_omega), 0);
+    if (window) clear_l2_window(st);
     SE3_LAUNCH_CHECK("se3_igso3_sample");
 }
 
