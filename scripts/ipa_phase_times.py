@@ -26,3 +26,18 @@ d = t[:, 1:] - t[:, :-1]
 names = ["staging(+alloc)", "sync+MMA1+wait", "passA(+bias wait)", "passB", "sync+MMA2+wait", "epilogue", "dealloc"]
 print("mean cycles per phase:", {n: round(v) for n, v in zip(names, d.mean(0).tolist())}, "total", round((t[:, 7] - t[:, 0]).mean().item()))
 print("p90:", {n: round(v) for n, v in zip(names, d.quantile(0.9, dim=0).tolist())})
+# persistent editions: cycles from a CTA's first stamp to its last one = the kernel's duration in SM cycles (against the event
+# time of the same launch this gives the clock the SMs actually ran at)
+G = int(os.environ.get('IPA_GRID', 0))
+if G:
+    tt = buf.view(-1, 16).double().cpu()
+    first = tt[:G, 0]
+    last = torch.stack([tt[c::G, 7].max() for c in range(G)])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record(); run(); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    span = (last - first)
+    print(f"persistent CTAs: span cycles mean {span.mean():.0f} max {span.max():.0f}; pass 1 + pass 2 event time {ms * 1e3:.1f} us")
+    gt = torch.stack([tt[c::G, 14].max() - tt[c::G, 14].min() for c in range(G)])       # ns between the CTA's first and last item end
+    cy = torch.stack([tt[c::G, 7].max() - tt[c::G, 7].min() for c in range(G)])
+    print(f"SM clock inside the kernel: {(cy / gt).mean():.3f} GHz (min {(cy / gt).min():.3f}, max {(cy / gt).max():.3f}); kernel wall span {(tt[:, 14].max() - tt[:, 14].min()) / 1e3:.1f} us from the first item end to the last")

@@ -59,6 +59,11 @@ __device__ __forceinline__ float ld_peer_f32(const float* own_smem_ptr, uint32_t
     return v;
 }
 
+// Work queue of the persistent 128-thread edition: {items handed out beyond the first gridDim.x, CTAs that have left}.  The
+// last CTA to leave zeroes its slot again, so a slot is zero whenever no launch is using it; launches take the slots in turn.
+constexpr int kSchedSlots = 64;
+__device__ unsigned int g_sched[kSchedSlots][2];
+
 struct Pass1Smem {
     uint8_t *q, *k, *vs, *vp, *p;
     float *kp, *kb, *frm, *raw, *xo;
@@ -111,13 +116,17 @@ __device__ __forceinline__ Pass1Smem carve1(uint8_t* base, int L, int LK, int Lp
 // kWide (always with kSplit, and alone for 129..256 key rows, where shared memory admits one CTA per SM anyway): 256 threads;
 //                 warps w and w + 4 share a TMEM lane quadrant (= 32 query rows) and take one half of the key columns each.
 // kPtsBf16: the point records are bf16 (one projection GEMM writes scalar and point records side by side) instead of fp32.
-template <typename OutT, bool kSplit, bool kWide, bool kPtsBf16>
+// kPersist (always with kWide; alone = the 128-thread edition for L <= 128 with four persistent CTAs per SM): the CTA walks
+//                 every gridDim.x-th item and issues the next item's copies as soon as the second product has consumed the
+//                 operands.  Without it: one item per CTA, taken from the grid coordinates.
+template <typename OutT, bool kSplit, bool kWide, bool kPtsBf16, bool kPersist = kWide>
 __global__ void __launch_bounds__(kWide ? 256 : 128, kWide ? 1 : 4)
 k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_pts,
                const __grid_constant__ CUtensorMap map_bias, const float* __restrict__ rot, const float* __restrict__ trans, const __nv_bfloat16* __restrict__ pair_bias_t,
                const float* __restrict__ key_bias, const float* __restrict__ head_weight, OutT* __restrict__ out,
                __nv_bfloat16* __restrict__ pbuf, float* __restrict__ inv_sum, const se3_ipa_shape sh, int LpB, int LpT, int Bpad, int tmem_cols,
-               const void* __restrict__ pts, int pts_stride, long long* __restrict__ dbg, int head0) {
+               const void* __restrict__ pts, int pts_stride, long long* __restrict__ dbg, int head0, unsigned int* __restrict__ sched) {
+    static_assert(kPersist || !kWide, "the 256-thread editions are persistent");
     constexpr int kRawRow = kPtsBf16 ? 96 : 192;            // bytes of one staged point record [qp 12 | kp 12 | vp 24]
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t bar, bar_bias, bar_in;
@@ -126,6 +135,7 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     static_assert(kWide || !kSplit, "the split edition runs 256 threads");
     constexpr int kThreads = kWide ? 256 : 128;
     __shared__ uint32_t tmem_slot;
+    __shared__ int s_next;                                 // next item of this CTA (dynamic schedule)
     const int L = sh.len, H = sh.heads;
     const uint32_t rank = kSplit ? cluster_ctarank() : 0u;
     const int k0 = kSplit ? (int)rank * LpB : 0;                      // first key of this CTA
@@ -140,12 +150,12 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     // Work items (sample b, head h, query tile).  Narrow edition: one per CTA, from the grid coordinates.  256-thread editions:
     // item = (b * H + h) * ntile + tile, this CTA (cluster) takes every `item_step`-th one starting at its own index, so that
     // the CTAs running at any moment work on neighbouring (sample, head) pairs whose record slices share DRAM pages.
-    const int item_step = kWide ? (int)(kSplit ? gridDim.x >> 1 : gridDim.x) : 1;
-    const int item_first = kWide ? (int)(kSplit ? blockIdx.x >> 1 : blockIdx.x) : 0;
-    const int n_items = kWide ? ntile * H * sh.batch : 1;
+    const int item_step = kPersist ? (int)(kSplit ? gridDim.x >> 1 : gridDim.x) : 1;
+    const int item_first = kPersist ? (int)(kSplit ? blockIdx.x >> 1 : blockIdx.x) : 0;
+    const int n_items = kPersist ? ntile * H * sh.batch : 1;
     int item = item_first;
     // optional phase timestamps: 16 clock64 slots per item, written by thread 0 (scripts/ipa_phase_times.py)
-#define SE3_STAMP(k) do { if (dbg && threadIdx.x == 0) dbg[(kWide ? (int64_t)item * (kSplit ? 2 : 1) + (int64_t)rank : ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (k)] = clock64(); } while (0)
+#define SE3_STAMP(k) do { if (dbg && threadIdx.x == 0) dbg[(kPersist ? (int64_t)item * (kSplit ? 2 : 1) + (int64_t)rank : ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (k)] = clock64(); } while (0)
 
     // pair-bias tile of this (head, query tile): bf16 [L keys][ncol queries], fetched by TMA into the region that
     // later holds P (P is only written after every warp has finished the logit pass)
@@ -168,7 +178,7 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     float* s_trn = s.frm + LK * 9;
     const bool bulk_frames = ((L & 3) == 0) && ((reinterpret_cast<uintptr_t>(rot) | reinterpret_cast<uintptr_t>(trans)) & 15) == 0;
     auto decode = [&](const int it, int& b_, int& h_, int& q0_) {
-        if constexpr (kWide) {
+        if constexpr (kPersist) {
             const int bh = it / ntile;
             b_ = bh / H; h_ = bh - b_ * H; q0_ = (it - bh * ntile) * 128;
         } else {
@@ -200,6 +210,19 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         tc::mbar_fence_init();
         if (item < n_items) issue_loads(item);
     }
+    // 128-thread persistent edition: items beyond the first gridDim.x are handed out by an atomic counter, one item ahead of
+    // their use (the SMs do not run at the same pace: with a fixed round-robin schedule the slowest CTA took 13 % longer than
+    // the average one and set the kernel's duration).  Consecutive tickets go to whichever CTAs ask next, so the CTAs running at
+    // any moment still work on neighbouring (sample, head) records.
+    constexpr bool kDynamic = kPersist && !kWide;
+    int ticket = 0;                                        // thread 0: drawn early, published (s_next) at the end of the item
+    auto fetch_next = [&]() {                              // thread 0 only
+        if constexpr (kDynamic) ticket = (int)gridDim.x + (int)atomicAdd(&sched[0], 1u);
+    };
+    if (kDynamic && tid == 0) { fetch_next(); s_next = ticket; }
+    // who issues the next item's copies and draws the next ticket: L <= 96 leaves the warp of lane quadrant 3 without query rows,
+    // so its first thread does it while warps 0..2 are in the epilogue
+    const int prefetcher = (kDynamic && L <= 96) ? 96 : 0;
     tc::fence_before();
     __syncthreads();   // the barriers are initialised, the TMEM base address is published
     tc::fence_after();
@@ -207,8 +230,10 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const int nchunk = Lp / 16;
     const uint32_t lane_base = (uint32_t)(warp & 3) * 32;
 
-  for (uint32_t par = 0; item < n_items; item += item_step, par ^= 1u) {
+  for (uint32_t par = 0; item < n_items; par ^= 1u) {
     SE3_STAMP(0);
+    int item_next = item + item_step;
+    if constexpr (kDynamic) item_next = s_next;            // written by thread 0 before the barrier that ended the previous item
     int b, h, q0;
     decode(item, b, h, q0);
     const int i = q0 + qrow;
@@ -471,10 +496,13 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     tc::mbar_wait(&bar, 1);
     tc::fence_after();
     SE3_STAMP(5);
-    if constexpr (kWide) {
-        // both products have consumed their shared-memory operands and the raw points sit in their own buffer: the next item's
-        // copies fly under this item's epilogue and the draining probability tile
-        if (tid == 0 && item + item_step < n_items) issue_loads(item + item_step);
+    if constexpr (kPersist) {
+        // both products have consumed their shared-memory operands (the P operand too, whose front the 128-thread edition reuses
+        // for the raw point records): the next item's copies fly under this item's epilogue
+        if (tid == prefetcher && item_next < n_items) {
+            issue_loads(item_next);
+            fetch_next();                                  // the ticket after that one: its latency hides under the next item
+        }
     }
 
     auto load_acc = [&](float (&o)[NV]) {
@@ -540,13 +568,26 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             finish(o);
         }
     }
+    if (kDynamic && tid == prefetcher) s_next = ticket;
     tc::fence_before();
     __syncthreads();   // every warp has read its accumulator rows: TMEM and the operand buffers belong to the next item
     tc::fence_after();
     SE3_STAMP(6);
     SE3_STAMP(7);
-    if constexpr (!kWide) break;
+    if (dbg && threadIdx.x == 0) {   // wall-clock time of the same instant: clock64 / globaltimer differences give the SM clock
+        long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        dbg[(kPersist ? (int64_t)item * (kSplit ? 2 : 1) + (int64_t)rank : ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + 14] = gt;
+    }
+    if constexpr (!kPersist) break;
+    item = item_next;
   }
+    if constexpr (kDynamic) {
+        if (tid == 0 && atomicAdd(&sched[1], 1u) == gridDim.x - 1) {   // last CTA out: the slot is zero again for its next launch
+            sched[0] = 0;
+            sched[1] = 0;
+        }
+    }
     if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)tmem_cols);
 #undef SE3_STAMP
 }
@@ -614,6 +655,12 @@ long long* g_phase_dbg = nullptr;  // set by se3_debug_set_phase_buffer
 bool pingpong_disabled() {   // work in progress: opt-in with SE3DIFF_B200_IPA_PP=1 until it beats the one-item-per-CTA edition
     const char* v = getenv("SE3DIFF_B200_IPA_PP");
     return !(v && v[0] == '1');
+}
+
+// SE3DIFF_B200_IPA_PERSIST=0: L <= 128 runs the one-item-per-CTA edition instead of the persistent one (measurement switch)
+bool narrow_persistent() {
+    static const bool v = [] { const char* e = getenv("SE3DIFF_B200_IPA_PERSIST"); return !(e && e[0] == '0'); }();
+    return v;
 }
 
 template <typename OutT, bool kPtsBf16>
@@ -694,11 +741,28 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const void* pts, int p
             const int gsz = v ? atoi(v) : 0;
             if (gsz > 0 && gsz < sh.heads) group = gsz;
         }
+        if (!wide && group == sh.heads && narrow_persistent()) {     // four persistent CTAs per SM
+            auto kp = k_ipa_tc_pass1<OutT, false, false, kPtsBf16, true>;
+            e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+            if (e != cudaSuccess) { set_error("ipa_tc pass1 smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
+            const int resident = (512 / cols) * sms;
+            static unsigned int launch_no = 0;
+            unsigned int* sched = nullptr;
+            e = cudaGetSymbolAddress((void**)&sched, g_sched);
+            if (e != cudaSuccess) { set_error("ipa_tc pass1 work queue: %s", cudaGetErrorString(e)); return SE3_ECUDA; }
+            sched += 2 * (launch_no++ % kSchedSlots);
+            kp<<<dim3((unsigned)(n_items < resident ? n_items : resident), 1, 1), 128, smem1, st>>>(map_q, map_kv, map_pts, map_bias, rot, trans, pair_bias, key_bias,
+                                                                                                     head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad, cols, pts,
+                                                                                                     pts_stride, g_phase_dbg, 0, sched);
+            count_launch();
+            if (int rc = check_launch("se3_ipa_attention_tc_fwd(pass 1)")) return rc;
+            return pass2(0, sh.heads);
+        }
         for (int h0 = 0; h0 < sh.heads; h0 += group) {
             const int nh = sh.heads - h0 < group ? sh.heads - h0 : group;
             const dim3 g1 = wide ? dim3((unsigned)(n_items < sms ? n_items : sms), 1, 1) : dim3(ntile, nh, sh.batch);
             k1<<<g1, wide ? 256 : 128, smem1, st>>>(map_q, map_kv, map_pts, map_bias, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad,
-                                                    cols, pts, pts_stride, g_phase_dbg, h0);
+                                                    cols, pts, pts_stride, g_phase_dbg, h0, nullptr);
             count_launch();
             if (int rc = check_launch("se3_ipa_attention_tc_fwd(pass 1)")) return rc;
             if (int rc = pass2(h0, nh)) return rc;
@@ -726,7 +790,7 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const void* pts, int p
         if (ncl > n_items) ncl = n_items;
         cfg.gridDim = dim3(2 * ncl, 1, 1);
         e = cudaLaunchKernelEx(&cfg, k1, map_q, map_kv, map_pts, map_bias, rot, trans, pair_bias, key_bias, head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad, cols,
-                               pts, pts_stride, g_phase_dbg, 0);
+                               pts, pts_stride, g_phase_dbg, 0, (unsigned int*)nullptr);
         if (e != cudaSuccess) { set_error("ipa_tc pass1 (split) launch: %s", cudaGetErrorString(e)); return SE3_ECUDA; }
         count_launch();
         if (int rc = check_launch("se3_ipa_attention_tc_fwd(pass 1)")) return rc;
