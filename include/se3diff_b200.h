@@ -294,9 +294,11 @@ int se3_ipa_attention_fwd(const float* proj, const float* rot, const float* tran
  *                p_ws[b, h, i, j] * d_out[b*L + i, pair block h, c] (summed over B when pair_batch = 1: a GEMM over the
  *                samples, left to the caller's BLAS)
  *   d_hw_rows  : [B*L, H] fp32, per-row partials of d head_weight (sum over rows = the gradient; deterministic)
- * One CTA per (sample, head) keeps the L keys, the L query records and both L x L matrices in shared memory:
- * len <= SE3_IPA_BWD_MAX_LEN and (2*len*(2*dk+36) + 2*len*(len|1) + len) * 4 bytes <= 227 KB. */
-#define SE3_IPA_BWD_MAX_LEN 128
+ * len <= 128 (and (2*len*(2*dk+36) + 2*len*(len|1) + len) * 4 bytes <= 227 KB): one CTA per (sample, head) keeps the L keys,
+ * the L query records and both L x L matrices in shared memory.  Longer sequences up to SE3_IPA_BWD_MAX_LEN run as two
+ * kernels (query rows in tiles of 64 with the keys staged in chunks; then key columns in tiles of 128) that meet in
+ * p_ws / ds_ws. */
+#define SE3_IPA_BWD_MAX_LEN 512
 int se3_ipa_attention_bwd(const float* proj, const float* rot, const float* trans, const float* pair_bias,
                           const float* pair_value, const float* key_bias, const float* head_weight,
                           float scalar_weight, const float* out, const float* d_out, float* d_proj, float* p_ws,

@@ -440,10 +440,12 @@ def ipa_attention_fwd(proj, rot, trans, pair_bias, pair_value, key_bias, head_we
 
 
 def ipa_bwd_supported(shape: L.IpaShape) -> bool:
-    """Shapes se3_ipa_attention_bwd takes: one CTA keeps the keys, the query records and two L x L matrices in shared memory."""
+    """Shapes se3_ipa_attention_bwd takes: L <= 128 with everything of a (sample, head) in shared memory, or -- up to L = 512 --
+    the tiled two-kernel edition, which parks the logits of 64 query rows in shared memory."""
     n, kw = shape.len, 2 * shape.dk + 36
-    return (shape.dk in (4, 8, 16, 32) and shape.pq == 4 and shape.pv == 8 and 0 < n <= 128 and 0 < shape.batch <= 65535
-            and (2 * n * kw + 2 * n * (n | 1) + n) * 4 <= 227 * 1024)
+    tiled = (64 * kw + 64 * (n | 1) + 2 * 64 * 65 + n) * 4
+    return (shape.dk in (4, 8, 16, 32) and shape.pq == 4 and shape.pv == 8 and 0 < n <= 512 and 0 < shape.batch <= 65535
+            and tiled <= 227 * 1024)
 
 
 def ipa_attention_bwd(proj, rot, trans, pair_bias, pair_value, key_bias, head_weight, scalar_weight: float, out, d_out,

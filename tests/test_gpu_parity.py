@@ -1482,8 +1482,12 @@ def test_backbone_atoms_and_physicality_filter():
 @pytest.mark.parametrize("B,L,H,dk,shared,masked,scale", [
     (5, 84, 4, 16, True, False, 1.0),       # the control model of config.yaml:12-22 on PDZ3
     (3, 57, 4, 16, False, True, 3.0),       # per-sample pair tensors, odd length, padded keys
-    (2, 128, 2, 8, True, False, 1.0),       # longest supported sequence
+    (2, 128, 2, 8, True, False, 1.0),       # longest sequence of the resident (one CTA per sample and head) edition
     (2, 33, 32, 16, True, False, 10.0),     # bioemu-v1.0 head count
+    (3, 200, 4, 16, True, True, 1.0),       # tiled two-kernel edition: ragged row / column tiles, padded keys
+    (2, 129, 2, 8, False, False, 3.0),      # ... one key past the resident edition, per-sample pair tensors
+    (2, 128, 2, 32, True, False, 1.0),      # ... dk = 32 at L = 128 (the resident edition's matrices do not fit)
+    (1, 512, 4, 16, True, False, 1.0),      # ... BASELINE config 5 length
 ])
 def test_ipa_backward_kernel_vs_torch_autograd(B, L, H, dk, shared, masked, scale, monkeypatch):
     """se3_ipa_attention_bwd (behind ops.IpaAttention, used by the differentiable forward) against torch autograd of the

@@ -275,9 +275,10 @@ def test_ipa_backward_shape_gate_and_cpu_refusal():
 
     ok = lambda B, n, H, dk: ops.ipa_bwd_supported(ops.ipa_shape(B, n, H, dk, 1, head_major=False))
     assert ok(1280, 84, 4, 16) and ok(64, 56, 4, 16) and ok(2, 128, 2, 8) and ok(2, 128, 32, 16)
-    assert not ok(2, 129, 4, 16)                      # keys of a (sample, head) no longer fit one CTA
-    assert not ok(2, 128, 4, 32)                      # 235 KB of shared memory
-    assert ok(2, 96, 4, 32)
+    assert ok(2, 129, 4, 16) and ok(2, 512, 4, 16)    # tiled two-kernel edition (keys of a (sample, head) no longer fit one CTA)
+    assert ok(2, 128, 4, 32)                          # 235 KB of shared memory for the resident edition: tiled edition
+    assert ok(2, 96, 4, 32) and ok(2, 512, 4, 32)
+    assert not ok(2, 513, 4, 16)                      # SE3_IPA_BWD_MAX_LEN
     assert not ok(0, 84, 4, 16) and not ok(70000, 84, 4, 16) and not ok(2, 84, 4, 12)
     sh = ops.ipa_shape(1, 8, 2, 4, 1, head_major=False)
     x = torch.zeros(8, sh.proj_stride)
