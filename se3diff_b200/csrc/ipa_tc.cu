@@ -389,14 +389,18 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < 12; ++k) q2[k] = make_float2(qp[k], qp[k]);
         const float2 hw2 = make_float2(hw, hw), l2e2 = make_float2(kLog2e, kLog2e);
-        auto chunk = [&](const int c, auto partial_tag) {
-            constexpr bool kPartial = decltype(partial_tag)::value;   // the last chunk when L % 16 != 0: skip padding keys
-            uint32_t r[16];
-            tc::tmem_ld16(tc::tmem_addr(tmem, lane_base, c * 16), r);
+        // A step is 8 key columns (4 key pairs): the body is instantiated twice (whole steps / the step with padding keys) and
+        // walked by a rolled loop -- unrolling 16 columns doubled the code of this pass for no gain in schedule (two key pairs
+        // are in flight either way, the register budget is what bounds that) and the four resident CTAs, each in another phase,
+        // compete for the instruction cache.
+        auto chunk = [&](const int col0, auto partial_tag) {
+            constexpr bool kPartial = decltype(partial_tag)::value;   // the last step when L % 8 != 0: skip padding keys
+            uint32_t r[8];
+            tc::tmem_ld8(tc::tmem_addr(tmem, lane_base, col0), r);
             tc::tmem_wait_ld();
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int j = c * 16 + 2 * u;
+            for (int u = 0; u < 4; ++u) {
+                const int j = col0 + 2 * u;
                 if (kPartial && j >= LK) {                 // padding keys (warp-uniform): no distance work
                     r[2 * u] = r[2 * u + 1] = __float_as_uint(-CUDART_INF_F);
                     continue;
@@ -428,11 +432,11 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 r[2 * u] = __float_as_uint(l2.x);
                 r[2 * u + 1] = __float_as_uint(l2.y);
             }
-            tc::tmem_st16(tc::tmem_addr(tmem, lane_base, c * 16), r);
+            tc::tmem_st8(tc::tmem_addr(tmem, lane_base, col0), r);
         };
-        const int nfull = LK / 16;
-        for (int c = c_begin; c < c_end; ++c) {
-            if (c < nfull) chunk(c, std::false_type{}); else chunk(c, std::true_type{});
+#pragma unroll 1
+        for (int col0 = c_begin * 16; col0 < c_end * 16; col0 += 8) {
+            if (col0 + 8 <= LK) chunk(col0, std::false_type{}); else chunk(col0, std::true_type{});
         }
         tc::tmem_wait_st();
     }
