@@ -4,6 +4,8 @@
 // in one pass: one warp per row, the row lives in registers (D <= 1024), two-pass mean/variance, 128-bit
 // accesses.  Replaces 4-5 ATen launches (broadcast bias add, residual add, layer_norm, dtype cast) and
 // their ~7 passes over the [N, D] activations by one kernel that reads x, y once and writes x, out once.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -156,17 +158,59 @@ k_gelu_bf16(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t nvec)
     }
 }
 
+// The fp32 residual stream is read and rewritten by this kernel twice per layer and by nothing else in between: at the bench shape
+// it is 44 MB, a third of the 126 MB L2, but the ~400 MB the GEMMs and the attention stream through L2 between two visits evict
+// it.  Its accesses therefore carry a persisting-L2 access-policy window (a launch attribute: it survives stream capture as a
+// kernel-node attribute); the device's persisting carve-out is raised once to what the stream needs.  SE3DIFF_B200_L2_RESIDUAL=0
+// turns it off.  Returns the fraction of the window that may persist (0 = no window).
+inline float residual_l2_fraction(size_t bytes) {
+    static const bool on = [] { const char* v = getenv("SE3DIFF_B200_L2_RESIDUAL"); return !(v && v[0] == '0'); }();
+    if (!on || bytes < ((size_t)8 << 20)) return 0.f;
+    int dev = 0, max_persist = 0, max_window = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev) != cudaSuccess || max_persist <= 0 || max_window <= 0 ||
+        bytes > (size_t)max_window) {
+        (void)cudaGetLastError();
+        return 0.f;
+    }
+    const size_t want = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
+    size_t have = 0;
+    if (cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize) != cudaSuccess || (have < want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess)) {
+        (void)cudaGetLastError();
+        return 0.f;
+    }
+    return (float)want / (float)bytes;
+}
+
 template <typename OutT, typename YT>
 int launch(float* x, const YT* y, const float* bias, const float* gamma, const float* beta, float eps, OutT* out, int64_t rows,
            int dim, cudaStream_t st) {
-    const unsigned grid = (unsigned)((rows * 32 + 255) / 256);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((rows * 32 + 255) / 256), 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    const size_t xbytes = (size_t)rows * dim * sizeof(float);
+    const float frac = residual_l2_fraction(xbytes);
+    if (frac > 0.f) {
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = x;
+        attr[0].val.accessPolicyWindow.num_bytes = xbytes;
+        attr[0].val.accessPolicyWindow.hitRatio = frac;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    cudaError_t e;
     switch (dim / 128) {
-        case 1: k_residual_layernorm<1, OutT, YT><<<grid, 256, 0, st>>>(x, y, bias, gamma, beta, eps, out, rows); break;
-        case 2: k_residual_layernorm<2, OutT, YT><<<grid, 256, 0, st>>>(x, y, bias, gamma, beta, eps, out, rows); break;
-        case 4: k_residual_layernorm<4, OutT, YT><<<grid, 256, 0, st>>>(x, y, bias, gamma, beta, eps, out, rows); break;
-        case 8: k_residual_layernorm<8, OutT, YT><<<grid, 256, 0, st>>>(x, y, bias, gamma, beta, eps, out, rows); break;
+        case 1: e = cudaLaunchKernelEx(&cfg, k_residual_layernorm<1, OutT, YT>, x, y, bias, gamma, beta, eps, out, rows); break;
+        case 2: e = cudaLaunchKernelEx(&cfg, k_residual_layernorm<2, OutT, YT>, x, y, bias, gamma, beta, eps, out, rows); break;
+        case 4: e = cudaLaunchKernelEx(&cfg, k_residual_layernorm<4, OutT, YT>, x, y, bias, gamma, beta, eps, out, rows); break;
+        case 8: e = cudaLaunchKernelEx(&cfg, k_residual_layernorm<8, OutT, YT>, x, y, bias, gamma, beta, eps, out, rows); break;
         default: set_error("se3_residual_layernorm: dim must be 128, 256, 512 or 1024 (got %d)", dim); return SE3_EUNSUPPORTED;
     }
+    if (e != cudaSuccess) { set_error("se3_residual_layernorm launch: %s", cudaGetErrorString(e)); return SE3_ECUDA; }
     count_launch();
     return check_launch("se3_residual_layernorm");
 }
@@ -219,6 +263,9 @@ extern "C" int se3_gelu_bf16(const void* in, void* out, int64_t n, se3_stream_t 
     SE3_REQUIRE(in && out, "null pointer");
     SE3_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "pointers must be 16-byte aligned");
     const int64_t nvec = n / 8;
+    // (a persisting-L2 window over the in-place hidden activations, like the one of the residual stream, was measured: the kernel
+    // does not get faster -- the GEMM that refills the buffer writes with the normal policy -- and the two windows together
+    // overrun the 79 MB carve-out: residual kernel 17.0 -> 19.5 us)
     k_gelu_bf16<<<(unsigned)((nvec + 1023) / 1024), 256, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, nvec);
     count_launch();
     return check_launch("se3_gelu_bf16");
