@@ -389,22 +389,20 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < 12; ++k) q2[k] = make_float2(qp[k], qp[k]);
         const float2 hw2 = make_float2(hw, hw), l2e2 = make_float2(kLog2e, kLog2e);
-        // A step is 8 key columns (4 key pairs): the body is instantiated twice (whole steps / the step with padding keys) and
-        // walked by a rolled loop -- unrolling 16 columns doubled the code of this pass for no gain in schedule (two key pairs
-        // are in flight either way, the register budget is what bounds that) and the four resident CTAs, each in another phase,
-        // compete for the instruction cache.
-        auto chunk = [&](const int col0, auto partial_tag) {
-            constexpr bool kPartial = decltype(partial_tag)::value;   // the last step when L % 8 != 0: skip padding keys
+        // A step is 8 key columns (4 key pairs), ONE body walked by a rolled loop.  The kernel's loop is ~2400 instructions
+        // (38 KB) for a 32 KB instruction cache per SM, the four resident CTAs sit in different phases, and ncu shows 7 % of the
+        // instruction-line requests missing there and the GPC-level instruction cache behind it at 75 % of its request rate
+        // (profiles/r3a_ipa_tc_ncu_raw.csv: sm__icc_request_hit_rate, gcc__cache_requests_type_instruction): every instruction
+        // of this loop that exists twice costs.  Unrolling 16 columns bought no better schedule (two key pairs are in flight
+        // either way, the register budget bounds that); the step that straddles the last key computes its padding columns like
+        // real ones (their key points are zero) and overwrites them afterwards; steps past the last key are not computed.
+        auto chunk = [&](const int col0) {
             uint32_t r[8];
             tc::tmem_ld8(tc::tmem_addr(tmem, lane_base, col0), r);
             tc::tmem_wait_ld();
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int j = col0 + 2 * u;
-                if (kPartial && j >= LK) {                 // padding keys (warp-uniform): no distance work
-                    r[2 * u] = r[2 * u + 1] = __float_as_uint(-CUDART_INF_F);
-                    continue;
-                }
                 const float4* kp4 = reinterpret_cast<const float4*>(s.kp + j * 12);   // pair block: 24 floats
                 float2 ds = make_float2(0.f, 0.f);
 #pragma unroll
@@ -424,19 +422,32 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     ds = __fadd2_rn(ds, make_float2(fast_sqrt(d2.x), fast_sqrt(d2.y)));
                 }
                 const float pb0 = __bfloat162float(bias_col[j * ncol]);
-                const float pb1 = (!kPartial || j + 1 < LK) ? __bfloat162float(bias_col[(j + 1) * ncol]) : 0.f;
+                const float pb1 = __bfloat162float(bias_col[(j + 1) * ncol]);      // (past the last key: stale shared memory, overwritten below)
                 const float2 kb2 = *reinterpret_cast<const float2*>(s.kb + j);
                 float2 l2 = __ffma2_rn(hw2, ds, make_float2(__uint_as_float(r[2 * u]), __uint_as_float(r[2 * u + 1])));
                 l2 = __fadd2_rn(__ffma2_rn(make_float2(pb0, pb1), l2e2, l2), kb2);
-                m = fmaxf(m, fmaxf(l2.x, l2.y));
                 r[2 * u] = __float_as_uint(l2.x);
                 r[2 * u + 1] = __float_as_uint(l2.y);
             }
+            if (col0 + 8 > LK) {                           // warp-uniform: padding keys of the straddling step
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (col0 + u >= LK) r[u] = __float_as_uint(-CUDART_INF_F);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) m = fmaxf(m, fmaxf(__uint_as_float(r[2 * u]), __uint_as_float(r[2 * u + 1])));
             tc::tmem_st8(tc::tmem_addr(tmem, lane_base, col0), r);
         };
 #pragma unroll 1
         for (int col0 = c_begin * 16; col0 < c_end * 16; col0 += 8) {
-            if (col0 + 8 <= LK) chunk(col0, std::false_type{}); else chunk(col0, std::true_type{});
+            if (col0 < LK) {
+                chunk(col0);
+            } else {                                       // only padding keys
+                uint32_t r[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r[u] = __float_as_uint(-CUDART_INF_F);
+                tc::tmem_st8(tc::tmem_addr(tmem, lane_base, col0), r);
+            }
         }
         tc::tmem_wait_st();
     }
