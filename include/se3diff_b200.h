@@ -33,7 +33,7 @@ typedef void* se3_stream_t; /* cudaStream_t */
 
 const char* se3_last_error(void);
 /* bumped whenever a signature or a by-value struct of this header changes; the loader compares it with the header it was written against */
-#define SE3_ABI_VERSION 2
+#define SE3_ABI_VERSION 3
 int se3_abi_version(void);
 /* number of kernels launched by this library in the calling thread since the last reset
  * (bench.py's `gpu_launches`). */
@@ -324,7 +324,10 @@ int se3_ipa_attention_bwd(const float* proj, const float* rot, const float* tran
  *                       sequence by the caller)
  *   out               : fp32 or bf16 (out_is_bf16) concat layout
  *   p_workspace / inv_workspace : scratch of the sizes reported by se3_ipa_tc_workspace_bytes (un-normalised probabilities,
- *                       bf16 row-major [H][L][round_up(B,128)][Lp], and 1/rowsum fp32 [H][L][round_up(B,128)])
+ *                       bf16 row-major [H][L][round_up(B,128)][Lp], and 1/rowsum fp32 [H][L][round_up(B,128)] followed by
+ *                       64 bytes of work-queue state for the persistent pass-1 kernel: ABI version 3).  Those 64 bytes must be
+ *                       ZERO before the first call with a workspace (one cudaMemset after allocating it); every call leaves
+ *                       them zero.  Calls that may run concurrently need their own workspaces.
  * Of h_shape only batch, len, heads, dk, pq, pv, pair_batch are read. */
 int64_t se3_ipa_tc_workspace_bytes(const se3_ipa_shape* h_shape, int64_t* p_bytes, int64_t* inv_bytes);
 int se3_ipa_attention_tc_fwd(const void* scalars_bf16, int64_t scalar_stride, const void* points, int points_are_bf16,

@@ -59,10 +59,12 @@ __device__ __forceinline__ float ld_peer_f32(const float* own_smem_ptr, uint32_t
     return v;
 }
 
-// Work queue of the persistent 128-thread edition: {items handed out beyond the first gridDim.x, CTAs that have left}.  The
-// last CTA to leave zeroes its slot again, so a slot is zero whenever no launch is using it; launches take the slots in turn.
-constexpr int kSchedSlots = 64;
-__device__ unsigned int g_sched[kSchedSlots][2];
+// Work queue of the persistent 128-thread edition: {items handed out beyond the first gridDim.x, CTAs that have left} in the
+// 64 bytes that follow the row sums in the caller's workspace (se3_ipa_tc_workspace_bytes) -- per workspace, so concurrent
+// calls on other streams (which need their own workspaces anyway) and graph replays cannot meet in it.  The bytes are zero
+// before the first call (the caller's one-time memset, see the header) and the last CTA to leave zeroes them again (a memset
+// node ahead of every launch instead was measured at +4 us per call inside a CUDA graph).
+constexpr int64_t kQueueBytes = 64;
 
 struct Pass1Smem {
     uint8_t *q, *k, *vs, *vp, *p;
@@ -598,7 +600,7 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     item = item_next;
   }
     if constexpr (kDynamic) {
-        if (tid == 0 && atomicAdd(&sched[1], 1u) == gridDim.x - 1) {   // last CTA out: the slot is zero again for its next launch
+        if (tid == 0 && atomicAdd(&sched[1], 1u) == gridDim.x - 1) {   // last CTA out: the queue is zero again for the next call
             sched[0] = 0;
             sched[1] = 0;
         }
@@ -761,11 +763,7 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const void* pts, int p
             e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
             if (e != cudaSuccess) { set_error("ipa_tc pass1 smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
             const int resident = (512 / cols) * sms;
-            static unsigned int launch_no = 0;
-            unsigned int* sched = nullptr;
-            e = cudaGetSymbolAddress((void**)&sched, g_sched);
-            if (e != cudaSuccess) { set_error("ipa_tc pass1 work queue: %s", cudaGetErrorString(e)); return SE3_ECUDA; }
-            sched += 2 * (launch_no++ % kSchedSlots);
+            unsigned int* sched = reinterpret_cast<unsigned int*>(inv_sum + (int64_t)sh.heads * L * Bpad);
             kp<<<dim3((unsigned)(n_items < resident ? n_items : resident), 1, 1), 128, smem1, st>>>(map_q, map_kv, map_pts, map_bias, rot, trans, pair_bias, key_bias,
                                                                                                      head_weight, out, pbuf, inv_sum, sh, LpB, Lp, Bpad, cols, pts,
                                                                                                      pts_stride, g_phase_dbg, 0, sched);
@@ -823,7 +821,7 @@ void se3_debug_set_phase_buffer(long long* buf) { g_phase_dbg = buf; }
 int64_t se3_ipa_tc_workspace_bytes(const se3_ipa_shape* h_shape, int64_t* p_bytes, int64_t* inv_bytes) {
     if (!h_shape) return SE3_EINVAL;
     const int64_t Lp = (h_shape->len + 15) / 16 * 16, Bpad = (h_shape->batch + 127) / 128 * 128;
-    const int64_t pb = (int64_t)h_shape->heads * h_shape->len * Bpad * Lp * 2, ib = (int64_t)h_shape->heads * h_shape->len * Bpad * 4;
+    const int64_t pb = (int64_t)h_shape->heads * h_shape->len * Bpad * Lp * 2, ib = (int64_t)h_shape->heads * h_shape->len * Bpad * 4 + kQueueBytes;
     if (p_bytes) *p_bytes = pb;
     if (inv_bytes) *inv_bytes = ib;
     return pb + ib;

@@ -615,7 +615,8 @@ def pair_project(x2d, w_bias, w_value, pair_weight: float, heads: int, dk: int, 
 def ipa_tc_workspace(shape: L.IpaShape, device) -> tuple[torch.Tensor, torch.Tensor]:
     pb, ib = C.c_int64(0), C.c_int64(0)
     L.lib().se3_ipa_tc_workspace_bytes(C.byref(shape), C.byref(pb), C.byref(ib))
-    return (torch.empty(pb.value // 2, dtype=torch.bfloat16, device=device), torch.empty(ib.value // 4, dtype=torch.float32, device=device))
+    # the row-sum buffer ends in 64 bytes of work-queue state that must be zero before the first call (include/se3diff_b200.h)
+    return (torch.empty(pb.value // 2, dtype=torch.bfloat16, device=device), torch.zeros(ib.value // 4, dtype=torch.float32, device=device))
 
 
 def ipa_split_perms(heads: int, dk: int = 16):
