@@ -3,6 +3,7 @@ the drop-in host layer), against the CPU oracle on identical seeded inputs and a
 reference-generated goldens.  Tolerances: bit-exact for integer / index work; fp32 frames and SDE
 algebra <= 1e-5 relative per step (north_star), in practice ~1e-6."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -17,6 +18,7 @@ from oracle.score_model import ScoreModelOracle
 pytestmark = pytest.mark.gpu
 T = torch.from_numpy
 DEV = "cuda"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(autouse=True)
@@ -735,6 +737,53 @@ def test_ipa_tensor_core_operator_vs_fp64(B, L, scale):
             err = (got[:, a:b].double() - want_cmp[:, a:b]).abs().max().item()
             ref_max = max(1.0, want_cmp[:, a:b].abs().max().item())
             assert err <= 1.5e-2 * ref_max * (2.0 if odt == torch.bfloat16 else 1.0), (name, odt, err, ref_max)
+
+
+def test_ipa_tc_persistent_work_queue_is_per_workspace():
+    """The persistent pass-1 kernel draws its work items from a counter in the last 64 bytes of the row-sum workspace (zero before the
+    first call, re-zeroed by the kernel): repeated calls on one workspace, and calls with their own workspaces overlapping on two
+    streams, give bit-identical results to the one-item-per-CTA launch -- no item is skipped or done twice."""
+    from ipa_tc_reference import H, make, split
+    from se3diff_b200 import ops
+
+    B, L = 64, 84
+    proj, rot, trans, pb, pv, hw, shape = make(B, L, seed=7, pos_scale=1.5)
+    pvp, pbt = ops.ipa_tc_pack_pair_value(pv, H), ops.ipa_tc_pack_pair_bias(pb.permute(0, 2, 3, 1))
+    sc, pt = split(proj)
+    both = torch.cat([sc, pt.to(torch.bfloat16)], dim=1)
+    ws = [ops.ipa_tc_workspace(shape, DEV) for _ in range(2)]
+    assert all(float(w[1][-16:].abs().sum()) == 0.0 for w in ws)             # queue state starts at zero
+    run = lambda w, out=None: ops.ipa_attention_tc_fwd(both[:, :1536], both[:, 1536:], rot, trans, pbt, pvp, None, hw, shape, w, out=out,
+                                                       out_dtype=torch.bfloat16)
+    os.environ["SE3DIFF_B200_IPA_PERSIST"] = "0"
+    try:
+        import subprocess, sys
+        code = ("import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r); from ipa_tc_reference import H, make, split; from se3diff_b200 import ops\n"
+                "proj, rot, trans, pb, pv, hw, shape = make(64, 84, seed=7, pos_scale=1.5)\n"
+                "pvp, pbt = ops.ipa_tc_pack_pair_value(pv, H), ops.ipa_tc_pack_pair_bias(pb.permute(0, 2, 3, 1)); sc, pt = split(proj)\n"
+                "both = torch.cat([sc, pt.to(torch.bfloat16)], dim=1); ws = ops.ipa_tc_workspace(shape, 'cuda')\n"
+                "o = ops.ipa_attention_tc_fwd(both[:, :1536], both[:, 1536:], rot, trans, pbt, pvp, None, hw, shape, ws, out_dtype=torch.bfloat16)\n"
+                "torch.save(o.cpu(), sys.argv[1])") % (ROOT, os.path.join(ROOT, "tests"))
+        import tempfile
+        with tempfile.TemporaryDirectory() as td:                            # the switch is read once per process: one-item launch in a child
+            path = os.path.join(td, "o.pt")
+            r = subprocess.run([sys.executable, "-c", code, path], capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            want = torch.load(path).to(DEV)
+    finally:
+        del os.environ["SE3DIFF_B200_IPA_PERSIST"]
+    for _ in range(3):
+        assert torch.equal(run(ws[0]), want)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = [torch.empty_like(want) for _ in range(2)]
+    torch.cuda.synchronize()
+    for _ in range(4):
+        for st, w, o in ((s1, ws[0], outs[0]), (s2, ws[1], outs[1])):
+            with torch.cuda.stream(st):
+                run(w, out=o)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], want) and torch.equal(outs[1], want)
+    assert all(float(w[1][-16:].abs().sum()) == 0.0 for w in ws)             # ... and is zero again
 
 
 @pytest.mark.parametrize("L,H", [(84, 32), (11, 4), (57, 32), (130, 8), (16, 1)])
