@@ -173,7 +173,10 @@ inline float residual_l2_fraction(size_t bytes) {
         (void)cudaGetLastError();
         return 0.f;
     }
-    const size_t want = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
+    // only a stream that fits the carve-out whole, and leaves at least half of the L2 to everything else: a partial window over
+    // the 128 MB stream of L = 512, B = 128 pinned 79 MB at random and cost BASELINE config 5 20 % (4.18 -> 5.0 s per step)
+    if (bytes > (size_t)max_persist || bytes > ((size_t)64 << 20)) return 0.f;
+    const size_t want = bytes;
     size_t have = 0;
     if (cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize) != cudaSuccess || (have < want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess)) {
         (void)cudaGetLastError();
