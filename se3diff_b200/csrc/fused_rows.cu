@@ -163,7 +163,7 @@ k_gelu_bf16(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t nvec)
 // it.  Its accesses therefore carry a persisting-L2 access-policy window (a launch attribute: it survives stream capture as a
 // kernel-node attribute); the device's persisting carve-out is raised once to what the stream needs.  SE3DIFF_B200_L2_RESIDUAL=0
 // turns it off.  Returns the fraction of the window that may persist (0 = no window).
-inline float residual_l2_fraction(size_t bytes) {
+inline float residual_l2_fraction(size_t bytes, cudaStream_t st) {
     static const bool on = [] { const char* v = getenv("SE3DIFF_B200_L2_RESIDUAL"); return !(v && v[0] == '0'); }();
     if (!on || bytes < ((size_t)8 << 20)) return 0.f;
     int dev = 0, max_persist = 0, max_window = 0;
@@ -176,13 +176,19 @@ inline float residual_l2_fraction(size_t bytes) {
     // only a stream that fits the carve-out whole, and leaves at least half of the L2 to everything else: a partial window over
     // the 128 MB stream of L = 512, B = 128 pinned 79 MB at random and cost BASELINE config 5 20 % (4.18 -> 5.0 s per step)
     if (bytes > (size_t)max_persist || bytes > ((size_t)64 << 20)) return 0.f;
-    const size_t want = bytes;
     size_t have = 0;
-    if (cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize) != cudaSuccess || (have < want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess)) {
-        (void)cudaGetLastError();
-        return 0.f;
+    if (cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize) != cudaSuccess) { (void)cudaGetLastError(); return 0.f; }
+    if (have < bytes) {
+        // the carve-out is raised outside stream capture only (a device-limit change is not a capturable call); a first launch
+        // that happens under capture simply goes without the window
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone ||
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return 0.f;
+        }
     }
-    return (float)want / (float)bytes;
+    return 1.0f;
 }
 
 template <typename OutT, typename YT>
@@ -194,7 +200,7 @@ int launch(float* x, const YT* y, const float* bias, const float* gamma, const f
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     const size_t xbytes = (size_t)rows * dim * sizeof(float);
-    const float frac = residual_l2_fraction(xbytes);
+    const float frac = residual_l2_fraction(xbytes, st);
     if (frac > 0.f) {
         attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
         attr[0].val.accessPolicyWindow.base_ptr = x;
