@@ -20,8 +20,8 @@
 //
 // Longer sequences (L > 128, or a record size whose L x L matrices do not fit) run the same two phases as TWO kernels that meet in
 // the P / dS workspaces the caller wants anyway: k_ipa_bwd_rows -- one CTA per (sample, head, 64 query rows), keys staged in
-// chunks of 64, the rows' logits parked in shared memory between the three sweeps (maximum, sum, gradients), P / dS tiles
-// written coalesced; k_ipa_bwd_cols -- one CTA per (sample, head, 128 key columns) walks P / dS down the rows (coalesced global
+// chunks of 32 or 64, the rows' logits parked in shared memory between the three sweeps (maximum, sum, gradients), P / dS tiles
+// written coalesced; k_ipa_bwd_cols -- one CTA per (sample, head, 64 key columns) walks P / dS down the rows (coalesced global
 // reads) with the query records staged in chunks of 64 rows.
 #include <math_constants.h>
 
@@ -423,10 +423,13 @@ k_ipa_bwd(const float* __restrict__ proj, const float* __restrict__ rot, const f
 
 
 // ---- tiled edition (L > 128): phase 1 ---------------------------------------------------------------------------------
-constexpr int kRowTile = 64, kKeyChunk = 64, kColTile = 128, kRowChunk = 64;
+// (key chunks of 32 where that lets two CTAs of the rows kernel share an SM -- with 64 it needed 116 KB at L = 256: one CTA of four
+// warps per SM, issue-active 17 %; chunks of 64 where only one fits anyway; column tiles of 64 with three CTAs per SM instead of
+// one 256-thread CTA at 215 registers)
+constexpr int kRowTile = 64, kColTile = 64, kRowChunk = 64;
 
-template <int DK>
-__global__ void __launch_bounds__(2 * kRowTile, 1)
+template <int DK, int kKeyChunk>
+__global__ void __launch_bounds__(2 * kRowTile, kKeyChunk == 32 ? 2 : 1)
 k_ipa_bwd_rows(const float* __restrict__ proj, const float* __restrict__ rot, const float* __restrict__ trans,
                const float* __restrict__ pair_bias, const float* __restrict__ pair_value, const float* __restrict__ key_bias,
                const float* __restrict__ head_weight, float scalar_weight, const float* __restrict__ out,
@@ -592,7 +595,7 @@ k_ipa_bwd_rows(const float* __restrict__ proj, const float* __restrict__ rot, co
 
 // ---- tiled edition: phase 2 (runs after k_ipa_bwd_rows on the same stream) -----------------------------------------------
 template <int DK>
-__global__ void __launch_bounds__(2 * kColTile, 1)
+__global__ void __launch_bounds__(2 * kColTile, 3)
 k_ipa_bwd_cols(const float* __restrict__ proj, const float* __restrict__ rot, const float* __restrict__ trans,
                const float* __restrict__ head_weight, float scalar_weight, const float* __restrict__ out,
                const float* __restrict__ d_out, float* __restrict__ d_proj, const float* __restrict__ p_ws,
@@ -707,7 +710,7 @@ k_ipa_bwd_cols(const float* __restrict__ proj, const float* __restrict__ rot, co
 }
 
 size_t resident_smem_bytes(int L, int KW) { return ((size_t)2 * L * KW + (size_t)2 * L * (L | 1) + L) * sizeof(float); }
-size_t rows_smem_bytes(int L, int KW) { return ((size_t)kKeyChunk * KW + (size_t)kRowTile * (L | 1) + (size_t)2 * kRowTile * (kKeyChunk + 1) + L) * sizeof(float); }
+size_t rows_smem_bytes(int L, int KW, int kc) { return ((size_t)kc * KW + (size_t)kRowTile * (L | 1) + (size_t)2 * kRowTile * (kc + 1) + L) * sizeof(float); }
 
 template <int DK>
 int launch(const float* proj, const float* rot, const float* trans, const float* pair_bias, const float* pair_value,
@@ -716,9 +719,10 @@ int launch(const float* proj, const float* rot, const float* trans, const float*
     constexpr int KW = 2 * DK + 3 * PQ + 3 * PV;
     const int L = sh.len;
     if (L > 128 || resident_smem_bytes(L, KW) > (size_t)227 * 1024) {   // tiled edition: two kernels meeting in the P / dS workspaces
-        const size_t smem_r = rows_smem_bytes(L, KW), smem_c = (size_t)kRowChunk * KW * sizeof(float);
+        const bool two_fit = 2 * (rows_smem_bytes(L, KW, 32) + 1024) <= (size_t)227 * 1024;
+        const size_t smem_r = rows_smem_bytes(L, KW, two_fit ? 32 : 64), smem_c = (size_t)kRowChunk * KW * sizeof(float);
         if (smem_r > (size_t)227 * 1024) { set_error("se3_ipa_attention_bwd: len=%d needs %zu bytes of shared memory per CTA", L, smem_r); return SE3_EUNSUPPORTED; }
-        auto kr = k_ipa_bwd_rows<DK>;
+        auto kr = two_fit ? k_ipa_bwd_rows<DK, 32> : k_ipa_bwd_rows<DK, 64>;
         auto kc = k_ipa_bwd_cols<DK>;
         cudaError_t e = cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
         if (e != cudaSuccess) { set_error("ipa bwd (rows) smem attribute (%zu bytes): %s", smem_r, cudaGetErrorString(e)); return SE3_ECUDA; }

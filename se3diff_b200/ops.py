@@ -443,7 +443,7 @@ def ipa_bwd_supported(shape: L.IpaShape) -> bool:
     """Shapes se3_ipa_attention_bwd takes: L <= 128 with everything of a (sample, head) in shared memory, or -- up to L = 512 --
     the tiled two-kernel edition, which parks the logits of 64 query rows in shared memory."""
     n, kw = shape.len, 2 * shape.dk + 36
-    tiled = (64 * kw + 64 * (n | 1) + 2 * 64 * 65 + n) * 4
+    tiled = (64 * kw + 64 * (n | 1) + 2 * 64 * 65 + n) * 4      # the larger of the two key-chunk plans of k_ipa_bwd_rows
     return (shape.dk in (4, 8, 16, 32) and shape.pq == 4 and shape.pv == 8 and 0 < n <= 512 and 0 < shape.batch <= 65535
             and tiled <= 227 * 1024)
 
