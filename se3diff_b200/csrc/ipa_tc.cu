@@ -1,6 +1,8 @@
 // K4 (tensor-core edition) -- DiG invariant point attention on tcgen05 / TMEM, two passes.
 //
-// Pass 1, one CTA per (sample b, head h, 128-query-row tile):
+// Pass 1, one work item per (sample b, head h, 128-query-row tile).  L <= 128: four persistent 128-thread CTAs per SM draw items
+// from an atomic work queue (in the caller's workspace) and fetch the next item's operands under the current item's epilogue;
+// longer sequences: one persistent 256-thread CTA (or 2-CTA cluster) per SM.  Per item:
 //   stage  Q (x scalar_weight x log2e), K as bf16 UMMA operands; key points to the global frame (fp32, smem);
 //          V^T = [v (16) | v_pt - c hi (24) | v_pt - c lo (24)] as the bf16 B operand of the second MMA
 //          (global point coordinates re-centred on the sample's first residue and split hi + lo so the
