@@ -33,7 +33,7 @@ typedef void* se3_stream_t; /* cudaStream_t */
 
 const char* se3_last_error(void);
 /* bumped whenever a signature or a by-value struct of this header changes; the loader compares it with the header it was written against */
-#define SE3_ABI_VERSION 3
+#define SE3_ABI_VERSION 4
 int se3_abi_version(void);
 /* number of kernels launched by this library in the calling thread since the last reset
  * (bench.py's `gpu_launches`). */
@@ -238,7 +238,9 @@ int se3_igso3_sample(const float* sigma, const float* sigma_grid, int num_sigma,
                      const float* cdf_index, se3_stream_t stream);
 /* Guide records over the CDF rows: [0,1) is cut into G = 2^k >= num_omega/2 bins and each (row, bin) owns one aligned
  * 32-byte record {lo | hi << 16, cdf[lo-1 .. lo+5]} with lo/hi = lower_bound(row, bin edges): a lookup reads ONE L2
- * sector (binary search inside [lo, hi] only for flat stretches of the CDF) instead of 11 scattered probes.
+ * sector instead of 11 scattered probes.  Bins that hold more than five grid points (flat stretches of the CDF) carry the
+ * lower bounds of their eight sub-bin edges instead of CDF values (ABI version 4: records built by an older library must be
+ * rebuilt; they are derived data and are never stored in the npz caches).
  * index: se3_igso3_cdf_index_floats(num_rows, num_omega) floats, 32-byte aligned; num_omega <= 65535. */
 int64_t se3_igso3_cdf_index_floats(int num_rows, int num_omega);
 int se3_igso3_build_cdf_index(const float* cdf, int num_rows, int num_omega, float* index, se3_stream_t stream);

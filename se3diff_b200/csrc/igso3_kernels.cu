@@ -249,27 +249,42 @@ __device__ __forceinline__ int lower_bound(const float* __restrict__ a, int n, f
 }
 // Same result for a (nearly) geometric grid such as sigma(t) = s_min (s_max/s_min)^t on linspace t: a log-linear
 // guess from the end points followed by an exact local fix-up costs 2-3 probes instead of log2(n) = 10.
-__device__ __forceinline__ int lower_bound_geometric(const float* __restrict__ a, int n, float v) {
-    const float a0 = __ldg(a), a1 = __ldg(a + n - 1);
+__device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// how a small grid is read (the read-only path of global memory)
+struct GlobalGrid { const float* p; __device__ __forceinline__ float operator()(int i) const { return __ldg(p + i); } };
+template <typename Grid>
+__device__ __forceinline__ int lower_bound_geometric(const Grid a, int n, float v) {
+    const float a0 = a(0), a1 = a(n - 1);
     if (!(v > a0)) return 0;
     if (v > a1) return n;
-    // the guess may be off by one or two slots (approximate log2 / division); the two loops below make it exact
-    int k = (int)ceilf(__fdividef(__log2f(v) - __log2f(a0), __log2f(a1) - __log2f(a0)) * (float)(n - 1));
-    k = min(max(k, 0), n - 1);
-    while (k > 0 && !(__ldg(a + k - 1) < v)) --k;      // a[k-1] >= v: answer is further left
-    while (k < n && __ldg(a + k) < v) ++k;             // a[k] < v: answer is further right
+    // a[0] < v <= a[n-1]: the answer lies in [1, n-1].  The guess (flush-to-zero MUFU forms: the plain __log2f / __fdividef carry
+    // denormal guards, 16 more instructions per rotation) may be off by a slot or two; both neighbours of the guess are fetched
+    // in ONE round trip and settle the usual case, the two loops below make every other case exact
+    const float l0 = lg2_ftz(a0);
+    int k = (int)ceilf((lg2_ftz(v) - l0) * rcp_ftz(lg2_ftz(a1) - l0) * (float)(n - 1));
+    k = min(max(k, 1), n - 1);
+    const float below = a(k - 1), at = a(k);
+    if (below < v && !(at < v)) return k;
+    while (k > 0 && !(a(k - 1) < v)) --k;              // a[k-1] >= v: answer is further left
+    while (k < n && a(k) < v) ++k;                     // a[k] < v: answer is further right
     return k;
 }
 
 // Guide records over a CDF row: the unit interval is cut into G = 2^k bins (G ~ n/2) and bin g of a row owns ONE aligned
 // 32-byte record
 //     word 0    : lo | hi << 16,  lo = lower_bound(row, g/G), hi = lower_bound(row, (g+1)/G)
-//     words 1..7: cdf[lo-1 .. lo+5]  (+inf past the row end; word 1 is unused when lo == 0)
-// For u in [g/G, (g+1)/G) the answer of lower_bound(row, u) lies in [lo, hi]; when hi - lo <= 5 (the usual case: a
-// bin holds ~2 grid points) the record also contains both CDF values the interpolation needs, so one lookup costs ONE
-// L2 sector instead of the 11 scattered probes of a binary search -- the sampling kernel is bound by L2 sector traffic,
-// not by arithmetic.  Longer runs (flat stretches of the CDF) fall back to a binary search inside [lo, hi].  u * G and
-// g / G are exact in fp32 (power-of-two scaling), so the result is exactly lower_bound(row, u) = sum(cdf < u).
+//     words 1..7: hi - lo <= 5 (the usual case: a bin holds ~2 grid points): cdf[lo-1 .. lo+5]  (+inf past the row end; word 1
+//                 is unused when lo == 0) -- the record also contains both CDF values the interpolation needs, so the lookup
+//                 costs ONE L2 sector instead of the 11 scattered probes of a binary search (the sampling kernel is bound by
+//                 L2 sector traffic and by the latency of dependent probes, not by arithmetic);
+//                 hi - lo > 5 (flat stretches of the CDF -- its x^9 start on the cubic omega grid and its Gaussian tail; ~3 % of
+//                 the draws, i.e. about every second warp has one): lower_bound(row, (8g + k)/(8G)), k = 1..7 -- the bin's
+//                 eight sub-bins, which narrow [lo, hi] eightfold; the seven entries around the narrowed range are then fetched
+//                 in ONE round trip and a bounded binary search only remains for the few sub-bins that still hold more than five
+//                 grid points (before: 4.4 dependent L2 probes per such warp).
+// u * G, u * 8G and the bin edges are exact in fp32 (power-of-two scaling), so the result is exactly lower_bound(row, u) =
+// sum(cdf < u).
 __host__ __device__ inline int guide_bins(int n) {   // smallest power of two >= n/2, within [8, 4096]: n = 2000 -> 1024
     int g = 8;
     while (g < (n + 1) / 2 && g < 4096) g *= 2;
@@ -283,43 +298,64 @@ __global__ void k_build_cdf_index(const float* __restrict__ cdf, int rows, int n
     const float* c = cdf + (int64_t)row * n;
     const int lo = lower_bound(c, n, (float)g / (float)G);
     const int hi = g + 1 < G ? lower_bound(c, n, (float)(g + 1) / (float)G) : n;
-    float4 a, b;
+    float w[8];
     const float inf = __int_as_float(0x7f800000);
-    auto at = [&](int k) { const int i = lo - 1 + k; return (i >= 0 && i < n) ? c[i] : inf; };
-    a.x = __uint_as_float((uint32_t)lo | ((uint32_t)hi << 16));
-    a.y = at(0); a.z = at(1); a.w = at(2);
-    b.x = at(3); b.y = at(4); b.z = at(5); b.w = at(6);
+    w[0] = __uint_as_float((uint32_t)lo | ((uint32_t)hi << 16));
+    if (hi - lo <= 5) {
+        for (int k = 0; k < 7; ++k) { const int i = lo - 1 + k; w[1 + k] = (i >= 0 && i < n) ? c[i] : inf; }
+    } else {
+        for (int k = 1; k < 8; ++k) w[k] = __uint_as_float((uint32_t)lower_bound(c, n, (float)(8 * g + k) / (float)(8 * G)));
+    }
     float4* dst = reinterpret_cast<float4*>(index + t * 8);
-    dst[0] = a;
-    dst[1] = b;
+    dst[0] = make_float4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_float4(w[4], w[5], w[6], w[7]);
 }
 
-// lower_bound(row, u) through the guide records, also returning cdf[max(stop-1,0)] and cdf[min(stop,n-1)] (the two values
-// the reference interpolates between, so3_sde.py:1268-1281) with `stop` already clipped to n-1
+// v[k] = cdf[lo - 1 + k] for a range [lo, hi] with hi - lo <= 5 that holds lower_bound(row, u): the index, and the two values the
+// reference interpolates between (cdf[max(stop-1,0)], cdf[stop]; so3_sde.py:1268-1281).  False when u lies above the whole row.
+__device__ __forceinline__ bool settle_short_range(const float (&v)[7], int lo, int hi, int n, float u, int& stop, float& c0, float& c1) {
+    // p[k] = "cdf[lo+k] < u" is monotone in k (sorted row), cnt = number of true ones; the two values the interpolation needs
+    // are v[cnt] (= cdf[stop-1]) and v[cnt+1] (= cdf[stop]): nested selects on the predicates
+    bool p[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) p[k] = (k < hi - lo) && (v[1 + k] < u);
+    const int cnt = (int)p[0] + (int)p[1] + (int)p[2] + (int)p[3] + (int)p[4];
+    stop = lo + cnt;
+    if (stop >= n) return false;                 // (stop == n: u above the whole row -> generic path)
+    float lo_v = v[0], hi_v = v[1];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { lo_v = p[k] ? v[k + 1] : lo_v; hi_v = p[k] ? v[k + 2] : hi_v; }
+    c1 = hi_v;
+    c0 = stop > 0 ? lo_v : hi_v;                 // start = max(stop - 1, 0)
+    return true;
+}
+
+// lower_bound(row, u) through the guide records, also returning cdf[max(stop-1,0)] and cdf[min(stop,n-1)] with `stop` already
+// clipped to n-1
 __device__ __forceinline__ int lookup_guided(const float* __restrict__ row, const float* __restrict__ rec_row, int n, int G, float u,
                                              float& c0, float& c1) {
     int lo = 0, hi = n;
     if (u >= 0.0f && u < 1.0f) {
         const int g = min((int)(u * (float)G), G - 1);
-        const float4 a = __ldg(reinterpret_cast<const float4*>(rec_row + (int64_t)g * 8)), b = __ldg(reinterpret_cast<const float4*>(rec_row + (int64_t)g * 8) + 1);
+        const float* rec = rec_row + g * 8;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(rec)), b = __ldg(reinterpret_cast<const float4*>(rec) + 1);
         const uint32_t w = __float_as_uint(a.x);
         lo = (int)(w & 0xffffu); hi = (int)(w >> 16);
+        int stop;
         if (hi - lo <= 5) {
             const float v[7] = {a.y, a.z, a.w, b.x, b.y, b.z, b.w};   // cdf[lo-1+k]
-            // p[k] = "cdf[lo+k] < u" is monotone in k (sorted row), cnt = number of true ones; the two values the
-            // interpolation needs are v[cnt] (= cdf[stop-1]) and v[cnt+1] (= cdf[stop]): nested selects on the predicates
-            bool p[5];
+            if (settle_short_range(v, lo, hi, n, u, stop, c0, c1)) return stop;
+        } else {
+            // long bin: its sub-bin [ (8g+s)/(8G), (8g+s+1)/(8G) ) narrows the range (the record was just fetched: L1 hits)
+            const int s = min(max((int)(u * (float)(8 * G)) - 8 * g, 0), 7);
+            const int slo = s > 0 ? (int)__float_as_uint(__ldg(rec + s)) : lo;
+            const int shi = s < 7 ? (int)__float_as_uint(__ldg(rec + s + 1)) : hi;
+            lo = slo; hi = shi;
+            if (hi - lo <= 5) {
+                float v[7];
 #pragma unroll
-            for (int k = 0; k < 5; ++k) p[k] = (k < hi - lo) && (v[1 + k] < u);
-            const int cnt = (int)p[0] + (int)p[1] + (int)p[2] + (int)p[3] + (int)p[4];
-            const int stop = lo + cnt;
-            if (stop < n) {                              // (stop == n: u above the whole row -> generic path below)
-                float lo_v = v[0], hi_v = v[1];
-#pragma unroll
-                for (int k = 0; k < 5; ++k) { lo_v = p[k] ? v[k + 1] : lo_v; hi_v = p[k] ? v[k + 2] : hi_v; }
-                c1 = hi_v;
-                c0 = stop > 0 ? lo_v : hi_v;             // start = max(stop - 1, 0)
-                return stop;
+                for (int k = 0; k < 7; ++k) { const int i = lo - 1 + k; v[k] = (i >= 0 && i < n) ? __ldg(row + i) : __int_as_float(0x7f800000); }
+                if (settle_short_range(v, lo, hi, n, u, stop, c0, c1)) return stop;
             }
         }
     }
@@ -353,11 +389,12 @@ __device__ __forceinline__ void philox(uint64_t seed, uint64_t idx, uint32_t str
 }
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }  // [0,1)
 
-// ---- per-rotation pieces of the sampler, shared by the tile edition and the pipelined edition ---------------------------------
+// ---- per-rotation pieces of the sampler ------------------------------------------------------------------------------------------
 struct SampleDraw { int stop; float c0, c1, sg, uu, nx, ny, nz; };
 
 // everything that does not need the operand tiles: the uniform (passed in or Philox), the sigma row, the CDF lookup
-__device__ __forceinline__ SampleDraw sample_lookup(int64_t e, bool have_normals, float u_in, float sg_in, bool have_sigma, const float* __restrict__ sigma_grid,
+template <typename Grid>
+__device__ __forceinline__ SampleDraw sample_lookup(int64_t e, bool have_normals, float u_in, float sg_in, bool have_sigma, const Grid sigma_grid,
                                                     int num_sigma, const float* __restrict__ cdf, int num_omega, uint64_t seed,
                                                     const float* __restrict__ cdf_index, int guide_bins_n) {
     SampleDraw d = {0, 0.f, 0.f, sg_in, u_in, 0.f, 0.f, 0.f};
@@ -366,14 +403,16 @@ __device__ __forceinline__ SampleDraw sample_lookup(int64_t e, bool have_normals
         // the same law as the reference's normalised Gaussian triple (so3_sde.py:1229-1242), which would take four uniforms,
         // two logarithms and a second block -- and the CDF uniform from the third.  (Bit parity with the reference's torch
         // generator is the business of the noise-passed-in mode; this mode only has to draw from the same distribution.)
+        // The direction is a UNIT vector by construction (sample_compose does not normalise it); its trigonometry is the short
+        // fused-FMA sincos of the frame kernels (libdevice sincospif is twice as long without FMA contraction in this unit).
         uint32_t r[4];
         philox(seed, (uint64_t)e, 0u, r);
-        const float z = 2.0f * u01(r[0]) - 1.0f;
-        const float rho = sqrtf(fmaxf(1.0f - z * z, 0.0f));
+        const float z = fmaf(2.0f, u01(r[0]), -1.0f);
+        float rho;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rho) : "f"(fmaxf(fmaf(-z, z, 1.0f), 0.0f)));
         float sp, cp;
-        sincospif(2.0f * u01(r[1]), &sp, &cp);
+        sincos_fused(6.283185307179586f * u01(r[1]), &sp, &cp);
         d.nx = rho * cp; d.ny = rho * sp; d.nz = z;
-        if (d.nx == 0.0f && d.ny == 0.0f && d.nz == 0.0f) d.nz = 1.0f;
         d.uu = u01(r[2]);
     }
     int row = 0;
@@ -381,9 +420,10 @@ __device__ __forceinline__ SampleDraw sample_lookup(int64_t e, bool have_normals
         row = lower_bound_geometric(sigma_grid, num_sigma, d.sg);  // torch.bucketize(sigma, sigma_grid)
         row = row < num_sigma ? row : num_sigma - 1;   // the reference would raise (so3_sde.py:1633)
     }
-    const float* c = cdf + (int64_t)row * num_omega;
+    // (32-bit offsets: se3_igso3_sample checks num_sigma * num_omega and the record count against 2^31)
+    const float* c = cdf + (uint32_t)row * (uint32_t)num_omega;
     if (cdf_index) {
-        d.stop = lookup_guided(c, cdf_index + (int64_t)row * guide_bins_n * 8, num_omega, guide_bins_n, d.uu, d.c0, d.c1);
+        d.stop = lookup_guided(c, cdf_index + (uint32_t)row * (uint32_t)(guide_bins_n * 8), num_omega, guide_bins_n, d.uu, d.c0, d.c1);
     } else {
         int stop = lower_bound(c, num_omega, d.uu);
         stop = stop < num_omega ? stop : num_omega - 1;
@@ -394,67 +434,144 @@ __device__ __forceinline__ SampleDraw sample_lookup(int64_t e, bool have_normals
 }
 
 // angle by interpolation (bit-exact against torch.lerp), axis-angle -> rotation, [x .] r written over the rotation slot `s_rot9`
-__device__ __forceinline__ float sample_compose(const SampleDraw& d, bool have_sigma, bool have_x, const float* __restrict__ omega_grid, float tol,
+// unit_axis: (nx, ny, nz) already has norm one (Philox mode)
+template <typename Grid>
+__device__ __forceinline__ float sample_compose(const SampleDraw& d, bool have_sigma, bool have_x, bool unit_axis, const Grid omega_grid, float tol,
                                                 float* s_rot9) {
     const int start = d.stop > 0 ? d.stop - 1 : 0;
     const float delta = fmaxf(d.c1 - d.c0, tol);
     float w = (d.uu - d.c0) / delta;
     w = fminf(fmaxf(w, 0.0f), 1.0f);
-    const float o0 = __ldg(omega_grid + start), o1 = __ldg(omega_grid + d.stop);
+    const float o0 = omega_grid(start), o1 = omega_grid(d.stop);
     // torch.lerp (CPU/CUDA kernels): w < 0.5 ? a + w*(b-a) : b - (b-a)*(1-w)
     const float diff = o1 - o0;
     // ATen contracts both branches into one FMA (CPU: vec::fmadd in lerp_vec / -mfma scalar code; CUDA: nvcc -fmad), and this
     // translation unit is built with -fmad=false, so the FMAs are spelled out
     float ang = w < 0.5f ? fmaf(w, diff, o0) : fmaf(-diff, 1.0f - w, o1);
     if (have_sigma && d.sg < tol) ang = 0.0f;  // SampleIGSO3._process_angles
-    // axis-angle -> rotation and x . r with explicit FMAs (common.cuh: so3_apply_rotvec_fused): the angle above is the
-    // bit-exact part of this kernel; the matrix entries depend on sin / cos and agree with the reference to ~1e-6 either way
-    float scale;                                             // ang / |n|: one MUFU.RSQ (the matrix entries are the ~1e-6 part of this kernel)
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(scale) : "f"(fmaf(d.nx, d.nx, fmaf(d.ny, d.ny, d.nz * d.nz))));
-    scale *= ang;
-    float xr[9], o[9];
+    // Axis-angle -> rotation straight from the UNIT axis and the angle (Rodrigues: E = I + sin(ang) K + (1 - cos(ang)) K^2 with
+    // K^2 = n n^T - I): no rotation vector is formed, so neither its norm nor the two divisions by it (nor the Taylor branch
+    // that guards them) exist.  The angle above is the bit-exact part of this kernel; the matrix entries depend on sin / cos and
+    // agree with the reference to ~1e-6 either way (same tolerance as before).
+    float ax = d.nx, ay = d.ny, az = d.nz;
+    if (!unit_axis) {
+        float inv;                                           // 1 / |n|: one MUFU.RSQ
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fmaf(d.nx, d.nx, fmaf(d.ny, d.ny, d.nz * d.nz))));
+        ax *= inv; ay *= inv; az *= inv;
+    }
+    float sn, cs;
+    sincos_fused(ang, &sn, &cs);
+    const float b = 1.0f - cs;
+    const float bx = b * ax, by = b * ay;
+    const float sx = sn * ax, sy = sn * ay, sz = sn * az;
+    const float e00 = fmaf(-b, fmaf(ay, ay, az * az), 1.0f), e11 = fmaf(-b, fmaf(ax, ax, az * az), 1.0f), e22 = fmaf(-b, fmaf(ax, ax, ay * ay), 1.0f);
+    const float e01 = fmaf(bx, ay, -sz), e10 = fmaf(bx, ay, sz);
+    const float e02 = fmaf(bx, az, sy), e20 = fmaf(bx, az, -sy);
+    const float e12 = fmaf(by, az, -sx), e21 = fmaf(by, az, sx);
     if (have_x) {
+        float xr[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) xr[k] = s_rot9[k];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float r0 = xr[i * 3], r1 = xr[i * 3 + 1], r2 = xr[i * 3 + 2];
+            s_rot9[i * 3] = fmaf(r2, e20, fmaf(r1, e10, r0 * e00));
+            s_rot9[i * 3 + 1] = fmaf(r2, e21, fmaf(r1, e11, r0 * e01));
+            s_rot9[i * 3 + 2] = fmaf(r2, e22, fmaf(r1, e12, r0 * e02));
+        }
     } else {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) xr[k] = (k % 4 == 0) ? 1.0f : 0.0f;
+        s_rot9[0] = e00; s_rot9[1] = e01; s_rot9[2] = e02;
+        s_rot9[3] = e10; s_rot9[4] = e11; s_rot9[5] = e12;
+        s_rot9[6] = e20; s_rot9[7] = e21; s_rot9[8] = e22;
     }
-    so3_apply_rotvec_fused(xr, d.nx * scale, d.ny * scale, d.nz * scale, tol, o);
-#pragma unroll
-    for (int k = 0; k < 9; ++k) s_rot9[k] = o[k];
     return ang;
 }
 
-__global__ void __launch_bounds__(kTile)
-k_sample(const float* __restrict__ sigma, const float* __restrict__ sigma_grid, int num_sigma, const float* __restrict__ cdf,
-         const float* __restrict__ omega_grid, int num_omega, const float* __restrict__ normals, const float* __restrict__ u,
-         uint64_t seed, const float* __restrict__ x, float* __restrict__ out, float* __restrict__ angle_out, int64_t n,
-         float tol, const float* __restrict__ cdf_index, int guide_bins_n, int64_t first_index) {
-    __shared__ __align__(16) float s_rot[kTile * 9];
-    __shared__ __align__(16) float s_nrm[kTile * 3];
-    const int64_t first = (int64_t)blockIdx.x * kTile;
-    const int count = (int)min((int64_t)kTile, n - first);
-    // three independent fetches per rotation -- the operand tiles, (sigma, u), and the guide record that depends on (sigma, u)
-    // -- are put in flight together: the tiles by cp.async, so the table lookup proceeds under them
-    // (per warp: each warp moves, computes and stores its own 32 rotations; only __syncwarp() between the phases)
-    if (x) warp_tile_load_async<9>(x, s_rot, first, count);
-    if (normals) warp_tile_load_async<3>(normals, s_nrm, first, count);
+struct SampleArgs {
+    const float *sigma, *sigma_grid, *cdf, *omega_grid, *normals, *u, *x, *cdf_index;
+    float *out, *angle_out;
+    uint64_t seed;
+    int64_t n;
+    int num_sigma, num_omega, guide_bins_n;
+    float tol;
+};
+
+// ragged last tile / unaligned operand arrays: every choice is made at run time (one tile per call takes this path, or all of them)
+__device__ __noinline__ void sample_tile_generic(const SampleArgs& a, float* s_rot, float* s_nrm, int64_t first, int count) {
+    if (a.x) warp_tile_load_async<9>(a.x, s_rot, first, count);
+    if (a.normals) warp_tile_load_async<3>(a.normals, s_nrm, first, count);
     const int t = threadIdx.x;
     const int64_t e = first + t;
     SampleDraw d = {};
     if (t < count)
-        d = sample_lookup(first_index + e, normals != nullptr, normals ? u[e] : 0.f, sigma ? sigma[e] : 0.f, sigma != nullptr, sigma_grid, num_sigma, cdf,
-                          num_omega, seed, cdf_index, guide_bins_n);      // (first_index: this launch's offset inside the caller's array = Philox counter)
+        d = sample_lookup(e, a.normals != nullptr, a.normals ? a.u[e] : 0.f, a.sigma ? a.sigma[e] : 0.f, a.sigma != nullptr, GlobalGrid{a.sigma_grid}, a.num_sigma, a.cdf,
+                          a.num_omega, a.seed, a.cdf_index, a.guide_bins_n);
     tile_load_wait();
     __syncwarp();
     if (t < count) {
-        if (normals) { d.nx = s_nrm[t * 3]; d.ny = s_nrm[t * 3 + 1]; d.nz = s_nrm[t * 3 + 2]; }
-        const float ang = sample_compose(d, sigma != nullptr, x != nullptr, omega_grid, tol, s_rot + t * 9);
-        if (angle_out) angle_out[e] = ang;
+        if (a.normals) { d.nx = s_nrm[t * 3]; d.ny = s_nrm[t * 3 + 1]; d.nz = s_nrm[t * 3 + 2]; }
+        const float ang = sample_compose(d, a.sigma != nullptr, a.x != nullptr, a.normals == nullptr, GlobalGrid{a.omega_grid}, a.tol, s_rot + t * 9);
+        if (a.angle_out) a.angle_out[e] = ang;
     }
     __syncwarp();
-    warp_tile_store<9>(out, s_rot, first, count);
+    warp_tile_store<9>(a.out, s_rot, first, count);
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+// One rotation per thread, 256 per CTA; every warp moves, computes and stores its own 32 rotations (only __syncwarp() between the
+// phases).  Three independent fetches per rotation -- the operand tiles, (sigma, u), and the guide record that depends on
+// (sigma, u) -- are in flight together: the tiles by cp.async, so the table lookup proceeds under them.
+// Which operands exist is a template parameter and full, 16-byte-aligned tiles take a straight-line path: the run-time edition of
+// the same body spent ~150 of its ~510 instructions per rotation on null-pointer / raggedness / alignment tests, 64-bit address
+// arithmetic and constant-bank reloads (ncu source counters of the r2 capture), and the kernel is bound by its instruction
+// stream and the latency of its dependent lookups at 64 resident warps per SM: 32 registers are part of the design.
+// Measured and dropped (r4): persistent CTAs that stage the sigma and omega grids (4 + 8 KB) in shared memory once, to take the
+// scattered grid reads off the L1 data pipe (the busiest unit, 69 % in the r2 capture) -- 40 registers (48 warps per SM):
+// 0.55 / 0.50 of the HBM roof against 0.61 / 0.55; capped at 32 registers: 0.37.  A single 256-bit load of the guide record
+// (ld.global.v8.f32) crashes ptxas 12.9 in this kernel.
+template <bool kX, bool kNormals, bool kSigma>
+__global__ void __launch_bounds__(kTile)
+k_sample(const __grid_constant__ SampleArgs a, const int fast) {
+    __shared__ __align__(16) float s_rot[kTile * 9];
+    __shared__ __align__(16) float s_nrm[kNormals ? kTile * 3 : 4];
+    const int64_t first = (int64_t)blockIdx.x * kTile;
+    const int t = threadIdx.x;
+    if (!fast || a.n - first < kTile) {
+        sample_tile_generic(a, s_rot, s_nrm, first, (int)min((int64_t)kTile, a.n - first));
+        return;
+    }
+    const int64_t e = first + t;
+    // the lookup chain starts from these two: issued before anything else
+    const float sg = kSigma ? __ldg(a.sigma + e) : 0.f;
+    const float uin = kNormals ? __ldg(a.u + e) : 0.f;
+    const int lane = t & 31;
+    const int wbase = t & ~31;                              // first rotation of this warp inside the tile
+    const int64_t wfirst = first + wbase;
+    float* rot_w = s_rot + wbase * 9;                       // the warp's 32 x 9 floats = 72 16-byte pieces
+    if (kX) {
+        const float4* src = reinterpret_cast<const float4*>(a.x + wfirst * 9) + lane;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(rot_w) + (uint32_t)lane * 16u;
+        cp_async16(dst, src);
+        cp_async16(dst + 512u, src + 32);
+        if (lane < 8) cp_async16(dst + 1024u, src + 64);
+    }
+    if (kNormals) {
+        if (lane < 24) cp_async16((uint32_t)__cvta_generic_to_shared(s_nrm + wbase * 3) + (uint32_t)lane * 16u, reinterpret_cast<const float4*>(a.normals + wfirst * 3) + lane);
+    }
+    SampleDraw d = sample_lookup(e, kNormals, uin, sg, kSigma, GlobalGrid{a.sigma_grid}, a.num_sigma, a.cdf, a.num_omega, a.seed, a.cdf_index, a.guide_bins_n);
+    tile_load_wait();
+    __syncwarp();
+    if (kNormals) { d.nx = s_nrm[t * 3]; d.ny = s_nrm[t * 3 + 1]; d.nz = s_nrm[t * 3 + 2]; }
+    const float ang = sample_compose(d, kSigma, kX, !kNormals, GlobalGrid{a.omega_grid}, a.tol, s_rot + t * 9);
+    if (a.angle_out) a.angle_out[e] = ang;
+    __syncwarp();
+    float4* dst = reinterpret_cast<float4*>(a.out + wfirst * 9) + lane;
+    const float4* s4 = reinterpret_cast<const float4*>(rot_w) + lane;
+    dst[0] = s4[0];
+    dst[32] = s4[32];
+    if (lane < 8) dst[64] = s4[64];
 }
 
 // Persisting-L2 access window over a lookup table for the launches enqueued on `st` until clear_l2_window (SE3DIFF_B200_L2_WINDOW=0
@@ -590,6 +707,8 @@ int se3_igso3_sample(const float* sigma, const float* sigma_grid, int num_sigma,
     SE3_REQUIRE(cdf && omega_grid && out, "null pointer");
     SE3_REQUIRE(!sigma || (sigma_grid && num_sigma >= 1), "sigma given without sigma_grid");
     SE3_REQUIRE((normals == nullptr) == (u == nullptr), "normals and u must be given together");
+    SE3_REQUIRE((int64_t)(sigma ? num_sigma : 1) * num_omega < (int64_t)1 << 31, "table too large (32-bit offsets inside the kernel)");
+    SE3_REQUIRE((int64_t)(sigma ? num_sigma : 1) * guide_bins(num_omega) * 8 < (int64_t)1 << 31, "guide records too large (32-bit offsets inside the kernel)");
     // (A pipelined per-warp edition like k_em_pipe was measured and dropped: 0.529 -> 0.536 of the HBM roof with the noise passed
     // in, 0.478 -> 0.399 in Philox mode -- this kernel is bound by its ~250 instructions per rotation at 64 resident warps, and
     // the ring costs occupancy.)
@@ -603,8 +722,17 @@ int se3_igso3_sample(const float* sigma, const float* sigma_grid, int num_sigma,
         if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone)
             window = set_l2_window(st, index, (size_t)num_sigma * guide_bins(num_omega) * 32);
     }
-    k_sample<<<(unsigned)((n + kTile - 1) / kTile), kTile, 0, st>>>(sigma, sigma_grid, num_sigma, cdf, omega_grid, num_omega, normals, u, seed, x, out, angle_out, n, tol,
-                                                                    index, guide_bins(num_omega), 0);
+    const SampleArgs a = {sigma, sigma_grid, cdf, omega_grid, normals, u, x, index, out, angle_out, seed, n, num_sigma, num_omega, guide_bins(num_omega), tol};
+    // straight-line path: 16-byte-aligned operand arrays
+    const int fast = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(normals) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    const unsigned grid = (unsigned)((n + kTile - 1) / kTile);
+    const int which = (x ? 4 : 0) | (normals ? 2 : 0) | (sigma ? 1 : 0);
+    switch (which) {
+#define SE3_SAMPLE_CASE(w, X, N, S) case w: k_sample<X, N, S><<<grid, kTile, 0, st>>>(a, fast); break;
+        SE3_SAMPLE_CASE(0, false, false, false) SE3_SAMPLE_CASE(1, false, false, true) SE3_SAMPLE_CASE(2, false, true, false) SE3_SAMPLE_CASE(3, false, true, true)
+        SE3_SAMPLE_CASE(4, true, false, false) SE3_SAMPLE_CASE(5, true, false, true) SE3_SAMPLE_CASE(6, true, true, false) SE3_SAMPLE_CASE(7, true, true, true)
+#undef SE3_SAMPLE_CASE
+    }
     if (window) clear_l2_window(st);
     SE3_LAUNCH_CHECK("se3_igso3_sample");
 }
