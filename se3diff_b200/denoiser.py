@@ -16,6 +16,7 @@ reference (denoiser.py:219-221).
 """
 from __future__ import annotations
 
+import os
 from collections import defaultdict
 from typing import NamedTuple
 
@@ -142,6 +143,35 @@ def _dpm_graphed(key, keep_alive, batch, score_model, steps, device):
     return _loop_graphed(key, keep_alive, batch, lambda static: _dpm_loop(static, score_model, steps, device), device)
 
 
+_SIDE_STREAMS: dict = {}
+
+
+def _score_and_control(score_fn, control_fn, device):
+    """`(score_fn(), control_fn())` for one state of a recording rollout.  The two evaluations are independent (denoiser.py:299-303
+    calls them back to back on the same batch), and the 0.19 M-parameter control model is a chain of small, latency-bound
+    launches: it runs on a side stream -- inside a whole-loop capture that makes it a parallel branch of the graph -- so that it
+    fills the tails of the score model's kernels instead of queueing behind them.  Same kernels on the same inputs: results are
+    bit-identical to the sequential order.  Ordering: the side stream waits for everything the main stream has enqueued (the
+    state), the main stream waits for the side stream before it consumes the control; tensors either stream allocated are only
+    released after such a join.  `SE3DIFF_B200_FORK_CONTROL=0` keeps one stream (measurement switch)."""
+    device = torch.device(device)
+    if device.type != "cuda" or os.environ.get("SE3DIFF_B200_FORK_CONTROL", "1") == "0":
+        return score_fn(), control_fn()
+    main = torch.cuda.current_stream(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    side = _SIDE_STREAMS.get(idx)
+    if side is None:
+        if torch.cuda.is_current_stream_capturing():
+            return score_fn(), control_fn()
+        side = _SIDE_STREAMS[idx] = torch.cuda.Stream(device)   # (a high-priority side stream measured the same: 291 vs 289 ms per rollout)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        u = control_fn()
+    out = score_fn()
+    main.wait_stream(side)
+    return out, u
+
+
 def _tree_map(fn, tree):
     if torch.is_tensor(tree):
         return fn(tree)
@@ -265,8 +295,11 @@ def _em_loop(batch, sdes, score_model, finetune_model, num_steps, max_t, min_t, 
         for st in steps:
             t = _t(st.t, B, device)
             pos, rot = b["pos"], b["node_orientations"]
-            out = score_model(b, t)
-            u = finetune_model(b, t) if record else None
+            if record and not S._HOST_NOISE:
+                out, u = _score_and_control(lambda: score_model(b, t), lambda: finetune_model(b, t), device)
+            else:
+                out = score_model(b, t)
+                u = finetune_model(b, t) if record else None
             z = {f: S.noise_randn((pos.shape[0], 3), device) for f in fields}  # per-field draw order = sdes key order
             rot, pos, dw_rot, dw_pos = ops.frame_update_em(
                 rot, pos, out["node_orientations"], out["pos"], z["node_orientations"], z["pos"], st.scalars,
@@ -335,6 +368,11 @@ def _heun_finetune_loop(batch, sdes, score_model, finetune_model, num_steps, max
     bi, B = batch["batch"], batch.num_graphs
     lengths = batch_lengths(batch)
 
+    def both(state, time):
+        if S._HOST_NOISE:
+            return _get_score(state, sdes, score_model, time), finetune_model(state, time)
+        return _score_and_control(lambda: _get_score(state, sdes, score_model, time), lambda: finetune_model(state, time), device)
+
     def recorded(batch):
         """The whole rollout on stacked outputs.  Control flow uses the HOST copies of the time grid only (no device reads), so the
         loop can be captured as one CUDA graph."""
@@ -345,16 +383,16 @@ def _heun_finetune_loop(batch, sdes, score_model, finetune_model, num_steps, max
             churn = i > 0 and 0.0 < float(ts[i]) < 1.0
             t_hat = t - noise * dts_dev[i] if churn else t
             hat = batch.replace(**{f: nois[f].forward_sde_step(x=batch[f], t=t, dt=(t_hat - t)[0], batch_idx=bi)[0] for f in fields})
-            sc_h, u_h = _get_score(hat, sdes, score_model, t_hat), finetune_model(hat, t_hat)
+            sc_h, u_h = both(hat, t_hat)
             if churn:
-                sc, u = _get_score(batch, sdes, score_model, t), finetune_model(batch, t)
+                sc, u = both(batch, t)
             else:
                 sc, u = sc_h, u_h
             dh = {f: pred[f].reverse_drift_and_diffusion(x=hat[f], t=t_hat, score=sc_h[f], finetune_score=u_h[f], batch_idx=bi)[0] for f in fields}
             step = (t_next - t_hat)[0]
             new = batch.replace(**{f: pred[f].update_given_drift_and_diffusion(x=hat[f], dt=step, drift=dh[f], diffusion=0.0)[1] for f in fields})
             if float(ts[i] + dts[i]) > 0.0:                    # = t_next, evaluated on the host in the same fp32 arithmetic
-                sc_n, u_n = _get_score(new, sdes, score_model, t_next), finetune_model(new, t_next)
+                sc_n, u_n = both(new, t_next)
                 avg = {f: (pred[f].reverse_drift_and_diffusion(x=new[f], t=t_next, score=sc_n[f], finetune_score=u_n[f], batch_idx=bi)[0]
                            + dh[f]) / 2 for f in fields}
                 new = batch.replace(**{f: pred[f].update_given_drift_and_diffusion(x=hat[f], dt=step, drift=avg[f], diffusion=0.0)[1] for f in fields})
