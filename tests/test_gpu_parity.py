@@ -1673,7 +1673,8 @@ def test_recording_rollout_graphs_match_eager_across_weight_updates(sampler, ext
     """The fine-tune rollouts (denoiser.py:267-348, 464-620) replay ONE captured graph of the whole recording loop -- states,
     controls and Brownian increments of every step.  With the same seed a replay must equal the eager rollout bit for bit, and it
     must stay valid after the control model's weights were updated in place (an optimizer step between rollouts): the derived
-    weight / pair tensors the graph reads are refreshed inside their storage."""
+    weight / pair tensors the graph reads are refreshed inside their storage.  The eager truth evaluates score and control model
+    one after the other on one stream; the other runs put the control model on the side stream / parallel graph branch."""
     from se3diff_b200 import denoiser, shortcuts
 
     g, m, fm, sdes, batch, S = _traj_setup()
@@ -1693,14 +1694,20 @@ def test_recording_rollout_graphs_match_eager_across_weight_updates(sampler, ext
 
     monkeypatch.setenv("SE3DIFF_B200_CUDA_GRAPH", "0")
     monkeypatch.setenv("SE3DIFF_B200_MODEL_GRAPH", "0")
+    monkeypatch.setenv("SE3DIFF_B200_FORK_CONTROL", "0")
     state = {k: v.clone() for k, v in fm.state_dict().items()}
     torch.manual_seed(5)
     ref_a = flat(fn(**kw))
+    monkeypatch.delenv("SE3DIFF_B200_FORK_CONTROL")
+    torch.manual_seed(5)
+    assert torch.equal(flat(fn(**kw)), ref_a), "eager, control model on the side stream"
+    monkeypatch.setenv("SE3DIFF_B200_FORK_CONTROL", "0")
     bump()
     torch.manual_seed(5)
     ref_b = flat(fn(**kw))
     assert not torch.equal(ref_a, ref_b), "the control must matter"
     fm.load_state_dict(state)
+    monkeypatch.delenv("SE3DIFF_B200_FORK_CONTROL")
     monkeypatch.setenv("SE3DIFF_B200_CUDA_GRAPH", "1")
     monkeypatch.setenv("SE3DIFF_B200_MODEL_GRAPH", "1")
     before = dict(denoiser.GRAPH_STATS)
