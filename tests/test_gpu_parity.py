@@ -463,6 +463,56 @@ def test_igso3_guide_records_equal_binary_search():
     assert torch.equal(au, ab)
 
 
+def test_igso3_sampler_straight_line_path_equals_the_runtime_path():
+    """`se3_igso3_sample` runs full, 16-byte-aligned tiles through a path specialised on which operands exist and everything else
+    (the ragged last tile; operand arrays that start at an odd rotation) through the run-time edition of the same body: every
+    operand combination must give the same bits either way, and the in-kernel Philox draw is a function of (seed, element index)
+    only.  Also the law of the Philox direction (z = 2a - 1, phi = 2 pi b): a uniform direction has E[n] = 0, E[n_k^2] = 1/3."""
+    from se3diff_b200 import ops
+
+    gen = torch.Generator(device=DEV).manual_seed(11)
+    sig_grid = 0.02 * (2.33 / 0.02) ** torch.linspace(0.001, 1.0, 200, device=DEV)
+    om = torch.linspace(0.0, 1, 501, device=DEV, dtype=torch.float64) ** 3 * math.pi
+    cdf = ops.igso3_build_cdf(sig_grid, om, 500)
+    omg, idx = om[1:].float(), ops.igso3_build_cdf_index(cdf)
+    n = 5 * 256 + 37                                             # five full tiles and a ragged one
+    big_x = ops.so3_exp(torch.randn(n + 1, 3, generator=gen, device=DEV))
+    big_z = torch.randn(n + 1, 3, generator=gen, device=DEV)
+    sigma = 0.02 * (2.33 / 0.02) ** torch.rand(n, generator=gen, device=DEV)
+    u = torch.rand(n, generator=gen, device=DEV)
+    x_odd, z_odd = big_x[1:], big_z[1:]                          # contiguous, but 36 / 12 bytes past a 16-byte boundary
+    assert x_odd.data_ptr() % 16 != 0 and z_odd.data_ptr() % 16 != 0
+    x_al, z_al = x_odd.clone(), z_odd.clone()
+    for with_x in (False, True):
+        for with_sigma in (False, True):
+            for noise_in in (False, True):
+                kw = dict(cdf_index=idx, want_angle=True, seed=77)
+                table = cdf if with_sigma else cdf[-1:].contiguous()
+                if with_sigma:
+                    kw.update(sigma=sigma, sigma_grid=sig_grid)
+                else:
+                    kw.update(cdf_index=ops.igso3_build_cdf_index(table))
+                fast = dict(kw, **({"x": x_al} if with_x else {}), **({"normals": z_al, "u": u} if noise_in else {}))
+                slow = dict(kw, **({"x": x_odd} if with_x else {}), **({"normals": z_odd, "u": u} if noise_in else {}))
+                if not with_x and not noise_in:
+                    continue                                      # nothing to misalign: covered by the prefix check below
+                r_f, a_f = ops.igso3_sample(table, omg, n, **fast)
+                r_s, a_s = ops.igso3_sample(table, omg, n, **slow)
+                assert torch.equal(a_f, a_s) and torch.equal(r_f, r_s), (with_x, with_sigma, noise_in)
+    # Philox mode: element e of a long call equals element e of a short one (ragged tile = run-time path, full tile = straight line)
+    r_long, a_long = ops.igso3_sample(cdf, omg, n, sigma=sigma, sigma_grid=sig_grid, cdf_index=idx, want_angle=True, seed=5)
+    r_short, a_short = ops.igso3_sample(cdf, omg, 200, sigma=sigma[:200].contiguous(), sigma_grid=sig_grid, cdf_index=idx, want_angle=True, seed=5)
+    assert torch.equal(r_long[:200], r_short) and torch.equal(a_long[:200], a_short)
+    # direction law: rotation vector / angle of a large uniform-SO(3) draw
+    m = 400_000
+    rot, ang = ops.igso3_sample(cdf[-1:].contiguous(), omg, m, want_angle=True, seed=9)
+    axis = ops.so3_log(rot) / ang.clamp_min(1e-6)[:, None]
+    keep = (ang > 0.2) & (ang < 3.0)                             # away from the log map's singular ends
+    axis = axis[keep]
+    assert (axis.norm(dim=-1) - 1).abs().max() < 1e-3
+    assert axis.mean(0).abs().max() < 6e-3 and ((axis ** 2).mean(0) - 1 / 3).abs().max() < 4e-3
+
+
 # ------------------------------------------------------------------------------------------------
 # K4 + score model
 # ------------------------------------------------------------------------------------------------
