@@ -536,15 +536,16 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 // scattered grid reads off the L1 data pipe (the busiest unit, 69 % in the r2 capture) -- 40 registers (48 warps per SM):
 // 0.55 / 0.50 of the HBM roof against 0.61 / 0.55; capped at 32 registers: 0.37.  A single 256-bit load of the guide record
 // (ld.global.v8.f32) crashes ptxas 12.9 in this kernel.
+constexpr int kSampleTile = 128;   // rotations (= threads) per CTA (256: -1 %, 64: the same; the warps of a CTA are independent)
 template <bool kX, bool kNormals, bool kSigma>
-__global__ void __launch_bounds__(kTile)
+__global__ void __launch_bounds__(kSampleTile)
 k_sample(const __grid_constant__ SampleArgs a, const int fast) {
-    __shared__ __align__(16) float s_rot[kTile * 9];
-    __shared__ __align__(16) float s_nrm[kNormals ? kTile * 3 : 4];
-    const int64_t first = (int64_t)blockIdx.x * kTile;
+    __shared__ __align__(16) float s_rot[kSampleTile * 9];
+    __shared__ __align__(16) float s_nrm[kNormals ? kSampleTile * 3 : 4];
+    const int64_t first = (int64_t)blockIdx.x * kSampleTile;
     const int t = threadIdx.x;
-    if (!fast || a.n - first < kTile) {
-        sample_tile_generic(a, s_rot, s_nrm, first, (int)min((int64_t)kTile, a.n - first));
+    if (!fast || a.n - first < kSampleTile) {
+        sample_tile_generic(a, s_rot, s_nrm, first, (int)min((int64_t)kSampleTile, a.n - first));
         return;
     }
     const int64_t e = first + t;
@@ -730,10 +731,10 @@ int se3_igso3_sample(const float* sigma, const float* sigma_grid, int num_sigma,
     const SampleArgs a = {sigma, sigma_grid, cdf, omega_grid, normals, u, x, index, out, angle_out, seed, n, num_sigma, num_omega, guide_bins(num_omega), tol};
     // straight-line path: 16-byte-aligned operand arrays
     const int fast = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(normals) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-    const unsigned grid = (unsigned)((n + kTile - 1) / kTile);
+    const unsigned grid = (unsigned)((n + kSampleTile - 1) / kSampleTile);
     const int which = (x ? 4 : 0) | (normals ? 2 : 0) | (sigma ? 1 : 0);
     switch (which) {
-#define SE3_SAMPLE_CASE(w, X, N, S) case w: k_sample<X, N, S><<<grid, kTile, 0, st>>>(a, fast); break;
+#define SE3_SAMPLE_CASE(w, X, N, S) case w: k_sample<X, N, S><<<grid, kSampleTile, 0, st>>>(a, fast); break;
         SE3_SAMPLE_CASE(0, false, false, false) SE3_SAMPLE_CASE(1, false, false, true) SE3_SAMPLE_CASE(2, false, true, false) SE3_SAMPLE_CASE(3, false, true, true)
         SE3_SAMPLE_CASE(4, true, false, false) SE3_SAMPLE_CASE(5, true, false, true) SE3_SAMPLE_CASE(6, true, true, false) SE3_SAMPLE_CASE(7, true, true, true)
 #undef SE3_SAMPLE_CASE
