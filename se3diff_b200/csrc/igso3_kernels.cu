@@ -525,7 +525,7 @@ __device__ __noinline__ void sample_tile_generic(const SampleArgs& a, float* s_r
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
 }
-// One rotation per thread, 256 per CTA; every warp moves, computes and stores its own 32 rotations (only __syncwarp() between the
+// One rotation per thread, kSampleTile per CTA; every warp moves, computes and stores its own 32 rotations (only __syncwarp() between the
 // phases).  Three independent fetches per rotation -- the operand tiles, (sigma, u), and the guide record that depends on
 // (sigma, u) -- are in flight together: the tiles by cp.async, so the table lookup proceeds under them.
 // Which operands exist is a template parameter and full, 16-byte-aligned tiles take a straight-line path: the run-time edition of
