@@ -146,16 +146,17 @@ def _dpm_graphed(key, keep_alive, batch, score_model, steps, device):
 _SIDE_STREAMS: dict = {}
 
 
-def _score_and_control(score_fn, control_fn, device):
+def _score_and_control(score_fn, control_fn, device, distinct: bool = True):
     """`(score_fn(), control_fn())` for one state of a recording rollout.  The two evaluations are independent (denoiser.py:299-303
     calls them back to back on the same batch), and the 0.19 M-parameter control model is a chain of small, latency-bound
     launches: it runs on a side stream -- inside a whole-loop capture that makes it a parallel branch of the graph -- so that it
     fills the tails of the score model's kernels instead of queueing behind them.  Same kernels on the same inputs: results are
     bit-identical to the sequential order.  Ordering: the side stream waits for everything the main stream has enqueued (the
     state), the main stream waits for the side stream before it consumes the control; tensors either stream allocated are only
-    released after such a join.  `SE3DIFF_B200_FORK_CONTROL=0` keeps one stream (measurement switch)."""
+    released after such a join.  `SE3DIFF_B200_FORK_CONTROL=0` keeps one stream (measurement switch); so does `distinct=False`
+    (one module passed as both models: its attention workspace must not be used by two streams at once)."""
     device = torch.device(device)
-    if device.type != "cuda" or os.environ.get("SE3DIFF_B200_FORK_CONTROL", "1") == "0":
+    if not distinct or device.type != "cuda" or os.environ.get("SE3DIFF_B200_FORK_CONTROL", "1") == "0":
         return score_fn(), control_fn()
     main = torch.cuda.current_stream(device)
     idx = device.index if device.index is not None else torch.cuda.current_device()
@@ -296,7 +297,7 @@ def _em_loop(batch, sdes, score_model, finetune_model, num_steps, max_t, min_t, 
             t = _t(st.t, B, device)
             pos, rot = b["pos"], b["node_orientations"]
             if record and not S._HOST_NOISE:
-                out, u = _score_and_control(lambda: score_model(b, t), lambda: finetune_model(b, t), device)
+                out, u = _score_and_control(lambda: score_model(b, t), lambda: finetune_model(b, t), device, finetune_model is not score_model)
             else:
                 out = score_model(b, t)
                 u = finetune_model(b, t) if record else None
@@ -371,7 +372,8 @@ def _heun_finetune_loop(batch, sdes, score_model, finetune_model, num_steps, max
     def both(state, time):
         if S._HOST_NOISE:
             return _get_score(state, sdes, score_model, time), finetune_model(state, time)
-        return _score_and_control(lambda: _get_score(state, sdes, score_model, time), lambda: finetune_model(state, time), device)
+        return _score_and_control(lambda: _get_score(state, sdes, score_model, time), lambda: finetune_model(state, time), device,
+                                  finetune_model is not score_model)
 
     def recorded(batch):
         """The whole rollout on stacked outputs.  Control flow uses the HOST copies of the time grid only (no device reads), so the
