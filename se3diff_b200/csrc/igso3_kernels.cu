@@ -536,48 +536,71 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 // scattered grid reads off the L1 data pipe (the busiest unit, 69 % in the r2 capture) -- 40 registers (48 warps per SM):
 // 0.55 / 0.50 of the HBM roof against 0.61 / 0.55; capped at 32 registers: 0.37.  A single 256-bit load of the guide record
 // (ld.global.v8.f32) crashes ptxas 12.9 in this kernel.
-constexpr int kSampleTile = 128;   // rotations (= threads) per CTA (256: -1 %, 64: the same; the warps of a CTA are independent)
+constexpr int kSampleTile = 128;   // rotations (= threads) per tile (256: -1 %, 64: the same; the warps of a CTA are independent)
+// Tiles per CTA.  With two, the second tile's (sigma, u) and operand tiles are in flight while the first is computed: 40 registers
+// instead of 32 (48 resident warps per SM instead of 64).  Measured at n = 1e7 (fraction of the HBM roof, random sigma | one sigma):
+// Philox mode 0.556 | 0.767 with one tile, 0.591 | 0.745 with two; noise passed in 0.618 | 0.911 and 0.626 | 0.862 -- so the Philox
+// mode takes two and the parity mode one.  (Two tiles capped at 32 registers: 0.35 with the noise passed in.)
+__host__ __device__ constexpr int sample_tiles(bool noise_passed_in) { return noise_passed_in ? 1 : 2; }
 template <bool kX, bool kNormals, bool kSigma>
 __global__ void __launch_bounds__(kSampleTile)
 k_sample(const __grid_constant__ SampleArgs a, const int fast) {
-    __shared__ __align__(16) float s_rot[kSampleTile * 9];
-    __shared__ __align__(16) float s_nrm[kNormals ? kSampleTile * 3 : 4];
-    const int64_t first = (int64_t)blockIdx.x * kSampleTile;
+    constexpr int kSampleTiles = sample_tiles(kNormals);
+    __shared__ __align__(16) float s_rot[kSampleTiles][kSampleTile * 9];
+    __shared__ __align__(16) float s_nrm[kSampleTiles][kNormals ? kSampleTile * 3 : 4];
+    const int64_t first0 = (int64_t)blockIdx.x * (kSampleTile * kSampleTiles);
     const int t = threadIdx.x;
-    if (!fast || a.n - first < kSampleTile) {
-        sample_tile_generic(a, s_rot, s_nrm, first, (int)min((int64_t)kSampleTile, a.n - first));
-        return;
-    }
-    const int64_t e = first + t;
-    // the lookup chain starts from these two: issued before anything else
-    const float sg = kSigma ? __ldg(a.sigma + e) : 0.f;
-    const float uin = kNormals ? __ldg(a.u + e) : 0.f;
     const int lane = t & 31;
-    const int wbase = t & ~31;                              // first rotation of this warp inside the tile
-    const int64_t wfirst = first + wbase;
-    float* rot_w = s_rot + wbase * 9;                       // the warp's 32 x 9 floats = 72 16-byte pieces
-    if (kX) {
-        const float4* src = reinterpret_cast<const float4*>(a.x + wfirst * 9) + lane;
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(rot_w) + (uint32_t)lane * 16u;
-        cp_async16(dst, src);
-        cp_async16(dst + 512u, src + 32);
-        if (lane < 8) cp_async16(dst + 1024u, src + 64);
+    const int wbase = t & ~31;                              // first rotation of this warp inside a tile
+    float sg[kSampleTiles], uin[kSampleTiles];
+    bool full[kSampleTiles];
+    // the lookup chains start from (sigma, u): issued before anything else, for every tile of the CTA
+#pragma unroll
+    for (int k = 0; k < kSampleTiles; ++k) {
+        const int64_t first = first0 + k * kSampleTile;
+        full[k] = fast && a.n - first >= kSampleTile;
+        sg[k] = (kSigma && full[k]) ? __ldg(a.sigma + first + t) : 0.f;
+        uin[k] = (kNormals && full[k]) ? __ldg(a.u + first + t) : 0.f;
     }
-    if (kNormals) {
-        if (lane < 24) cp_async16((uint32_t)__cvta_generic_to_shared(s_nrm + wbase * 3) + (uint32_t)lane * 16u, reinterpret_cast<const float4*>(a.normals + wfirst * 3) + lane);
+#pragma unroll
+    for (int k = 0; k < kSampleTiles; ++k) {
+        if (full[k]) {
+            const int64_t wfirst = first0 + k * kSampleTile + wbase;
+            if (kX) {
+                const float4* src = reinterpret_cast<const float4*>(a.x + wfirst * 9) + lane;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_rot[k] + wbase * 9) + (uint32_t)lane * 16u;   // the warp's 32 x 9 floats = 72 16-byte pieces
+                cp_async16(dst, src);
+                cp_async16(dst + 512u, src + 32);
+                if (lane < 8) cp_async16(dst + 1024u, src + 64);
+            }
+            if (kNormals) {
+                if (lane < 24) cp_async16((uint32_t)__cvta_generic_to_shared(s_nrm[k] + wbase * 3) + (uint32_t)lane * 16u, reinterpret_cast<const float4*>(a.normals + wfirst * 3) + lane);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    SampleDraw d = sample_lookup(e, kNormals, uin, sg, kSigma, GlobalGrid{a.sigma_grid}, a.num_sigma, a.cdf, a.num_omega, a.seed, a.cdf_index, a.guide_bins_n);
-    tile_load_wait();
-    __syncwarp();
-    if (kNormals) { d.nx = s_nrm[t * 3]; d.ny = s_nrm[t * 3 + 1]; d.nz = s_nrm[t * 3 + 2]; }
-    const float ang = sample_compose(d, kSigma, kX, !kNormals, GlobalGrid{a.omega_grid}, a.tol, s_rot + t * 9);
-    if (a.angle_out) a.angle_out[e] = ang;
-    __syncwarp();
-    float4* dst = reinterpret_cast<float4*>(a.out + wfirst * 9) + lane;
-    const float4* s4 = reinterpret_cast<const float4*>(rot_w) + lane;
-    dst[0] = s4[0];
-    dst[32] = s4[32];
-    if (lane < 8) dst[64] = s4[64];
+#pragma unroll
+    for (int k = 0; k < kSampleTiles; ++k) {
+        const int64_t first = first0 + k * kSampleTile;
+        if (first >= a.n) break;
+        if (!full[k]) {                                     // ragged last tile / unaligned arrays: the run-time edition
+            sample_tile_generic(a, s_rot[k], s_nrm[k], first, (int)min((int64_t)kSampleTile, a.n - first));
+            continue;
+        }
+        const int64_t e = first + t;
+        SampleDraw d = sample_lookup(e, kNormals, uin[k], sg[k], kSigma, GlobalGrid{a.sigma_grid}, a.num_sigma, a.cdf, a.num_omega, a.seed, a.cdf_index, a.guide_bins_n);
+        if (k + 1 < kSampleTiles) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (kNormals) { d.nx = s_nrm[k][t * 3]; d.ny = s_nrm[k][t * 3 + 1]; d.nz = s_nrm[k][t * 3 + 2]; }
+        const float ang = sample_compose(d, kSigma, kX, !kNormals, GlobalGrid{a.omega_grid}, a.tol, s_rot[k] + t * 9);
+        if (a.angle_out) a.angle_out[e] = ang;
+        __syncwarp();
+        float4* dst = reinterpret_cast<float4*>(a.out + (first + wbase) * 9) + lane;
+        const float4* s4 = reinterpret_cast<const float4*>(s_rot[k] + wbase * 9) + lane;
+        dst[0] = s4[0];
+        dst[32] = s4[32];
+        if (lane < 8) dst[64] = s4[64];
+    }
 }
 
 // Persisting-L2 access window over a lookup table for the launches enqueued on `st` until clear_l2_window (SE3DIFF_B200_L2_WINDOW=0
@@ -731,7 +754,8 @@ int se3_igso3_sample(const float* sigma, const float* sigma_grid, int num_sigma,
     const SampleArgs a = {sigma, sigma_grid, cdf, omega_grid, normals, u, x, index, out, angle_out, seed, n, num_sigma, num_omega, guide_bins(num_omega), tol};
     // straight-line path: 16-byte-aligned operand arrays
     const int fast = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(normals) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-    const unsigned grid = (unsigned)((n + kSampleTile - 1) / kSampleTile);
+    const int per_cta = kSampleTile * sample_tiles(normals != nullptr);
+    const unsigned grid = (unsigned)((n + per_cta - 1) / per_cta);
     const int which = (x ? 4 : 0) | (normals ? 2 : 0) | (sigma ? 1 : 0);
     switch (which) {
 #define SE3_SAMPLE_CASE(w, X, N, S) case w: k_sample<X, N, S><<<grid, kSampleTile, 0, st>>>(a, fast); break;
