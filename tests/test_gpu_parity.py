@@ -761,7 +761,9 @@ def test_analytic_score_moments_on_gpu():
 
 
 @pytest.mark.parametrize("B,L,scale", [(3, 84, 1.5), (130, 20, 1.5), (2, 57, 1.5), (2, 200, 1.5), (300, 131, 1.5), (2, 84, 100.0), (2, 256, 1.5),
-                                       (2, 257, 1.5), (3, 300, 1.5), (2, 512, 1.5), (1, 500, 100.0)])
+                                       (2, 257, 1.5), (3, 300, 1.5), (2, 512, 1.5), (1, 500, 100.0),
+                                       # the shortest chains and the edition / chunk boundaries (16-key chunks; narrow <= 128 < wide)
+                                       (3, 1, 1.5), (2, 2, 1.5), (2, 7, 1.5), (2, 16, 1.5), (2, 17, 1.5), (2, 96, 1.5), (2, 97, 1.5), (130, 128, 1.5), (2, 129, 1.5)])
 def test_ipa_tensor_core_operator_vs_fp64(B, L, scale):
     """se3_ipa_attention_tc_fwd (tcgen05 two-pass; L > 256: keys split over a 2-CTA cluster) against an fp64 evaluation of
     SAAttention.forward between the projections and fc_out (structure_module.py:131-216) on the same bf16-rounded
