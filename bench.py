@@ -296,7 +296,10 @@ def main():
                 if torch.is_tensor(v):
                     rep[k] = v.pin_memory()
             h2d_rep = rep.h2d_nbytes()
-            t_p = timed(lambda k: one_step(5000 + rank * B + k, rep, False).to("cpu"), min(args.warmup, 2), args.steps)
+            # warm-up: the caching allocator settles after the third call (each of the first calls adds one 1 GB block by cudaMalloc:
+            # the incoming copy, the copy the context cache still holds, the one being released -- scripts/time_e2e_pyg_parts.py:
+            # 370 ms per call and no allocator traffic from then on, +40..110 ms on the calls before)
+            t_p = timed(lambda k: one_step(5000 + rank * B + k, rep, False).to("cpu"), max(args.warmup, 4), args.steps)
             extras["e2e_pyg"] = {"value": world * B * L * S * args.steps / t_p, "unit": UNIT, "h2d_bytes_per_step": h2d_rep, "d2h_bytes_per_step": d2h,
                                  "ms_per_step": t_p / args.steps * 1e3,
                                  "note": "host batch with the pair embedding replicated B times (what PyG's Batch.from_data_list holds at sample.py:223), pinned"}
