@@ -33,7 +33,7 @@ typedef void* se3_stream_t; /* cudaStream_t */
 
 const char* se3_last_error(void);
 /* bumped whenever a signature or a by-value struct of this header changes; the loader compares it with the header it was written against */
-#define SE3_ABI_VERSION 4
+#define SE3_ABI_VERSION 5
 int se3_abi_version(void);
 /* number of kernels launched by this library in the calling thread since the last reset
  * (bench.py's `gpu_launches`). */
@@ -319,8 +319,11 @@ int se3_ipa_attention_bwd(const float* proj, const float* rot, const float* tran
  *                  (row pitch = scalar_stride = point_stride); their 2^-9 rounding is of the size of the bf16 GEMM-operand
  *                  rounding the local points already carry
  * Other differences from se3_ipa_attention_fwd:
- *   pair_bias_packed  : TRANSPOSED bf16 [H][L (key j)][round_up(L,8) (query i)] = pair_weight*pair_bias(x2d), zero padded;
- *                       the (head, query-tile) slab is fetched by TMA into shared memory
+ *   pair_bias_packed  : bf16 pair_weight*pair_bias(x2d), zero padded, as se3_ipa_tc_pack_pair / se3_pair_project write it
+ *                       (se3_ipa_tc_packed_pair_bytes gives the size): L <= 128: query-major [H][L (query i)][pitch (key j)], pitch =
+ *                       a whole number of 8-key chunks, odd where 8 * chunks <= 128 allows (one conflict-free 16-byte shared-memory
+ *                       read per query row and 8-key logit step); L > 128: TRANSPOSED [H][L (key j)][round_up(L,8) (query i)].
+ *                       The (head, query-tile) slab is fetched by TMA into shared memory
  *   pair_value_packed : bf16 [L][H][Lp/8][16][8] with Lp = round_up(L,16): pair_value[i, j, h*16+c] stored at
  *                       [i][h][j/8][c][j%8], zero for j >= L (the UMMA K-major operand layout, built once per
  *                       sequence by the caller)

@@ -39,7 +39,7 @@ class IpaShape(C.Structure):
         "off_vp", "hs_scalar", "hs_point", "hs_vpoint", "pair_batch")]
 
 
-ABI_VERSION = 4   # SE3_ABI_VERSION of include/se3diff_b200.h this module's signature table was written against
+ABI_VERSION = 5   # SE3_ABI_VERSION of include/se3diff_b200.h this module's signature table was written against
 
 # name -> argtypes (all return int unless listed in _RESTYPES).  Must list every symbol of the header.
 SIGNATURES = {

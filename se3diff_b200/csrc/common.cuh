@@ -12,6 +12,19 @@ void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 void count_launch(int n = 1);
 
+// Packed pair bias of the tensor-core IPA operator (bf16, one slab per head; written by se3_ipa_tc_pack_pair / se3_pair_project,
+// read by pass 1 of se3_ipa_attention_tc_fwd).
+//   L <= 128 (one query tile): QUERY-major [H][L(i)][pitch(j)], keys >= L zero.  The thread of query row i reads the eight biases of
+//            an 8-column logit step as ONE 16-byte LDS; the pitch is a whole number of 16-byte chunks, odd where the slab allows it
+//            (eight consecutive rows then start in eight different bank groups: the quarter-warp phases of LDS.128 are conflict-free).
+//   L  > 128: KEY-major [H][L(j)][round_up(L, 8)(i)], queries >= L zero: a (keys x 128 queries) box of a 2-D tensor map per query tile.
+__host__ __device__ constexpr bool ipa_bias_query_major(int L) { return L <= 128; }
+__host__ __device__ constexpr int ipa_bias_pitch(int L) {
+    const int chunks = (L + 7) / 8;
+    if (!ipa_bias_query_major(L)) return chunks * 8;
+    return (chunks | 1) * 8 <= 128 ? (chunks | 1) * 8 : chunks * 8;   // the slab [L][pitch] shares the 256 * round_up(L, 16) bytes of the P operand
+}
+
 #define SE3_REQUIRE(cond, msg)                       \
     do {                                             \
         if (!(cond)) {                               \

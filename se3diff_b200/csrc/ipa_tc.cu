@@ -123,7 +123,9 @@ __device__ __forceinline__ Pass1Smem carve1(uint8_t* base, int L, int LK, int Lp
 // kPersist (always with kWide; alone = the 128-thread edition for L <= 128 with four persistent CTAs per SM): the CTA walks
 //                 every gridDim.x-th item and issues the next item's copies as soon as the second product has consumed the
 //                 operands.  Without it: one item per CTA, taken from the grid coordinates.
-template <typename OutT, bool kSplit, bool kWide, bool kPtsBf16, bool kPersist = kWide>
+// kKeyBias = false: the caller passed no key bias (no padded / unknown residues: every BASELINE configuration) -- the logit pass then
+//                 neither loads nor adds the staged zeros (2 LDS.128 + 4 FADD2 of the ~225 instructions of an 8-column step).
+template <typename OutT, bool kSplit, bool kWide, bool kPtsBf16, bool kPersist = kWide, bool kKeyBias = true>
 __global__ void __launch_bounds__(kWide ? 256 : 128, kWide ? 1 : 4)
 k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_pts,
                const __grid_constant__ CUtensorMap map_bias, const float* __restrict__ rot, const float* __restrict__ trans, const __nv_bfloat16* __restrict__ pair_bias_t,
@@ -163,10 +165,11 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
     // pair-bias tile of this (head, query tile): bf16 [L keys][ncol queries], fetched by TMA into the region that
     // later holds P (P is only written after every warp has finished the logit pass)
-    const int Lpi = (L + 7) & ~7;                         // row pitch of the transposed bias matrix
-    // L <= 128: the whole [L][Lpi] matrix of the head, one bulk copy.  Longer sequences: a [keys][128 queries] box of the 2-D
-    // tensor map (columns past the matrix edge are zero-filled), slab pitch 128
-    const int ncol = Lpi <= 128 ? Lpi : 128;              // multiple of 8 -> 16-byte rows
+    const int Lpi = ipa_bias_pitch(L);                    // row pitch of the packed bias matrix (common.cuh)
+    // L <= 128: the whole QUERY-major [L][Lpi keys] matrix of the head, one bulk copy (the thread of a query row reads the eight
+    // biases of a logit step as one 16-byte LDS).  Longer sequences: a [keys][128 queries] box of the 2-D tensor map over the
+    // key-major matrix (columns past the matrix edge are zero-filled), slab pitch 128
+    const int ncol = kWide ? 128 : Lpi;                   // multiple of 8 -> 16-byte rows
     const __nv_bfloat16* s_bias = reinterpret_cast<const __nv_bfloat16*>(s.p);
     // ---- staging: six TMA tile copies + two bulk copies per item, issued by one thread --------------------------------
     // scalars: bf16 head-major records [q 16 | k 16 | v 16] (q already carries scalar_weight * log2 e).  A 16-byte wide,
@@ -386,7 +389,8 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     if (warp_ok) {
         // ---- pass A: logits (log2 domain) -> TMEM, row max -------------------------------------------------
         const float hw = head_weight[h] * kLog2e;
-        const __nv_bfloat16* bias_col = s_bias + min(qrow, ncol - 1);   // [j][query]: conflict-free 2-byte LDS
+        // 256-thread editions: [j][query] slab, conflict-free 2-byte LDS per key.  128-thread edition: this row's [keys] line
+        const __nv_bfloat16* bias_col = kWide ? s_bias + min(qrow, ncol - 1) : s_bias + min(qrow, L - 1) * Lpi;
         // Packed fp32x2 arithmetic (FADD2/FMUL2/FFMA2, sm_100): two keys per instruction.  The key points are staged
         // NEGATED and interleaved by key pair ([pair][component][2]) so that q + (-k) is a single packed add.
         float2 q2[12];
@@ -403,12 +407,14 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         auto chunk = [&](const int col0) {
             uint32_t r[8];
             tc::tmem_ld8(tc::tmem_addr(tmem, lane_base, col0), r);
+            uint4 pbq = make_uint4(0u, 0u, 0u, 0u);          // 128-thread edition: the step's eight pair biases, one LDS.128
+            if constexpr (!kWide) pbq = *reinterpret_cast<const uint4*>(bias_col + col0);
             tc::tmem_wait_ld();
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int j = col0 + 2 * u;
                 const float4* kp4 = reinterpret_cast<const float4*>(s.kp + j * 12);   // pair block: 24 floats
-                float2 ds = make_float2(0.f, 0.f);
+                float2 ds;                                                            // sum over the four points, started by the first
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
                     // components 3p, 3p+1, 3p+2 of the pair: float4 #(3p/2) ... laid out {c_j, c_j1, c'_j, c'_j1}
@@ -423,13 +429,21 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     float2 d2 = __fmul2_rn(dx, dx);
                     d2 = __ffma2_rn(dy, dy, d2);
                     d2 = __ffma2_rn(dz, dz, d2);
-                    ds = __fadd2_rn(ds, make_float2(fast_sqrt(d2.x), fast_sqrt(d2.y)));
+                    const float2 dn = make_float2(fast_sqrt(d2.x), fast_sqrt(d2.y));
+                    ds = p == 0 ? dn : __fadd2_rn(ds, dn);
                 }
-                const float pb0 = __bfloat162float(bias_col[j * ncol]);
-                const float pb1 = __bfloat162float(bias_col[(j + 1) * ncol]);      // (past the last key: stale shared memory, overwritten below)
-                const float2 kb2 = *reinterpret_cast<const float2*>(s.kb + j);
+                float pb0, pb1;
+                if constexpr (kWide) {
+                    pb0 = __bfloat162float(bias_col[j * ncol]);
+                    pb1 = __bfloat162float(bias_col[(j + 1) * ncol]);              // (past the last key: stale shared memory, overwritten below)
+                } else {
+                    const uint32_t w = u == 0 ? pbq.x : u == 1 ? pbq.y : u == 2 ? pbq.z : pbq.w;   // keys j | j + 1 (zero past the last key)
+                    pb0 = __uint_as_float(w << 16);
+                    pb1 = __uint_as_float(w & 0xffff0000u);
+                }
                 float2 l2 = __ffma2_rn(hw2, ds, make_float2(__uint_as_float(r[2 * u]), __uint_as_float(r[2 * u + 1])));
-                l2 = __fadd2_rn(__ffma2_rn(make_float2(pb0, pb1), l2e2, l2), kb2);
+                l2 = __ffma2_rn(make_float2(pb0, pb1), l2e2, l2);
+                if constexpr (kKeyBias) l2 = __fadd2_rn(l2, *reinterpret_cast<const float2*>(s.kb + j));
                 r[2 * u] = __float_as_uint(l2.x);
                 r[2 * u + 1] = __float_as_uint(l2.y);
             }
@@ -761,7 +775,7 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const void* pts, int p
             if (gsz > 0 && gsz < sh.heads) group = gsz;
         }
         if (!wide && group == sh.heads && narrow_persistent()) {     // four persistent CTAs per SM
-            auto kp = k_ipa_tc_pass1<OutT, false, false, kPtsBf16, true>;
+            auto kp = key_bias ? k_ipa_tc_pass1<OutT, false, false, kPtsBf16, true, true> : k_ipa_tc_pass1<OutT, false, false, kPtsBf16, true, false>;
             e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
             if (e != cudaSuccess) { set_error("ipa_tc pass1 smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
             const int resident = (512 / cols) * sms;

@@ -58,7 +58,7 @@ struct PpPlan {
 };
 // Shared memory of ONE warpgroup.
 __host__ __device__ inline PpPlan pp_plan(int L, bool pts_bf16) {
-    const uint32_t Lq = (uint32_t)(L + 15) & ~15u, Lpi = (uint32_t)(L + 7) & ~7u;
+    const uint32_t Lq = (uint32_t)(L + 15) & ~15u, Lpi = (uint32_t)ipa_bias_pitch(L);
     auto up = [](uint32_t x) { return (x + 127u) & ~127u; };
     PpPlan p;
     uint32_t o = 0;
@@ -70,7 +70,7 @@ __host__ __device__ inline PpPlan pp_plan(int L, bool pts_bf16) {
     p.vp = o; o += Lq * (NVP * 2);                                   // [Lq/8][NVP/8][8][8] bf16
     p.ops = o;                                                       // A operands 4 x [2][128][16 B] fp16, B operands 4 x [2][Lq][16 B]; later P [Lq/8][128][16 B]
     { const uint32_t a = 16384u + Lq * 128u, b = Lq * 256u; o += a > b ? a : b; }
-    p.bias = o; o += up((uint32_t)L * Lpi * 2);                      // bf16 [L keys][Lpi queries]
+    p.bias = o; o += up((uint32_t)L * Lpi * 2);                      // bf16 [L queries][Lpi keys] (common.cuh: ipa_bias_pitch)
     p.kb = o; o += up(Lq * 4);
     p.hmax = o; o += 1024;
     p.total = o;
@@ -361,7 +361,7 @@ k_ipa_tc_pass1_pp(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             SE3_STAMP(3);
             float m = -CUDART_INF_F;
             const float hw = head_weight[h] * kLog2e;
-            const uint32_t bias_col = tc::smem_u32(s_bias + min(row, Lpi - 1));   // [j][query]: conflict-free 2-byte LDS
+            const uint32_t bias_col = tc::smem_u32(s_bias + min(row, L - 1) * Lpi);   // [query][j]: this row's biases, key by key
             for (int c = g; c < nck; c += 2) {
                 const int j0 = c * 16;                         // this group's chunk: 16 keys, S and four D_p = 80 registers
                 tc::mbar_wait(&bar.st_full[g], n_full & 1u);
@@ -395,7 +395,7 @@ k_ipa_tc_pass1_pp(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                                          : 0.f;
                     }
                     tc::tmem_wait_ld();
-                    uint32_t bj = bias_col + (uint32_t)(j0 * Lpi * 2);   // walked key by key (precomputed offsets would cost 15 registers)
+                    uint32_t bj = bias_col + (uint32_t)(j0 * 2);   // walked key by key
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {
                         const float4 kb4 = *reinterpret_cast<const float4*>(s_kb + j0 + 4 * q4);   // -inf on padding keys
@@ -406,7 +406,7 @@ k_ipa_tc_pass1_pp(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                             float lg = fmaf(hw, ds[u], __uint_as_float(s[u]) + kbv[e]);
                             if (u < nk) lg = fmaf(lds_bf16(bj), kLog2e, lg);
                             asm volatile("" : "+r"(bj));       // keep the address a loop-carried register
-                            bj += (uint32_t)(Lpi * 2);
+                            bj += 2u;
                             m = fmaxf(m, lg);
                             s[u] = __float_as_uint(lg);
                         }

@@ -1,7 +1,8 @@
 // Operand packing of the tensor-core IPA operator's SHARED pair tensors (once per sequence and layer), and the row index sets that
 // turn the reference's fused projection weight into the operator's head-major records.
 //   pair bias  : pair_weight * Linear(x2d)  [L(i)][L(j)][H] fp32   (structure_module.py:179)
-//             -> bf16 [H][L(j)][round_up(L, 8)(i)], transposed and zero padded: the (head, query tile) slab pass 1 fetches by TMA
+//             -> bf16, zero padded, the (head, query tile) slab pass 1 fetches by TMA: L <= 128 query-major [H][L(i)][pitch(j)],
+//                longer chains key-major [H][L(j)][round_up(L, 8)(i)]  (common.cuh: ipa_bias_pitch)
 //   pair value : Linear(x2d)                [L(i)][L(j)][H*16] fp32 (structure_module.py:209)
 //             -> bf16 [L(i)][H][Lp/8][16][8] with Lp = round_up(L, 16): element (i, j, h*16+c) at [i][h][j/8][c][j%8], zero for
 //                j >= L -- the K-major UMMA operand of pass 2, one contiguous block per (query, head)
@@ -15,13 +16,15 @@ using namespace se3;
 namespace {
 
 __global__ void __launch_bounds__(256) k_pack_pair_bias(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int L, int H, int Lpi) {
-    // one thread per output element, i fastest (coalesced 2-byte stores; the reads of one warp touch 32 rows of H floats)
+    // one thread per output element, the padded index fastest (coalesced 2-byte stores; the reads of one warp touch 32 rows of H floats)
     const int64_t n = (int64_t)H * L * Lpi;
+    const bool qmajor = ipa_bias_query_major(L);
     for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
-        const int i = (int)(o % Lpi);
+        const int fast = (int)(o % Lpi);
         const int64_t r = o / Lpi;
-        const int j = (int)(r % L), h = (int)(r / L);
-        out[o] = __float2bfloat16_rn(i < L ? in[((int64_t)i * L + j) * H + h] : 0.f);
+        const int slow = (int)(r % L), h = (int)(r / L);
+        const int i = qmajor ? slow : fast, j = qmajor ? fast : slow;
+        out[o] = __float2bfloat16_rn(fast < L ? in[((int64_t)i * L + j) * H + h] : 0.f);
     }
 }
 
@@ -53,7 +56,7 @@ extern "C" {
 
 int64_t se3_ipa_tc_packed_pair_bytes(int len, int heads, int64_t* bias_bytes, int64_t* value_bytes) {
     if (len <= 0 || heads <= 0) return SE3_EINVAL;
-    const int64_t lpi = (len + 7) / 8 * 8, lp = (len + 15) / 16 * 16;
+    const int64_t lpi = ipa_bias_pitch(len), lp = (len + 15) / 16 * 16;
     const int64_t bb = (int64_t)heads * len * lpi * 2, vb = (int64_t)len * heads * lp * 16 * 2;
     if (bias_bytes) *bias_bytes = bb;
     if (value_bytes) *value_bytes = vb;
@@ -67,7 +70,7 @@ int se3_ipa_tc_pack_pair(const float* pair_bias, const float* pair_value, void* 
                 "each input needs its output (pass both NULL to skip one of the two packs)");
     SE3_REQUIRE(value_packed == nullptr || (reinterpret_cast<uintptr_t>(value_packed) & 15) == 0, "value_packed must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    const int lpi = (len + 7) / 8 * 8, lp = (len + 15) / 16 * 16;
+    const int lpi = ipa_bias_pitch(len), lp = (len + 15) / 16 * 16;
     if (pair_bias) {
         const int64_t n = (int64_t)heads * len * lpi;
         k_pack_pair_bias<<<(unsigned)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16), 256, 0, st>>>(pair_bias, (__nv_bfloat16*)bias_packed, len, heads, lpi);

@@ -82,13 +82,14 @@ template <bool kPacked>
 __global__ void __launch_bounds__(256)
 k_pair_project(const float* __restrict__ x2d, const float* __restrict__ w_cat, float pair_weight, void* __restrict__ bias_out, void* __restrict__ value_out,
                int64_t rows, int L, int H, int dk, int dp) {
-    const int lpi = (L + 7) & ~7, lp = (L + 15) & ~15;
+    const int lpi = ipa_bias_pitch(L), lp = (L + 15) & ~15;
+    const bool qmajor = ipa_bias_query_major(L);
     tile_gemm((int)rows, H + H * dk, dp, w_cat, [&](int m, int k) { return x2d[(int64_t)m * dp + k]; },
               [&](int m, int n, float acc) {
                   const int b = m / (L * L), ij = m - b * L * L, i = ij / L, j = ij - i * L;
                   if (n < H) {
                       const float v = pair_weight * acc;
-                      if (kPacked) reinterpret_cast<__nv_bfloat16*>(bias_out)[((int64_t)n * L + j) * lpi + i] = __float2bfloat16_rn(v);          // [H][j][i]
+                      if (kPacked) reinterpret_cast<__nv_bfloat16*>(bias_out)[((int64_t)n * L + (qmajor ? i : j)) * lpi + (qmajor ? j : i)] = __float2bfloat16_rn(v);   // [H][i][j] (L <= 128) or [H][j][i]
                       else reinterpret_cast<float*>(bias_out)[(((int64_t)b * H + n) * L + i) * L + j] = v;                                         // [Bp][H][i][j]
                   } else {
                       const int hc = n - H, h = hc / dk, c = hc - h * dk;
@@ -130,7 +131,7 @@ int se3_pair_project(const float* x2d, const float* w_bias_value, float pair_wei
     const dim3 grid((unsigned)((rows + TM - 1) / TM), (unsigned)((heads + heads * dk + TN - 1) / TN));
     if (packed) {
         // padding (queries >= L of the bias slabs, keys >= L of the value operand) must read as zero
-        const int64_t lpi = (len + 7) / 8 * 8, lp = (len + 15) / 16 * 16;
+        const int64_t lpi = ipa_bias_pitch(len), lp = (len + 15) / 16 * 16;
         if (lpi != len && cudaMemsetAsync(bias_out, 0, (size_t)heads * len * lpi * 2, st) != cudaSuccess) { set_error("se3_pair_project: memset"); return SE3_ECUDA; }
         if (lp != len && cudaMemsetAsync(value_out, 0, (size_t)len * heads * lp * 16 * 2, st) != cudaSuccess) { set_error("se3_pair_project: memset"); return SE3_ECUDA; }
         k_pair_project<true><<<grid, 256, 0, st>>>(x2d, w_bias_value, pair_weight, bias_out, value_out, rows, len, heads, dk, dim_pair);

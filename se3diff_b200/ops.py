@@ -545,6 +545,12 @@ def _packed_pair_sizes(length: int, heads: int):
     return bb.value, vb.value
 
 
+def ipa_tc_bias_pitch(length: int, heads: int = 1) -> int:
+    """Row pitch (bf16 elements) of the packed pair bias, as the library lays it out: query-major [H][L(i)][pitch(j)] for L <= 128,
+    key-major [H][L(j)][pitch(i)] for longer chains (csrc/common.cuh: ipa_bias_pitch)."""
+    return _packed_pair_sizes(length, heads)[0] // (2 * heads * length)
+
+
 def ipa_tc_pack_pair_value(pair_value: torch.Tensor, heads: int) -> torch.Tensor:
     """[1, L, L, H*16] (pair_value(x2d), structure_module.py:209) -> bf16 [L][H][Lp/8][16][8], the UMMA K-major
     operand layout read by pass 2 of the tensor-core attention (se3_ipa_tc_pack_pair)."""
@@ -561,13 +567,13 @@ def ipa_tc_pack_pair_value(pair_value: torch.Tensor, heads: int) -> torch.Tensor
 
 
 def ipa_tc_pack_pair_bias(pair_bias: torch.Tensor) -> torch.Tensor:
-    """[1, L(i), L(j), H] (= pair_weight * pair_bias(x2d), structure_module.py:179) -> bf16 [H][L(j)][round_up(L,8)(i)],
-    the transposed slab layout the tensor-core attention fetches with TMA (se3_ipa_tc_pack_pair)."""
+    """[1, L(i), L(j), H] (= pair_weight * pair_bias(x2d), structure_module.py:179) -> the bf16 slab layout the tensor-core attention
+    fetches with TMA (se3_ipa_tc_pack_pair): [H][L(i)][pitch(j)] for L <= 128, [H][L(j)][round_up(L,8)(i)] for longer chains."""
     Lq, heads = pair_bias.shape[1], pair_bias.shape[-1]
     if pair_bias.numel() != Lq * Lq * heads:
         raise ValueError(f"pair_bias must be [1, L, L, H], got {tuple(pair_bias.shape)}")
     pb = _dev(pair_bias, name="pair_bias")
-    out = torch.empty(heads, Lq, (Lq + 7) // 8 * 8, dtype=torch.bfloat16, device=pb.device)
+    out = torch.empty(heads, Lq, ipa_tc_bias_pitch(Lq, heads), dtype=torch.bfloat16, device=pb.device)
     assert out.numel() * 2 == _packed_pair_sizes(Lq, heads)[0]
     with _guard(pb):
         L.check(L.lib().se3_ipa_tc_pack_pair(_p(pb), None, _p(out), None, Lq, heads, _stream(pb)), "se3_ipa_tc_pack_pair")
@@ -596,12 +602,12 @@ def pair_embed(pair_dense, ln_weight, ln_bias, ln_eps: float, w_x2d, relpos_tabl
 
 def pair_project(x2d, w_bias, w_value, pair_weight: float, heads: int, dk: int, packed: bool):
     """One layer's pair tensors from x2d [Bp, L, L, dp] (structure_module.py:179, 209; se3_pair_project): fp32 ([Bp, H, L, L], [Bp, L, L, H*dk])
-    or, packed, the bf16 operands of the tensor-core attention ([H][L][round_up(L,8)], [L][H][Lp/8][16][8])."""
+    or, packed, the bf16 operands of the tensor-core attention ([H][L][ipa_tc_bias_pitch(L)], [L][H][Lp/8][16][8])."""
     x = _dev(x2d, name="x2d")
     Bp, Lq, dp = x.shape[0], x.shape[1], x.shape[-1]
     w = torch.cat([_dev(w_bias, name="w_bias"), _dev(w_value, name="w_value")], dim=0).contiguous()
     if packed:
-        bias = torch.empty(heads, Lq, (Lq + 7) // 8 * 8, dtype=torch.bfloat16, device=x.device)
+        bias = torch.empty(heads, Lq, ipa_tc_bias_pitch(Lq, heads), dtype=torch.bfloat16, device=x.device)
         value = torch.empty(Lq, heads, (Lq + 15) // 16 * 2, 16, 8, dtype=torch.bfloat16, device=x.device)
     else:
         bias = torch.empty(Bp, heads, Lq, Lq, dtype=torch.float32, device=x.device)

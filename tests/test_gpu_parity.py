@@ -838,7 +838,7 @@ def test_ipa_tc_persistent_work_queue_is_per_workspace():
     assert all(float(w[1][-16:].abs().sum()) == 0.0 for w in ws)             # ... and is zero again
 
 
-@pytest.mark.parametrize("L,H", [(84, 32), (11, 4), (57, 32), (130, 8), (16, 1)])
+@pytest.mark.parametrize("L,H", [(84, 32), (11, 4), (57, 32), (130, 8), (16, 1), (96, 2), (128, 2), (121, 1)])
 def test_tc_operand_packs_are_bit_exact(L, H):
     """se3_ipa_tc_pack_pair (the C-ABI entry that turns the per-sequence pair tensors of models.py:243-293 / structure_module.py:179,209
     into the TMA slab and UMMA operand layouts of se3_ipa_attention_tc_fwd) against permute / pad / round-to-bf16 in torch: byte
@@ -849,7 +849,12 @@ def test_tc_operand_packs_are_bit_exact(L, H):
     pb = torch.randn(1, L, L, H, generator=g).to(DEV)                  # [1, i, j, h]
     pv = torch.randn(1, L, L, H * 16, generator=g).to(DEV)
     got_b, got_v = ops.ipa_tc_pack_pair_bias(pb), ops.ipa_tc_pack_pair_value(pv, H)
-    want_b = torch.nn.functional.pad(pb[0].permute(2, 1, 0), (0, (-L) % 8)).contiguous().to(torch.bfloat16)          # [H, j, i_pad]
+    if L <= 128:    # one query tile: query-major rows of keys, an odd number of 16-byte chunks per row where the slab allows it
+        chunks = (L + 7) // 8
+        pitch = (chunks | 1) * 8 if (chunks | 1) * 8 <= 128 else chunks * 8
+        want_b = torch.nn.functional.pad(pb[0].permute(2, 0, 1), (0, pitch - L)).contiguous().to(torch.bfloat16)     # [H, i, j_pad]
+    else:
+        want_b = torch.nn.functional.pad(pb[0].permute(2, 1, 0), (0, (-L) % 8)).contiguous().to(torch.bfloat16)      # [H, j, i_pad]
     Lp = (L + 15) // 16 * 16
     want_v = torch.nn.functional.pad(pv.reshape(L, L, H, 16), (0, 0, 0, 0, 0, Lp - L)).view(L, Lp // 8, 8, H, 16).permute(0, 3, 1, 4, 2).contiguous().to(torch.bfloat16)
     assert got_b.shape == want_b.shape and torch.equal(got_b.view(torch.int16), want_b.view(torch.int16))

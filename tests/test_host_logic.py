@@ -25,7 +25,7 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(h, name), f"{name} declared in include/se3diff_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
     lib = _lib.lib()
-    assert lib.se3_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.se3_abi_version() == _lib.ABI_VERSION == 5
 
 
 def test_struct_layouts_match_header():
