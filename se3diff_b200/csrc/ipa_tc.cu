@@ -497,8 +497,8 @@ k_ipa_tc_pass1(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             tc::tmem_wait_ld();
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const float p0 = fast_ex2(__uint_as_float(r[2 * u]) - m), p1 = fast_ex2(__uint_as_float(r[2 * u + 1]) - m);
-                pk[u] = tc::pack_bf16(p0, p1);
+                const float2 d = __fadd2_rn(make_float2(__uint_as_float(r[2 * u]), __uint_as_float(r[2 * u + 1])), make_float2(-m, -m));   // one packed subtract per key pair
+                pk[u] = tc::pack_bf16(fast_ex2(d.x), fast_ex2(d.y));
             }
             const uint4 lo = make_uint4(pk[0], pk[1], pk[2], pk[3]), hi = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             *reinterpret_cast<uint4*>(s.p + ((size_t)(2 * c) * 128 + qrow) * 16) = lo;
