@@ -762,7 +762,8 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const void* pts, int p
     if (pass1_done) {
         return pass2(0, sh.heads);
     } else if (!split) {
-        auto k1 = wide ? k_ipa_tc_pass1<OutT, false, true, kPtsBf16> : k_ipa_tc_pass1<OutT, false, false, kPtsBf16>;
+        auto k1 = wide ? (key_bias ? k_ipa_tc_pass1<OutT, false, true, kPtsBf16, true, true> : k_ipa_tc_pass1<OutT, false, true, kPtsBf16, true, false>)
+                       : k_ipa_tc_pass1<OutT, false, false, kPtsBf16>;
         e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e != cudaSuccess) { set_error("ipa_tc pass1 smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
         // One-item-per-CTA edition: optionally run pass 1 / pass 2 per GROUP of heads, so that pass 2 finds the group's probability
@@ -798,7 +799,7 @@ int launch_tc(const __nv_bfloat16* scal, int scal_stride, const void* pts, int p
         }
         return SE3_OK;
     } else {
-        auto k1 = k_ipa_tc_pass1<OutT, true, true, kPtsBf16>;
+        auto k1 = key_bias ? k_ipa_tc_pass1<OutT, true, true, kPtsBf16, true, true> : k_ipa_tc_pass1<OutT, true, true, kPtsBf16, true, false>;
         e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e != cudaSuccess) { set_error("ipa_tc pass1 (split) smem attribute (%zu B): %s", smem1, cudaGetErrorString(e)); return SE3_ECUDA; }
         cudaLaunchConfig_t cfg = {};

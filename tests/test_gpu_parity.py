@@ -791,6 +791,34 @@ def test_ipa_tensor_core_operator_vs_fp64(B, L, scale):
             assert err <= 1.5e-2 * ref_max * (2.0 if odt == torch.bfloat16 else 1.0), (name, odt, err, ref_max)
 
 
+@pytest.mark.parametrize("B,L", [(3, 84), (2, 20), (2, 200), (2, 300)])
+def test_ipa_tensor_core_operator_with_key_bias(B, L):
+    """The same operator with an additive key bias (models.py:261-293: -inf on padded / unknown residues, here also finite values):
+    the kernels are compiled with and without the key-bias loads of the logit pass, this is the edition with them (128-thread,
+    256-thread and cluster-split)."""
+    from ipa_tc_reference import H, make, ref, split
+    from se3diff_b200 import ops
+
+    proj, rot, trans, pb, pv, hw, shape = make(B, L, seed=L + 1, pos_scale=1.5)
+    g = torch.Generator().manual_seed(L)
+    kb = (0.5 * torch.randn(B, L, generator=g)).to(DEV)
+    kb[0, L - 5:] = float("-inf")                      # a padded tail
+    kb[1, 3] = float("-inf")                           # an unknown residue in the middle
+    want = ref(proj, rot, trans, pb, pv, hw, B, L, key_bias=kb)
+    ws = ops.ipa_tc_workspace(shape, DEV)
+    pvp, pbt = ops.ipa_tc_pack_pair_value(pv, H), ops.ipa_tc_pack_pair_bias(pb.permute(0, 2, 3, 1))
+    sc, pt = split(proj)
+    got = ops.ipa_attention_tc_fwd(sc, pt, rot, trans, pbt, pvp, kb, hw, shape, ws, out_dtype=torch.float32)
+    assert torch.isfinite(got).all()
+    for name, a, b in (("scalar", 0, 512), ("point", 512, 1280), ("pair", 1280, 1792), ("norm", 1792, 2048)):
+        err = (got[:, a:b].double() - want[:, a:b]).abs().max().item()
+        ref_max = max(1.0, want[:, a:b].abs().max().item())
+        assert err <= 1.5e-2 * ref_max, (name, err, ref_max)
+    # and it is not the edition without: dropping the bias changes the result
+    plain = ops.ipa_attention_tc_fwd(sc, pt, rot, trans, pbt, pvp, None, hw, shape, ws, out_dtype=torch.float32)
+    assert (plain - got).abs().max() > 1e-2
+
+
 def test_ipa_tc_persistent_work_queue_is_per_workspace():
     """The persistent pass-1 kernel draws its work items from a counter in the last 64 bytes of the row-sum workspace (zero before the
     first call, re-zeroed by the kernel): repeated calls on one workspace, and calls with their own workspaces overlapping on two
