@@ -540,7 +540,8 @@ constexpr int kSampleTile = 128;   // rotations (= threads) per tile (256: -1 %,
 // Tiles per CTA.  With two, the second tile's (sigma, u) and operand tiles are in flight while the first is computed: 40 registers
 // instead of 32 (48 resident warps per SM instead of 64).  Measured at n = 1e7 (fraction of the HBM roof, random sigma | one sigma):
 // Philox mode 0.556 | 0.767 with one tile, 0.591 | 0.745 with two; noise passed in 0.618 | 0.911 and 0.626 | 0.862 -- so the Philox
-// mode takes two and the parity mode one.  (Two tiles capped at 32 registers: 0.35 with the noise passed in.)
+// mode takes two and the parity mode one.  (Two tiles capped at 32 registers: 0.35 with the noise passed in.  Philox mode with three /
+// four tiles: 0.50 / 0.32 | 0.70 / 0.55 -- the registers of the extra chains cost more resident warps than the chains hide.)
 __host__ __device__ constexpr int sample_tiles(bool noise_passed_in) { return noise_passed_in ? 1 : 2; }
 template <bool kX, bool kNormals, bool kSigma>
 __global__ void __launch_bounds__(kSampleTile)
