@@ -28,6 +28,31 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.se3_abi_version() == _lib.ABI_VERSION == 5
 
 
+def test_packed_pair_operand_sizes_follow_the_documented_layout():
+    """se3_ipa_tc_packed_pair_bytes (host-side, no GPU): the packed pair bias is [H][L][pitch] with pitch a whole number of 8-element
+    chunks that covers L; for L <= 128 (query-major rows read with one 16-byte shared-memory load per logit step) the chunk count
+    is odd where 8 * chunks <= 128 allows it -- eight consecutive rows then start in eight different bank groups -- and the slab fits
+    the 256 * round_up(L, 16) bytes of the probability operand it lands in; the pair values are [L][H][round_up(L,16)/8][16][8]."""
+    from se3diff_b200 import ops
+
+    for L in list(range(1, 140)) + [200, 256, 257, 300, 511, 512]:
+        for H in (1, 4, 32):
+            bias_bytes, value_bytes = ops._packed_pair_sizes(L, H)
+            assert bias_bytes % (2 * H * L) == 0
+            pitch = bias_bytes // (2 * H * L)
+            assert pitch == ops.ipa_tc_bias_pitch(L, H) and pitch % 8 == 0 and L <= pitch <= L + 15
+            if L <= 128:
+                chunks = pitch // 8
+                assert chunks % 2 == 1 or pitch == 128, (L, pitch)
+                assert L * pitch * 2 <= 256 * ((L + 15) // 16 * 16), (L, pitch)
+                words = pitch // 2                                   # 4-byte words between consecutive rows
+                if chunks % 2 == 1:                                  # eight consecutive rows: eight distinct groups of four banks
+                    assert len({(words * r % 32) // 4 for r in range(8)}) == 8, (L, pitch)
+            else:
+                assert pitch == (L + 7) // 8 * 8
+            assert value_bytes == L * H * ((L + 15) // 16 * 16) * 16 * 2
+
+
 def test_struct_layouts_match_header():
     from se3diff_b200 import _lib
 
